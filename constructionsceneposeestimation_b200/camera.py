@@ -1,0 +1,87 @@
+"""Camera conventions of the reference, packed into the per-frame block the kernels read.
+
+SURVEY §8a rows R4 and R5:
+  * pose 7-vector ``[x, y, z, qx, qy, qz, qw]`` = camera position and camera->world rotation
+    in USD camera axes (-Z forward, +Y up), gcd.py:587-605;
+  * intrinsics from aperture / focal length, gcd.py:646-649 and 2035-2053.
+"""
+from __future__ import annotations
+
+from typing import Mapping, Optional, Sequence
+
+import numpy as np
+
+from ._lib import CAM_STRIDE
+
+# the reference's fallback constants when the Camera API fails (gcd.py:2047-2053, 643-645)
+DEFAULT_FOCAL_LENGTH = 18.14
+DEFAULT_HORIZONTAL_APERTURE = 20.955
+DEFAULT_VERTICAL_APERTURE = 15.2908
+# clipping range set at gcd.py:1437
+DEFAULT_NEAR, DEFAULT_FAR = 0.5, 250.0
+
+
+def camera_params(width: int, height: int, focal_length: float = 12.0, horizontal_aperture: float = 25.0) -> dict:
+    """The ``camera_params`` dict the reference writes (gcd.py:2036-2045); defaults are the
+    script's own focal length / aperture (gcd.py:1442-1443)."""
+    return {
+        "horizontal_aperture": horizontal_aperture,
+        "vertical_aperture": horizontal_aperture * (height / width),
+        "focal_length": focal_length,
+        "width": width,
+        "height": height,
+    }
+
+
+def intrinsics(params: Mapping, width: Optional[int] = None, height: Optional[int] = None):
+    """(fx, fy, cx, cy) exactly as gcd.py:639-649 derives them."""
+    f = params.get("focal_length", DEFAULT_FOCAL_LENGTH)
+    ha = params.get("horizontal_aperture", DEFAULT_HORIZONTAL_APERTURE)
+    va = params.get("vertical_aperture", DEFAULT_VERTICAL_APERTURE)
+    w = params.get("width", width)
+    h = params.get("height", height)
+    fx = (w * f) / ha
+    fy = (h * f) / va
+    return fx, fy, w / 2.0, h / 2.0
+
+
+def quat_xyzw_to_matrix(q: Sequence[float]) -> np.ndarray:
+    """Rotation matrix of a scalar-last quaternion, normalised first (what scipy's
+    ``Rotation.from_quat(q).as_matrix()`` returns; used at gcd.py:681)."""
+    q = np.asarray(q, dtype=np.float64)
+    n = np.sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3])
+    if not n > 0.0:
+        raise ValueError("zero-norm camera quaternion")
+    x, y, z, w = q / n
+    x2, y2, z2, w2 = x * x, y * y, z * z, w * w
+    xy, zw, xz, yw, yz, xw = x * y, z * w, x * z, y * w, y * z, x * w
+    return np.array(
+        [
+            [x2 - y2 - z2 + w2, 2.0 * (xy - zw), 2.0 * (xz + yw)],
+            [2.0 * (xy + zw), -x2 + y2 - z2 + w2, 2.0 * (yz - xw)],
+            [2.0 * (xz - yw), 2.0 * (yz + xw), -x2 - y2 + z2 + w2],
+        ],
+        dtype=np.float64,
+    )
+
+
+def pose_from_usd_matrix(m: np.ndarray):
+    """(t, Rcw) from a USD local-to-world 4x4 (row-vector convention): translation is the last
+    row, and the column-convention rotation is the transpose of the upper 3x3 (gcd.py:599-601)."""
+    m = np.asarray(m, dtype=np.float64).reshape(4, 4)
+    return m[3, :3].copy(), m[:3, :3].T.copy()
+
+
+def pack_camera(pose7: Sequence[float], params: Mapping, near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR,
+                out: Optional[np.ndarray] = None) -> np.ndarray:
+    """One ``double[CAM_STRIDE]`` camera block (layout in include/cspe.h)."""
+    blk = np.zeros(CAM_STRIDE, dtype=np.float64) if out is None else out
+    pose7 = np.asarray(pose7, dtype=np.float64)
+    blk[0:3] = pose7[0:3]
+    blk[3:12] = quat_xyzw_to_matrix(pose7[3:7]).reshape(9)
+    fx, fy, cx, cy = intrinsics(params)
+    blk[12:16] = (fx, fy, cx, cy)
+    blk[16], blk[17] = near, far
+    blk[18], blk[19] = params["width"], params["height"]
+    blk[20:24] = 0.0
+    return blk

@@ -1,0 +1,324 @@
+// K2 — per-object transform, 3D-box corner projection and poses.
+//
+// Replaces the reference's per-object Python loop (gcd.py:1924-1950) and its callee
+// bboxDict_to_transform (gcd.py:553-584): world centre, world size, Euler xyz of the pure
+// rotation — and adds what the reference leaves out: the 8 projected box corners and the
+// object-in-camera 6-DoF pose.
+//
+// One warp per (frame, slot); lanes 0-7 own one corner each, lane 0 then does the pose.  This
+// is 4x4-transform work on <= a few thousand objects: FP64 FMA-free scalar math (the library is
+// built with -fmad=false so every operation rounds exactly like the numpy oracle's), no
+// tensor cores.  Launch/latency bound; amortised by batching frames into one launch.
+#include <math.h>
+
+#include "cspe_common.cuh"
+
+namespace cspe {
+namespace {
+
+struct Mat3 {
+  double m[3][3];
+};
+
+__device__ __forceinline__ double det3(const Mat3& a) {
+  return a.m[0][0] * (a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1]) -
+         a.m[0][1] * (a.m[1][0] * a.m[2][2] - a.m[1][2] * a.m[2][0]) +
+         a.m[0][2] * (a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0]);
+}
+
+// cofactor matrix C with inverse-transpose = C / det
+__device__ __forceinline__ void cofactor3(const Mat3& a, Mat3& c) {
+  c.m[0][0] = a.m[1][1] * a.m[2][2] - a.m[1][2] * a.m[2][1];
+  c.m[0][1] = a.m[1][2] * a.m[2][0] - a.m[1][0] * a.m[2][2];
+  c.m[0][2] = a.m[1][0] * a.m[2][1] - a.m[1][1] * a.m[2][0];
+  c.m[1][0] = a.m[0][2] * a.m[2][1] - a.m[0][1] * a.m[2][2];
+  c.m[1][1] = a.m[0][0] * a.m[2][2] - a.m[0][2] * a.m[2][0];
+  c.m[1][2] = a.m[0][1] * a.m[2][0] - a.m[0][0] * a.m[2][1];
+  c.m[2][0] = a.m[0][1] * a.m[1][2] - a.m[0][2] * a.m[1][1];
+  c.m[2][1] = a.m[0][2] * a.m[1][0] - a.m[0][0] * a.m[1][2];
+  c.m[2][2] = a.m[0][0] * a.m[1][1] - a.m[0][1] * a.m[1][0];
+}
+
+__device__ __forceinline__ double frob2(const Mat3& a) {
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) s += a.m[i][j] * a.m[i][j];
+  return s;
+}
+
+// Orthogonal polar factor of a (== U @ Vt of its SVD, gcd.py:573-574) by scaled Newton
+// iteration X <- (g X + X^-T / g) / 2.  Returns false when a is singular / non-finite.
+__device__ bool polar3(const Mat3& a, Mat3& x) {
+  x = a;
+  for (int it = 0; it < 32; ++it) {
+    const double d = det3(x);
+    if (!(fabs(d) > 0.0) || !isfinite(d)) return false;
+    Mat3 c;
+    cofactor3(x, c);
+    const double inv_d = 1.0 / d;
+    const double nx = frob2(x);
+    double ny = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        c.m[i][j] *= inv_d;
+        ny += c.m[i][j] * c.m[i][j];
+      }
+    if (!(nx > 0.0) || !isfinite(ny)) return false;
+    const double g = sqrt(sqrt(ny / nx));
+    const double ig = 1.0 / g;
+    double diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double nv = 0.5 * (g * x.m[i][j] + ig * c.m[i][j]);
+        const double dl = nv - x.m[i][j];
+        diff += dl * dl;
+        x.m[i][j] = nv;
+      }
+    if (diff <= 1e-30 * 3.0) break;  // ||dX||_F <= 1e-15 * ||Q||_F (Q orthogonal: ||Q||_F^2 = 3)
+  }
+  return true;
+}
+
+// scipy Rotation.as_euler('xyz', degrees=True) (extrinsic), incl. its gimbal-lock rule
+// (third angle := 0 when |cos b| <= 1e-7); gcd.py:576.
+__device__ void euler_xyz_deg(const Mat3& r, double* e) {
+  const double kRad2Deg = 57.295779513082320876798154814105;
+  const double cb = hypot(r.m[0][0], r.m[1][0]);
+  const double b = atan2(-r.m[2][0], cb);
+  double a, c;
+  if (cb > 1e-7) {
+    a = atan2(r.m[2][1], r.m[2][2]);
+    c = atan2(r.m[1][0], r.m[0][0]);
+  } else {
+    c = 0.0;
+    a = r.m[2][0] < 0.0 ? atan2(r.m[0][1], r.m[1][1]) : atan2(-r.m[0][1], r.m[1][1]);
+  }
+  e[0] = a * kRad2Deg;
+  e[1] = b * kRad2Deg;
+  e[2] = c * kRad2Deg;
+}
+
+// rotation matrix -> unit quaternion xyzw with w >= 0 (Shepperd's branch on the largest term)
+__device__ void quat_xyzw(const Mat3& r, double* q) {
+  const double t = r.m[0][0] + r.m[1][1] + r.m[2][2];
+  double x, y, z, w;
+  if (t >= r.m[0][0] && t >= r.m[1][1] && t >= r.m[2][2]) {
+    w = 1.0 + t;
+    x = r.m[2][1] - r.m[1][2];
+    y = r.m[0][2] - r.m[2][0];
+    z = r.m[1][0] - r.m[0][1];
+  } else if (r.m[0][0] >= r.m[1][1] && r.m[0][0] >= r.m[2][2]) {
+    x = 1.0 - t + 2.0 * r.m[0][0];
+    y = r.m[1][0] + r.m[0][1];
+    z = r.m[2][0] + r.m[0][2];
+    w = r.m[2][1] - r.m[1][2];
+  } else if (r.m[1][1] >= r.m[2][2]) {
+    x = r.m[1][0] + r.m[0][1];
+    y = 1.0 - t + 2.0 * r.m[1][1];
+    z = r.m[2][1] + r.m[1][2];
+    w = r.m[0][2] - r.m[2][0];
+  } else {
+    x = r.m[2][0] + r.m[0][2];
+    y = r.m[2][1] + r.m[1][2];
+    z = 1.0 - t + 2.0 * r.m[2][2];
+    w = r.m[1][0] - r.m[0][1];
+  }
+  const double n = sqrt(x * x + y * y + z * z + w * w);
+  double s = 1.0 / n;
+  if (w < 0.0) s = -s;
+  q[0] = x * s;
+  q[1] = y * s;
+  q[2] = z * s;
+  q[3] = w * s;
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    project_objects_kernel(const unsigned char* __restrict__ records, int rec_stride, int recs_per_frame,
+                           const int32_t* __restrict__ obj_record, const double* __restrict__ cam, int B, int N,
+                           double* __restrict__ uv, double* __restrict__ zc_out, double* __restrict__ pose,
+                           double* __restrict__ loose, uint8_t* __restrict__ flags) {
+  const long long obj = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (obj >= static_cast<long long>(B) * N) return;
+  const int lane = threadIdx.x & 31;
+  const int frame = static_cast<int>(obj / N);
+  const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+
+  const int rec = obj_record[obj];
+  if (rec < 0 || rec >= recs_per_frame) {
+    // no record for this slot: defined outputs, flags 0
+    if (lane < 8) {
+      uv[obj * 16 + lane * 2 + 0] = kNaN;
+      uv[obj * 16 + lane * 2 + 1] = kNaN;
+      zc_out[obj * 8 + lane] = kNaN;
+    }
+    if (lane < CSPE_POSE_STRIDE) pose[obj * CSPE_POSE_STRIDE + lane] = kNaN;
+    if (lane < 4) loose[obj * 4 + lane] = kNaN;
+    if (lane == 0) flags[obj] = 0;
+    return;
+  }
+
+  const float* rp = reinterpret_cast<const float*>(records + (static_cast<long long>(frame) * recs_per_frame + rec) *
+                                                                 static_cast<long long>(rec_stride));
+  // [0] semanticId, [1..6] extents, [7..22] transform (row-vector convention), [23] occlusionRatio
+  const float ext_min[3] = {__ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3)};
+  const float ext_max[3] = {__ldg(rp + 4), __ldg(rp + 5), __ldg(rp + 6)};
+  double T[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T[i][j] = static_cast<double>(__ldg(rp + 7 + i * 4 + j));
+
+  const double* cm = cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE;
+  const double t[3] = {cm[0], cm[1], cm[2]};
+  double Rcw[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Rcw[i][j] = cm[3 + i * 3 + j];
+  const double fx = cm[12], fy = cm[13], cx0 = cm[14], cy0 = cm[15], nearc = cm[16];
+
+  // ---- corners (lanes 0..7; other lanes shadow corner lane&7 so shuffles stay full-warp) ----
+  const int k = lane & 7;
+  const double c[3] = {static_cast<double>((k & 1) ? ext_max[0] : ext_min[0]),
+                       static_cast<double>((k & 2) ? ext_max[1] : ext_min[1]),
+                       static_cast<double>((k & 4) ? ext_max[2] : ext_min[2])};
+  double d[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const double pw = ((c[0] * T[0][j] + c[1] * T[1][j]) + c[2] * T[2][j]) + T[3][j];
+    d[j] = pw - t[j];
+  }
+  double pc[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) pc[i] = (Rcw[0][i] * d[0] + Rcw[1][i] * d[1]) + Rcw[2][i] * d[2];
+  const double z = -pc[2];
+  const double u = cx0 + (fx * pc[0]) / z;
+  const double v = cy0 - (fy * pc[1]) / z;
+  const bool front = z > nearc;
+  if (lane < 8) {
+    uv[obj * 16 + lane * 2 + 0] = u;
+    uv[obj * 16 + lane * 2 + 1] = v;
+    zc_out[obj * 8 + lane] = z;
+  }
+  const unsigned fm = __ballot_sync(0xffffffffu, front) & 0xffu;
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+  double umin = front ? u : kInf, vmin = front ? v : kInf, umax = front ? u : -kInf, vmax = front ? v : -kInf;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  if (lane != 0) return;
+
+  if (fm) {
+    loose[obj * 4 + 0] = umin;
+    loose[obj * 4 + 1] = vmin;
+    loose[obj * 4 + 2] = umax;
+    loose[obj * 4 + 3] = vmax;
+  } else {
+    loose[obj * 4 + 0] = loose[obj * 4 + 1] = loose[obj * 4 + 2] = loose[obj * 4 + 3] = kNaN;
+  }
+
+  // ---- pose (lane 0) ----
+  double* po = pose + obj * CSPE_POSE_STRIDE;
+  // gcd.py:566: centre of the local box, float32 mean like np.mean on the f32 corner array
+  double cl[3], cw[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) cl[i] = static_cast<double>(__fmul_rn(__fadd_rn(ext_min[i], ext_max[i]), 0.5f));
+#pragma unroll
+  for (int j = 0; j < 3; ++j) cw[j] = ((cl[0] * T[0][j] + cl[1] * T[1][j]) + cl[2] * T[2][j]) + T[3][j];
+  // gcd.py:578-582: size_world = ||rot[:,k]|| * |max - min| (f32 norm, f32 difference)
+  double size[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const float a0 = __ldg(rp + 7 + i * 4 + 0), a1 = __ldg(rp + 7 + i * 4 + 1), a2 = __ldg(rp + 7 + i * 4 + 2);
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2));
+    const float sc = __fsqrt_rn(n2);
+    const float ext = fabsf(__fsub_rn(ext_max[i], ext_min[i]));
+    size[i] = static_cast<double>(sc) * static_cast<double>(ext);
+  }
+  // rot = M[:3,:3] with M = T^T (gcd.py:568,572): rot[a][b] = T[b][a]
+  Mat3 rot, rwo;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = 0; b < 3; ++b) rot.m[a][b] = T[b][a];
+  const double dr = det3(rot);
+  bool pose_ok = isfinite(dr) && dr > 0.0 && polar3(rot, rwo);
+  pose_ok = pose_ok && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]);
+
+  double tco[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double d0 = cw[0] - t[0], d1 = cw[1] - t[1], d2 = cw[2] - t[2];
+    tco[i] = (Rcw[0][i] * d0 + Rcw[1][i] * d1) + Rcw[2][i] * d2;
+  }
+  po[0] = tco[0];
+  po[1] = tco[1];
+  po[2] = tco[2];
+  if (pose_ok) {
+    Mat3 rco;  // Rcw^T * R_wo
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        rco.m[i][j] = (Rcw[0][i] * rwo.m[0][j] + Rcw[1][i] * rwo.m[1][j]) + Rcw[2][i] * rwo.m[2][j];
+    quat_xyzw(rco, po + 3);
+    euler_xyz_deg(rwo, po + 13);
+  } else {
+    po[3] = po[4] = po[5] = po[6] = kNaN;
+    po[13] = po[14] = po[15] = kNaN;
+  }
+  po[7] = cw[0];
+  po[8] = cw[1];
+  po[9] = cw[2];
+  po[10] = size[0];
+  po[11] = size[1];
+  po[12] = size[2];
+
+  uint8_t fl = CSPE_OBJ_HAS_RECORD;
+  if (fm) fl |= CSPE_OBJ_ANY_FRONT;
+  if (fm == 0xffu) fl |= CSPE_OBJ_ALL_FRONT;
+  if (pose_ok) fl |= CSPE_OBJ_POSE_VALID;
+  flags[obj] = fl;
+}
+
+}  // namespace
+}  // namespace cspe
+
+using namespace cspe;
+
+extern "C" int cspe_project_objects(const void* records, int rec_stride, int recs_per_frame,
+                                    const int32_t* obj_record, const double* cam, int B, int N, double* uv,
+                                    double* z, double* pose, double* loose, uint8_t* flags, void* stream) {
+  CSPE_REQUIRE(B >= 0 && N >= 0 && recs_per_frame >= 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_project_objects: negative size (B=%d N=%d recs_per_frame=%d)", B, N, recs_per_frame);
+  if (B == 0 || N == 0) return CSPE_OK;
+  CSPE_REQUIRE(rec_stride >= CSPE_BBOX3D_RECORD_BYTES && rec_stride % 4 == 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_project_objects: rec_stride %d (need >= %d and a multiple of 4)", rec_stride,
+               CSPE_BBOX3D_RECORD_BYTES);
+  CSPE_REQUIRE(obj_record && cam && uv && z && pose && loose && flags, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_project_objects: null pointer");
+  CSPE_REQUIRE(recs_per_frame == 0 || records != nullptr, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_project_objects: records is null");
+  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 3) == 0 && (reinterpret_cast<uintptr_t>(cam) & 7) == 0,
+               CSPE_ERR_INVALID_ARGUMENT, "cspe_project_objects: misaligned records/cam");
+  const long long total = static_cast<long long>(B) * N;
+  const long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  CSPE_REQUIRE(blocks < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_project_objects: too many objects");
+  project_objects_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned char*>(records), rec_stride, recs_per_frame, obj_record, cam, B, N, uv, z, pose,
+      loose, flags);
+  CSPE_LAUNCH_OK("project_objects_kernel");
+  return CSPE_OK;
+}

@@ -1,0 +1,134 @@
+"""Host-side serialisation of emitted records: the reference's label JSON, COCO and YOLO.
+
+SURVEY §8a rows R7 / S6.  ``reference_label`` keeps the reference's ``label_%06d.json`` schema
+(gcd.py:2056-2064 frame dict, gcd.py:1938-1946 object dict, ``json.dump(indent=2,
+ensure_ascii=False)`` gcd.py:613) key for key and only ADDS fields.
+"""
+from __future__ import annotations
+
+import json
+import math
+from typing import Dict, Iterable, List, Mapping, Optional, Sequence
+
+import numpy as np
+
+from ._lib import OBJ_POSE_VALID
+from .classes import CLASS_NAMES, CLASS_TABLE, SceneObject
+
+
+def _finite_list(a) -> list:
+    return [float(v) if math.isfinite(v) else None for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def object_entry(rec: np.void, obj: SceneObject, keypoints: Optional[Mapping] = None) -> Dict[str, object]:
+    """One element of ``objects`` — reference keys first (gcd.py:1938-1946), extras after."""
+    pose = rec["pose"]
+    valid = bool(int(rec["flags"]) & OBJ_POSE_VALID)
+    entry: Dict[str, object] = {
+        "inst_idx": int(rec["inst_idx"]),
+        "class_id": int(rec["class_id"]),
+        "class_name": obj.class_name,
+        "center": _finite_list(pose[7:10]),
+        "size": _finite_list(pose[10:13]),
+        "rotation": _finite_list(pose[13:16]) if valid else None,
+        "prim_path": obj.prim_path,
+        # ---- additions ([SPEC] stages) ----
+        "pixel_count": int(rec["count"]),
+        "bbox_2d_tight": [int(rec["x_min"]), int(rec["y_min"]), int(rec["x_max"]), int(rec["y_max"])],
+        "bbox_2d_loose": [int(v) for v in rec["loose"]],
+        "occlusion": float(rec["occlusion"]),
+        "truncation": float(rec["truncation"]),
+        "fill": float(rec["fill"]),
+        "bbox_3d_projected": [[_f(u), _f(v)] for u, v in rec["uv"]],
+        "bbox_3d_depth": _finite_list(rec["z"]),
+        "pose_in_camera": {
+            "translation": _finite_list(pose[0:3]),
+            "quaternion_xyzw": _finite_list(pose[3:7]) if valid else None,
+        },
+        "flags": int(rec["flags"]),
+    }
+    if keypoints is not None:
+        entry["keypoints"] = keypoints
+    return entry
+
+
+def _f(v) -> Optional[float]:
+    v = float(v)
+    return v if math.isfinite(v) else None
+
+
+def reference_label(frame_id: int, camera_pose: Sequence[float], camera_params: Mapping, height: int, width: int,
+                    records: np.ndarray, objects: Sequence[SceneObject],
+                    keypoints_by_slot: Optional[Mapping[int, Mapping]] = None) -> Dict[str, object]:
+    """The frame dict of gcd.py:2056-2064."""
+    kps = keypoints_by_slot or {}
+    objs = [object_entry(r, objects[int(r["inst_idx"])], kps.get(int(r["inst_idx"]))) for r in records]
+    return {
+        "frame_id": int(frame_id),
+        "camera_pose": [float(v) for v in camera_pose],
+        "camera_params": dict(camera_params),
+        "objects": objs,
+        "instance_mask_shape": [int(height), int(width)],
+        "num_objects": len(objs),
+        "class_mapping": dict(CLASS_TABLE),
+    }
+
+
+def dump_label_json(label: Mapping, path) -> None:
+    """Same call as the reference's save_label_json (gcd.py:608-613)."""
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(label, f, indent=2, ensure_ascii=False)
+
+
+def yolo_lines(records: np.ndarray) -> List[str]:
+    """``class cx cy w h`` normalised to the image, one line per kept object."""
+    return [
+        f"{int(r['class_id'])} {r['yolo'][0]:.6f} {r['yolo'][1]:.6f} {r['yolo'][2]:.6f} {r['yolo'][3]:.6f}"
+        for r in records
+    ]
+
+
+def coco_categories() -> List[Dict[str, object]]:
+    return [{"id": i, "name": n, "supercategory": "construction"} for i, n in enumerate(CLASS_NAMES)]
+
+
+def coco_annotations(records: np.ndarray, image_id: int, first_ann_id: int,
+                     keypoints_by_slot: Optional[Mapping[int, Mapping]] = None) -> List[Dict[str, object]]:
+    """COCO: bbox = [x_min, y_min, w, h] of the tight box, area = pixel count, iscrowd = 0;
+    keypoints = [x, y, v] * J with num_keypoints = sum(v > 0)."""
+    kps = keypoints_by_slot or {}
+    anns = []
+    for i, r in enumerate(records):
+        x0, y0, x1, y1 = int(r["x_min"]), int(r["y_min"]), int(r["x_max"]), int(r["y_max"])
+        ann: Dict[str, object] = {
+            "id": first_ann_id + i,
+            "image_id": int(image_id),
+            "category_id": int(r["class_id"]),
+            "bbox": [x0, y0, x1 - x0 + 1, y1 - y0 + 1] if int(r["count"]) > 0 else [0, 0, 0, 0],
+            "area": int(r["count"]),
+            "iscrowd": 0,
+            "occlusion": float(r["occlusion"]),
+            "truncation": float(r["truncation"]),
+        }
+        kp = kps.get(int(r["inst_idx"]))
+        if kp is not None:
+            ann["keypoints"] = kp["keypoints"]
+            ann["num_keypoints"] = kp["num_keypoints"]
+        anns.append(ann)
+    return anns
+
+
+def coco_keypoint_block(kp: np.ndarray, vis: np.ndarray) -> Dict[str, object]:
+    """kp f64 [J,2], vis u8 [J] -> {"keypoints": [x,y,v]*J, "num_keypoints": n} (x,y zeroed when v == 0)."""
+    flat: List[float] = []
+    for (x, y), v in zip(kp, vis):
+        v = int(v)
+        if v == 0 or not (math.isfinite(x) and math.isfinite(y)):
+            flat += [0.0, 0.0, 0]
+        else:
+            flat += [float(x), float(y), v]
+    return {"keypoints": flat, "num_keypoints": int((np.asarray(vis) > 0).sum())}
+
+
+def coco_image(image_id: int, width: int, height: int, file_name: str) -> Dict[str, object]:
+    return {"id": int(image_id), "width": int(width), "height": int(height), "file_name": file_name}

@@ -1,0 +1,417 @@
+"""Replicator-Writer-style front end of the annotation hot path.
+
+``ConstructionLabelWriter.write(data)`` takes the annotator dict a Replicator writer receives
+(the same objects the reference's capture loop pulls by hand: depth gcd.py:1681, bbox3d
+gcd.py:1780-1790 / 1916-1922, instance segmentation gcd.py:1818-1842, camera gcd.py:1599 and
+2036-2045) and produces what the reference writes at gcd.py:2055-2072 — ``label_%06d.json``
+(same schema, extra fields added) and ``instance_mask_%06d.npy`` — plus COCO / YOLO records.
+
+Host Python only prepares small tables (prim path -> slot / class / record, camera block);
+pixels are touched exclusively by the CUDA kernels in libcspe.so.  No CPU fallback.
+
+Error conventions follow the reference: a bad object is skipped or flagged, never fatal
+(gcd.py:2024-2027); ``None`` / empty annotators are tolerated (gcd.py:1682, 1788, 1919).
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib, formats, ops
+from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
+from .camera import DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, pack_camera
+from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot,
+                      record_index_for)
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+_IDENTITY_POSE = [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]
+
+
+@dataclass
+class FrameTables:
+    """Host tables of one frame (cached per distinct scene signature)."""
+    objects: List[SceneObject]
+    obj_record: np.ndarray      # int32 [N]
+    slot_class: np.ndarray      # int32 [N]
+    lut_ids: np.ndarray         # int64 [K] instance ids that map to a slot
+    lut_slots: np.ndarray       # int32 [K]
+    max_id: int
+
+
+@dataclass
+class BatchLabels:
+    """Result of one batch: device outputs, pinned host copies and the event that fences them."""
+    frame_ids: List[int]
+    tables: List[FrameTables]
+    height: int
+    width: int
+    camera_poses: List[Sequence[float]]
+    camera_params: List[Mapping]
+    _rec_host: torch.Tensor
+    _nout_host: torch.Tensor
+    _event: torch.cuda.Event
+    _kp_host: Optional[torch.Tensor] = None
+    _vis_host: Optional[torch.Tensor] = None
+    person_slots: Optional[List[List[int]]] = None
+    device_outputs: Dict[str, torch.Tensor] = field(default_factory=dict)
+    _synced: bool = False
+
+    def synchronize(self) -> "BatchLabels":
+        if not self._synced:
+            self._event.synchronize()
+            self._synced = True
+        return self
+
+    @property
+    def n_out(self) -> np.ndarray:
+        self.synchronize()
+        return self._nout_host.numpy()
+
+    def records(self, f: int) -> np.ndarray:
+        """Structured records (``_lib.RECORD_DTYPE``) of batch frame ``f``, in inst_idx order."""
+        self.synchronize()
+        n = int(self._nout_host[f])
+        return self._rec_host[f].numpy().view(RECORD_DTYPE).reshape(-1)[:n]
+
+    def keypoints(self, f: int) -> Optional[Tuple[np.ndarray, np.ndarray]]:
+        if self._kp_host is None:
+            return None
+        self.synchronize()
+        return self._kp_host[f].numpy(), self._vis_host[f].numpy()
+
+    def keypoints_by_slot(self, f: int) -> Dict[int, Dict[str, object]]:
+        kv = self.keypoints(f)
+        if kv is None or self.person_slots is None:
+            return {}
+        kp, vis = kv
+        return {slot: formats.coco_keypoint_block(kp[p], vis[p])
+                for p, slot in enumerate(self.person_slots[f]) if slot >= 0 and p < kp.shape[0]}
+
+    def reference_label(self, f: int) -> Dict[str, object]:
+        return formats.reference_label(self.frame_ids[f], self.camera_poses[f], self.camera_params[f], self.height,
+                                       self.width, self.records(f), self.tables[f].objects,
+                                       self.keypoints_by_slot(f))
+
+    def __len__(self) -> int:
+        return len(self.frame_ids)
+
+
+def _info(annot) -> Mapping:
+    if isinstance(annot, Mapping):
+        info = annot.get("info")
+        return info if isinstance(info, Mapping) else {}
+    return {}
+
+
+def _payload(annot):
+    if isinstance(annot, Mapping):
+        return annot.get("data")
+    return annot
+
+
+class ConstructionLabelWriter:
+    """Drop-in writer for the reference's per-frame label path.
+
+    Parameters mirror the knobs the reference hard-codes: output directory layout
+    (``labels/`` as gcd.py:40), clipping range (gcd.py:1437), and the run-time crane part map
+    (gcd.py:124).  ``formats`` selects what ``write`` serialises: ``"json"`` (reference schema),
+    ``"yolo"``, ``"coco"``, ``"mask"`` (the real instance mask instead of the reference's -1
+    placeholder, gcd.py:2066-2069).
+    """
+
+    annotators = ["instance_segmentation", "distance_to_image_plane", "bounding_box_3d", "camera_params",
+                  "skeleton_data"]
+
+    def __init__(self, output_dir: Optional[str] = None, device: Union[str, torch.device, None] = None,
+                 formats: Sequence[str] = ("json",), min_pixels: int = 1, keypoint_tolerance: float = 0.15,
+                 near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, split_people: bool = False,
+                 record_fallback: str = "first_mesh", crane_part_map: Optional[Mapping] = None,
+                 rank: int = 0, world_size: int = 1, max_pending: int = 2):
+        _lib.load()  # fail loudly right here if the CUDA library is missing
+        if not torch.cuda.is_available():
+            raise _lib.CspeLibraryError("ConstructionLabelWriter needs a CUDA device (no CPU fallback exists)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.output_dir = output_dir
+        self.formats = tuple(formats)
+        self.min_pixels = int(min_pixels)
+        self.keypoint_tolerance = float(keypoint_tolerance)
+        self.near, self.far = float(near), float(far)
+        self.record_fallback = record_fallback
+        self.resolver = ObjectRootResolver(crane_part_map, split_people=split_people)
+        self.rank, self.world_size = rank, world_size
+        self.max_pending = max_pending
+        self._tables_cache: Dict[Tuple, FrameTables] = {}
+        self._next_frame_id = 0
+        self._pending: List[Tuple[BatchLabels, Optional[List[np.ndarray]]]] = []
+        self._coco_images: List[Dict] = []
+        self._coco_annotations: List[Dict] = []
+        self.frames_written = 0
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+            self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=self.device)
+        if output_dir is not None:
+            os.makedirs(os.path.join(output_dir, "labels"), exist_ok=True)
+
+    # ------------------------------------------------------------------ host tables
+    def frame_tables(self, prim_paths: Sequence[str], id_to_labels: Mapping) -> FrameTables:
+        key = (tuple(prim_paths), tuple(id_to_labels.items()))
+        hit = self._tables_cache.get(key)
+        if hit is not None:
+            return hit
+        objects = aggregate_objects(prim_paths, self.resolver)
+        rec_idx = np.asarray(record_index_for(objects, prim_paths, self.record_fallback), dtype=np.int32).reshape(-1)
+        slot_class = np.asarray([o.class_id for o in objects], dtype=np.int32).reshape(-1)
+        mapping = id_to_slot(id_to_labels, objects, self.resolver)
+        ids = np.fromiter(mapping.keys(), dtype=np.int64, count=len(mapping))
+        slots = np.fromiter(mapping.values(), dtype=np.int32, count=len(mapping))
+        ok = (ids >= 0) & (ids < (1 << 32))
+        ids, slots = ids[ok], slots[ok]
+        tables = FrameTables(objects, rec_idx, slot_class, ids, slots, int(ids.max()) if ids.size else -1)
+        if len(self._tables_cache) > 4096:
+            self._tables_cache.clear()
+        self._tables_cache[key] = tables
+        return tables
+
+    # ------------------------------------------------------------------ public surface
+    def write(self, data: Mapping) -> None:
+        """One frame (Replicator ``Writer.write`` signature)."""
+        self.write_batch([data])
+
+    def write_batch(self, frames: Sequence[Mapping]) -> BatchLabels:
+        """Annotate a list of frame dicts in one set of launches and queue them for serialisation."""
+        labels = self.annotate_batch(frames)
+        masks = None
+        if "mask" in self.formats and self.output_dir is not None:
+            masks = [_payload(fr.get("instance_segmentation")) for fr in frames]
+        self._pending.append((labels, masks))
+        while len(self._pending) > self.max_pending:
+            self._serialise(*self._pending.pop(0))
+        return labels
+
+    def flush(self) -> None:
+        while self._pending:
+            self._serialise(*self._pending.pop(0))
+
+    def on_final_frame(self) -> Dict[str, object]:
+        """Flush pending frames, gather the per-class histogram across ranks and write the summary."""
+        self.flush()
+        hist = self.gather_class_histogram()
+        summary = {
+            "frames": self.frames_written,
+            "rank": self.rank,
+            "world_size": self.world_size,
+            "class_histogram": {CLASS_NAMES[i]: int(hist["total"][i]) for i in range(NUM_CLASSES)},
+            "class_histogram_per_rank": hist["per_rank"].tolist(),
+        }
+        if self.output_dir is not None:
+            if "coco" in self.formats:
+                coco = {"images": self._coco_images, "annotations": self._coco_annotations,
+                        "categories": formats.coco_categories()}
+                with open(os.path.join(self.output_dir, f"coco_rank{self.rank:02d}.json"), "w", encoding="utf-8") as f:
+                    json.dump(coco, f)
+            if self.rank == 0:
+                with open(os.path.join(self.output_dir, "label_summary.json"), "w", encoding="utf-8") as f:
+                    json.dump(summary, f, indent=2)
+        return summary
+
+    def gather_class_histogram(self) -> Dict[str, np.ndarray]:
+        """S7: all-gather of the int64[10] histogram (NCCL when torch.distributed is up)."""
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            from .sharding import all_gather_histogram
+
+            per_rank = all_gather_histogram(self.class_hist)
+        else:
+            per_rank = self.class_hist.detach().cpu().numpy().reshape(1, NUM_CLASSES)
+        return {"per_rank": per_rank, "total": per_rank.sum(axis=0)}
+
+    # ------------------------------------------------------------------ the hot path
+    def annotate_batch(self, frames: Sequence[Mapping]) -> BatchLabels:
+        if len(frames) == 0:
+            raise ValueError("annotate_batch needs at least one frame")
+        B = len(frames)
+        dev = self.device
+
+        # ---- host: per-frame tables ----------------------------------------------------
+        tables: List[FrameTables] = []
+        rec_arrays: List[Optional[np.ndarray]] = []
+        cams = np.zeros((B, CAM_STRIDE), dtype=np.float64)
+        frame_ids: List[int] = []
+        poses, params_list = [], []
+        masks: List[ArrayLike] = []
+        for i, fr in enumerate(frames):
+            seg = fr.get("instance_segmentation")
+            mask = _payload(seg)
+            if mask is None:
+                raise ValueError(f"frame {i}: instance_segmentation annotator is missing")
+            masks.append(mask)
+            bbox = fr.get("bounding_box_3d")
+            prim_paths = list(_info(bbox).get("primPaths", []) or [])  # tolerated empty, gcd.py:1788
+            recs = _payload(bbox)
+            if recs is not None and len(recs) != len(prim_paths):
+                n = min(len(recs), len(prim_paths))
+                recs, prim_paths = recs[:n], prim_paths[:n]
+            tables.append(self.frame_tables(prim_paths, _info(seg).get("idToLabels", {}) or {}))
+            rec_arrays.append(recs if recs is not None and len(recs) else None)
+            H, W = int(mask.shape[-2]), int(mask.shape[-1])
+            params = fr.get("camera_params") or default_camera_params(W, H)
+            pose = fr.get("camera_pose")
+            if pose is None:
+                pose = _IDENTITY_POSE
+            pack_camera(pose, params, self.near, self.far, out=cams[i])
+            poses.append(pose)
+            params_list.append(params)
+            fid = fr.get("frame_id")
+            frame_ids.append(int(fid) if fid is not None else self._next_frame_id + i)
+        H, W = int(masks[0].shape[-2]), int(masks[0].shape[-1])
+        for i, m in enumerate(masks):
+            if tuple(m.shape[-2:]) != (H, W):
+                raise ValueError(f"frame {i}: mask shape {tuple(m.shape)} differs from {(H, W)} (one resolution per batch)")
+        frame_base = frame_ids[0]
+        contiguous_ids = all(frame_ids[i] == frame_base + i for i in range(B))
+        self._next_frame_id = max(self._next_frame_id, max(frame_ids) + 1)
+
+        N = max(1, max(len(t.objects) for t in tables))
+        R = max(1, max((len(r) for r in rec_arrays if r is not None), default=1))
+        same_tables = all(t is tables[0] for t in tables)
+        L = max(1, max(t.max_id for t in tables) + 1)
+        lut = np.full((1 if same_tables else B, L), -1, dtype=np.int32)
+        obj_record = np.full((B, N), -1, dtype=np.int32)
+        slot_class = np.full((B, N), -1, dtype=np.int32)
+        rec_bytes = np.zeros((B, R, BBOX3D_DTYPE.itemsize), dtype=np.uint8)
+        for i, t in enumerate(tables):
+            n = len(t.objects)
+            obj_record[i, :n] = t.obj_record
+            slot_class[i, :n] = t.slot_class
+            if i == 0 or not same_tables:
+                lut[i if not same_tables else 0, t.lut_ids] = t.lut_slots
+            r = rec_arrays[i]
+            if r is not None:
+                r = np.ascontiguousarray(r)
+                if r.dtype.itemsize != BBOX3D_DTYPE.itemsize:
+                    raise ValueError(f"frame {i}: bounding_box_3d record itemsize {r.dtype.itemsize} != 96")
+                rec_bytes[i, : len(r)] = r.view(np.uint8).reshape(len(r), -1)
+            else:
+                obj_record[i, :] = -1
+
+        # ---- device: uploads + kernels on the writer's stream ----------------------------
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            d_mask = self._stack_to_device(masks, torch.int32)
+            d_lut = torch.from_numpy(lut if not same_tables else lut[0]).to(dev, non_blocking=True)
+            d_obj_record = torch.from_numpy(obj_record).to(dev, non_blocking=True)
+            d_slot_class = torch.from_numpy(slot_class).to(dev, non_blocking=True)
+            d_rec = torch.from_numpy(rec_bytes).to(dev, non_blocking=True)
+            d_cam = torch.from_numpy(cams).to(dev, non_blocking=True)
+
+            scan = ops.mask_scan(d_mask, d_lut, N)
+            uv, z, pose, loose, flags = ops.project_objects(d_rec, d_obj_record, d_cam)
+            kp_host = vis_host = None
+            person_slots = None
+            d_kp = d_vis = None
+            joints_list = [self._joints_of(fr) for fr in frames]
+            depth_list = [_payload(fr.get("distance_to_image_plane")) for fr in frames]
+            if all(j is not None and j.shape[0] > 0 for j in joints_list) and all(d is not None for d in depth_list) \
+                    and len({tuple(j.shape) for j in joints_list}) == 1:
+                d_depth = self._stack_to_device(depth_list, torch.float32)
+                d_joints = self._stack_to_device(joints_list, torch.float32)
+                d_kp, _kz, d_vis = ops.keypoints(d_joints, d_depth, d_cam, self.keypoint_tolerance)
+                person_slots = [self._person_slots(t, joints_list[i].shape[0]) for i, t in enumerate(tables)]
+            if contiguous_ids:
+                rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels,
+                                             frame_base, class_hist=self.class_hist)
+            else:
+                rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels, 0,
+                                             class_hist=self.class_hist)
+            rec_host = torch.empty(rec_dev.shape, dtype=torch.uint8, pin_memory=True)
+            nout_host = torch.empty(n_out.shape, dtype=torch.int32, pin_memory=True)
+            rec_host.copy_(rec_dev, non_blocking=True)
+            nout_host.copy_(n_out, non_blocking=True)
+            if d_kp is not None:
+                kp_host = torch.empty(d_kp.shape, dtype=torch.float64, pin_memory=True)
+                vis_host = torch.empty(d_vis.shape, dtype=torch.uint8, pin_memory=True)
+                kp_host.copy_(d_kp, non_blocking=True)
+                vis_host.copy_(d_vis, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(self.stream)
+
+        labels = BatchLabels(frame_ids, tables, H, W, poses, params_list, rec_host, nout_host, event, kp_host,
+                             vis_host, person_slots,
+                             {"scan": scan, "uv": uv, "z": z, "pose": pose, "loose": loose, "flags": flags,
+                              "records": rec_dev, "n_out": n_out})
+        if not contiguous_ids:
+            labels.synchronize()
+            for f in range(B):  # frame field was written relative to 0
+                labels._rec_host[f].numpy().view(RECORD_DTYPE).reshape(-1)["frame"][: int(nout_host[f])] = frame_ids[f]
+        return labels
+
+    # ------------------------------------------------------------------ helpers
+    def _stack_to_device(self, arrays: Sequence[ArrayLike], dtype: torch.dtype) -> torch.Tensor:
+        """[B, ...] device tensor from per-frame host arrays / device tensors (async copies)."""
+        first = arrays[0]
+        if len(arrays) == 1 and isinstance(first, torch.Tensor) and first.is_cuda:
+            t = first if first.dtype == dtype or (dtype == torch.int32 and first.dtype == torch.uint32) else first.to(dtype)
+            return t.contiguous().unsqueeze(0)
+        shape = tuple(first.shape)
+        out = torch.empty((len(arrays),) + shape, dtype=dtype, device=self.device)
+        for i, a in enumerate(arrays):
+            if isinstance(a, torch.Tensor):
+                src = a
+                if src.dtype == torch.uint32 and dtype == torch.int32:
+                    src = src.view(torch.int32)
+            else:
+                a = np.asarray(a)
+                if dtype == torch.int32 and a.dtype == np.uint32:
+                    a = a.view(np.int32)
+                elif dtype == torch.int32 and a.dtype != np.int32:
+                    a = a.astype(np.uint32).view(np.int32)
+                elif dtype == torch.float32 and a.dtype != np.float32:
+                    a = a.astype(np.float32)
+                src = torch.from_numpy(np.ascontiguousarray(a))
+            out[i].copy_(src, non_blocking=True)
+        return out
+
+    @staticmethod
+    def _joints_of(fr: Mapping) -> Optional[np.ndarray]:
+        sk = fr.get("skeleton_data")
+        if sk is None:
+            return None
+        j = sk.get("globalTranslations") if isinstance(sk, Mapping) else sk
+        if j is None:
+            return None
+        j = np.asarray(j, dtype=np.float32)
+        return j if j.ndim == 3 and j.shape[-1] == 3 else None
+
+    @staticmethod
+    def _person_slots(t: FrameTables, num_people: int) -> List[int]:
+        """Slot of person p = p-th ``human`` object in slot order (-1 when there are fewer)."""
+        humans = [o.inst_idx for o in t.objects if o.class_name == "human"]
+        return [humans[p] if p < len(humans) else -1 for p in range(num_people)]
+
+    def _serialise(self, labels: BatchLabels, masks: Optional[List[ArrayLike]]) -> None:
+        labels.synchronize()
+        for f in range(len(labels)):
+            fid = labels.frame_ids[f]
+            recs = labels.records(f)
+            if self.output_dir is not None:
+                ldir = os.path.join(self.output_dir, "labels")
+                if "json" in self.formats:
+                    formats.dump_label_json(labels.reference_label(f), os.path.join(ldir, f"label_{fid:06d}.json"))
+                if "yolo" in self.formats:
+                    with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
+                        fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))
+                if "mask" in self.formats and masks is not None:
+                    m = masks[f]
+                    m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+                    np.save(os.path.join(ldir, f"instance_mask_{fid:06d}.npy"), m.astype(np.int32, copy=False))
+            if "coco" in self.formats:
+                self._coco_images.append(formats.coco_image(fid, labels.width, labels.height, f"rgb_{fid:06d}.png"))
+                self._coco_annotations += formats.coco_annotations(recs, fid, len(self._coco_annotations) + 1,
+                                                                   labels.keypoints_by_slot(f))
+            self.frames_written += 1

@@ -1,0 +1,207 @@
+/*
+ * cspe.h — C ABI of libcspe.so: the B200-native (sm_100a) per-frame annotation hot path
+ * behind xander683/ConstructionScenePoseEstimation's generate_construction_data.py
+ * (abbreviated gcd.py below; all gcd.py:line citations are into that file of the reference).
+ *
+ * The reference has no FFI / plugin API (it is one Python script); its de-facto boundary is
+ * the Replicator annotator-dict surface consumed at gcd.py:1669-1681 (RGB, depth),
+ * gcd.py:1780-1790 / 1916-1922 (bounding_box_3d), gcd.py:1818-1842 (instance_segmentation)
+ * and the label file written at gcd.py:2055-2072.  Every entry point below names the span of
+ * gcd.py it replaces (or, for stages the reference leaves as a hole, the span where it plugs
+ * in).  The Python host side (constructionsceneposeestimation_b200.writer) binds these with
+ * ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns int: 0 = CSPE_OK, < 0 = CSPE_ERR_*; cspe_last_error() returns a
+ *     thread-local human-readable message for the last failure on the calling thread;
+ *   - all data pointers are DEVICE pointers unless the parameter name ends in _host;
+ *   - the caller owns every buffer; the library never allocates user-visible memory;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronises, so calls are CUDA-graph capturable;
+ *   - re-entrant per stream; no global state besides the thread-local error string and a
+ *     per-device cache of immutable device attributes.
+ */
+#ifndef CSPE_H_
+#define CSPE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSPE_ABI_VERSION 1
+
+enum {
+  CSPE_OK = 0,
+  CSPE_ERR_INVALID_ARGUMENT = -1, /* null pointer, negative size, misaligned buffer */
+  CSPE_ERR_UNSUPPORTED = -2,      /* shape outside what the kernels were built for */
+  CSPE_ERR_CUDA = -3,             /* a CUDA runtime call or launch failed */
+  CSPE_ERR_NO_DEVICE = -4         /* no sm_100 device is current */
+};
+
+/* ---- fixed layouts -------------------------------------------------------------------- */
+
+/* per-instance scan result, int32[5]: pixel count, then INCLUSIVE tight box.
+ * Absent instance: {0, W, H, -1, -1}. */
+#define CSPE_SCAN_FIELDS 5
+enum { CSPE_SCAN_COUNT = 0, CSPE_SCAN_XMIN = 1, CSPE_SCAN_YMIN = 2, CSPE_SCAN_XMAX = 3, CSPE_SCAN_YMAX = 4 };
+
+/* Replicator bounding_box_3d record as the reference indexes it (gcd.py:562-564:
+ * [0] semanticId u32, [1..6] x_min,y_min,z_min,x_max,y_max,z_max f32, [7] transform f32[4][4]
+ * (USD row-vector convention), [8] occlusionRatio f32) = 96 bytes. */
+#define CSPE_BBOX3D_RECORD_BYTES 96
+
+/* per-frame camera block, double[CSPE_CAM_STRIDE]:
+ *  [0..2]  t    camera position in world            (gcd.py:599 ExtractTranslation)
+ *  [3..11] Rcw  camera->world rotation, row-major, column-vector convention
+ *               (gcd.py:600-601 ExtractRotationMatrix().GetTranspose()), USD camera axes
+ *               (-Z forward, +Y up)
+ *  [12] fx [13] fy [14] cx [15] cy                   (gcd.py:646-649)
+ *  [16] near clip  [17] far clip                     (gcd.py:1437)
+ *  [18] W  [19] H  [20..23] reserved (0)                                                  */
+#define CSPE_CAM_STRIDE 24
+
+/* per-object pose block, double[CSPE_POSE_STRIDE]:
+ *  [0..2] t_co   object centre in the camera frame
+ *  [3..6] q_co   object->camera rotation, quaternion xyzw, w >= 0
+ *  [7..9] center_world  [10..12] size_world  [13..15] euler xyz degrees (gcd.py:553-584) */
+#define CSPE_POSE_STRIDE 16
+
+/* object flags (uint8) */
+enum {
+  CSPE_OBJ_HAS_RECORD = 1,  /* a bbox3d record was resolved for the slot */
+  CSPE_OBJ_ANY_FRONT = 2,   /* at least one 3D-box corner has z > near */
+  CSPE_OBJ_ALL_FRONT = 4,   /* all eight corners have z > near */
+  CSPE_OBJ_POSE_VALID = 8   /* rotation part is finite with det > 0 (scipy would not raise) */
+};
+
+/* keypoint visibility, COCO convention */
+enum { CSPE_KP_OUT = 0, CSPE_KP_OCCLUDED = 1, CSPE_KP_VISIBLE = 2 };
+
+/* One emitted label record (array-of-structs so a host can view the D2H buffer with one
+ * numpy structured dtype).  408 bytes, 8-byte aligned. */
+typedef struct cspe_record {
+  int32_t frame;       /* global frame id (frame_base + batch index) */
+  int32_t inst_idx;    /* slot = reference inst_idx (gcd.py:1876-1886) */
+  int32_t class_id;    /* gcd.py:69-106 */
+  int32_t count;       /* visible pixels */
+  int32_t x_min, y_min, x_max, y_max; /* tight box, inclusive */
+  int32_t flags;       /* CSPE_OBJ_* */
+  int32_t loose[4];    /* projected 3D box clipped to the image, inclusive ints; empty -> {0,0,-1,-1} */
+  int32_t pad0;
+  float occlusion;     /* 1 - visible_frac */
+  float fill;          /* count / tight_area */
+  float truncation;    /* 1 - clipped_area / unclipped_area of the projected 3D box */
+  float visible_frac;  /* min(1, count / loose_area) */
+  float yolo[4];       /* cx/W, cy/H, w/W, h/H of the tight box */
+  double uv[16];       /* 8 projected corners (u,v) in pixels */
+  double z[8];         /* camera depth of each corner (+ = in front) */
+  double pose[CSPE_POSE_STRIDE];
+} cspe_record;
+
+#define CSPE_NUM_CLASSES 10 /* class ids 0..9, gcd.py:69-106 */
+
+/* depth statistics block per frame (gcd.py:314-359), see cspe_depth_stats */
+typedef struct cspe_depth_stats_t {
+  int64_t valid_pixels; /* isfinite & > 0 */
+  int64_t zero_pixels;  /* == 0 */
+  int64_t inf_pixels;   /* isinf */
+  int64_t total_pixels;
+  float depth_min;      /* over valid pixels; 0 if none */
+  float depth_max;
+  double depth_sum;     /* f64 sum over valid pixels (mean = sum / valid_pixels) */
+} cspe_depth_stats_t;
+
+/* ---- library ---------------------------------------------------------------------------- */
+
+int cspe_version(void);              /* CSPE_ABI_VERSION */
+const char* cspe_last_error(void);   /* thread-local; "" if none */
+/* SM count and compute capability of the current device. */
+int cspe_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- K1: instance-ID mask scan  (fills the hole at gcd.py:1908-1910 / 2066-2069; input is
+ * the instance_segmentation annotator attached at gcd.py:1475) ----------------------------
+ * mask     uint32 [B][H][W] row-major, Replicator native ids
+ * id2slot  int32 LUT: slot = id < lut_len ? id2slot[frame*lut_stride + id] : -1;
+ *          slot < 0 or >= N means "ignore" (BACKGROUND 0, UNLABELLED 1, unmapped meshes).
+ *          Several ids may map to one slot (mesh -> object aggregation, gcd.py:1858-1891):
+ *          counts add, boxes union.  lut_stride = 0 shares one LUT across the batch.
+ * out      int32 [B][N][5]  (CSPE_SCAN_*), fully overwritten.
+ * Single pass over the mask: 4*H*W bytes read per frame.                                  */
+int cspe_mask_scan(const uint32_t* mask, int B, int H, int W,
+                   const int32_t* id2slot, int lut_len, int64_t lut_stride,
+                   int N, int32_t* out, void* stream);
+
+/* K1 without the initialisation: merges this mask's pixels into an `out` that already holds
+ * valid scan entries (counts add, boxes union) — e.g. a frame delivered in several tiles. */
+int cspe_mask_scan_accumulate(const uint32_t* mask, int B, int H, int W,
+                              const int32_t* id2slot, int lut_len, int64_t lut_stride,
+                              int N, int32_t* out, void* stream);
+
+/* K1 with the depth-quality statistics of gcd.py:314-359 fused into the same launch
+ * (depth float32 [B][H][W]; stats cspe_depth_stats_t[B], fully overwritten). */
+int cspe_mask_scan_depth_stats(const uint32_t* mask, const float* depth, int B, int H, int W,
+                               const int32_t* id2slot, int lut_len, int64_t lut_stride,
+                               int N, int32_t* out, cspe_depth_stats_t* stats, void* stream);
+
+/* ---- K2: per-object transform, projection and pose  (replaces the per-object loop
+ * gcd.py:1924-1950 -> bboxDict_to_transform gcd.py:553-584, and adds corner projection and
+ * the object-in-camera pose the reference leaves out) --------------------------------------
+ * records     bbox3d records, frame f record r at records + (f*recs_per_frame + r)*rec_stride
+ * obj_record  int32 [B][N]: record index of slot n in frame f, or -1 (no record -> flags 0)
+ * cam         double [B][CSPE_CAM_STRIDE]
+ * uv          double [B][N][8][2]   z double [B][N][8]   pose double [B][N][CSPE_POSE_STRIDE]
+ * loose       double [B][N][4] = u_min,v_min,u_max,v_max over in-front corners (NaN if none)
+ * flags       uint8  [B][N]                                                                */
+int cspe_project_objects(const void* records, int rec_stride, int recs_per_frame,
+                         const int32_t* obj_record, const double* cam, int B, int N,
+                         double* uv, double* z, double* pose, double* loose, uint8_t* flags,
+                         void* stream);
+
+/* ---- K3: skeleton keypoint projection + depth-buffer visibility ([SPEC]; "skelroot" is
+ * only a class keyword in the reference, gcd.py:105) ----------------------------------------
+ * joints  float32 [B][P][J][3] world positions (Replicator skeleton_data globalTranslations)
+ * depth   float32 [B][H][W] distance_to_image_plane (inf = no hit, gcd.py:318-321)
+ * kp      double [B][P][J][2] (u,v)   kz double [B][P][J] camera depth   vis uint8 [B][P][J] */
+int cspe_keypoints(const float* joints, int B, int P, int J,
+                   const float* depth, int H, int W, const double* cam, double tol,
+                   double* kp, double* kz, uint8_t* vis, void* stream);
+
+/* ---- K4: occlusion ratios, order-preserving compaction, record emission and class
+ * histogram  (replaces pose_list assembly gcd.py:1938-1946 and generalises the object
+ * counter gcd.py:361-372) -------------------------------------------------------------------
+ * scan        int32 [B][N][5] from K1;  uv/z/pose/loose/flags from K2
+ * slot_class  int32 [B][N] class id per slot (-1 = empty slot)
+ * records     cspe_record [B][N]: frame f's kept records are records[f*N .. f*N+n_out[f]),
+ *             in increasing inst_idx order (stable)
+ * n_out       int32 [B]
+ * class_hist  int64 [CSPE_NUM_CLASSES], ACCUMULATED (caller zeroes it at sweep start)      */
+int cspe_emit(const int32_t* scan, const double* uv, const double* z, const double* pose,
+              const double* loose, const uint8_t* flags, const int32_t* slot_class,
+              int B, int N, int H, int W, int min_pixels, int frame_base,
+              cspe_record* records, int32_t* n_out, int64_t* class_hist, void* stream);
+
+/* ---- next rows ------------------------------------------------------------- */
+
+/* f1: depth -> coloured point cloud (gcd.py:616-711).  One frame per call.
+ * depth float32 [H][W]; rgb uint8 [H][W][C] (C = 3 or 4) or NULL (white);
+ * cam double[CSPE_CAM_STRIDE] (uses t, Rcw, fx, fy, cx, cy exactly as gcd.py:664-685 does);
+ * out double [capacity][6] x,y,z,r,g,b in row-major pixel order (stable compaction);
+ * n_points int64[1]; scratch: cspe_pointcloud_workspace_bytes(H, W) bytes.
+ * Valid pixel: isfinite & > 0 & < 250 (gcd.py:655).  Points beyond capacity are dropped
+ * but still counted. */
+size_t cspe_pointcloud_workspace_bytes(int H, int W);
+int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_channels,
+                             int H, int W, const double* cam, double* out, int64_t capacity,
+                             int64_t* n_points, void* workspace, void* stream);
+
+/* f2: depth statistics alone (gcd.py:314-359); stats cspe_depth_stats_t[B]. */
+int cspe_depth_stats(const float* depth, int B, int H, int W, cspe_depth_stats_t* stats,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSPE_H_ */

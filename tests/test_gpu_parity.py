@@ -1,0 +1,464 @@
+"""GPU parity: every CUDA kernel, called through the C ABI, against the numpy oracle.
+
+Integers (counts, boxes, flags, visibility, record order, histogram) must be bit-exact;
+pixel coordinates within 1e-4 px and poses within 1e-5 relative (north_star's bar).
+"""
+import numpy as np
+import pytest
+
+from tests import helpers
+from oracle import labels as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def T(cuda_device):
+    import torch
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_device):
+    from constructionsceneposeestimation_b200 import ops
+    return ops
+
+
+def _scan_gpu(T, ops, mask, lut, N):
+    m = T.from_numpy(np.ascontiguousarray(mask).view(np.int32)).cuda()
+    l = T.from_numpy(np.ascontiguousarray(lut).astype(np.int32)).cuda()
+    out = ops.mask_scan(m, l, N)
+    T.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _random_mask(rng, B, H, W, n_ids, noise=False):
+    """Blobby (or per-pixel noise) uint32 masks with ids 0..n_ids+1 (0/1 unmapped)."""
+    if noise:
+        return rng.integers(0, n_ids + 2, size=(B, H, W), dtype=np.uint32)
+    mask = np.zeros((B, H, W), dtype=np.uint32)
+    for b in range(B):
+        for i in rng.permutation(n_ids):
+            h, w = int(rng.integers(1, max(2, H // 2 + 1))), int(rng.integers(1, max(2, W // 2 + 1)))
+            y, x = int(rng.integers(0, H - h + 1)), int(rng.integers(0, W - w + 1))
+            mask[b, y:y + h, x:x + w] = i + 2
+    return mask
+
+
+def _dense_lut(rng, n_ids, N, merge=False):
+    lut = np.full(n_ids + 2, -1, dtype=np.int32)
+    slots = rng.integers(0, N, size=n_ids) if merge else rng.permutation(max(n_ids, N))[:n_ids] % N
+    lut[2:] = slots
+    return lut
+
+
+# ------------------------------------------------------------------------------ K1 mask scan
+@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 7, 13), (1, 1, 64), (3, 9, 20), (2, 33, 40), (1, 64, 100),
+                                   (2, 45, 1280), (1, 37, 1922), (2, 16, 24), (1, 130, 4)])
+@pytest.mark.parametrize("noise", [False, True])
+def test_scan_shapes(T, ops, shape, noise):
+    B, H, W = shape
+    rng = np.random.default_rng(hash(shape) % 2**32 + noise)
+    n_ids, N = 9, 6
+    mask = _random_mask(rng, B, H, W, n_ids, noise)
+    lut = _dense_lut(rng, n_ids, N, merge=True)
+    got = _scan_gpu(T, ops, mask, lut, N)
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=False))
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=True))
+
+
+def test_scan_edge_cases(T, ops):
+    rng = np.random.default_rng(7)
+    H, W, N = 24, 60, 5
+    mask = np.zeros((1, H, W), dtype=np.uint32)
+    mask[0, 0, 0] = 2                    # single pixel in a corner
+    mask[0, H - 1, W - 1] = 3            # single pixel in the opposite corner
+    mask[0, :, 0] = np.where(mask[0, :, 0] == 0, 4, mask[0, :, 0])   # full-height column on the border
+    mask[0, 5, :] = 5                    # full-width row
+    mask[0, 10:12, 10:50] = 4_000_000_000  # id beyond the LUT (high bit set)
+    mask[0, 14, 3] = 7                   # id inside the LUT but mapped to -1
+    lut = np.array([-1, -1, 0, 1, 2, 3, 4, -1, 99, -5], dtype=np.int32)  # 99 >= N and -5 are ignored
+    got = _scan_gpu(T, ops, mask, lut, N)
+    want = O.mask_scan(mask, lut, N, fast=False)
+    assert np.array_equal(got, want)
+    assert tuple(got[0, 4]) == (0, W, H, -1, -1)  # absent slot
+
+
+def test_scan_empty_and_unmapped(T, ops):
+    mask = np.zeros((2, 16, 32), dtype=np.uint32)
+    lut = np.array([-1, -1, 0], dtype=np.int32)
+    got = _scan_gpu(T, ops, mask, lut, 3)
+    assert np.array_equal(got, np.tile(np.array([0, 32, 16, -1, -1], dtype=np.int32), (2, 3, 1)))
+    # zero-sized batch / zero slots do not launch anything and do not fail
+    out = ops.mask_scan(T.zeros((0, 16, 32), dtype=T.int32, device="cuda"), T.from_numpy(lut).cuda(), 3)
+    assert tuple(out.shape) == (0, 3, 5)
+    out = ops.mask_scan(T.zeros((1, 16, 32), dtype=T.int32, device="cuda"), T.from_numpy(lut).cuda(), 0)
+    assert tuple(out.shape) == (1, 0, 5)
+
+
+def test_scan_per_frame_lut_and_merge(T, ops):
+    rng = np.random.default_rng(11)
+    B, H, W, n_ids, N = 4, 50, 120, 30, 8
+    mask = _random_mask(rng, B, H, W, n_ids)
+    lut = np.stack([_dense_lut(rng, n_ids, N, merge=True) for _ in range(B)])
+    got = _scan_gpu(T, ops, mask, lut, N)
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=False))
+
+
+def test_scan_unaligned_base_pointer(T, ops):
+    """A mask whose base is only 4-byte aligned takes the non-bulk producer path."""
+    rng = np.random.default_rng(5)
+    H, W, n_ids, N = 40, 64, 6, 6
+    mask = _random_mask(rng, 1, H, W, n_ids)
+    lut = _dense_lut(rng, n_ids, N)
+    flat = T.zeros(H * W + 3, dtype=T.int32, device="cuda")
+    view = flat[1:1 + H * W].view(1, H, W)
+    view.copy_(T.from_numpy(mask.view(np.int32)))
+    assert view.data_ptr() % 16 != 0
+    out = ops.mask_scan(view, T.from_numpy(lut).cuda(), N)
+    T.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), O.mask_scan(mask, lut, N, fast=False))
+
+
+@pytest.mark.parametrize("W", [10240, 10244, 12000, 20484])
+def test_scan_wide_rows(T, ops, W):
+    """Rows wider than one 512-strip segment are split into column segments."""
+    rng = np.random.default_rng(W)
+    mask = _random_mask(rng, 2, 5, W, 12)
+    lut = _dense_lut(rng, 12, 12)
+    got = _scan_gpu(T, ops, mask, lut, 12)
+    assert np.array_equal(got, O.mask_scan(mask, lut, 12, fast=True))
+
+
+def test_scan_many_slots_global_table(T, ops):
+    """More slots than the shared-memory table holds -> direct global merges."""
+    rng = np.random.default_rng(3)
+    N = 4000
+    mask = rng.integers(0, N + 2, size=(2, 96, 200), dtype=np.uint32)
+    lut = np.concatenate([[-1, -1], rng.permutation(N)]).astype(np.int32)
+    got = _scan_gpu(T, ops, mask, lut, N)
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=True))
+
+
+def test_scan_sparse_ids(T, ops):
+    from constructionsceneposeestimation_b200 import synthetic
+    spec = synthetic.SceneSpec(640, 360, 24, 3, 17, config_id=9, sparse_ids=True)
+    frames = synthetic.make_batch(spec, 2)
+    o = helpers.oracle_pipeline(frames)
+    got = _scan_gpu(T, ops, o["mask"], o["lut"], o["obj_record"].shape[1])
+    assert np.array_equal(got, o["scan"])
+    assert got[..., 0].sum() > 0
+
+
+@pytest.mark.parametrize("cfg,nframes", [("c1", 2), ("c2", 3), ("c4", 1)])
+def test_scan_synthetic_configs(T, ops, cfg, nframes):
+    from constructionsceneposeestimation_b200 import synthetic
+    frames = synthetic.make_batch(synthetic.CONFIGS[cfg], nframes)
+    lut, obj_record, *_ = helpers.host_tables(frames)
+    mask = np.stack([fr["instance_segmentation"]["data"] for fr in frames])
+    N = obj_record.shape[1]
+    got = _scan_gpu(T, ops, mask, lut, N)
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=True))
+    if cfg == "c1":
+        assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=False))
+    assert (got[..., 0] > 0).sum() >= N // 4
+
+
+def test_scan_full_size_properties(T, ops):
+    """BASELINE config 2 at full size (64 x 1080p): size-independent properties instead of the
+    (slow) oracle — pixel conservation, idempotence, batch == per-frame, and box sanity."""
+    from constructionsceneposeestimation_b200 import synthetic
+    spec = synthetic.CONFIGS["c2"]
+    uniq = synthetic.make_batch(spec, 4)
+    lut4, obj_record, *_ = helpers.host_tables(uniq)
+    N, L = obj_record.shape[1], lut4.shape[1]
+    m4 = T.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in uniq]).view(np.int32)).cuda()
+    mask = m4.repeat(16, 1, 1)                   # 64 frames, 531 MB
+    lut = T.from_numpy(lut4).cuda().repeat(16, 1)
+    a = ops.mask_scan(mask, lut, N)
+    b = ops.mask_scan(mask, lut, N)
+    T.cuda.synchronize()
+    assert T.equal(a, b)                                              # idempotent / deterministic
+    assert T.equal(a[:4], ops.mask_scan(m4, T.from_numpy(lut4).cuda(), N))  # batch == sub-batch
+    assert T.equal(a[:4].repeat(16, 1, 1), a)                         # replicated frames agree
+    # pixel conservation: map EVERY id (incl. background) to its own slot -> counts sum to H*W
+    all_lut = T.arange(L, dtype=T.int32, device="cuda")
+    full = ops.mask_scan(mask, all_lut, L)
+    assert T.all(full[..., 0].sum(dim=1) == spec.height * spec.width)
+    got = a.cpu().numpy()
+    present = got[..., 0] > 0
+    assert np.all(got[present][:, 1] <= got[present][:, 3]) and np.all(got[present][:, 2] <= got[present][:, 4])
+    area = (got[..., 3] - got[..., 1] + 1) * (got[..., 4] - got[..., 2] + 1)
+    assert np.all(got[..., 0][present] <= area[present])
+    # and the first frames against the oracle itself
+    want = O.mask_scan(np.stack([f["instance_segmentation"]["data"] for f in uniq[:2]]), lut4[:2], N)
+    assert np.array_equal(got[:2], want)
+
+
+def test_scan_with_fused_depth_stats(T, ops):
+    from constructionsceneposeestimation_b200 import synthetic, _lib
+    frames = synthetic.make_batch(synthetic.CONFIGS["c1"], 3)
+    o = helpers.oracle_pipeline(frames)
+    depth = np.stack([f["distance_to_image_plane"] for f in frames])
+    depth[1, :5, :7] = 0.0
+    depth[2, 3, 3] = np.nan
+    depth[2, 4, 4] = -np.inf
+    N = o["obj_record"].shape[1]
+    scan, stats = ops.mask_scan_depth_stats(T.from_numpy(o["mask"].view(np.int32)).cuda(), T.from_numpy(depth).cuda(),
+                                            T.from_numpy(o["lut"]).cuda(), N)
+    alone = ops.depth_stats(T.from_numpy(depth).cuda())
+    T.cuda.synchronize()
+    assert np.array_equal(scan.cpu().numpy(), o["scan"])
+    for st in (stats, alone):
+        st = st.cpu().numpy().view(_lib.DEPTH_STATS_DTYPE).reshape(-1)
+        for b in range(3):
+            ref = O.depth_stats(depth[b])
+            assert int(st[b]["valid_pixels"]) == ref["valid_pixels"]
+            assert int(st[b]["zero_pixels"]) == ref["zero_pixels"]
+            assert int(st[b]["inf_pixels"]) == ref["inf_pixels"]
+            assert int(st[b]["total_pixels"]) == ref["total_pixels"]
+            assert float(st[b]["depth_min"]) == ref["depth_range"][0]
+            assert float(st[b]["depth_max"]) == ref["depth_range"][1]
+            mean = st[b]["depth_sum"] / max(1, st[b]["valid_pixels"])
+            assert abs(mean - ref["depth_mean"]) <= 1e-5 * abs(ref["depth_mean"])
+
+
+def test_depth_stats_degenerate(T, ops):
+    from constructionsceneposeestimation_b200 import _lib
+    depth = np.zeros((3, 9, 14), dtype=np.float32)
+    depth[1] = np.inf
+    depth[2] = np.nan
+    st = ops.depth_stats(T.from_numpy(depth).cuda()).cpu().numpy().view(_lib.DEPTH_STATS_DTYPE).reshape(-1)
+    for b in range(3):
+        ref = O.depth_stats(depth[b])
+        assert (int(st[b]["valid_pixels"]), int(st[b]["zero_pixels"]), int(st[b]["inf_pixels"])) == \
+            (ref["valid_pixels"], ref["zero_pixels"], ref["inf_pixels"])
+        assert float(st[b]["depth_min"]) == 0.0 and float(st[b]["depth_max"]) == 0.0 and st[b]["depth_sum"] == 0.0
+
+
+# ------------------------------------------------------------------------------ K2 projection / pose
+def _project_gpu(T, ops, records, obj_record, cam):
+    rb = T.from_numpy(np.ascontiguousarray(records).view(np.uint8).reshape(records.shape[0], records.shape[1], -1)).cuda()
+    out = ops.project_objects(rb, T.from_numpy(obj_record).cuda(), T.from_numpy(cam).cuda())
+    T.cuda.synchronize()
+    return [t.cpu().numpy() for t in out]
+
+
+@pytest.mark.parametrize("cfg", ["c1", "c2"])
+def test_project_objects(T, ops, cfg):
+    from constructionsceneposeestimation_b200 import synthetic
+    frames = synthetic.make_batch(synthetic.CONFIGS[cfg], 3)
+    o = helpers.oracle_pipeline(frames)
+    uv, z, pose, loose, flags = _project_gpu(T, ops, o["records"], o["obj_record"], o["cam"])
+    assert np.array_equal(flags, o["flags"])
+    assert np.allclose(uv, o["uv"], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL, equal_nan=True)
+    assert np.allclose(z, o["z"], rtol=helpers.REL_TOL, atol=1e-9, equal_nan=True)
+    assert np.allclose(loose, o["loose"], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL, equal_nan=True)
+    helpers.assert_pose_close(pose, o["pose"], (o["flags"] & O.OBJ_POSE_VALID) != 0)
+    # with -fmad=false the projection is the same IEEE sequence as the oracle's: expect identity
+    assert np.array_equal(uv, o["uv"], equal_nan=True) and np.array_equal(z, o["z"], equal_nan=True)
+
+
+def test_project_objects_edge_cases(T, ops):
+    rng = np.random.default_rng(2)
+    recs = np.zeros((1, 6), dtype=O.BBOX3D_DTYPE)
+    for i in range(6):
+        recs[0, i]["x_min"], recs[0, i]["y_min"], recs[0, i]["z_min"] = -1, -0.5, -0.25
+        recs[0, i]["x_max"], recs[0, i]["y_max"], recs[0, i]["z_max"] = 1, 0.5, 0.25
+        m = np.eye(4, dtype=np.float32)
+        m[3, :3] = (0, 0, -10)          # 10 m in front of an identity camera (-Z forward)
+        recs[0, i]["transform"] = m
+    recs[0, 1]["transform"][0, 0] = -1.0                 # mirrored: det < 0 -> scipy would raise
+    recs[0, 2]["transform"][:3, :3] = 0.0                # singular
+    recs[0, 3]["transform"][3, :3] = (0, 0, 10)          # behind the camera
+    recs[0, 4]["transform"][3, :3] = (0, 0, -0.6)        # straddles the near plane
+    recs[0, 5]["transform"][:3, :3] = np.array([[0, 0, -1], [0, 1, 0], [1, 0, 0]], dtype=np.float32)  # gimbal lock
+    cam = O.pack_camera([0, 0, 0, 0, 0, 0, 1], {"focal_length": 12.0, "horizontal_aperture": 25.0,
+                                                "vertical_aperture": 25.0 * 720 / 1280, "width": 1280, "height": 720})[None]
+    obj_record = np.array([[0, 1, 2, 3, 4, 5, -1, 17]], dtype=np.int32)
+    uv, z, pose, loose, flags = _project_gpu(T, ops, recs, obj_record, cam)
+    want = O.project_objects(recs, obj_record, cam)
+    assert np.array_equal(flags, want[4])
+    assert flags[0, 0] == 15 and not (flags[0, 1] & O.OBJ_POSE_VALID) and not (flags[0, 2] & O.OBJ_POSE_VALID)
+    assert not (flags[0, 3] & O.OBJ_ANY_FRONT) and (flags[0, 4] & O.OBJ_ANY_FRONT) and not (flags[0, 4] & O.OBJ_ALL_FRONT)
+    assert flags[0, 6] == 0 and flags[0, 7] == 0 and np.isnan(uv[0, 6]).all()
+    assert np.allclose(uv, want[0], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL, equal_nan=True)
+    helpers.assert_pose_close(pose, want[2], (want[4] & O.OBJ_POSE_VALID) != 0)
+    assert abs(pose[0, 5, 15]) < 1e-9 and abs(abs(pose[0, 5, 14]) - 90.0) < 1e-6  # third angle 0 in gimbal lock
+
+
+def test_reference_transform_matches_kernel(T, ops):
+    """R3: centre / size / Euler against the restated bboxDict_to_transform (gcd.py:553-584)."""
+    from constructionsceneposeestimation_b200 import synthetic
+    frames = synthetic.make_batch(synthetic.CONFIGS["c1"], 2)
+    o = helpers.oracle_pipeline(frames)
+    _, _, pose, _, flags = _project_gpu(T, ops, o["records"], o["obj_record"], o["cam"])
+    for f in range(2):
+        for n in range(o["obj_record"].shape[1]):
+            ri = o["obj_record"][f, n]
+            if ri < 0:
+                continue
+            center, size, euler = O.bbox_to_transform(o["records"][f, ri])
+            assert np.allclose(pose[f, n, 7:10], center, rtol=helpers.REL_TOL, atol=1e-9)
+            assert np.allclose(pose[f, n, 10:13], size, rtol=helpers.REL_TOL, atol=1e-9)
+            de = np.abs(pose[f, n, 13:16] - np.asarray(euler))
+            assert np.all(np.minimum(de, 360 - de) <= 1e-3)  # the reference's SVD runs in float32
+
+
+# ------------------------------------------------------------------------------ K3 keypoints
+@pytest.mark.parametrize("J", [17, 101])
+def test_keypoints(T, ops, J):
+    from constructionsceneposeestimation_b200 import synthetic
+    spec = synthetic.SceneSpec(1920, 1080, 60, 50, J, config_id=3)
+    frames = synthetic.make_batch(spec, 2)
+    o = helpers.oracle_pipeline(frames)
+    kp, kz, vis = ops.keypoints(T.from_numpy(o["joints"]).cuda(), T.from_numpy(o["depth"]).cuda(),
+                                T.from_numpy(o["cam"]).cuda(), 0.15)
+    T.cuda.synchronize()
+    assert np.array_equal(vis.cpu().numpy(), o["vis"])
+    assert np.allclose(kp.cpu().numpy(), o["kp"], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL)
+    assert np.array_equal(kp.cpu().numpy(), o["kp"]) and np.array_equal(kz.cpu().numpy(), o["kz"])
+    counts = np.bincount(o["vis"].ravel(), minlength=3)
+    assert counts[2] > 0 and counts[0] + counts[1] > 0  # the case exercises more than one flag
+
+
+def test_keypoints_edges(T, ops):
+    """Joints exactly on pixel/frustum borders, behind the camera, on inf / nan depth."""
+    H, W = 8, 10
+    params = {"focal_length": 10.0, "horizontal_aperture": 10.0, "vertical_aperture": 8.0, "width": W, "height": H}
+    cam = O.pack_camera([0, 0, 0, 0, 0, 0, 1], params)[None]   # fx = fy = 10, cx = 5, cy = 4
+    depth = np.full((1, H, W), 2.0, dtype=np.float32)
+    depth[0, 0, 0] = np.inf
+    depth[0, 1, 1] = np.nan
+    depth[0, 2, 2] = 1.0
+    pts = [(-1.0, 0.8, -2.0),    # u = 0, v = 0 -> pixel (0,0): inf depth -> occluded (flag 1)
+           (1.0, -0.8, -2.0),    # u = 10 -> out (u == W)
+           (-0.8, 0.6, -2.0),    # u = 1, v = 1 -> nan depth -> occluded
+           (-0.6, 0.4, -2.0),    # pixel (2,2) depth 1.0 < z - tol -> occluded
+           (0.0, 0.0, -2.0),     # centre, depth 2.0 -> visible
+           (0.0, 0.0, -2.15),    # z = d + tol exactly -> visible
+           (0.0, 0.0, -2.1500001),
+           (0.0, 0.0, 2.0),      # behind
+           (0.0, 0.0, -0.5),     # z == near -> not in view
+           (0.0, 0.0, 0.0)]      # z = 0 -> nan/inf projection
+    joints = np.array(pts, dtype=np.float32).reshape(1, 1, -1, 3)
+    kp, kz, vis = ops.keypoints(T.from_numpy(joints).cuda(), T.from_numpy(depth).cuda(), T.from_numpy(cam).cuda(), 0.15)
+    T.cuda.synchronize()
+    want = O.keypoints(joints, depth, cam, 0.15)
+    assert np.array_equal(vis.cpu().numpy(), want[2])
+    assert np.array_equal(kp.cpu().numpy(), want[0], equal_nan=True)
+    assert list(want[2].ravel()[:5]) == [1, 0, 1, 1, 2]
+
+
+# ------------------------------------------------------------------------------ K4 emit + end to end
+def _emit_gpu(T, ops, o, H, W, min_pixels, frame_base):
+    from constructionsceneposeestimation_b200 import _lib
+    args = [T.from_numpy(o[k]).cuda() for k in ("scan", "uv", "z", "pose", "loose", "flags", "slot_class")]
+    rec, n_out, hist = ops.emit(*args, H, W, min_pixels, frame_base)
+    T.cuda.synchronize()
+    return rec.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(rec.shape[0], -1), n_out.cpu().numpy(), hist.cpu().numpy()
+
+
+@pytest.mark.parametrize("min_pixels", [0, 1, 400])
+def test_emit(T, ops, min_pixels):
+    from constructionsceneposeestimation_b200 import synthetic
+    frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 3)
+    o = helpers.oracle_pipeline(frames, min_pixels=min_pixels, frame_base=40)
+    H, W = o["mask"].shape[1:]
+    rec, n_out, hist = _emit_gpu(T, ops, o, H, W, min_pixels, 40)
+    assert np.array_equal(n_out, o["n_out"]) and np.array_equal(hist, o["hist"])
+    assert n_out.sum() > 0
+    for f in range(3):
+        got, want = rec[f, : n_out[f]], o["recs"][f, : n_out[f]]
+        helpers.assert_records_equal(got, want, pose_tol=False)
+        assert np.array_equal(got["pose"], want["pose"], equal_nan=True)  # K4 only copies poses
+        assert np.all(np.diff(got["inst_idx"]) > 0)                       # stable order
+
+
+def test_emit_many_slots(T, ops):
+    """N > one 256-slot chunk: the running base of the block scan."""
+    rng = np.random.default_rng(1)
+    B, N, H, W = 2, 700, 100, 200
+    scan = np.zeros((B, N, 5), dtype=np.int32)
+    scan[..., 0] = rng.integers(0, 50, size=(B, N))
+    scan[..., 1], scan[..., 2] = rng.integers(0, 50, size=(B, N)), rng.integers(0, 50, size=(B, N))
+    scan[..., 3], scan[..., 4] = scan[..., 1] + rng.integers(0, 50, size=(B, N)), scan[..., 2] + rng.integers(0, 50, size=(B, N))
+    o = dict(scan=scan, uv=rng.normal(100, 80, size=(B, N, 8, 2)), z=rng.uniform(1, 30, size=(B, N, 8)),
+             pose=rng.normal(size=(B, N, 16)), loose=np.sort(rng.normal(100, 90, size=(B, N, 2, 2)), axis=2).reshape(B, N, 4),
+             flags=rng.integers(0, 16, size=(B, N)).astype(np.uint8), slot_class=rng.integers(-1, 10, size=(B, N)).astype(np.int32))
+    # loose is (umin, vmin, umax, vmax): reorder the sorted pairs
+    lo = o["loose"].reshape(B, N, 2, 2)
+    o["loose"] = np.concatenate([lo[:, :, 0, :], lo[:, :, 1, :]], axis=-1).copy()
+    rec, n_out, hist = _emit_gpu(T, ops, o, H, W, 5, 0)
+    want, wn, wh = O.emit(o["scan"], o["uv"], o["z"], o["pose"], o["loose"], o["flags"], o["slot_class"], H, W, 5, 0)
+    assert np.array_equal(n_out, wn) and np.array_equal(hist, wh)
+    for f in range(B):
+        helpers.assert_records_equal(rec[f, : n_out[f]], want[f, : wn[f]], pose_tol=False)
+
+
+def test_writer_end_to_end(T, ops, tmp_path):
+    """Writer.write_batch on annotator dicts == oracle pipeline; files follow the reference schema."""
+    import json
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(1280, 720, 20, 4, 17, config_id=1), 3)
+    o = helpers.oracle_pipeline(frames)
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "yolo", "coco", "mask"), split_people=True)
+    labels = w.write_batch(frames)
+    summary = w.on_final_frame()
+    assert np.array_equal(labels.n_out, o["n_out"])
+    for f in range(3):
+        helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
+        kp, vis = labels.keypoints(f)
+        assert np.array_equal(vis, o["vis"][f]) and np.allclose(kp, o["kp"][f], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL)
+        lab = json.loads((tmp_path / "labels" / f"label_{f:06d}.json").read_text())
+        assert list(lab)[:7] == ["frame_id", "camera_pose", "camera_params", "objects", "instance_mask_shape",
+                                 "num_objects", "class_mapping"]                      # gcd.py:2056-2064
+        assert lab["num_objects"] == int(o["n_out"][f]) == len(lab["objects"])
+        assert list(lab["objects"][0])[:7] == ["inst_idx", "class_id", "class_name", "center", "size", "rotation",
+                                               "prim_path"]                          # gcd.py:1938-1946
+        assert np.load(tmp_path / "labels" / f"instance_mask_{f:06d}.npy").shape == (720, 1280)
+        assert len((tmp_path / "labels" / f"label_{f:06d}.txt").read_text().splitlines()) == int(o["n_out"][f])
+    assert sum(summary["class_histogram"].values()) == int(o["n_out"].sum())
+    assert np.array_equal(np.asarray(summary["class_histogram_per_rank"])[0], o["hist"])
+    coco = json.loads((tmp_path / "coco_rank00.json").read_text())
+    assert len(coco["annotations"]) == int(o["n_out"].sum()) and len(coco["images"]) == 3
+    assert any("keypoints" in a for a in coco["annotations"])
+
+
+def test_writer_tolerates_empty_annotators(T, ops):
+    """gcd.py:1682/1788/1919: None or empty annotators never raise; the frame just has no objects."""
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    w = ConstructionLabelWriter(None)
+    mask = np.zeros((32, 48), dtype=np.uint32)
+    for bbox in (None, {"data": np.zeros((0,), dtype=O.BBOX3D_DTYPE), "info": {"primPaths": []}}, {"info": {}}):
+        labels = w.annotate_batch([{"instance_segmentation": {"data": mask, "info": {"idToLabels": {}}},
+                                    "bounding_box_3d": bbox}])
+        assert int(labels.n_out[0]) == 0 and len(labels.records(0)) == 0
+
+
+def test_pointcloud(T, ops):
+    """f1: depth_to_pointcloud_with_rgb (gcd.py:616-711): same points, same order."""
+    from constructionsceneposeestimation_b200 import synthetic, camera
+    spec = synthetic.SceneSpec(320, 180, 12, 2, 17, config_id=6, with_rgb=True)
+    fr = synthetic.make_frame(spec, 0)
+    depth, rgb = fr["distance_to_image_plane"].copy(), fr["rgb"]
+    depth[5, 5], depth[6, 6], depth[7, 7] = 0.0, -1.0, np.nan
+    want = O.depth_to_pointcloud(depth, rgb, fr["camera_params"], fr["camera_pose"])
+    cam = T.from_numpy(camera.pack_camera(fr["camera_pose"], fr["camera_params"])).cuda()
+    pts, n = ops.depth_to_pointcloud(T.from_numpy(depth).cuda(), T.from_numpy(rgb).cuda(), cam)
+    T.cuda.synchronize()
+    n = int(n.item())
+    assert n == len(want)
+    got = pts[:n].cpu().numpy()
+    assert np.array_equal(got[:, 3:], want[:, 3:])
+    assert np.allclose(got[:, :3], want[:, :3], rtol=helpers.REL_TOL, atol=1e-9)
+    # rgb <= 1 everywhere -> the x255 rule (gcd.py:693); no rgb -> white; nothing valid -> 0 points
+    dark = (rgb > 127).astype(np.uint8)
+    want2 = O.depth_to_pointcloud(depth, dark, fr["camera_params"], fr["camera_pose"])
+    pts2, n2 = ops.depth_to_pointcloud(T.from_numpy(depth).cuda(), T.from_numpy(dark).cuda(), cam)
+    assert np.array_equal(pts2[: int(n2.item())].cpu().numpy()[:, 3:], want2[:, 3:])
+    pts3, n3 = ops.depth_to_pointcloud(T.from_numpy(depth).cuda(), None, cam)
+    assert int(n3.item()) == n and bool((pts3[:n, 3:] == 255.0).all())
+    _, n4 = ops.depth_to_pointcloud(T.full((180, 320), float("inf"), device="cuda"), None, cam)
+    assert int(n4.item()) == 0
