@@ -7,16 +7,23 @@
 //
 // Design (B200 / sm_100a):
 //   * persistent grid, one CTA per SM, warp-specialised: 1 producer warp + 16 consumer warps;
-//   * the producer streams row-group tiles (<= 40 KB) into a 4-stage shared-memory ring with
-//     1-D bulk async copies (TMA, SASS UBLKCP) signalled on mbarriers, L2 evict_first;
-//   * each consumer thread owns a 20-pixel column strip (5 x 16 B: an odd number of 16-byte
-//     chunks makes the per-lane LDS.128 pattern bank-conflict free) and walks DOWN the rows of
-//     its CTA's band, so the ids it meets are coherent; it keeps the two most recent ids with
-//     their partial {count, xmin, xmax, ymin, ymax} in registers and touches shared memory
-//     only when a third id shows up;
-//   * evicted entries are merged into a per-CTA shared-memory table with red.shared
-//     add/min/max; the table is merged into global memory with red.global once per
-//     (CTA, frame).
+//   * a tile is 32 rows x 320 pixels; the producer warp streams tiles into a 4-stage
+//     shared-memory ring with one 1-D bulk async copy per row (TMA, SASS UBLKCP; lane r issues
+//     row r) signalled on mbarriers, L2 evict_first.  Rows land with a 1296-byte pitch
+//     (1280 + 16) so the consumers' LDS.128 pattern is bank-conflict free;
+//   * consumer warp w owns the 20-pixel column strip w of the tile and its LANES RUN DOWN THE
+//     ROWS (lane l = row l).  Object silhouettes are dominated by near-vertical edges, so either
+//     all lanes of a warp see a uniform strip (fast path: 5 LDS.128 + ~12 LOP3) or all of them
+//     cross the same edge together (slow path, but with every lane active) — the warp does not
+//     diverge on edges the way a lanes-along-x mapping does;
+//   * each thread keeps the two most recent ids with their partial {count, xmin, xmax, ymin,
+//     ymax} in registers and touches shared memory only when a third id shows up; evicted
+//     entries merge into a per-CTA shared-memory table with red.shared add/min/max through a
+//     shared-memory copy of the frame's id->slot LUT; the table merges into global memory with
+//     red.global once per (CTA, frame);
+//   * work is a contiguous range of passes per CTA, but the pass order inside a frame is
+//     stride-permuted so every CTA samples busy and empty image regions alike (a plain
+//     contiguous split left SMs idle 43 % of the time on instance-dense frames).
 //
 // Integer only, order independent => bit-exact against the numpy oracle.
 #include <limits.h>
@@ -26,16 +33,20 @@
 namespace cspe {
 namespace {
 
-constexpr int kStripPx = 20;
-constexpr int kConsumerWarps = 16;
+constexpr int kStripPx = 20;                      // 5 x 16 B
+constexpr int kConsumerWarps = 16;                // = strips per tile row
 constexpr int kConsumers = kConsumerWarps * 32;   // 512
 constexpr int kThreads = kConsumers + 32;         // + producer warp
+constexpr int kTileRows = 32;                     // = lanes
+constexpr int kTileCols = kConsumerWarps * kStripPx;   // 320 px = 1280 B per row
+constexpr int kPitchBytes = kTileCols * 4 + 16;   // 1296: lane l -> 16-byte bank group (l + ...) % 8
 constexpr int kStages = 4;
-constexpr int kTileBytes = kConsumers * kStripPx * 4;  // 40960
-constexpr int kStageBytes = kTileBytes + 128;          // slack for partial-strip over-read
+constexpr int kStageBytes = kTileRows * kPitchBytes;   // 41472
 constexpr int kBarBytes = 2 * kStages * 8;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kMaxSmemSlots = (kSmemLimit - kStages * kStageBytes - kBarBytes - 64) / (CSPE_SCAN_FIELDS * 4);
+constexpr int kSmemFixed = kStages * kStageBytes + kBarBytes + 64;
+constexpr int kSmemFree = kSmemLimit - kSmemFixed;     // for the slot table and the LUT copy
+constexpr int kDepthLoads = kTileRows * kTileCols / 4 / kConsumers;  // float4 per thread per tile = 5
 
 struct ScanParams {
   const uint32_t* mask;
@@ -46,14 +57,12 @@ struct ScanParams {
   long long lut_stride;
   long long total_passes;
   int B, H, W, N, lut_len;
-  int seg_w;    // columns per segment (W if W <= 10240)
-  int nseg;     // column segments per row
-  int spr;      // strips per segment row
-  int rpp;      // rows per pass
-  int gpf;      // row groups per frame
-  int pitch;    // smem row pitch in pixels (multiple of 4)
-  int active;   // consumer threads that own a strip
-  int bulk;     // 1: bulk async copies (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
+  int nseg;      // 320-px column segments per row
+  int nrb;       // 32-row blocks per frame
+  int ppf;       // passes per frame = nseg * nrb
+  int stride;    // pass permutation inside a frame: q -> (q * stride) % ppf, gcd(stride, ppf) = 1
+  int bulk;      // 1: bulk async copies (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
+  int smem_lut;  // 1: the frame's LUT is staged in shared memory
 };
 
 struct Entry {
@@ -92,10 +101,9 @@ __device__ __forceinline__ void red_global_max(int32_t* p, int v) {
 // Merge one evicted register entry into the CTA table (shared) or straight into `out`.
 template <bool kSmemTable>
 __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx, int ymn, int ymx,
-                                         const int32_t* __restrict__ lut, int lut_len, int N,
-                                         int32_t* tab) {
+                                         const int32_t* lut, int lut_len, int N, int32_t* tab) {
   if (id >= static_cast<uint32_t>(lut_len)) return;
-  const int slot = __ldg(lut + id);
+  const int slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
   if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
   int32_t* e = tab + slot * CSPE_SCAN_FIELDS;
   if (kSmemTable) {
@@ -186,7 +194,9 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   return r;
 }
 
-#define CSPE_STEP(V, X)                                                                 \
+
+// make `V` the MRU entry e0 (swap with e1, or evict e1)
+#define CSPE_SWITCH(V)                                                                  \
   do {                                                                                  \
     const uint32_t v__ = (V);                                                           \
     if (v__ != e0.id) {                                                                 \
@@ -202,11 +212,15 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
         entry_reset(e0, v__);                                                           \
       }                                                                                 \
     }                                                                                   \
-    e0.cnt += 1;                                                                        \
-    e0.xmn = min(e0.xmn, (X));                                                          \
-    e0.xmx = max(e0.xmx, (X));                                                          \
+  } while (0)
+
+#define CSPE_ACCUM(CNT, X0, X1)                                                         \
+  do {                                                                                  \
+    e0.cnt += (CNT);                                                                    \
+    e0.xmn = min(e0.xmn, (X0));                                                         \
+    e0.xmx = max(e0.xmx, (X1));                                                         \
     e0.ymn = min(e0.ymn, y);                                                            \
-    e0.ymx = y;                                                                         \
+    e0.ymx = max(e0.ymx, y);                                                            \
   } while (0)
 
 template <bool kSmemTable, bool kDepth>
@@ -215,11 +229,11 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   int32_t* table = reinterpret_cast<int32_t*>(empty_bar + kStages);
+  int32_t* lut_s = table + (kSmemTable ? p.N * CSPE_SCAN_FIELDS : 0);
 
   const int tid = threadIdx.x;
   const long long p_begin = p.total_passes * blockIdx.x / gridDim.x;
   const long long p_end = p.total_passes * (blockIdx.x + 1) / gridDim.x;
-  const int ppf = p.nseg * p.gpf;
 
   if (tid == 0) {
 #pragma unroll
@@ -234,54 +248,49 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
   }
   __syncthreads();
 
-  // decode the first pass
-  int frame = static_cast<int>(p_begin / ppf);
-  int q = static_cast<int>(p_begin % ppf);
-  int seg = q / p.gpf;
-  int g = q % p.gpf;
+  // virtual pass index v -> (frame, q); the tile is pq = (q * stride) % ppf -> (row block, segment)
+  int frame = static_cast<int>(p_begin / p.ppf);
+  int q = static_cast<int>(p_begin % p.ppf);
+  int pq = static_cast<int>((static_cast<long long>(q) * p.stride) % p.ppf);
 
   if (tid >= kConsumers) {
     // ===================== producer warp =====================
     const int lane = tid - kConsumers;
-    if (p.bulk && lane != 0) return;
     const uint64_t policy = l2_policy_evict_first();
     int it = 0;
     for (long long pp = p_begin; pp < p_end; ++pp, ++it) {
       const int stage = it % kStages;
       const uint32_t parity = (it / kStages) & 1;
-      mbar_wait(&empty_bar[stage], parity ^ 1);
-      const int row0 = g * p.rpp;
-      const int rows = min(p.rpp, p.H - row0);
-      const int col0 = seg * p.seg_w;
-      const int cols = min(p.seg_w, p.W - col0);
+      const int rb = pq / p.nseg, seg = pq - rb * p.nseg;
+      const int row0 = rb * kTileRows;
+      const int rows = min(kTileRows, p.H - row0);
+      const int col0 = seg * kTileCols;
+      const int cols = min(kTileCols, p.W - col0);
       unsigned char* dst = smem + stage * kStageBytes;
       const uint32_t* src = p.mask + (static_cast<long long>(frame) * p.H + row0) * p.W + col0;
+      mbar_wait(&empty_bar[stage], parity ^ 1);
       if (p.bulk) {
-        if (p.nseg == 1) {
-          const uint32_t bytes = static_cast<uint32_t>(rows) * p.W * 4u;
-          mbar_arrive_expect_tx(&full_bar[stage], bytes);
-          bulk_g2s(dst, src, bytes, &full_bar[stage], policy);
-        } else {
-          const uint32_t row_bytes = static_cast<uint32_t>(cols) * 4u;
-          mbar_arrive_expect_tx(&full_bar[stage], row_bytes * rows);
-          for (int r = 0; r < rows; ++r)
-            bulk_g2s(dst + static_cast<size_t>(r) * p.pitch * 4, src + static_cast<long long>(r) * p.W, row_bytes,
-                     &full_bar[stage], policy);
-        }
+        const uint32_t row_bytes = static_cast<uint32_t>(cols) * 4u;
+        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], row_bytes * rows);
+        __syncwarp();
+        if (lane < rows)
+          bulk_g2s(dst + lane * kPitchBytes, src + static_cast<long long>(lane) * p.W, row_bytes, &full_bar[stage],
+                   policy);
       } else {
         // unaligned fallback: the producer warp copies with 4-byte loads
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
-        for (int r = 0; r < rows; ++r)
-          for (int c = lane; c < cols; c += 32) d32[r * p.pitch + c] = __ldg(src + static_cast<long long>(r) * p.W + c);
+        for (int r = 0; r < rows; ++r) {
+          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + r * kPitchBytes);
+          for (int c = lane; c < cols; c += 32) d32[c] = __ldg(src + static_cast<long long>(r) * p.W + c);
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);  // release: orders the warp's stores (after __syncwarp)
       }
-      if (++g == p.gpf) {
-        g = 0;
-        if (++seg == p.nseg) {
-          seg = 0;
-          ++frame;
-        }
+      pq += p.stride;
+      if (pq >= p.ppf) pq -= p.ppf;
+      if (++q == p.ppf) {
+        q = 0;
+        pq = 0;
+        ++frame;
       }
     }
     return;
@@ -289,10 +298,8 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
 
   // ===================== consumer warps =====================
   const int lane = tid & 31;
-  const int r = tid / p.spr;
-  const int s = tid - r * p.spr;
-  const bool owner = tid < p.active;
-  const int sm_off = (r * p.pitch + s * kStripPx) * 4;
+  const int wid = tid >> 5;
+  const int sm_off = lane * kPitchBytes + wid * (kStripPx * 4);
   Entry e0, e1;
   entry_reset(e0, 0u);
   entry_reset(e1, 0u);
@@ -300,16 +307,28 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
   if (kDepth) depth_acc_reset(dacc);
 
   int cur_frame = frame;
-  const int32_t* lut = p.lut + static_cast<long long>(cur_frame) * p.lut_stride;
-  int32_t* tab = kSmemTable ? table : p.out + static_cast<long long>(cur_frame) * p.N * CSPE_SCAN_FIELDS;
+  const int32_t* lut = nullptr;
+  int32_t* tab = nullptr;
 
-  auto flush_frame = [&]() {
+  auto open_frame = [&]() {
+    const int32_t* glut = p.lut + static_cast<long long>(cur_frame) * p.lut_stride;
+    if (p.smem_lut) {
+      for (int i = tid; i < p.lut_len; i += kConsumers) lut_s[i] = __ldg(glut + i);
+      named_bar_sync(1, kConsumers);
+      lut = lut_s;
+    } else {
+      lut = glut;
+    }
+    tab = kSmemTable ? table : p.out + static_cast<long long>(cur_frame) * p.N * CSPE_SCAN_FIELDS;
+  };
+
+  auto close_frame = [&]() {
     if (e0.cnt) flush_entry<kSmemTable>(e0.id, e0.cnt, e0.xmn, e0.xmx, e0.ymn, e0.ymx, lut, p.lut_len, p.N, tab);
     if (e1.cnt) flush_entry<kSmemTable>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut, p.lut_len, p.N, tab);
     entry_reset(e0, 0u);
     entry_reset(e1, 0u);
+    if (kSmemTable || p.smem_lut) named_bar_sync(1, kConsumers);  // all flushes landed / LUT no longer read
     if (kSmemTable) {
-      named_bar_sync(1, kConsumers);
       int32_t* gout = p.out + static_cast<long long>(cur_frame) * p.N * CSPE_SCAN_FIELDS;
       for (int i = tid; i < p.N * CSPE_SCAN_FIELDS; i += kConsumers) {
         const int f = i % CSPE_SCAN_FIELDS;
@@ -327,32 +346,36 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
     if (kDepth) depth_acc_flush(dacc, p.stats + cur_frame);
   };
 
+  if (p_begin < p_end) open_frame();
+
   int it = 0;
   for (long long pp = p_begin; pp < p_end; ++pp, ++it) {
     if (frame != cur_frame) {
-      flush_frame();
+      close_frame();
       cur_frame = frame;
-      lut = p.lut + static_cast<long long>(cur_frame) * p.lut_stride;
-      if (!kSmemTable) tab = p.out + static_cast<long long>(cur_frame) * p.N * CSPE_SCAN_FIELDS;
+      open_frame();
     }
     const int stage = it % kStages;
     const uint32_t parity = (it / kStages) & 1;
-    const int row0 = g * p.rpp;
-    const int rows = min(p.rpp, p.H - row0);
+    const int rb = pq / p.nseg, seg = pq - rb * p.nseg;
+    const int row0 = rb * kTileRows;
+    const int rows = min(kTileRows, p.H - row0);
+    const int col0 = seg * kTileCols;
 
-    // fused depth statistics: the depth tile is order-free, so it is read straight from
-    // global memory with coalesced 16-byte streaming loads issued BEFORE the mask wait.
-    float4 dv[5];
+    // fused depth statistics: the depth tile is order-free, so it is read straight from global
+    // memory with coalesced 16-byte streaming loads issued BEFORE the mask wait.
+    float4 dv[kDepthLoads];
     int dn = 0;
     if (kDepth) {
-      const long long px0 = (static_cast<long long>(frame) * p.H + row0) * p.W;  // nseg == 1 guaranteed by host
-      const float4* d4 = reinterpret_cast<const float4*>(p.depth + px0);
-      const int n16 = rows * p.W / 4;
+      const int cols4 = min(kTileCols, p.W - col0) >> 2;  // W % 4 == 0 guaranteed by the host
+      const float* dbase = p.depth + (static_cast<long long>(frame) * p.H + row0) * p.W + col0;
+      const int n16 = rows * cols4;
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {
+      for (int k = 0; k < kDepthLoads; ++k) {
         const int i = tid + k * kConsumers;
         if (i < n16) {
-          dv[k] = ldg_stream_f4(d4 + i);
+          const int r = i / cols4, c4 = i - r * cols4;
+          dv[k] = ldg_stream_f4(reinterpret_cast<const float4*>(dbase + static_cast<long long>(r) * p.W) + c4);
           dn = k + 1;
         }
       }
@@ -360,52 +383,53 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
 
     mbar_wait(&full_bar[stage], parity);
 
-    if (owner && r < rows) {
-      const int x0 = seg * p.seg_w + s * kStripPx;
-      const int len = min(kStripPx, p.W - x0);
-      const int y = row0 + r;
+    const int x0 = col0 + wid * kStripPx;
+    const int len = min(kStripPx, p.W - x0);
+    if (lane < rows && len > 0) {
+      const int y = row0 + lane;
       const unsigned char* base = smem + stage * kStageBytes + sm_off;
       bool done = false;
       if (len == kStripPx) {
         const uint4* sp = reinterpret_cast<const uint4*>(base);
         const uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
-        const uint32_t id = e0.id;
-        uint32_t d = (q0.x ^ id) | (q0.y ^ id) | (q0.z ^ id) | (q0.w ^ id);
-        d |= (q1.x ^ id) | (q1.y ^ id) | (q1.z ^ id) | (q1.w ^ id);
-        d |= (q2.x ^ id) | (q2.y ^ id) | (q2.z ^ id) | (q2.w ^ id);
-        d |= (q3.x ^ id) | (q3.y ^ id) | (q3.z ^ id) | (q3.w ^ id);
-        d |= (q4.x ^ id) | (q4.y ^ id) | (q4.z ^ id) | (q4.w ^ id);
-        if (d == 0) {
-          e0.cnt += kStripPx;
-          e0.xmn = min(e0.xmn, x0);
-          e0.xmx = max(e0.xmx, x0 + kStripPx - 1);
-          e0.ymn = min(e0.ymn, y);
-          e0.ymx = y;
+        const uint32_t a = q0.x;
+        uint32_t d = (q0.y ^ a) | (q0.z ^ a) | (q0.w ^ a);
+        d |= (q1.x ^ a) | (q1.y ^ a) | (q1.z ^ a) | (q1.w ^ a);
+        d |= (q2.x ^ a) | (q2.y ^ a) | (q2.z ^ a) | (q2.w ^ a);
+        d |= (q3.x ^ a) | (q3.y ^ a) | (q3.z ^ a) | (q3.w ^ a);
+        d |= (q4.x ^ a) | (q4.y ^ a) | (q4.z ^ a) | (q4.w ^ a);
+        if (d == 0) {  // the whole strip is one id
+          CSPE_SWITCH(a);
+          CSPE_ACCUM(kStripPx, x0, x0 + kStripPx - 1);
           done = true;
         }
       }
-      if (!done && len > 0) {
+      if (!done) {
         const uint32_t* px = reinterpret_cast<const uint32_t*>(base);
         int j = 0;
 #pragma unroll 1
         for (; j + 4 <= len; j += 4) {
           const uint4 qv = *reinterpret_cast<const uint4*>(px + j);
           const int x = x0 + j;
-          if (((qv.x ^ e0.id) | (qv.y ^ e0.id) | (qv.z ^ e0.id) | (qv.w ^ e0.id)) == 0) {
-            e0.cnt += 4;
-            e0.xmn = min(e0.xmn, x);
-            e0.xmx = max(e0.xmx, x + 3);
-            e0.ymn = min(e0.ymn, y);
-            e0.ymx = y;
+          if (((qv.y ^ qv.x) | (qv.z ^ qv.x) | (qv.w ^ qv.x)) == 0) {
+            CSPE_SWITCH(qv.x);
+            CSPE_ACCUM(4, x, x + 3);
           } else {
-            CSPE_STEP(qv.x, x);
-            CSPE_STEP(qv.y, x + 1);
-            CSPE_STEP(qv.z, x + 2);
-            CSPE_STEP(qv.w, x + 3);
+            CSPE_SWITCH(qv.x);
+            CSPE_ACCUM(1, x, x);
+            CSPE_SWITCH(qv.y);
+            CSPE_ACCUM(1, x + 1, x + 1);
+            CSPE_SWITCH(qv.z);
+            CSPE_ACCUM(1, x + 2, x + 2);
+            CSPE_SWITCH(qv.w);
+            CSPE_ACCUM(1, x + 3, x + 3);
           }
         }
 #pragma unroll 1
-        for (; j < len; ++j) CSPE_STEP(px[j], x0 + j);
+        for (; j < len; ++j) {
+          CSPE_SWITCH(px[j]);
+          CSPE_ACCUM(1, x0 + j, x0 + j);
+        }
       }
     }
     __syncwarp();
@@ -413,19 +437,19 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
 
     if (kDepth) {
 #pragma unroll
-      for (int k = 0; k < 5; ++k)
+      for (int k = 0; k < kDepthLoads; ++k)
         if (k < dn) depth_acc_add4(dacc, dv[k]);
     }
 
-    if (++g == p.gpf) {
-      g = 0;
-      if (++seg == p.nseg) {
-        seg = 0;
-        ++frame;
-      }
+    pq += p.stride;
+    if (pq >= p.ppf) pq -= p.ppf;
+    if (++q == p.ppf) {
+      q = 0;
+      pq = 0;
+      ++frame;
     }
   }
-  flush_frame();
+  if (p_begin < p_end) close_frame();
 }
 
 __global__ void scan_init_kernel(int32_t* out, long long n_entries, int W, int H) {
@@ -513,23 +537,39 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
   p.W = W;
   p.N = N;
   p.lut_len = lut_len;
-  const int max_seg = kConsumers * kStripPx;
-  p.seg_w = W < max_seg ? W : max_seg;
-  p.nseg = (W + p.seg_w - 1) / p.seg_w;
-  p.spr = (p.seg_w + kStripPx - 1) / kStripPx;
-  p.rpp = kConsumers / p.spr;
-  if (p.rpp > H) p.rpp = H;
-  p.gpf = (H + p.rpp - 1) / p.rpp;
-  p.pitch = (p.seg_w + 3) & ~3;
-  p.active = p.rpp * p.spr;
+  p.nseg = (W + kTileCols - 1) / kTileCols;
+  p.nrb = (H + kTileRows - 1) / kTileRows;
+  const long long ppf = static_cast<long long>(p.nseg) * p.nrb;
+  CSPE_REQUIRE(ppf < (1ll << 30), CSPE_ERR_UNSUPPORTED, "cspe_mask_scan: frame of %dx%d has too many tiles", W, H);
+  p.ppf = static_cast<int>(ppf);
+  p.total_passes = ppf * B;
   p.bulk = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
-  p.total_passes = static_cast<long long>(B) * p.nseg * p.gpf;
+  const int grid = static_cast<int>(p.total_passes < sms ? p.total_passes : sms);
 
-  const bool smem_table = N <= kMaxSmemSlots;
-  const size_t smem_bytes = static_cast<size_t>(kStages) * kStageBytes + kBarBytes +
-                            (smem_table ? static_cast<size_t>(N) * CSPE_SCAN_FIELDS * 4 : 0);
-  const long long grid_ll = p.total_passes < sms ? p.total_passes : sms;
-  const int grid = static_cast<int>(grid_ll);
+  // pass permutation: when several CTAs share a frame, stride the tile order so each CTA's
+  // contiguous range samples the whole frame (busy and empty regions alike)
+  const long long per_cta = p.total_passes / grid;
+  int stride = 1;
+  if (per_cta < ppf) {
+    stride = static_cast<int>((ppf + per_cta - 1) / per_cta);
+    auto gcd = [](long long x, long long y) {
+      while (y) {
+        const long long t = x % y;
+        x = y;
+        y = t;
+      }
+      return x;
+    };
+    while (gcd(stride, ppf) != 1) ++stride;
+    if (stride >= ppf) stride = 1;
+  }
+  p.stride = stride;
+
+  const size_t table_bytes = static_cast<size_t>(N) * CSPE_SCAN_FIELDS * 4;
+  const size_t lut_bytes = static_cast<size_t>(lut_len) * 4;
+  const bool smem_table = table_bytes <= static_cast<size_t>(kSmemFree);
+  p.smem_lut = lut_len > 0 && (smem_table ? table_bytes : 0) + lut_bytes <= static_cast<size_t>(kSmemFree);
+  const size_t smem_bytes = kSmemFixed + (smem_table ? table_bytes : 0) + (p.smem_lut ? lut_bytes : 0);
 
   auto kern = smem_table ? mask_scan_kernel<true, kDepth> : mask_scan_kernel<false, kDepth>;
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
@@ -606,8 +646,7 @@ extern "C" int cspe_mask_scan_depth_stats(const uint32_t* mask, const float* dep
   CSPE_REQUIRE(B <= 0 || stats != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_mask_scan_depth_stats: stats is null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool fusable = B > 0 && N > 0 && H > 0 && W > 0 && depth != nullptr && (W % 4 == 0) &&
-                       W <= kConsumers * kStripPx && (reinterpret_cast<uintptr_t>(mask) & 15) == 0 &&
-                       (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+                       (reinterpret_cast<uintptr_t>(mask) & 15) == 0 && (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
   if (!fusable) {
     // shapes the fused kernel does not cover: same results from the two separate launches
     int rc = cspe_mask_scan(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, stream);

@@ -1,0 +1,206 @@
+"""Freeze golden vectors by RUNNING the reference's own functions (build container only).
+
+    python tests/golden/make_golden.py
+
+Reads /root/reference/generate_construction_data.py through oracle.reference_extract (AST
+extraction, nothing copied), feeds seeded inputs to the reference functions on the hot path and
+writes their outputs next to this script.  The GPU box has no /root/reference; tests there (and
+everywhere) replay these fixtures.  numpy/scipy versions used are recorded in the fixtures.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import scipy
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parents[1]
+sys.path.insert(0, str(ROOT))
+
+from oracle import reference_extract  # noqa: E402
+
+BBOX3D_DTYPE = np.dtype(
+    [("semanticId", "<u4"), ("x_min", "<f4"), ("y_min", "<f4"), ("z_min", "<f4"), ("x_max", "<f4"),
+     ("y_max", "<f4"), ("z_max", "<f4"), ("transform", "<f4", (4, 4)), ("occlusionRatio", "<f4")]
+)
+
+CRANE = "/World/GroundPlane/tn__Pk7501SLD_PNR3879_fPM"
+FENCE = ("/World/GroundPlane/Construction_Site_Construction_Zeppelin_Rental_GmbH_Metal_Construction_Site_"
+         "Fencing_height_2,_")
+
+
+def golden_paths():
+    """Real scene patterns (gcd.py:128-141), every crane child of gcd.py:110-121, keyword
+    fallbacks, case games and paths that match nothing."""
+    paths = [
+        f"{FENCE}03", f"{FENCE}03/Mesh_0", f"{FENCE}25/Geom/panel/mesh", f"{FENCE.lower()}07/mesh",
+        "/World/GroundPlane/construction_site_fencing_height_2,_09/Mesh",
+        "/World/Tree/Tree", "/World/Tree/Tree/trunk", "/World/Tree/Tree_01", "/World/Tree/Tree_11/leaves/mesh_3",
+        "/world/tree/tree_05/x", "/World/Tree", "/Other/World/Tree/Tree_02/a/b",
+        "/World/GroundPlane/Cone001", "/World/GroundPlane/Cone001/Cone001", "/World/GroundPlane/Cone001_01/Cone001",
+        "/World/GroundPlane/Cone001_02/Cone001/mesh", "/World/GroundPlane/cone001_07/x", "/World/Props/TrafficCone_3/mesh",
+        CRANE, f"{CRANE}/S104GG03A_SW/mesh", f"{CRANE}/S104S01KB_SW", f"{CRANE}/S104HZ01KA_SW/a/b",
+        f"{CRANE}/S104H01KB_SW/x", f"{CRANE}/S104HZ02KA_SW/x", f"{CRANE}/S104KZ01KA_SW/x",
+        f"{CRANE}/tn__S104EKB_AS_SW_jJ7/part_0", f"{CRANE}/S104KZ02KA_SW/part", f"{CRANE}/tn__HHK320KA_SW_lG/m",
+        f"{CRANE}/tn__HHK319_SW_oD/m", f"{CRANE}/UnknownChild/mesh", f"{CRANE}/Some/boom_segment/mesh",
+        f"{CRANE}/x/chassis_plate", f"{CRANE}/x/Drehwerk", f"{CRANE}/x/teleskop_1", f"{CRANE}/x/Arm",
+        f"{CRANE.lower()}/s104gg03a_sw/mesh", "/World/Other/pk7_copy/mast/mesh", "/World/Other/PK7/whatever",
+        f"{CRANE}/exact/mapped/mesh", f"{CRANE}/exact/mapped/other",
+        "/World/GroundPlane/tn__09684481_", "/World/GroundPlane/tn__09684481_/body/mesh", "/World/x/09684481/y",
+        "/World/GroundPlane/DHGen", "/World/GroundPlane/DHGen/SkelRoot/body", "/World/GroundPlane/DHGen_03/SkelRoot/body",
+        "/World/people/dhgen_female_01/mesh", "/World/Characters/worker/SkelRoot/mesh", "/World/Human_01/mesh",
+        "/World/Props/Dumper_old/mesh", "/World/Props/crane_hook", "/World/Props/CraneBoom_spare", "/World/a/cranebase",
+        "/World/Props/fence_post", "/World/construction_site_sign", "/World/GroundPlane/SomeUnlabelledProp/mesh",
+        "/World/GroundPlane", "", "/", "BACKGROUND", "UNLABELLED", "/World/Tree/Trees_are_green/mesh",
+    ]
+    return paths
+
+
+def make_paths(ref):
+    paths = golden_paths()
+    crane_map = {f"{CRANE}/exact/mapped/mesh": ("craneboom", 8), f"{CRANE}/S104GG03A_SW/mesh": ("cranecolumn", 7)}
+    out = {"paths": paths, "crane_part_map": {k: list(v) for k, v in crane_map.items()}}
+    reference_extract.set_crane_part_map({})
+    out["without_map"] = [list(ref.get_object_root(p)) for p in paths]
+    reference_extract.set_crane_part_map(crane_map)
+    out["with_map"] = [list(ref.get_object_root(p)) for p in paths]
+    reference_extract.set_crane_part_map({})
+    out["construction_class"] = dict(ref.construction_class)
+    out["crane_child_map"] = {k: list(v) for k, v in ref.CRANE_PART_CHILD_MAP.items()}
+    (HERE / "object_roots.json").write_text(json.dumps(out, indent=1, ensure_ascii=False))
+    return len(paths)
+
+
+def random_records(rng, n):
+    from scipy.spatial.transform import Rotation
+
+    recs = np.zeros(n, dtype=BBOX3D_DTYPE)
+    for i in range(n):
+        lo = rng.uniform(-3, 0, 3)
+        hi = lo + rng.uniform(0.05, 6, 3)
+        rot = Rotation.random(random_state=int(rng.integers(1 << 31))).as_matrix()
+        scale = rng.uniform(0.3, 2.5, 3) if i % 3 else np.full(3, rng.uniform(0.5, 2.0))
+        shear = np.eye(3) + (rng.normal(0, 0.05, (3, 3)) if i % 5 == 0 else 0)
+        m = np.eye(4)
+        m[:3, :3] = (rot @ np.diag(scale) @ shear).T   # USD row-vector convention
+        m[3, :3] = rng.uniform(-25, 25, 3)
+        recs[i]["semanticId"] = i % 6
+        recs[i]["x_min"], recs[i]["y_min"], recs[i]["z_min"] = lo
+        recs[i]["x_max"], recs[i]["y_max"], recs[i]["z_max"] = hi
+        recs[i]["transform"] = m.astype(np.float32)
+        recs[i]["occlusionRatio"] = rng.uniform()
+    # axis-aligned, pure yaw, and a near-gimbal pitch
+    recs[0]["transform"] = np.eye(4, dtype=np.float32)
+    yaw = Rotation.from_euler("z", 37.0, degrees=True).as_matrix()
+    recs[1]["transform"][:3, :3] = yaw.T.astype(np.float32)
+    gim = Rotation.from_euler("xyz", [20.0, 89.5, -40.0], degrees=True).as_matrix()
+    recs[2]["transform"][:3, :3] = gim.T.astype(np.float32)
+    return recs
+
+
+def make_transforms(ref):
+    rng = np.random.default_rng(20261018)
+    recs = random_records(rng, 64)
+    centers, sizes, eulers = [], [], []
+    for r in recs:
+        c, s, e = ref.bboxDict_to_transform(r)
+        centers.append(c), sizes.append(s), eulers.append(e)
+    np.savez(HERE / "bbox_to_transform.npz", records=recs, center=np.array(centers), size=np.array(sizes),
+             euler=np.array(eulers))
+    # the mirrored case raises inside scipy (gcd.py:1949 swallows it)
+    bad = recs[5].copy()
+    bad["transform"][0, :3] *= -1
+    try:
+        ref.bboxDict_to_transform(bad)
+        raised = False
+    except Exception:
+        raised = True
+    return len(recs), raised
+
+
+def make_pointcloud(ref):
+    rng = np.random.default_rng(7)
+    H, W = 24, 32
+    depth = rng.uniform(0.2, 300.0, (H, W)).astype(np.float32)
+    depth[rng.uniform(size=(H, W)) < 0.2] = np.inf
+    depth[0, 0], depth[1, 1], depth[2, 2], depth[3, 3] = 0.0, -2.0, np.nan, 250.0
+    rgb = rng.integers(0, 256, (H, W, 4), dtype=np.uint8)
+    params = {"horizontal_aperture": 25.0, "vertical_aperture": 25.0 * H / W, "focal_length": 12.0, "width": W,
+              "height": H}
+    pose = [3.0, -4.0, 2.5, 0.1825742, 0.3651484, 0.5477226, 0.7302967]
+    out = ref.depth_to_pointcloud_with_rgb(depth, rgb, params, pose)
+    dark = (rgb > 200).astype(np.uint8)            # max <= 1 -> the x255 rule (gcd.py:693)
+    out_dark = ref.depth_to_pointcloud_with_rgb(depth, dark, params, pose)
+    out_defaults = ref.depth_to_pointcloud_with_rgb(depth, rgb, {}, pose)   # script default intrinsics
+    none = ref.depth_to_pointcloud_with_rgb(np.full((H, W), np.inf, dtype=np.float32), rgb, params, pose)
+    assert none is None
+    np.savez(HERE / "pointcloud.npz", depth=depth, rgb=rgb, dark=dark, pose=np.array(pose), out=out, out_dark=out_dark,
+             out_defaults=out_defaults, params=json.dumps(params))
+    return out.shape
+
+
+def make_depth_stats(ref):
+    rng = np.random.default_rng(11)
+    cases = {}
+    d0 = rng.uniform(0.5, 250.0, (45, 80)).astype(np.float32)
+    d0[rng.uniform(size=d0.shape) < 0.2] = np.inf
+    d0[:3, :5] = 0.0
+    d0[10, 10] = np.nan
+    d0[11, 11] = -np.inf
+    d0[12, 12] = -3.0
+    cases["mixed"] = d0
+    cases["all_zero"] = np.zeros((9, 14), dtype=np.float32)
+    cases["all_inf"] = np.full((9, 14), np.inf, dtype=np.float32)
+    cases["big"] = rng.uniform(0.5, 250.0, (360, 640)).astype(np.float32)
+    results = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        logger = ref.DataQualityLogger(tmp)
+        for name, d in cases.items():
+            logger.log_frame_start(0, [0, 0, 0])
+            logger.log_depth(True, d)
+            results[name] = logger.current_frame["depth"]
+    np.savez(HERE / "depth_stats.npz", **cases, results=json.dumps(results))
+    return list(results)
+
+
+def make_label_json(ref):
+    label = {
+        "frame_id": 7, "camera_pose": [1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 1.0],
+        "camera_params": {"horizontal_aperture": 25.0, "vertical_aperture": 14.0625, "focal_length": 12.0,
+                          "width": 1280, "height": 720},
+        "objects": [{"inst_idx": 0, "class_id": 2, "class_name": "fence", "center": [1.5, -2.25, 1.0],
+                     "size": [3.5, 0.1, 2.0], "rotation": [0.0, -0.0, 37.0], "prim_path": f"{FENCE}03"}],
+        "instance_mask_shape": [720, 1280], "num_objects": 1, "class_mapping": dict(ref.construction_class),
+    }
+    with tempfile.TemporaryDirectory() as tmp:
+        p = Path(tmp) / "label.json"
+        ref.save_label_json(label, str(p))
+        text = p.read_text(encoding="utf-8")
+    (HERE / "label_schema.json").write_text(json.dumps({"label": label, "text": text}, ensure_ascii=False, indent=1))
+    return len(text)
+
+
+def main():
+    ref = reference_extract.load()
+    import contextlib
+    import io
+
+    with contextlib.redirect_stdout(io.StringIO()):  # the reference functions print progress text
+        n_paths = make_paths(ref)
+        n_recs, raised = make_transforms(ref)
+        pc_shape = make_pointcloud(ref)
+        stats = make_depth_stats(ref)
+        n_text = make_label_json(ref)
+    meta = {"numpy": np.__version__, "scipy": scipy.__version__, "paths": n_paths, "records": n_recs,
+            "mirrored_transform_raises": raised, "pointcloud_shape": list(pc_shape), "depth_cases": stats,
+            "label_text_bytes": n_text, "source": str(reference_extract.REFERENCE_SCRIPT)}
+    (HERE / "META.json").write_text(json.dumps(meta, indent=1))
+    print(json.dumps(meta, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -331,10 +331,10 @@ def test_keypoints_edges(T, ops):
     depth[0, 0, 0] = np.inf
     depth[0, 1, 1] = np.nan
     depth[0, 2, 2] = 1.0
-    pts = [(-1.0, 0.8, -2.0),    # u = 0, v = 0 -> pixel (0,0): inf depth -> occluded (flag 1)
-           (1.0, -0.8, -2.0),    # u = 10 -> out (u == W)
-           (-0.8, 0.6, -2.0),    # u = 1, v = 1 -> nan depth -> occluded
-           (-0.6, 0.4, -2.0),    # pixel (2,2) depth 1.0 < z - tol -> occluded
+    pts = [(-1.0, 0.75, -2.0),   # u = 0, v = 0.25 -> pixel (0,0): inf depth -> occluded (flag 1)
+           (1.0, -0.75, -2.0),   # u = 10 -> out (u == W)
+           (-0.75, 0.5, -2.0),   # u = 1.25, v = 1.5 -> pixel (1,1): nan depth -> occluded
+           (-0.5, 0.25, -2.0),   # u = 2.5, v = 2.75 -> pixel (2,2): depth 1.0 < z - tol -> occluded
            (0.0, 0.0, -2.0),     # centre, depth 2.0 -> visible
            (0.0, 0.0, -2.15),    # z = d + tol exactly -> visible
            (0.0, 0.0, -2.1500001),
