@@ -7,46 +7,54 @@
 //
 // Design (B200 / sm_100a):
 //   * persistent grid, one CTA per SM, warp-specialised: 1 producer warp + 16 consumer warps;
-//   * a tile is 32 rows x 320 pixels; the producer warp streams tiles into a 4-stage
-//     shared-memory ring with one 1-D bulk async copy per row (TMA, SASS UBLKCP; lane r issues
-//     row r) signalled on mbarriers, L2 evict_first.  Rows land with a 1296-byte pitch
-//     (1280 + 16) so the consumers' LDS.128 pattern is bank-conflict free;
-//   * consumer warp w owns the 20-pixel column strip w of the tile and its LANES RUN DOWN THE
-//     ROWS (lane l = row l).  Object silhouettes are dominated by near-vertical edges, so either
-//     all lanes of a warp see a uniform strip (fast path: 5 LDS.128 + ~12 LOP3) or all of them
-//     cross the same edge together (slow path, but with every lane active) — the warp does not
-//     diverge on edges the way a lanes-along-x mapping does;
+//   * the batch is one 2-D tensor [B*H rows][W] behind a TMA tensor map; a tile is 8 boxes of
+//     32 px x 64 rows (128-byte rows, SWIZZLE_128B) = 256 px x 64 rows = 64 KB, streamed into a
+//     3-stage shared-memory ring by cp.async.bulk.tensor.2d (SASS UTMALDG) signalled on
+//     mbarriers, L2 evict_first.  (Measured: this geometry streams at 6.6 TB/s; one 1-D bulk
+//     copy per row segment capped at 4.3 TB/s because every bulk op costs ~85 cycles of TMA.)
+//   * consumer warp w owns box (w & 7) and row half (w >> 3) of the tile: a 32-pixel column
+//     strip whose LANES RUN DOWN THE ROWS (lane l = row l).  Object silhouettes are dominated by
+//     near-vertical edges, so either all lanes of a warp see a uniform strip (fast path:
+//     8 LDS.128 + 16 LOP3) or all of them cross the same edge together (slow path, every lane
+//     active) — the warp does not diverge on edges the way a lanes-along-x mapping does.  The
+//     128-byte swizzle makes both paths' LDS.128 bank-conflict free;
 //   * each thread keeps the two most recent ids with their partial {count, xmin, xmax, ymin,
 //     ymax} in registers and touches shared memory only when a third id shows up; evicted
-//     entries merge into a per-CTA shared-memory table with red.shared add/min/max through a
-//     shared-memory copy of the frame's id->slot LUT; the table merges into global memory with
-//     red.global once per (CTA, frame);
+//     entries are reduced across the warp, then merged into a per-CTA shared-memory table with
+//     red.shared add/min/max through a shared-memory copy of the frame's id->slot LUT; the table
+//     merges into global memory with red.global once per (CTA, frame);
 //   * work is a contiguous range of passes per CTA, but the pass order inside a frame is
 //     stride-permuted so every CTA samples busy and empty image regions alike (a plain
 //     contiguous split left SMs idle 43 % of the time on instance-dense frames).
+//   * masks whose rows are not 16-byte aligned (W % 4 != 0 or a misaligned base) cannot use
+//     TMA: the producer warp then fills the same swizzled layout with plain loads.
 //
 // Integer only, order independent => bit-exact against the numpy oracle.
+#include <cuda.h>
 #include <limits.h>
+#include <string.h>
 
 #include "cspe_common.cuh"
 
 namespace cspe {
 namespace {
 
-constexpr int kStripPx = 20;                      // 5 x 16 B
-constexpr int kConsumerWarps = 16;                // = strips per tile row
+constexpr int kStripPx = 32;                      // one TMA box row = 128 B = 8 x 16 B
+constexpr int kBoxRows = 64;
+constexpr int kBoxBytes = kStripPx * 4 * kBoxRows;     // 8192
+constexpr int kBoxesPerTile = 8;
+constexpr int kConsumerWarps = 16;                // 8 boxes x 2 row halves
 constexpr int kConsumers = kConsumerWarps * 32;   // 512
 constexpr int kThreads = kConsumers + 32;         // + producer warp
-constexpr int kTileRows = 32;                     // = lanes
-constexpr int kTileCols = kConsumerWarps * kStripPx;   // 320 px = 1280 B per row
-constexpr int kPitchBytes = kTileCols * 4 + 16;   // 1296: lane l -> 16-byte bank group (l + ...) % 8
-constexpr int kStages = 4;
-constexpr int kStageBytes = kTileRows * kPitchBytes;   // 41472
+constexpr int kTileRows = kBoxRows;               // 64
+constexpr int kTileCols = kBoxesPerTile * kStripPx;    // 256 px
+constexpr int kStages = 3;
+constexpr int kStageBytes = kBoxesPerTile * kBoxBytes; // 65536
 constexpr int kBarBytes = 2 * kStages * 8;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kSmemFixed = kStages * kStageBytes + kBarBytes + 64;
+constexpr int kSmemFixed = kStages * kStageBytes + kBarBytes + 80;
 constexpr int kSmemFree = kSmemLimit - kSmemFixed;     // for the slot table and the LUT copy
-constexpr int kDepthLoads = kTileRows * kTileCols / 4 / kConsumers;  // float4 per thread per tile = 5
+constexpr int kDepthLoads = kTileRows * kTileCols / 4 / kConsumers;  // float4 per thread per tile = 8
 
 struct ScanParams {
   const uint32_t* mask;
@@ -57,13 +65,22 @@ struct ScanParams {
   long long lut_stride;
   long long total_passes;
   int B, H, W, N, lut_len;
-  int nseg;      // 320-px column segments per row
-  int nrb;       // 32-row blocks per frame
+  int nseg;      // 256-px column segments per row
+  int nrb;       // 64-row blocks per frame
   int ppf;       // passes per frame = nseg * nrb
   int stride;    // pass permutation inside a frame: q -> (q * stride) % ppf, gcd(stride, ppf) = 1
-  int bulk;      // 1: bulk async copies (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
+  int tma;       // 1: tensor-map TMA (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
   int smem_lut;  // 1: the frame's LUT is staged in shared memory
 };
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 
 struct Entry {
   uint32_t id;
@@ -102,6 +119,20 @@ __device__ __forceinline__ void red_global_max(int32_t* p, int v) {
 template <bool kSmemTable>
 __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx, int ymn, int ymx,
                                          const int32_t* lut, int lut_len, int N, int32_t* tab) {
+  // Lanes run down the rows of one strip, so a whole warp usually evicts the SAME id at the
+  // same moment: reduce across the converged lanes first and let one lane do the merge
+  // (otherwise the five reds below are 32-way same-address conflicts).
+  const unsigned active = __activemask();
+  int same;
+  __match_all_sync(active, id, &same);
+  if (same) {
+    cnt = __reduce_add_sync(active, cnt);
+    xmn = __reduce_min_sync(active, xmn);
+    xmx = __reduce_max_sync(active, xmx);
+    ymn = __reduce_min_sync(active, ymn);
+    ymx = __reduce_max_sync(active, ymx);
+    if ((threadIdx.x & 31) != __ffs(active) - 1) return;
+  }
   if (id >= static_cast<uint32_t>(lut_len)) return;
   const int slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
   if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
@@ -195,6 +226,7 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
 }
 
 
+
 // make `V` the MRU entry e0 (swap with e1, or evict e1)
 #define CSPE_SWITCH(V)                                                                  \
   do {                                                                                  \
@@ -224,8 +256,9 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   } while (0)
 
 template <bool kSmemTable, bool kDepth>
-__global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
+__global__ void __launch_bounds__(kThreads, 1)
+    mask_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B boxes need 1024-byte alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
   int32_t* table = reinterpret_cast<int32_t*>(empty_bar + kStages);
@@ -256,6 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
   if (tid >= kConsumers) {
     // ===================== producer warp =====================
     const int lane = tid - kConsumers;
+    if (p.tma && lane != 0) return;
     const uint64_t policy = l2_policy_evict_first();
     int it = 0;
     for (long long pp = p_begin; pp < p_end; ++pp, ++it) {
@@ -263,25 +297,27 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
       const uint32_t parity = (it / kStages) & 1;
       const int rb = pq / p.nseg, seg = pq - rb * p.nseg;
       const int row0 = rb * kTileRows;
-      const int rows = min(kTileRows, p.H - row0);
       const int col0 = seg * kTileCols;
-      const int cols = min(kTileCols, p.W - col0);
       unsigned char* dst = smem + stage * kStageBytes;
-      const uint32_t* src = p.mask + (static_cast<long long>(frame) * p.H + row0) * p.W + col0;
       mbar_wait(&empty_bar[stage], parity ^ 1);
-      if (p.bulk) {
-        const uint32_t row_bytes = static_cast<uint32_t>(cols) * 4u;
-        if (lane == 0) mbar_arrive_expect_tx(&full_bar[stage], row_bytes * rows);
-        __syncwarp();
-        if (lane < rows)
-          bulk_g2s(dst + lane * kPitchBytes, src + static_cast<long long>(lane) * p.W, row_bytes, &full_bar[stage],
-                   policy);
+      if (p.tma) {
+        // boxes that start beyond W are skipped; a box is always written in full (zero fill
+        // past the tensor edge), so the byte count is whole boxes
+        const int nbox = min(kBoxesPerTile, (p.W - col0 + kStripPx - 1) / kStripPx);
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(nbox) * kBoxBytes);
+        const int y = frame * p.H + row0;
+        for (int b = 0; b < nbox; ++b)
+          tma_load_2d(dst + b * kBoxBytes, &tmap, col0 + b * kStripPx, y, &full_bar[stage], policy);
       } else {
-        // unaligned fallback: the producer warp copies with 4-byte loads
-        for (int r = 0; r < rows; ++r) {
-          uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + r * kPitchBytes);
-          for (int c = lane; c < cols; c += 32) d32[c] = __ldg(src + static_cast<long long>(r) * p.W + c);
-        }
+        // unaligned fallback: the producer warp fills the same swizzled layout with 4-byte loads
+        const int rows = min(kTileRows, p.H - row0);
+        const int cols = min(kTileCols, p.W - col0);
+        const uint32_t* src = p.mask + (static_cast<long long>(frame) * p.H + row0) * p.W + col0;
+        for (int r = 0; r < rows; ++r)
+          for (int c = lane; c < cols; c += 32) {
+            const int off = (c >> 5) * kBoxBytes + r * 128 + ((((c & 31) >> 2) ^ (r & 7)) << 4) + ((c & 3) << 2);
+            *reinterpret_cast<uint32_t*>(dst + off) = __ldg(src + static_cast<long long>(r) * p.W + c);
+          }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);  // release: orders the warp's stores (after __syncwarp)
       }
@@ -299,7 +335,10 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
   // ===================== consumer warps =====================
   const int lane = tid & 31;
   const int wid = tid >> 5;
-  const int sm_off = lane * kPitchBytes + wid * (kStripPx * 4);
+  const int box = wid & (kBoxesPerTile - 1);
+  const int trow = (wid >> 3) * 32 + lane;          // row inside the tile, 0..63
+  const int sw = lane & 7;                          // = trow & 7: the 128-byte swizzle phase of this row
+  const int sm_off = box * kBoxBytes + trow * 128;
   Entry e0, e1;
   entry_reset(e0, 0u);
   entry_reset(e1, 0u);
@@ -383,52 +422,54 @@ __global__ void __launch_bounds__(kThreads, 1) mask_scan_kernel(const ScanParams
 
     mbar_wait(&full_bar[stage], parity);
 
-    const int x0 = col0 + wid * kStripPx;
+    const int x0 = col0 + box * kStripPx;
     const int len = min(kStripPx, p.W - x0);
-    if (lane < rows && len > 0) {
-      const int y = row0 + lane;
+    if (trow < rows && len > 0) {
+      const int y = row0 + trow;
       const unsigned char* base = smem + stage * kStageBytes + sm_off;
-      bool done = false;
-      if (len == kStripPx) {
-        const uint4* sp = reinterpret_cast<const uint4*>(base);
-        const uint4 q0 = sp[0], q1 = sp[1], q2 = sp[2], q3 = sp[3], q4 = sp[4];
-        const uint32_t a = q0.x;
-        uint32_t d = (q0.y ^ a) | (q0.z ^ a) | (q0.w ^ a);
-        d |= (q1.x ^ a) | (q1.y ^ a) | (q1.z ^ a) | (q1.w ^ a);
-        d |= (q2.x ^ a) | (q2.y ^ a) | (q2.z ^ a) | (q2.w ^ a);
-        d |= (q3.x ^ a) | (q3.y ^ a) | (q3.z ^ a) | (q3.w ^ a);
-        d |= (q4.x ^ a) | (q4.y ^ a) | (q4.z ^ a) | (q4.w ^ a);
-        if (d == 0) {  // the whole strip is one id
-          CSPE_SWITCH(a);
-          CSPE_ACCUM(kStripPx, x0, x0 + kStripPx - 1);
-          done = true;
-        }
-      }
-      if (!done) {
-        const uint32_t* px = reinterpret_cast<const uint32_t*>(base);
-        int j = 0;
+      // logical 16-byte chunk k of this row lives at physical chunk k ^ sw; pixels past `len`
+      // (partial last strip) are zero fill or stale and are masked out below
+      const uint4 q0 = *reinterpret_cast<const uint4*>(base + ((0 ^ sw) << 4));
+      const uint4 q1 = *reinterpret_cast<const uint4*>(base + ((1 ^ sw) << 4));
+      const uint4 q2 = *reinterpret_cast<const uint4*>(base + ((2 ^ sw) << 4));
+      const uint4 q3 = *reinterpret_cast<const uint4*>(base + ((3 ^ sw) << 4));
+      const uint4 q4 = *reinterpret_cast<const uint4*>(base + ((4 ^ sw) << 4));
+      const uint4 q5 = *reinterpret_cast<const uint4*>(base + ((5 ^ sw) << 4));
+      const uint4 q6 = *reinterpret_cast<const uint4*>(base + ((6 ^ sw) << 4));
+      const uint4 q7 = *reinterpret_cast<const uint4*>(base + ((7 ^ sw) << 4));
+      const uint32_t a = q0.x;
+      uint32_t d = (q0.y ^ a) | (q0.z ^ a) | (q0.w ^ a);
+      d |= (q1.x ^ a) | (q1.y ^ a) | (q1.z ^ a) | (q1.w ^ a);
+      d |= (q2.x ^ a) | (q2.y ^ a) | (q2.z ^ a) | (q2.w ^ a);
+      d |= (q3.x ^ a) | (q3.y ^ a) | (q3.z ^ a) | (q3.w ^ a);
+      d |= (q4.x ^ a) | (q4.y ^ a) | (q4.z ^ a) | (q4.w ^ a);
+      d |= (q5.x ^ a) | (q5.y ^ a) | (q5.z ^ a) | (q5.w ^ a);
+      d |= (q6.x ^ a) | (q6.y ^ a) | (q6.z ^ a) | (q6.w ^ a);
+      d |= (q7.x ^ a) | (q7.y ^ a) | (q7.z ^ a) | (q7.w ^ a);
+      if (d == 0 && len == kStripPx) {
+        // fast path: the whole strip is one id
+        CSPE_SWITCH(a);
+        CSPE_ACCUM(kStripPx, x0, x0 + kStripPx - 1);
+      } else {
+        // run decomposition: bit j of `bm` marks a run start (pixel j differs from pixel j-1);
+        // all lanes of the warp that are here build the mask in lockstep, then walk their runs
+        const uint32_t v[kStripPx] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z,
+                                      q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y,
+                                      q5.z, q5.w, q6.x, q6.y, q6.z, q6.w, q7.x, q7.y, q7.z, q7.w};
+        uint32_t bm = 0;
+#pragma unroll
+        for (int j = 1; j < kStripPx; ++j) bm |= (v[j] != v[j - 1]) ? (1u << j) : 0u;
+        if (len < kStripPx) bm &= (1u << len) - 1u;
+        int s0 = 0;
 #pragma unroll 1
-        for (; j + 4 <= len; j += 4) {
-          const uint4 qv = *reinterpret_cast<const uint4*>(px + j);
-          const int x = x0 + j;
-          if (((qv.y ^ qv.x) | (qv.z ^ qv.x) | (qv.w ^ qv.x)) == 0) {
-            CSPE_SWITCH(qv.x);
-            CSPE_ACCUM(4, x, x + 3);
-          } else {
-            CSPE_SWITCH(qv.x);
-            CSPE_ACCUM(1, x, x);
-            CSPE_SWITCH(qv.y);
-            CSPE_ACCUM(1, x + 1, x + 1);
-            CSPE_SWITCH(qv.z);
-            CSPE_ACCUM(1, x + 2, x + 2);
-            CSPE_SWITCH(qv.w);
-            CSPE_ACCUM(1, x + 3, x + 3);
-          }
-        }
-#pragma unroll 1
-        for (; j < len; ++j) {
-          CSPE_SWITCH(px[j]);
-          CSPE_ACCUM(1, x0 + j, x0 + j);
+        while (s0 < len) {
+          const uint32_t t = bm & (0xfffffffeu << s0);
+          const int e = t ? __ffs(t) - 2 : len - 1;   // last pixel of the run starting at s0
+          const uint32_t id =
+              *reinterpret_cast<const uint32_t*>(base + (((s0 >> 2) ^ sw) << 4) + ((s0 & 3) << 2));
+          CSPE_SWITCH(id);
+          CSPE_ACCUM(e - s0 + 1, x0 + s0, x0 + e);
+          s0 = e + 1;
         }
       }
     }
@@ -519,6 +560,23 @@ int check_common(const uint32_t* mask, int B, int H, int W, const int32_t* id2sl
   return 1;  // work to do
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+TensorMapEncodeFn tensor_map_encoder() {
+  static TensorMapEncodeFn fn = []() -> TensorMapEncodeFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<TensorMapEncodeFn>(p);
+  }();
+  return fn;
+}
+
 template <bool kDepth>
 int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* stats, int B, int H, int W,
                 const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
@@ -541,10 +599,27 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
   p.nrb = (H + kTileRows - 1) / kTileRows;
   const long long ppf = static_cast<long long>(p.nseg) * p.nrb;
   CSPE_REQUIRE(ppf < (1ll << 30), CSPE_ERR_UNSUPPORTED, "cspe_mask_scan: frame of %dx%d has too many tiles", W, H);
+  CSPE_REQUIRE(static_cast<long long>(B) * H < (1ll << 31), CSPE_ERR_UNSUPPORTED,
+               "cspe_mask_scan: B*H = %lld rows exceeds the int32 tensor coordinate", static_cast<long long>(B) * H);
   p.ppf = static_cast<int>(ppf);
   p.total_passes = ppf * B;
-  p.bulk = (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(mask) & 15) == 0);
   const int grid = static_cast<int>(p.total_passes < sms ? p.total_passes : sms);
+
+  // TMA needs 16-byte aligned rows; otherwise the producer warp copies by hand
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  p.tma = 0;
+  TensorMapEncodeFn encode = tensor_map_encoder();
+  if (encode != nullptr && (W % 4 == 0) && (reinterpret_cast<uintptr_t>(mask) & 15) == 0) {
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(B) * H};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(W) * 4};
+    const cuuint32_t box[2] = {kStripPx, kBoxRows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint32_t*>(mask), gdim, gstride, box,
+                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    p.tma = (r == CUDA_SUCCESS) ? 1 : 0;
+  }
 
   // pass permutation: when several CTAs share a frame, stride the tile order so each CTA's
   // contiguous range samples the whole frame (busy and empty regions alike)
@@ -573,7 +648,7 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
 
   auto kern = smem_table ? mask_scan_kernel<true, kDepth> : mask_scan_kernel<false, kDepth>;
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  kern<<<grid, kThreads, smem_bytes, st>>>(p);
+  kern<<<grid, kThreads, smem_bytes, st>>>(p, tmap);
   CSPE_LAUNCH_OK("mask_scan_kernel");
   return CSPE_OK;
 }
