@@ -5,10 +5,10 @@
 // rotation — and adds what the reference leaves out: the 8 projected box corners and the
 // object-in-camera 6-DoF pose.
 //
-// One warp per (frame, slot); lanes 0-7 own one corner each, lane 0 then does the pose.  This
-// is 4x4-transform work on <= a few thousand objects: FP64 FMA-free scalar math (the library is
-// built with -fmad=false so every operation rounds exactly like the numpy oracle's), no
-// tensor cores.  Launch/latency bound; amortised by batching frames into one launch.
+// One thread per (frame, slot).  This is 4x4-transform work on <= a few thousand objects: FP64
+// FMA-free scalar math (the library is built with -fmad=false so every operation rounds exactly
+// like the numpy oracle's), no tensor cores.  Latency bound; amortised by batching frames into
+// one launch and hidden behind the mask scan on a side stream.
 #include <math.h>
 
 #include "cspe_common.cuh"
@@ -138,30 +138,35 @@ __device__ void quat_xyzw(const Mat3& r, double* q) {
   q[3] = w * s;
 }
 
-constexpr int kWarpsPerBlock = 8;
+// One THREAD per (frame, slot), 64-thread blocks: the work per object is a serial FP64 chain
+// (polar iteration, atan2, sqrt), so latency — not throughput — sets the kernel time; small
+// blocks with a modest register footprint co-reside with the persistent mask-scan CTA on every
+// SM when the caller forks K2 onto a side stream (pipeline.py), which hides K2 entirely.
+constexpr int kProjThreads = 64;
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kProjThreads)
     project_objects_kernel(const unsigned char* __restrict__ records, int rec_stride, int recs_per_frame,
-                           const int32_t* __restrict__ obj_record, const double* __restrict__ cam, int B, int N,
+                           const int32_t* __restrict__ obj_record, const double* __restrict__ cam, long long total, int N,
                            double* __restrict__ uv, double* __restrict__ zc_out, double* __restrict__ pose,
                            double* __restrict__ loose, uint8_t* __restrict__ flags) {
-  const long long obj = static_cast<long long>(blockIdx.x) * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (obj >= static_cast<long long>(B) * N) return;
-  const int lane = threadIdx.x & 31;
+  const long long obj = static_cast<long long>(blockIdx.x) * kProjThreads + threadIdx.x;
+  if (obj >= total) return;
   const int frame = static_cast<int>(obj / N);
   const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
+  double* po = pose + obj * CSPE_POSE_STRIDE;
 
   const int rec = obj_record[obj];
   if (rec < 0 || rec >= recs_per_frame) {
     // no record for this slot: defined outputs, flags 0
-    if (lane < 8) {
-      uv[obj * 16 + lane * 2 + 0] = kNaN;
-      uv[obj * 16 + lane * 2 + 1] = kNaN;
-      zc_out[obj * 8 + lane] = kNaN;
-    }
-    if (lane < CSPE_POSE_STRIDE) pose[obj * CSPE_POSE_STRIDE + lane] = kNaN;
-    if (lane < 4) loose[obj * 4 + lane] = kNaN;
-    if (lane == 0) flags[obj] = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) uv[obj * 16 + i] = kNaN;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) zc_out[obj * 8 + i] = kNaN;
+#pragma unroll
+    for (int i = 0; i < CSPE_POSE_STRIDE; ++i) po[i] = kNaN;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) loose[obj * 4 + i] = kNaN;
+    flags[obj] = 0;
     return;
   }
 
@@ -170,11 +175,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   // [0] semanticId, [1..6] extents, [7..22] transform (row-vector convention), [23] occlusionRatio
   const float ext_min[3] = {__ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3)};
   const float ext_max[3] = {__ldg(rp + 4), __ldg(rp + 5), __ldg(rp + 6)};
+  float T32[4][3];
   double T[4][3];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) T[i][j] = static_cast<double>(__ldg(rp + 7 + i * 4 + j));
+    for (int j = 0; j < 3; ++j) {
+      T32[i][j] = __ldg(rp + 7 + i * 4 + j);
+      T[i][j] = static_cast<double>(T32[i][j]);
+    }
 
   const double* cm = cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE;
   const double t[3] = {cm[0], cm[1], cm[2]};
@@ -185,41 +194,38 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     for (int j = 0; j < 3; ++j) Rcw[i][j] = cm[3 + i * 3 + j];
   const double fx = cm[12], fy = cm[13], cx0 = cm[14], cy0 = cm[15], nearc = cm[16];
 
-  // ---- corners (lanes 0..7; other lanes shadow corner lane&7 so shuffles stay full-warp) ----
-  const int k = lane & 7;
-  const double c[3] = {static_cast<double>((k & 1) ? ext_max[0] : ext_min[0]),
-                       static_cast<double>((k & 2) ? ext_max[1] : ext_min[1]),
-                       static_cast<double>((k & 4) ? ext_max[2] : ext_min[2])};
-  double d[3];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    const double pw = ((c[0] * T[0][j] + c[1] * T[1][j]) + c[2] * T[2][j]) + T[3][j];
-    d[j] = pw - t[j];
-  }
-  double pc[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) pc[i] = (Rcw[0][i] * d[0] + Rcw[1][i] * d[1]) + Rcw[2][i] * d[2];
-  const double z = -pc[2];
-  const double u = cx0 + (fx * pc[0]) / z;
-  const double v = cy0 - (fy * pc[1]) / z;
-  const bool front = z > nearc;
-  if (lane < 8) {
-    uv[obj * 16 + lane * 2 + 0] = u;
-    uv[obj * 16 + lane * 2 + 1] = v;
-    zc_out[obj * 8 + lane] = z;
-  }
-  const unsigned fm = __ballot_sync(0xffffffffu, front) & 0xffu;
+  // ---- the 8 corners: bit0 -> x, bit1 -> y, bit2 -> z picks max over min ----
   const double kInf = __longlong_as_double(0x7ff0000000000000ll);
-  double umin = front ? u : kInf, vmin = front ? v : kInf, umax = front ? u : -kInf, vmax = front ? v : -kInf;
+  double umin = kInf, vmin = kInf, umax = -kInf, vmax = -kInf;
+  unsigned fm = 0;
 #pragma unroll
-  for (int o = 4; o > 0; o >>= 1) {
-    umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-    vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  for (int k = 0; k < 8; ++k) {
+    const double c[3] = {static_cast<double>((k & 1) ? ext_max[0] : ext_min[0]),
+                         static_cast<double>((k & 2) ? ext_max[1] : ext_min[1]),
+                         static_cast<double>((k & 4) ? ext_max[2] : ext_min[2])};
+    double d[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double pw = ((c[0] * T[0][j] + c[1] * T[1][j]) + c[2] * T[2][j]) + T[3][j];
+      d[j] = pw - t[j];
+    }
+    double pc[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) pc[i] = (Rcw[0][i] * d[0] + Rcw[1][i] * d[1]) + Rcw[2][i] * d[2];
+    const double z = -pc[2];
+    const double u = cx0 + (fx * pc[0]) / z;
+    const double v = cy0 - (fy * pc[1]) / z;
+    uv[obj * 16 + k * 2 + 0] = u;
+    uv[obj * 16 + k * 2 + 1] = v;
+    zc_out[obj * 8 + k] = z;
+    if (z > nearc) {
+      fm |= 1u << k;
+      umin = fmin(umin, u);
+      vmin = fmin(vmin, v);
+      umax = fmax(umax, u);
+      vmax = fmax(vmax, v);
+    }
   }
-  if (lane != 0) return;
-
   if (fm) {
     loose[obj * 4 + 0] = umin;
     loose[obj * 4 + 1] = vmin;
@@ -229,8 +235,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     loose[obj * 4 + 0] = loose[obj * 4 + 1] = loose[obj * 4 + 2] = loose[obj * 4 + 3] = kNaN;
   }
 
-  // ---- pose (lane 0) ----
-  double* po = pose + obj * CSPE_POSE_STRIDE;
+  // ---- pose ----
   // gcd.py:566: centre of the local box, float32 mean like np.mean on the f32 corner array
   double cl[3], cw[3];
 #pragma unroll
@@ -238,14 +243,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 #pragma unroll
   for (int j = 0; j < 3; ++j) cw[j] = ((cl[0] * T[0][j] + cl[1] * T[1][j]) + cl[2] * T[2][j]) + T[3][j];
   // gcd.py:578-582: size_world = ||rot[:,k]|| * |max - min| (f32 norm, f32 difference)
-  double size[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    const float a0 = __ldg(rp + 7 + i * 4 + 0), a1 = __ldg(rp + 7 + i * 4 + 1), a2 = __ldg(rp + 7 + i * 4 + 2);
+    const float a0 = T32[i][0], a1 = T32[i][1], a2 = T32[i][2];
     const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1)), __fmul_rn(a2, a2));
     const float sc = __fsqrt_rn(n2);
     const float ext = fabsf(__fsub_rn(ext_max[i], ext_min[i]));
-    size[i] = static_cast<double>(sc) * static_cast<double>(ext);
+    po[10 + i] = static_cast<double>(sc) * static_cast<double>(ext);
   }
   // rot = M[:3,:3] with M = T^T (gcd.py:568,572): rot[a][b] = T[b][a]
   Mat3 rot, rwo;
@@ -257,15 +261,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   bool pose_ok = isfinite(dr) && dr > 0.0 && polar3(rot, rwo);
   pose_ok = pose_ok && isfinite(cw[0]) && isfinite(cw[1]) && isfinite(cw[2]);
 
-  double tco[3];
+  const double d0 = cw[0] - t[0], d1 = cw[1] - t[1], d2 = cw[2] - t[2];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const double d0 = cw[0] - t[0], d1 = cw[1] - t[1], d2 = cw[2] - t[2];
-    tco[i] = (Rcw[0][i] * d0 + Rcw[1][i] * d1) + Rcw[2][i] * d2;
-  }
-  po[0] = tco[0];
-  po[1] = tco[1];
-  po[2] = tco[2];
+  for (int i = 0; i < 3; ++i) po[i] = (Rcw[0][i] * d0 + Rcw[1][i] * d1) + Rcw[2][i] * d2;
   if (pose_ok) {
     Mat3 rco;  // Rcw^T * R_wo
 #pragma unroll
@@ -282,9 +280,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
   po[7] = cw[0];
   po[8] = cw[1];
   po[9] = cw[2];
-  po[10] = size[0];
-  po[11] = size[1];
-  po[12] = size[2];
 
   uint8_t fl = CSPE_OBJ_HAS_RECORD;
   if (fm) fl |= CSPE_OBJ_ANY_FRONT;
@@ -314,10 +309,10 @@ extern "C" int cspe_project_objects(const void* records, int rec_stride, int rec
   CSPE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 3) == 0 && (reinterpret_cast<uintptr_t>(cam) & 7) == 0,
                CSPE_ERR_INVALID_ARGUMENT, "cspe_project_objects: misaligned records/cam");
   const long long total = static_cast<long long>(B) * N;
-  const long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long blocks = (total + kProjThreads - 1) / kProjThreads;
   CSPE_REQUIRE(blocks < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_project_objects: too many objects");
-  project_objects_kernel<<<static_cast<unsigned>(blocks), kWarpsPerBlock * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const unsigned char*>(records), rec_stride, recs_per_frame, obj_record, cam, B, N, uv, z, pose,
+  project_objects_kernel<<<static_cast<unsigned>(blocks), kProjThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned char*>(records), rec_stride, recs_per_frame, obj_record, cam, total, N, uv, z, pose,
       loose, flags);
   CSPE_LAUNCH_OK("project_objects_kernel");
   return CSPE_OK;
