@@ -1,0 +1,179 @@
+"""Host-side logic without a GPU: synthetic annotators, tables, formats, sharding (gloo, world 2)."""
+import json
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from constructionsceneposeestimation_b200 import classes, formats, sharding, synthetic
+from oracle import labels as O
+from tests import helpers
+
+
+# ------------------------------------------------------------------ synthetic annotator frames
+def test_synthetic_frame_shape_and_determinism():
+    spec = synthetic.SceneSpec(320, 180, 20, 3, 17, config_id=1)
+    a, b = synthetic.make_frame(spec, 5), synthetic.make_frame(spec, 5)
+    mask, depth = a["instance_segmentation"]["data"], a["distance_to_image_plane"]
+    assert mask.shape == (180, 320) and mask.dtype == np.uint32
+    assert depth.shape == (180, 320) and depth.dtype == np.float32
+    assert np.array_equal(mask, b["instance_segmentation"]["data"]) and a["camera_pose"] == b["camera_pose"]
+    assert not np.array_equal(mask, synthetic.make_frame(spec, 6)["instance_segmentation"]["data"])
+    recs, paths = a["bounding_box_3d"]["data"], a["bounding_box_3d"]["info"]["primPaths"]
+    assert recs.dtype.itemsize == 96 and len(recs) == len(paths)
+    labels = a["instance_segmentation"]["info"]["idToLabels"]
+    assert labels["0"] == "BACKGROUND" and labels["1"] == "UNLABELLED"
+    assert set(np.unique(mask)) <= {int(k) for k in labels}            # every painted id is labelled
+    assert np.isinf(depth).any() and np.isfinite(depth).any()           # sky + ground
+    assert a["skeleton_data"]["globalTranslations"].shape == (3, 17, 3)
+    assert len(classes.aggregate_objects(paths, classes.ObjectRootResolver(split_people=True))) == 20
+
+
+def test_synthetic_masks_agree_with_boxes():
+    """Every object's tight 2D box lies inside the projection of its 3D box (what the painter promises)."""
+    frames = synthetic.make_batch(synthetic.SceneSpec(480, 270, 30, 3, 17, config_id=2), 2)
+    o = helpers.oracle_pipeline(frames)
+    seen = 0
+    for f in range(2):
+        for r in o["recs"][f, : o["n_out"][f]]:
+            if not (r["flags"] & O.OBJ_ALL_FRONT):
+                continue
+            u, v = r["uv"][:, 0], r["uv"][:, 1]
+            assert r["x_min"] >= np.floor(u.min()) - 1 and r["x_max"] <= np.ceil(u.max()) + 1
+            assert r["y_min"] >= np.floor(v.min()) - 1 and r["y_max"] <= np.ceil(v.max()) + 1
+            assert 0.0 <= r["occlusion"] <= 1.0 and 0.0 < r["fill"] <= 1.0
+            seen += 1
+    assert seen >= 10
+
+
+def test_sparse_ids_and_reference_people_rule():
+    spec = synthetic.SceneSpec(320, 180, 16, 4, 17, config_id=3, sparse_ids=True, split_people=False)
+    fr = synthetic.make_frame(spec, 0)
+    ids = [int(k) for k in fr["instance_segmentation"]["info"]["idToLabels"]]
+    assert max(ids) > 10_000                                             # spread up to 2**20
+    objs = classes.aggregate_objects(fr["bounding_box_3d"]["info"]["primPaths"], classes.ObjectRootResolver())
+    humans = [o for o in objs if o.class_name == "human"]
+    assert len(humans) == 1 and humans[0].prim_path == "/World/GroundPlane/DHGen" and humans[0].mesh_count == 4
+
+
+# ------------------------------------------------------------------ tables
+def test_id_to_slot_and_record_lookup():
+    res = classes.ObjectRootResolver()
+    crane = classes.CRANE_ROOT
+    paths = ["/World/Tree/Tree_01", "/World/Tree/Tree_01/trunk", "/World/GroundPlane/Cone001_02/Cone001",
+             f"{crane}/S104GG03A_SW/m0", f"{crane}/S104S01KB_SW/m1", "/World/Unknown/thing"]
+    objs = classes.aggregate_objects(paths, res)
+    assert [(o.prim_path, o.class_id, o.mesh_count) for o in objs] == [
+        ("/World/Tree/Tree_01", 1, 2), ("/World/GroundPlane/Cone001_02", 0, 1), (f"{crane}#cranebase", 6, 2)]
+    assert classes.record_index_for(objs, paths, "reference") == [0, -1, 3]
+    assert classes.record_index_for(objs, paths, "first_mesh") == [0, 2, 3]
+    with pytest.raises(ValueError):
+        classes.record_index_for(objs, paths, "nope")
+    labels = {"0": "BACKGROUND", "1": "UNLABELLED", "7": "/World/Tree/Tree_01/leaves", 9: paths[3],
+              "11": {"class": "cone"}, "12": {"primPath": paths[2]}, "13": "/World/Tree/Tree_77/x"}
+    assert classes.id_to_slot(labels, objs, res) == {7: 0, 9: 2, 12: 1}
+
+
+# ------------------------------------------------------------------ formats
+def _oracle_records():
+    frames = synthetic.make_batch(synthetic.SceneSpec(320, 180, 14, 2, 17, config_id=4), 1)
+    o = helpers.oracle_pipeline(frames)
+    return frames[0], o, o["recs"][0, : o["n_out"][0]]
+
+
+def test_reference_label_schema_and_extras(tmp_path):
+    fr, o, recs = _oracle_records()
+    kps = {int(recs[0]["inst_idx"]): formats.coco_keypoint_block(o["kp"][0, 0], o["vis"][0, 0])}
+    lab = formats.reference_label(3, fr["camera_pose"], fr["camera_params"], 180, 320, recs, o["objects"][0], kps)
+    assert list(lab) == ["frame_id", "camera_pose", "camera_params", "objects", "instance_mask_shape", "num_objects",
+                         "class_mapping"]                                     # gcd.py:2056-2064
+    assert lab["instance_mask_shape"] == [180, 320] and lab["num_objects"] == len(recs)
+    assert lab["class_mapping"] == classes.CLASS_TABLE
+    obj = lab["objects"][0]
+    assert list(obj)[:7] == ["inst_idx", "class_id", "class_name", "center", "size", "rotation", "prim_path"]
+    assert obj["bbox_2d_tight"] == [int(recs[0][k]) for k in ("x_min", "y_min", "x_max", "y_max")]
+    assert len(obj["bbox_3d_projected"]) == 8 and "keypoints" in obj
+    p = tmp_path / "l.json"
+    formats.dump_label_json(lab, p)
+    assert json.loads(p.read_text(encoding="utf-8"))["objects"][0]["prim_path"] == obj["prim_path"]
+
+
+def test_yolo_and_coco():
+    fr, o, recs = _oracle_records()
+    lines = formats.yolo_lines(recs)
+    assert len(lines) == len(recs)
+    c, cx, cy, w, h = lines[0].split()
+    assert int(c) == recs[0]["class_id"] and 0 < float(w) <= 1 and 0 < float(h) <= 1
+    assert abs(float(cx) - (recs[0]["x_min"] + recs[0]["x_max"] + 1) / 2 / 320) < 1e-5
+    anns = formats.coco_annotations(recs, image_id=3, first_ann_id=10)
+    assert [a["id"] for a in anns] == list(range(10, 10 + len(recs)))
+    a0 = anns[0]
+    assert a0["bbox"] == [int(recs[0]["x_min"]), int(recs[0]["y_min"]), int(recs[0]["x_max"] - recs[0]["x_min"] + 1),
+                          int(recs[0]["y_max"] - recs[0]["y_min"] + 1)]
+    assert a0["area"] == recs[0]["count"] and a0["iscrowd"] == 0
+    blk = formats.coco_keypoint_block(o["kp"][0, 0], o["vis"][0, 0])
+    assert len(blk["keypoints"]) == 17 * 3 and blk["num_keypoints"] == int((o["vis"][0, 0] > 0).sum())
+    assert [c["name"] for c in formats.coco_categories()][:6] == ["trafficcone", "tree", "fence", "crane", "dumper", "human"]
+
+
+# ------------------------------------------------------------------ sharding
+@pytest.mark.parametrize("frames,world", [(100_000, 8), (64, 3), (5, 8), (0, 4), (257, 2)])
+def test_frame_ranges_partition(frames, world):
+    ranges = [sharding.frame_range(r, world, frames) for r in range(world)]
+    assert ranges[0][0] == 0 and ranges[-1][1] == frames
+    assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))              # contiguous, no gap, no overlap
+    sizes = [b - a for a, b in ranges]
+    assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sharding.frame_range(world, world, frames)
+
+
+def test_rig_ranges_and_batches():
+    pairs = [p for r in range(8) for p in sharding.rig_frame_range(r, 8, 10, 4)]
+    assert pairs == [(i // 4, i % 4) for i in range(40)]                      # config 4: 4-camera rig flattened
+    assert sharding.batches(3, 200, 64) == [(3, 67), (67, 131), (131, 195), (195, 200)]
+    assert sharding.batches(5, 5, 64) == []
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _shard_worker(rank, world, port, n_frames, out_dir):
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = sharding.frame_range(rank, world, n_frames)
+    spec = synthetic.SceneSpec(256, 144, 12, 2, 17, config_id=7)
+    frames = [synthetic.make_frame(spec, i) for i in range(lo, hi)]
+    o = helpers.oracle_pipeline(frames, frame_base=lo)       # stands in for the kernels on this CPU box
+    gathered = sharding.all_gather_histogram(torch.from_numpy(o["hist"]))
+    ids = [int(r["frame"]) for f in range(len(frames)) for r in o["recs"][f, : o["n_out"][f]]]
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), gathered=gathered, local=o["hist"], frame_ids=np.array(ids),
+             n_out=o["n_out"])
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_and_histogram_allgather(tmp_path):
+    """World size 2 over gloo: the union of the shards equals the single-process run and the
+    all-gathered per-class histogram sums to the bincount over every emitted record (S7)."""
+    import torch.multiprocessing as mp
+
+    n_frames, world = 5, 2
+    mp.spawn(_shard_worker, args=(world, _free_port(), n_frames, str(tmp_path)), nprocs=world, join=True)
+    spec = synthetic.SceneSpec(256, 144, 12, 2, 17, config_id=7)
+    single = helpers.oracle_pipeline([synthetic.make_frame(spec, i) for i in range(n_frames)])
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    assert np.array_equal(parts[0]["gathered"], parts[1]["gathered"])         # every rank sees every rank
+    assert np.array_equal(parts[0]["gathered"], np.stack([p["local"] for p in parts]))
+    assert np.array_equal(parts[0]["gathered"].sum(axis=0), single["hist"])
+    all_classes = np.concatenate([single["recs"][f, : single["n_out"][f]]["class_id"] for f in range(n_frames)])
+    assert np.array_equal(single["hist"], np.bincount(all_classes, minlength=10))
+    assert np.array_equal(np.concatenate([p["n_out"] for p in parts]), single["n_out"])
+    want_ids = [f for f in range(n_frames) for _ in range(single["n_out"][f])]
+    assert list(np.concatenate([p["frame_ids"] for p in parts])) == want_ids   # global frame ids, in order
