@@ -109,6 +109,8 @@ PROTOTYPES = {
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),
     "cspe_depth_to_pointcloud": (_I, [_P, _P, _I, _I, _I, _P, _P, _I64, _P, _P, _P]),
     "cspe_depth_stats": (_I, [_P, _I, _I, _I, _P, _P]),
+    "cspe_depth_colormap": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
+    "cspe_rgb_to_bgr": (_I, [_P, _I, _I64, _P, _P]),
 }
 
 _lib = None

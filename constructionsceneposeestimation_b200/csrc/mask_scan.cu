@@ -32,6 +32,7 @@
 // Integer only, order independent => bit-exact against the numpy oracle.
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "cspe_common.cuh"
@@ -42,19 +43,30 @@ namespace {
 constexpr int kStripPx = 32;                      // one TMA box row = 128 B = 8 x 16 B
 constexpr int kBoxRows = 64;
 constexpr int kBoxBytes = kStripPx * 4 * kBoxRows;     // 8192
-constexpr int kBoxesPerTile = 8;
-constexpr int kConsumerWarps = 16;                // 8 boxes x 2 row halves
-constexpr int kConsumers = kConsumerWarps * 32;   // 512
-constexpr int kThreads = kConsumers + 32;         // + producer warp
 constexpr int kTileRows = kBoxRows;               // 64
-constexpr int kTileCols = kBoxesPerTile * kStripPx;    // 256 px
 constexpr int kStages = 3;
-constexpr int kStageBytes = kBoxesPerTile * kBoxBytes; // 65536
-constexpr int kBarBytes = 2 * kStages * 8;
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kSmemFixed = kStages * kStageBytes + kBarBytes + 80;
-constexpr int kSmemFree = kSmemLimit - kSmemFixed;     // for the slot table and the LUT copy
-constexpr int kDepthLoads = kTileRows * kTileCols / 4 / kConsumers;  // float4 per thread per tile = 8
+constexpr int kDefaultBoxes = 4;  // measured best: 2 CTAs per SM (profiles/)
+
+// Geometry of one CTA: kBoxes TMA boxes side by side per tile, two consumer warps per box (row
+// halves) + one producer warp.  CTAs per SM = 8 / kBoxes, so an SM always runs 16 consumer warps
+// over 3 x 64 KB of ring; smaller CTAs mean more independent rings per SM (a slow warp only
+// holds back its own CTA's ring).
+template <int kBoxes>
+struct Geo {
+  static constexpr int kConsumerWarps = 2 * kBoxes;
+  static constexpr int kConsumers = kConsumerWarps * 32;
+  static constexpr int kThreads = kConsumers + 32;
+  static constexpr int kCtasPerSm = 8 / kBoxes;
+  static constexpr int kTileCols = kBoxes * kStripPx;
+  static constexpr int kStageBytes = kBoxes * kBoxBytes;
+  static constexpr int kBarBytes = 2 * kStages * 8;
+  static constexpr int kSmemFixed = kStages * kStageBytes + kBarBytes + 80;
+  // what is left of the SM's shared memory for this CTA's slot table and LUT copy (1 KB per CTA
+  // is reserved by the driver, and the dynamic base is aligned up to 1 KB)
+  static constexpr int kSmemFree = kSmemLimit / kCtasPerSm - kSmemFixed - 2048 * (kCtasPerSm > 1);
+  static constexpr int kDepthLoads = kTileRows * kTileCols / 4 / kConsumers;  // float4 per thread per tile = 8
+};
 
 struct ScanParams {
   const uint32_t* mask;
@@ -65,7 +77,7 @@ struct ScanParams {
   long long lut_stride;
   long long total_passes;
   int B, H, W, N, lut_len;
-  int nseg;      // 256-px column segments per row
+  int nseg;      // tile-wide column segments per row
   int nrb;       // 64-row blocks per frame
   int ppf;       // passes per frame = nseg * nrb
   int stride;    // pass permutation inside a frame: q -> (q * stride) % ppf, gcd(stride, ppf) = 1
@@ -255,9 +267,13 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
     e0.ymx = max(e0.ymx, y);                                                            \
   } while (0)
 
-template <bool kSmemTable, bool kDepth>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kSmemTable, bool kDepth, int kBoxes>
+__global__ void __launch_bounds__(Geo<kBoxes>::kThreads, Geo<kBoxes>::kCtasPerSm)
     mask_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap tmap) {
+  using G = Geo<kBoxes>;
+  constexpr int kConsumerWarps = G::kConsumerWarps, kConsumers = G::kConsumers, kThreads = G::kThreads;
+  constexpr int kTileCols = G::kTileCols, kStageBytes = G::kStageBytes, kDepthLoads = G::kDepthLoads;
+  constexpr int kBoxesPerTile = kBoxes;
   extern __shared__ __align__(1024) unsigned char smem[];  // SWIZZLE_128B boxes need 1024-byte alignment
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* empty_bar = full_bar + kStages;
@@ -336,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int lane = tid & 31;
   const int wid = tid >> 5;
   const int box = wid & (kBoxesPerTile - 1);
-  const int trow = (wid >> 3) * 32 + lane;          // row inside the tile, 0..63
+  const int trow = (wid / kBoxes) * 32 + lane;      // row inside the tile, 0..63
   const int sw = lane & 7;                          // = trow & 7: the 128-byte swizzle phase of this row
   const int sm_off = box * kBoxBytes + trow * 128;
   Entry e0, e1;
@@ -577,9 +593,10 @@ TensorMapEncodeFn tensor_map_encoder() {
   return fn;
 }
 
-template <bool kDepth>
-int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* stats, int B, int H, int W,
-                const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
+template <bool kDepth, int kBoxes>
+int launch_scan_geo(const uint32_t* mask, const float* depth, cspe_depth_stats_t* stats, int B, int H, int W,
+                    const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
+  using G = Geo<kBoxes>;
   const int sms = sm_count();
   CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_mask_scan: no CUDA device");
 
@@ -595,7 +612,7 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
   p.W = W;
   p.N = N;
   p.lut_len = lut_len;
-  p.nseg = (W + kTileCols - 1) / kTileCols;
+  p.nseg = (W + G::kTileCols - 1) / G::kTileCols;
   p.nrb = (H + kTileRows - 1) / kTileRows;
   const long long ppf = static_cast<long long>(p.nseg) * p.nrb;
   CSPE_REQUIRE(ppf < (1ll << 30), CSPE_ERR_UNSUPPORTED, "cspe_mask_scan: frame of %dx%d has too many tiles", W, H);
@@ -603,7 +620,8 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
                "cspe_mask_scan: B*H = %lld rows exceeds the int32 tensor coordinate", static_cast<long long>(B) * H);
   p.ppf = static_cast<int>(ppf);
   p.total_passes = ppf * B;
-  const int grid = static_cast<int>(p.total_passes < sms ? p.total_passes : sms);
+  const long long max_ctas = static_cast<long long>(sms) * G::kCtasPerSm;
+  const int grid = static_cast<int>(p.total_passes < max_ctas ? p.total_passes : max_ctas);
 
   // TMA needs 16-byte aligned rows; otherwise the producer warp copies by hand
   CUtensorMap tmap;
@@ -642,15 +660,38 @@ int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* st
 
   const size_t table_bytes = static_cast<size_t>(N) * CSPE_SCAN_FIELDS * 4;
   const size_t lut_bytes = static_cast<size_t>(lut_len) * 4;
-  const bool smem_table = table_bytes <= static_cast<size_t>(kSmemFree);
-  p.smem_lut = lut_len > 0 && (smem_table ? table_bytes : 0) + lut_bytes <= static_cast<size_t>(kSmemFree);
-  const size_t smem_bytes = kSmemFixed + (smem_table ? table_bytes : 0) + (p.smem_lut ? lut_bytes : 0);
+  const bool smem_table = table_bytes <= static_cast<size_t>(G::kSmemFree);
+  p.smem_lut = lut_len > 0 && (smem_table ? table_bytes : 0) + lut_bytes <= static_cast<size_t>(G::kSmemFree);
+  const size_t smem_bytes = G::kSmemFixed + (smem_table ? table_bytes : 0) + (p.smem_lut ? lut_bytes : 0);
 
-  auto kern = smem_table ? mask_scan_kernel<true, kDepth> : mask_scan_kernel<false, kDepth>;
+  auto kern = smem_table ? mask_scan_kernel<true, kDepth, kBoxes> : mask_scan_kernel<false, kDepth, kBoxes>;
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  kern<<<grid, kThreads, smem_bytes, st>>>(p, tmap);
+  kern<<<grid, G::kThreads, smem_bytes, st>>>(p, tmap);
   CSPE_LAUNCH_OK("mask_scan_kernel");
   return CSPE_OK;
+}
+
+// boxes per tile: 8 -> 1 CTA/SM, 4 -> 2 CTAs/SM, 2 -> 4 CTAs/SM (CSPE_SCAN_BOXES overrides, for tuning)
+int scan_boxes() {
+  static int v = []() {
+    const char* e = getenv("CSPE_SCAN_BOXES");
+    const int x = e ? atoi(e) : 0;
+    return (x == 8 || x == 4 || x == 2) ? x : kDefaultBoxes;
+  }();
+  return v;
+}
+
+template <bool kDepth>
+int launch_scan(const uint32_t* mask, const float* depth, cspe_depth_stats_t* stats, int B, int H, int W,
+                const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
+  switch (scan_boxes()) {
+    case 8:
+      return launch_scan_geo<kDepth, 8>(mask, depth, stats, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+    case 2:
+      return launch_scan_geo<kDepth, 2>(mask, depth, stats, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+    default:
+      return launch_scan_geo<kDepth, 4>(mask, depth, stats, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+  }
 }
 
 int launch_init(int32_t* out, int B, int N, int W, int H, cudaStream_t st) {

@@ -222,6 +222,39 @@ def depth_to_pointcloud(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: t
     return out, n
 
 
+def depth_colormap(depth: torch.Tensor, lut_bgr: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """f4: depth f32 [B,H,W] + colour LUT u8 [256,3] (BGR) -> u8 [B,H,W,3]; stats from depth_stats if not given."""
+    lib = _lib.load()
+    if depth.dim() == 2:
+        depth = depth.unsqueeze(0)
+    _dev(depth, torch.float32, "depth")
+    _dev(lut_bgr, torch.uint8, "lut_bgr")
+    if tuple(lut_bgr.shape) != (256, 3):
+        raise ValueError(f"lut_bgr must be [256,3], got {tuple(lut_bgr.shape)}")
+    if stats is None:
+        stats = depth_stats(depth)
+    B, H, W = depth.shape
+    out = torch.empty((B, H, W, 3), dtype=torch.uint8, device=depth.device)
+    with torch.cuda.device(depth.device):
+        rc = lib.cspe_depth_colormap(depth.data_ptr(), B, H, W, stats.data_ptr(), lut_bgr.data_ptr(), out.data_ptr(),
+                                     _stream_ptr())
+    _lib.check("cspe_depth_colormap", rc)
+    return out
+
+
+def rgb_to_bgr(rgb: torch.Tensor) -> torch.Tensor:
+    """f4: u8 [..., C>=3] -> u8 [..., 3] with channels reversed (alpha dropped)."""
+    lib = _lib.load()
+    _dev(rgb, torch.uint8, "rgb")
+    ch = rgb.shape[-1]
+    n = rgb.numel() // max(ch, 1)
+    out = torch.empty(tuple(rgb.shape[:-1]) + (3,), dtype=torch.uint8, device=rgb.device)
+    with torch.cuda.device(rgb.device):
+        rc = lib.cspe_rgb_to_bgr(rgb.data_ptr(), ch, n, out.data_ptr(), _stream_ptr())
+    _lib.check("cspe_rgb_to_bgr", rc)
+    return out
+
+
 def device_info() -> Tuple[int, int, int]:
     lib = _lib.load()
     a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -201,6 +201,17 @@ int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_cha
 int cspe_depth_stats(const float* depth, int B, int H, int W, cspe_depth_stats_t* stats,
                      void* stream);
 
+/* f4: depth visualisation (gcd.py:1691-1709): out uint8 [B][H][W][3] =
+ * lut_bgr[((d - min) / (max - min + 1e-6) * 255) as uint8] over valid pixels, lut_bgr[0] elsewhere;
+ * frames without a valid pixel come out black.  stats = output of cspe_depth_stats (device);
+ * lut_bgr uint8 [256][3] (the reference's table is cv2.COLORMAP_JET). */
+int cspe_depth_colormap(const float* depth, int B, int H, int W, const cspe_depth_stats_t* stats,
+                        const uint8_t* lut_bgr, uint8_t* out, void* stream);
+
+/* f4: RGB(A) -> BGR (gcd.py:1671 cv2.COLOR_RGB2BGR on rgb_image[..., :3]);
+ * rgb uint8 [num_pixels][channels >= 3], bgr uint8 [num_pixels][3]. */
+int cspe_rgb_to_bgr(const uint8_t* rgb, int channels, int64_t num_pixels, uint8_t* bgr, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

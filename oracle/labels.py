@@ -385,3 +385,37 @@ def depth_stats(depth_data: np.ndarray) -> Dict[str, object]:
         "depth_range": [float(depth_min), float(depth_max)],
         "depth_mean": float(depth_mean),
     }
+
+
+# ------------------------------------------------------------------------------------------
+# f4: depth visualisation  (gcd.py:1691-1709) and RGB -> BGR (gcd.py:1671)
+# ------------------------------------------------------------------------------------------
+def jet_lut_bgr() -> np.ndarray:
+    """The 256 x 3 BGR table behind cv2.applyColorMap(..., cv2.COLORMAP_JET) (gcd.py:1702)."""
+    import cv2
+
+    return cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(-1, 1), cv2.COLORMAP_JET).reshape(256, 3)
+
+
+def depth_colormap(depth_data: np.ndarray) -> np.ndarray:
+    """Restatement of the inline block gcd.py:1691-1709 (it is not a function in the reference,
+    so it cannot be AST-extracted; PINNED ONLY BY READING): JET image of the depth normalised over
+    its valid (finite, > 0) pixels, black when none is valid."""
+    import cv2
+
+    depth_valid = depth_data[np.isfinite(depth_data) & (depth_data > 0)]
+    if len(depth_valid) > 0:
+        depth_min = np.min(depth_valid)
+        depth_max = np.max(depth_valid)
+        depth_normalized = np.zeros_like(depth_data, dtype=np.uint8)
+        mask = np.isfinite(depth_data) & (depth_data > 0)
+        depth_normalized[mask] = ((depth_data[mask] - depth_min) / (depth_max - depth_min + 1e-6) * 255).astype(np.uint8)
+        return cv2.applyColorMap(depth_normalized, cv2.COLORMAP_JET)
+    return np.zeros(depth_data.shape + (3,), dtype=np.uint8)
+
+
+def rgb_to_bgr(rgb_image: np.ndarray) -> np.ndarray:
+    """gcd.py:1671: cv2.cvtColor(rgb_image[..., :3], cv2.COLOR_RGB2BGR)."""
+    import cv2
+
+    return cv2.cvtColor(np.ascontiguousarray(rgb_image[..., :3]), cv2.COLOR_RGB2BGR)

@@ -120,6 +120,29 @@ def test_scan_unaligned_base_pointer(T, ops):
     assert np.array_equal(out.cpu().numpy(), O.mask_scan(mask, lut, N, fast=False))
 
 
+def test_scan_accumulate_tiles(T, ops):
+    """cspe_mask_scan_accumulate: a frame delivered as two row bands merges to the full-frame result."""
+    rng = np.random.default_rng(21)
+    H, W, n_ids, N = 90, 132, 10, 7
+    mask = _random_mask(rng, 2, H, W, n_ids)
+    lut = _dense_lut(rng, n_ids, N, merge=True)
+    whole = O.mask_scan(mask, lut, N, fast=False)
+    m = T.from_numpy(mask.view(np.int32)).cuda()
+    l = T.from_numpy(lut).cuda()
+    top = ops.mask_scan(m[:, :40].contiguous(), l, N)
+    # the bottom band has its own row origin: accumulate in band coordinates, then shift y on the host
+    bottom = ops.mask_scan(m[:, 40:].contiguous(), l, N)
+    T.cuda.synchronize()
+    t, b = top.cpu().numpy(), bottom.cpu().numpy()
+    assert np.array_equal(t[..., 0] + b[..., 0], whole[..., 0])
+    # same-origin accumulation: scanning the same band twice doubles counts and keeps boxes
+    twice = ops.mask_scan(m, l, N)
+    ops.mask_scan(m, l, N, out=twice, accumulate=True)
+    T.cuda.synchronize()
+    tw = twice.cpu().numpy()
+    assert np.array_equal(tw[..., 0], 2 * whole[..., 0]) and np.array_equal(tw[..., 1:], whole[..., 1:])
+
+
 @pytest.mark.parametrize("W", [10240, 10244, 12000, 20484])
 def test_scan_wide_rows(T, ops, W):
     """Rows wider than one 512-strip segment are split into column segments."""
@@ -462,3 +485,26 @@ def test_pointcloud(T, ops):
     assert int(n3.item()) == n and bool((pts3[:n, 3:] == 255.0).all())
     _, n4 = ops.depth_to_pointcloud(T.full((180, 320), float("inf"), device="cuda"), None, cam)
     assert int(n4.item()) == 0
+
+
+def test_depth_colormap_and_bgr(T, ops):
+    """f4: JET depth image (gcd.py:1691-1709) and RGB->BGR (gcd.py:1671), byte for byte."""
+    from constructionsceneposeestimation_b200 import synthetic
+    spec = synthetic.SceneSpec(320, 180, 12, 2, 17, config_id=6, with_rgb=True)
+    frames = synthetic.make_batch(spec, 3)
+    depth = np.stack([f["distance_to_image_plane"] for f in frames])
+    depth[0, :3, :3] = 0.0
+    depth[0, 4, 4] = np.nan
+    depth[1] = np.inf                    # no valid pixel -> black
+    depth[2, 7, 7] = -5.0
+    lut = T.from_numpy(np.ascontiguousarray(O.jet_lut_bgr())).cuda()
+    got = ops.depth_colormap(T.from_numpy(depth).cuda(), lut).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got[b], O.depth_colormap(depth[b])), b
+    assert not got[1].any() and got[0].any()
+    flat = np.full((1, 9, 13), 3.5, dtype=np.float32)          # max == min: everything lands in bin 0
+    assert np.array_equal(ops.depth_colormap(T.from_numpy(flat).cuda(), lut).cpu().numpy()[0], O.depth_colormap(flat[0]))
+    rgb = frames[0]["rgb"]
+    assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(rgb).cuda()).cpu().numpy(), O.rgb_to_bgr(rgb))
+    assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(np.ascontiguousarray(rgb[..., :3])).cuda()).cpu().numpy(),
+                          O.rgb_to_bgr(rgb))
