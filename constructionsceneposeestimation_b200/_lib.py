@@ -111,6 +111,7 @@ PROTOTYPES = {
     "cspe_depth_stats": (_I, [_P, _I, _I, _I, _P, _P]),
     "cspe_depth_colormap": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_rgb_to_bgr": (_I, [_P, _I, _I64, _P, _P]),
+    "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
 }
 
 _lib = None

@@ -88,6 +88,26 @@ def yolo_lines(records: np.ndarray) -> List[str]:
     ]
 
 
+def yolo_text_batch(records: np.ndarray, n_out: np.ndarray, frames: Optional[int] = None):
+    """Native formatter (libcspe ``cspe_format_yolo_host``): records RECORD_DTYPE [B,N] + n_out int32 [B]
+    -> (bytes buffer, int64 offsets [frames+1]); frame f's YOLO text is buf[offsets[f]:offsets[f+1]],
+    byte-identical to ``"\n".join(yolo_lines(...)) + "\n"``."""
+    from . import _lib
+
+    lib = _lib.load()
+    records = np.ascontiguousarray(records)
+    n_out = np.ascontiguousarray(n_out, dtype=np.int32)
+    B, N = records.shape
+    frames = B if frames is None else frames
+    cap = int(n_out[:frames].sum()) * 96 + 16
+    buf = np.empty(cap, dtype=np.uint8)
+    offsets = np.empty(frames + 1, dtype=np.int64)
+    rc = lib.cspe_format_yolo_host(records.ctypes.data, n_out.ctypes.data, B, N, frames, buf.ctypes.data, cap,
+                                   offsets.ctypes.data)
+    _lib.check("cspe_format_yolo_host", rc)
+    return buf[:rc], offsets
+
+
 def coco_categories() -> List[Dict[str, object]]:
     return [{"id": i, "name": n, "supercategory": "construction"} for i, n in enumerate(CLASS_NAMES)]
 

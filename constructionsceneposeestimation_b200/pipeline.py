@@ -81,8 +81,10 @@ class LabelPipeline:
                 self._enqueue()
                 return
             if self.graph is None:
+                saved = self.class_hist.clone()
                 self._enqueue()  # warm-up outside capture (function attributes, lazy module load)
                 torch.cuda.current_stream(self.device).synchronize()
+                self.class_hist.copy_(saved)  # one run() = one accumulation, also on the capturing call
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     self._enqueue()

@@ -140,8 +140,9 @@ int cspe_mask_scan_accumulate(const uint32_t* mask, int B, int H, int W,
                               const int32_t* id2slot, int lut_len, int64_t lut_stride,
                               int N, int32_t* out, void* stream);
 
-/* K1 with the depth-quality statistics of gcd.py:314-359 fused into the same launch
- * (depth float32 [B][H][W]; stats cspe_depth_stats_t[B], fully overwritten). */
+/* K1 plus the depth-quality statistics of gcd.py:314-359 in one call (two HBM-bound launches on
+ * `stream`; a fused kernel measured slower).
+ * depth float32 [B][H][W]; stats cspe_depth_stats_t[B], fully overwritten. */
 int cspe_mask_scan_depth_stats(const uint32_t* mask, const float* depth, int B, int H, int W,
                                const int32_t* id2slot, int lut_len, int64_t lut_stride,
                                int N, int32_t* out, cspe_depth_stats_t* stats, void* stream);
@@ -211,6 +212,15 @@ int cspe_depth_colormap(const float* depth, int B, int H, int W, const cspe_dept
 /* f4: RGB(A) -> BGR (gcd.py:1671 cv2.COLOR_RGB2BGR on rgb_image[..., :3]);
  * rgb uint8 [num_pixels][channels >= 3], bgr uint8 [num_pixels][3]. */
 int cspe_rgb_to_bgr(const uint8_t* rgb, int channels, int64_t num_pixels, uint8_t* bgr, void* stream);
+
+/* f3: host-side YOLO serialisation of a D2H record buffer (no CUDA; all pointers are HOST
+ * pointers).  Formats the first `frames` frames of records_host [B][N] / n_out_host [B] as
+ * "class cx cy w h\n" lines with six decimals — byte-identical to Python's
+ * f"{c} {cx:.6f} {cy:.6f} {w:.6f} {h:.6f}" — back to back into out_host; offsets_host[f] /
+ * offsets_host[f+1] delimit frame f's text (offsets_host has frames + 1 entries).
+ * Returns the number of bytes written, or a negative CSPE_ERR_* (buffer too small, bad n_out). */
+int64_t cspe_format_yolo_host(const cspe_record* records_host, const int32_t* n_out_host, int B, int N,
+                              int frames, char* out_host, int64_t capacity, int64_t* offsets_host);
 
 #ifdef __cplusplus
 }

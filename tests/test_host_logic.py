@@ -177,3 +177,32 @@ def test_two_rank_shards_and_histogram_allgather(tmp_path):
     assert np.array_equal(np.concatenate([p["n_out"] for p in parts]), single["n_out"])
     want_ids = [f for f in range(n_frames) for _ in range(single["n_out"][f])]
     assert list(np.concatenate([p["frame_ids"] for p in parts])) == want_ids   # global frame ids, in order
+
+
+def test_native_yolo_formatter_matches_python(libcspe_path):
+    """f3: cspe_format_yolo_host is byte-identical to the Python formatter (no GPU needed)."""
+    rng = np.random.default_rng(5)
+    B, N = 5, 40
+    recs = np.zeros((B, N), dtype=O.RECORD_DTYPE)
+    n_out = rng.integers(0, N + 1, size=B).astype(np.int32)
+    n_out[1] = 0
+    recs["class_id"] = rng.integers(0, 10, size=(B, N))
+    vals = rng.uniform(0, 1, size=(B, N, 4)).astype(np.float32)
+    # rounding edge cases: exact ties at the 7th decimal, 0, 1, tiny and > 1 values
+    vals[0, 0] = [0.0, 1.0, 0.5, 0.0000005]
+    vals[0, 1] = [0.0000015, 0.9999995, 0.1234565, 2.5]
+    vals[0, 2] = [np.float32(1) / 3, np.float32(2) / 3, 1e-7, 0.999999]
+    vals[2, :, :] = (rng.integers(0, 2_000_001, size=(N, 4)) / 2_000_000).astype(np.float32)   # near-tie grid
+    recs["yolo"] = vals
+    buf, off = formats.yolo_text_batch(recs, n_out)
+    for f in range(B):
+        lines = formats.yolo_lines(recs[f, : n_out[f]])
+        want = ("\n".join(lines) + "\n") if lines else ""
+        assert bytes(buf[off[f]:off[f + 1]]).decode() == want, f
+    buf3, off3 = formats.yolo_text_batch(recs, n_out, frames=3)
+    assert off3.shape == (4,) and bytes(buf3) == bytes(buf[: off[3]])
+    bad = recs.copy()
+    bad["yolo"][0, 0, 0] = np.nan
+    from constructionsceneposeestimation_b200 import _lib
+    with pytest.raises(_lib.CspeError):
+        formats.yolo_text_batch(bad, n_out)
