@@ -44,6 +44,31 @@ int sm_count();  // cached per device; <= 0 on failure
     }                                                                                 \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------
+// Launch `kernel` so that it may start as soon as the kernel before it in `stream` has executed
+// griddepcontrol.launch_dependents in every CTA (or exited); after a kernel that never does, this
+// is an ordinary serialised launch.  A kernel launched this way must execute griddepcontrol.wait
+// before it touches anything the previous kernel writes.
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 // ---- device: mbarrier + bulk async copy (TMA 1D, SASS UBLKCP) ---------------------------
 #ifdef __CUDACC__
 

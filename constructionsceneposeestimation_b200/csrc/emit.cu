@@ -8,6 +8,7 @@
 //
 // One CTA per frame.  Bytes are negligible next to K1 (408 B per kept object).
 #include <math.h>
+#include <stddef.h>
 
 #include "cspe_common.cuh"
 
@@ -17,9 +18,18 @@ namespace cspe {
 namespace {
 
 constexpr int kEmitThreads = 256;
+constexpr int kHdrWords = 22;                                   // 88-byte integer/float header of cspe_record
+constexpr int kRecWords = sizeof(cspe_record) / 4;              // 102
+static_assert(offsetof(cspe_record, uv) == kHdrWords * 4, "header size");
+static_assert(offsetof(cspe_record, z) == offsetof(cspe_record, uv) + 128, "uv block");
+static_assert(offsetof(cspe_record, pose) == offsetof(cspe_record, z) + 64, "z block");
 
+// Phase 1: one thread per slot decides keep / computes the 88-byte header into shared memory
+// and its stable rank (ballot + prefix).  Phase 2: each warp writes its kept records
+// cooperatively — 102 coalesced 4-byte words per record (header from shared memory, the 40
+// doubles straight from K2's arrays) instead of one thread issuing ~100 serial stores.
 __global__ void __launch_bounds__(kEmitThreads)
-    emit_kernel(const int32_t* __restrict__ scan, const double* __restrict__ uv, const double* __restrict__ z,
+    emit_kernel(const int32_t* scan, int32_t* scan_reset, const double* __restrict__ uv, const double* __restrict__ z,
                 const double* __restrict__ pose, const double* __restrict__ loose, const uint8_t* __restrict__ flags,
                 const int32_t* __restrict__ slot_class, int N, int H, int W, int min_pixels, int frame_base,
                 cspe_record* __restrict__ records, int32_t* __restrict__ n_out,
@@ -27,22 +37,44 @@ __global__ void __launch_bounds__(kEmitThreads)
   __shared__ int warp_sums[kEmitThreads / 32];
   __shared__ int base_s;
   __shared__ int hist_s[CSPE_NUM_CLASSES];
+  __shared__ int32_t hdr_s[kEmitThreads][kHdrWords + 1];  // +1: odd pitch, conflict-free column writes
+  __shared__ int kept_s[kEmitThreads];                    // rank within the chunk -> thread (slot - n0)
   const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
   if (tid < CSPE_NUM_CLASSES) hist_s[tid] = 0;
   if (tid == 0) base_s = 0;
   __syncthreads();
+  // launched with programmatic stream serialisation: everything above overlapped the tail of the
+  // kernel before us; its results (and, transitively, the mask scan's) are complete after this
+  pdl_wait();
+
+  const int32_t* uv32 = reinterpret_cast<const int32_t*>(uv);
+  const int32_t* z32 = reinterpret_cast<const int32_t*>(z);
+  const int32_t* pose32 = reinterpret_cast<const int32_t*>(pose);
 
   for (int n0 = 0; n0 < N; n0 += kEmitThreads) {
     const int n = n0 + tid;
     const long long o = static_cast<long long>(f) * N + n;
     bool keep = false;
-    int cls = -1, cnt = 0;
+    int cls = -1, cnt = 0, x0 = 0, y0 = 0, x1 = -1, y1 = -1;
     uint8_t fl = 0;
     if (n < N) {
       cls = slot_class[o];
-      cnt = scan[o * CSPE_SCAN_FIELDS + CSPE_SCAN_COUNT];
+      const int32_t* sc = scan + o * CSPE_SCAN_FIELDS;
+      cnt = sc[CSPE_SCAN_COUNT];
+      x0 = sc[CSPE_SCAN_XMIN];
+      y0 = sc[CSPE_SCAN_YMIN];
+      x1 = sc[CSPE_SCAN_XMAX];
+      y1 = sc[CSPE_SCAN_YMAX];
+      if (scan_reset) {  // leave the entry as cspe_mask_scan's init would: the next batch can accumulate
+        int32_t* sr = scan_reset + o * CSPE_SCAN_FIELDS;
+        sr[CSPE_SCAN_COUNT] = 0;
+        sr[CSPE_SCAN_XMIN] = W;
+        sr[CSPE_SCAN_YMIN] = H;
+        sr[CSPE_SCAN_XMAX] = -1;
+        sr[CSPE_SCAN_YMAX] = -1;
+      }
       fl = flags[o];
       keep = (cls >= 0) && (cnt >= min_pixels) && (fl & CSPE_OBJ_ANY_FRONT);
     }
@@ -50,30 +82,19 @@ __global__ void __launch_bounds__(kEmitThreads)
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const int in_warp = __popc(bal & ((1u << lane) - 1u));
     if (lane == 0) warp_sums[wid] = __popc(bal);
-    __syncthreads();
-    int before = base_s;
-    int chunk_total = 0;
-#pragma unroll
-    for (int w = 0; w < kEmitThreads / 32; ++w) {
-      const int s = warp_sums[w];
-      if (w < wid) before += s;
-      chunk_total += s;
-    }
+
     if (keep) {
-      const int rank = before + in_warp;
-      cspe_record* r = records + static_cast<long long>(f) * N + rank;
-      const int x0 = scan[o * CSPE_SCAN_FIELDS + CSPE_SCAN_XMIN], y0 = scan[o * CSPE_SCAN_FIELDS + CSPE_SCAN_YMIN];
-      const int x1 = scan[o * CSPE_SCAN_FIELDS + CSPE_SCAN_XMAX], y1 = scan[o * CSPE_SCAN_FIELDS + CSPE_SCAN_YMAX];
-      r->frame = frame_base + f;
-      r->inst_idx = n;
-      r->class_id = cls;
-      r->count = cnt;
-      r->x_min = x0;
-      r->y_min = y0;
-      r->x_max = x1;
-      r->y_max = y1;
-      r->flags = fl;
-      r->pad0 = 0;
+      cspe_record h;  // only the header fields are filled; lives in registers
+      h.frame = frame_base + f;
+      h.inst_idx = n;
+      h.class_id = cls;
+      h.count = cnt;
+      h.x_min = x0;
+      h.y_min = y0;
+      h.x_max = x1;
+      h.y_max = y1;
+      h.flags = fl;
+      h.pad0 = 0;
       const int tw = x1 - x0 + 1, th = y1 - y0 + 1;
       const long long tight_area = static_cast<long long>(tw) * th;
       // loose box: projected 3D box clipped to the image and integerised
@@ -86,38 +107,86 @@ __global__ void __launch_bounds__(kEmitThreads)
       const int lw = max(0, lx1 - lx0 + 1), lh = max(0, ly1 - ly0 + 1);
       const long long loose_area = static_cast<long long>(lw) * lh;
       if (loose_area > 0) {
-        r->loose[0] = lx0;
-        r->loose[1] = ly0;
-        r->loose[2] = lx1;
-        r->loose[3] = ly1;
+        h.loose[0] = lx0;
+        h.loose[1] = ly0;
+        h.loose[2] = lx1;
+        h.loose[3] = ly1;
       } else {
-        r->loose[0] = 0;
-        r->loose[1] = 0;
-        r->loose[2] = -1;
-        r->loose[3] = -1;
+        h.loose[0] = 0;
+        h.loose[1] = 0;
+        h.loose[2] = -1;
+        h.loose[3] = -1;
       }
       const float fcnt = static_cast<float>(cnt);
       const float vis = loose_area > 0 ? fminf(1.0f, fcnt / static_cast<float>(loose_area)) : 0.0f;
-      r->visible_frac = vis;
-      r->occlusion = 1.0f - vis;
-      r->fill = cnt > 0 ? fcnt / static_cast<float>(tight_area) : 0.0f;  // min_pixels == 0 keeps unseen objects
+      h.visible_frac = vis;
+      h.occlusion = 1.0f - vis;
+      h.fill = cnt > 0 ? fcnt / static_cast<float>(tight_area) : 0.0f;  // min_pixels == 0 keeps unseen objects
       const double ua = (umax - umin) * (vmax - vmin);
       const double cwid = fmax(fmin(umax, dW) - fmax(umin, 0.0), 0.0);
       const double chei = fmax(fmin(vmax, dH) - fmax(vmin, 0.0), 0.0);
       const double ca = cwid * chei;
-      r->truncation = ua > 0.0 ? 1.0f - static_cast<float>(ca) / static_cast<float>(ua) : 1.0f;
+      h.truncation = ua > 0.0 ? 1.0f - static_cast<float>(ca) / static_cast<float>(ua) : 1.0f;
       const float fW = static_cast<float>(W), fH = static_cast<float>(H);
-      r->yolo[0] = cnt > 0 ? (static_cast<float>(x0 + x1 + 1) * 0.5f) / fW : 0.0f;
-      r->yolo[1] = cnt > 0 ? (static_cast<float>(y0 + y1 + 1) * 0.5f) / fH : 0.0f;
-      r->yolo[2] = cnt > 0 ? static_cast<float>(tw) / fW : 0.0f;
-      r->yolo[3] = cnt > 0 ? static_cast<float>(th) / fH : 0.0f;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) r->uv[k] = uv[o * 16 + k];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) r->z[k] = z[o * 8 + k];
-#pragma unroll
-      for (int k = 0; k < CSPE_POSE_STRIDE; ++k) r->pose[k] = pose[o * CSPE_POSE_STRIDE + k];
+      h.yolo[0] = cnt > 0 ? (static_cast<float>(x0 + x1 + 1) * 0.5f) / fW : 0.0f;
+      h.yolo[1] = cnt > 0 ? (static_cast<float>(y0 + y1 + 1) * 0.5f) / fH : 0.0f;
+      h.yolo[2] = cnt > 0 ? static_cast<float>(tw) / fW : 0.0f;
+      h.yolo[3] = cnt > 0 ? static_cast<float>(th) / fH : 0.0f;
+      int32_t* hs = hdr_s[tid];
+      hs[0] = h.frame;
+      hs[1] = h.inst_idx;
+      hs[2] = h.class_id;
+      hs[3] = h.count;
+      hs[4] = h.x_min;
+      hs[5] = h.y_min;
+      hs[6] = h.x_max;
+      hs[7] = h.y_max;
+      hs[8] = h.flags;
+      hs[9] = h.loose[0];
+      hs[10] = h.loose[1];
+      hs[11] = h.loose[2];
+      hs[12] = h.loose[3];
+      hs[13] = h.pad0;
+      hs[14] = __float_as_int(h.occlusion);
+      hs[15] = __float_as_int(h.fill);
+      hs[16] = __float_as_int(h.truncation);
+      hs[17] = __float_as_int(h.visible_frac);
+      hs[18] = __float_as_int(h.yolo[0]);
+      hs[19] = __float_as_int(h.yolo[1]);
+      hs[20] = __float_as_int(h.yolo[2]);
+      hs[21] = __float_as_int(h.yolo[3]);
       if (cls < CSPE_NUM_CLASSES) atomicAdd(&hist_s[cls], 1);
+    }
+    __syncthreads();  // warp_sums and hdr_s visible
+    int before = 0;
+    int chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < kEmitThreads / 32; ++w) {
+      const int s = warp_sums[w];
+      if (w < wid) before += s;
+      chunk_total += s;
+    }
+    if (keep) kept_s[before + in_warp] = tid;
+    __syncthreads();
+    // cooperative write: the kept records of this chunk are one contiguous run of 102-word
+    // records starting at rank `base_s`; all 256 threads stream it word by word (coalesced stores,
+    // independent loads), looking the source slot up through kept_s
+    {
+      const int chunk_base = base_s;
+      int32_t* dst = reinterpret_cast<int32_t*>(records + static_cast<long long>(f) * N + chunk_base);
+      const int words = chunk_total * kRecWords;
+#pragma unroll 4
+      for (int w = tid; w < words; w += kEmitThreads) {
+        const int r = w / kRecWords, k = w - r * kRecWords;
+        const int t = kept_s[r];
+        const long long so = static_cast<long long>(f) * N + n0 + t;
+        int32_t v;
+        if (k < kHdrWords) v = hdr_s[t][k];
+        else if (k < kHdrWords + 32) v = __ldg(uv32 + so * 32 + (k - kHdrWords));
+        else if (k < kHdrWords + 48) v = __ldg(z32 + so * 16 + (k - kHdrWords - 32));
+        else v = __ldg(pose32 + so * 32 + (k - kHdrWords - 48));
+        dst[w] = v;
+      }
     }
     __syncthreads();
     if (tid == 0) base_s += chunk_total;
@@ -133,10 +202,10 @@ __global__ void __launch_bounds__(kEmitThreads)
 
 using namespace cspe;
 
-extern "C" int cspe_emit(const int32_t* scan, const double* uv, const double* z, const double* pose,
-                         const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N, int H,
-                         int W, int min_pixels, int frame_base, cspe_record* records, int32_t* n_out,
-                         int64_t* class_hist, void* stream) {
+static int emit_impl(const int32_t* scan, int32_t* scan_reset, const double* uv, const double* z, const double* pose,
+                     const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N, int H, int W,
+                     int min_pixels, int frame_base, cspe_record* records, int32_t* n_out, int64_t* class_hist,
+                     void* stream) {
   CSPE_REQUIRE(B >= 0 && N >= 0 && H >= 0 && W >= 0, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_emit: negative size (B=%d N=%d H=%d W=%d)", B, N, H, W);
   if (B == 0) return CSPE_OK;
@@ -145,9 +214,25 @@ extern "C" int cspe_emit(const int32_t* scan, const double* uv, const double* z,
                CSPE_ERR_INVALID_ARGUMENT, "cspe_emit: null pointer");
   CSPE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 7) == 0 && (reinterpret_cast<uintptr_t>(class_hist) & 7) == 0,
                CSPE_ERR_INVALID_ARGUMENT, "cspe_emit: records/class_hist must be 8-byte aligned");
-  emit_kernel<<<static_cast<unsigned>(B), kEmitThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      scan, uv, z, pose, loose, flags, slot_class, N, H, W, min_pixels, frame_base, records, n_out,
-      reinterpret_cast<unsigned long long*>(class_hist));
-  CSPE_LAUNCH_OK("emit_kernel");
+  CSPE_CUDA_OK(launch_pdl(emit_kernel, dim3(static_cast<unsigned>(B)), dim3(kEmitThreads), 0,
+                          static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class, N,
+                          H, W, min_pixels, frame_base, records, n_out,
+                          reinterpret_cast<unsigned long long*>(class_hist)));
   return CSPE_OK;
+}
+
+extern "C" int cspe_emit(const int32_t* scan, const double* uv, const double* z, const double* pose,
+                         const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N, int H,
+                         int W, int min_pixels, int frame_base, cspe_record* records, int32_t* n_out,
+                         int64_t* class_hist, void* stream) {
+  return emit_impl(scan, nullptr, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, records,
+                   n_out, class_hist, stream);
+}
+
+extern "C" int cspe_emit_reset_scan(int32_t* scan, const double* uv, const double* z, const double* pose,
+                                    const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N,
+                                    int H, int W, int min_pixels, int frame_base, cspe_record* records,
+                                    int32_t* n_out, int64_t* class_hist, void* stream) {
+  return emit_impl(scan, scan, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, records,
+                   n_out, class_hist, stream);
 }

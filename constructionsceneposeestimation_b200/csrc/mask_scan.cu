@@ -265,7 +265,9 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
   } while (0)
 
 template <bool kSmemTable, int kBoxes>
-__global__ void __launch_bounds__(Geo<kBoxes>::kThreads, Geo<kBoxes>::kCtasPerSm)
+// 80 registers (no spills): leaves ~19 K registers per SM beside the two resident scan CTAs for
+// the small kernels that overlap with it
+__global__ void __maxnreg__(80)
     mask_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap tmap) {
   using G = Geo<kBoxes>;
   constexpr int kConsumerWarps = G::kConsumerWarps, kConsumers = G::kConsumers, kThreads = G::kThreads;
@@ -293,6 +295,16 @@ __global__ void __launch_bounds__(Geo<kBoxes>::kThreads, Geo<kBoxes>::kCtasPerSm
     for (int i = tid; i < p.N * CSPE_SCAN_FIELDS; i += kThreads) table[i] = table_identity(i % CSPE_SCAN_FIELDS);
   }
   __syncthreads();
+  // Programmatic dependent launch: every CTA of this persistent grid is resident once it gets
+  // here, so a kernel queued behind the scan with programmatic stream serialisation (K2, which
+  // does not read the scan's output) may start NOW and run in the registers/SM slots the scan
+  // leaves free — without ever displacing a scan CTA (its static work split needs all of them
+  // running together).  A no-op when nothing was launched that way.
+  pdl_launch_dependents();
+  // ... and this kernel is itself launched that way: block placement and the set-up above overlap
+  // the tail of the previous kernel (scan_init_kernel); its writes — and the mask, if a kernel
+  // produced it — are visible after this
+  pdl_wait();
 
   // virtual pass index v -> (frame, q); the tile is pq = (q * stride) % ppf -> (row block, segment)
   int frame = static_cast<int>(p_begin / p.ppf);
@@ -479,6 +491,7 @@ __global__ void __launch_bounds__(Geo<kBoxes>::kThreads, Geo<kBoxes>::kCtasPerSm
 }
 
 __global__ void scan_init_kernel(int32_t* out, long long n_entries, int W, int H) {
+  pdl_launch_dependents();  // the scan's CTAs may set up their rings while this finishes
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n_entries * CSPE_SCAN_FIELDS) return;
   const int f = static_cast<int>(i % CSPE_SCAN_FIELDS);
@@ -642,8 +655,7 @@ int launch_scan_geo(const uint32_t* mask, int B, int H, int W,
 
   auto kern = smem_table ? mask_scan_kernel<true, kBoxes> : mask_scan_kernel<false, kBoxes>;
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
-  kern<<<grid, G::kThreads, smem_bytes, st>>>(p, tmap);
-  CSPE_LAUNCH_OK("mask_scan_kernel");
+  CSPE_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(G::kThreads), smem_bytes, st, p, tmap));
   return CSPE_OK;
 }
 

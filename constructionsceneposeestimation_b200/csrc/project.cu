@@ -144,13 +144,34 @@ __device__ void quat_xyzw(const Mat3& r, double* q) {
 // SM when the caller forks K2 onto a side stream (pipeline.py), which hides K2 entirely.
 constexpr int kProjThreads = 64;
 
+__device__ __forceinline__ void project_one(const unsigned char* __restrict__ records, int rec_stride, int recs_per_frame,
+                                            const int32_t* __restrict__ obj_record, const double* __restrict__ cam,
+                                            long long obj, int N, double* __restrict__ uv, double* __restrict__ zc_out,
+                                            double* __restrict__ pose, double* __restrict__ loose,
+                                            uint8_t* __restrict__ flags);
+
 __global__ void __launch_bounds__(kProjThreads)
     project_objects_kernel(const unsigned char* __restrict__ records, int rec_stride, int recs_per_frame,
                            const int32_t* __restrict__ obj_record, const double* __restrict__ cam, long long total, int N,
                            double* __restrict__ uv, double* __restrict__ zc_out, double* __restrict__ pose,
-                           double* __restrict__ loose, uint8_t* __restrict__ flags) {
+                           double* __restrict__ loose, uint8_t* __restrict__ flags, int overlap_previous) {
+  pdl_launch_dependents();  // let the next kernel (K4) get its blocks placed; it waits for us before reading
+  // default: behave like an ordinary serialised launch (inputs may come from the previous kernel)
+  if (!overlap_previous) pdl_wait();
   const long long obj = static_cast<long long>(blockIdx.x) * kProjThreads + threadIdx.x;
-  if (obj >= total) return;
+  if (obj < total) project_one(records, rec_stride, recs_per_frame, obj_record, cam, obj, N, uv, zc_out, pose, loose, flags);
+  // overlap mode: the grid may have started while the kernel before it in the stream (the mask
+  // scan) was still running and nothing above depends on that kernel; waiting HERE makes this
+  // grid's completion imply its completion, so plain stream order still holds for whatever is
+  // queued next (K4 reads both).
+  if (overlap_previous) pdl_wait();
+}
+
+__device__ __forceinline__ void project_one(const unsigned char* __restrict__ records, int rec_stride, int recs_per_frame,
+                                            const int32_t* __restrict__ obj_record, const double* __restrict__ cam,
+                                            long long obj, int N, double* __restrict__ uv, double* __restrict__ zc_out,
+                                            double* __restrict__ pose, double* __restrict__ loose,
+                                            uint8_t* __restrict__ flags) {
   const int frame = static_cast<int>(obj / N);
   const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
   double* po = pose + obj * CSPE_POSE_STRIDE;
@@ -293,9 +314,9 @@ __global__ void __launch_bounds__(kProjThreads)
 
 using namespace cspe;
 
-extern "C" int cspe_project_objects(const void* records, int rec_stride, int recs_per_frame,
-                                    const int32_t* obj_record, const double* cam, int B, int N, double* uv,
-                                    double* z, double* pose, double* loose, uint8_t* flags, void* stream) {
+static int project_objects_impl(const void* records, int rec_stride, int recs_per_frame, const int32_t* obj_record,
+                                const double* cam, int B, int N, double* uv, double* z, double* pose, double* loose,
+                                uint8_t* flags, void* stream, int overlap_previous) {
   CSPE_REQUIRE(B >= 0 && N >= 0 && recs_per_frame >= 0, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_project_objects: negative size (B=%d N=%d recs_per_frame=%d)", B, N, recs_per_frame);
   if (B == 0 || N == 0) return CSPE_OK;
@@ -311,9 +332,32 @@ extern "C" int cspe_project_objects(const void* records, int rec_stride, int rec
   const long long total = static_cast<long long>(B) * N;
   const long long blocks = (total + kProjThreads - 1) / kProjThreads;
   CSPE_REQUIRE(blocks < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_project_objects: too many objects");
-  project_objects_kernel<<<static_cast<unsigned>(blocks), kProjThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const unsigned char*>(records), rec_stride, recs_per_frame, obj_record, cam, total, N, uv, z, pose,
-      loose, flags);
-  CSPE_LAUNCH_OK("project_objects_kernel");
+  // Same shared-memory carve-out as the mask scan (max shared): an SM cannot host kernels with
+  // different L1/shared splits at the same time, so without this K2 would wait for K1's persistent
+  // CTAs to leave instead of running beside them on the caller's side stream.
+  static const cudaError_t carve = cudaFuncSetAttribute(project_objects_kernel,
+                                                        cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                        cudaSharedmemCarveoutMaxShared);
+  (void)carve;
+  // Programmatic stream serialisation: if the kernel before this one in `stream` releases its
+  // dependents early (the mask scan does, right after its CTAs are resident), K2 starts beside it;
+  // after any other kernel this is an ordinary serialised launch.
+  CSPE_CUDA_OK(launch_pdl(project_objects_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kProjThreads), 0,
+                          static_cast<cudaStream_t>(stream), static_cast<const unsigned char*>(records), rec_stride,
+                          recs_per_frame, obj_record, cam, total, N, uv, z, pose, loose, flags, overlap_previous));
   return CSPE_OK;
+}
+
+extern "C" int cspe_project_objects(const void* records, int rec_stride, int recs_per_frame,
+                                    const int32_t* obj_record, const double* cam, int B, int N, double* uv,
+                                    double* z, double* pose, double* loose, uint8_t* flags, void* stream) {
+  return project_objects_impl(records, rec_stride, recs_per_frame, obj_record, cam, B, N, uv, z, pose, loose, flags,
+                              stream, 0);
+}
+
+extern "C" int cspe_project_objects_overlapped(const void* records, int rec_stride, int recs_per_frame,
+                                               const int32_t* obj_record, const double* cam, int B, int N, double* uv,
+                                               double* z, double* pose, double* loose, uint8_t* flags, void* stream) {
+  return project_objects_impl(records, rec_stride, recs_per_frame, obj_record, cam, B, N, uv, z, pose, loose, flags,
+                              stream, 1);
 }

@@ -1,10 +1,11 @@
 """Static-shape batch pipeline: K1 (mask scan) || K2 (projection/pose) -> K4 (emission).
 
-All buffers are allocated once; one call to :meth:`LabelPipeline.run` enqueues the whole batch.
-K2 does not depend on K1, so it is forked onto a side stream and joined before K4; with
-``use_graph=True`` the fork/join and the five launches are captured once into a CUDA graph and
-replayed (no per-launch host overhead, no tracing compiler — the kernels are the hand-written
-ones behind the C ABI).
+All buffers are allocated once; one call to :meth:`LabelPipeline.run` enqueues the whole batch on
+one stream.  K2 does not depend on K1: it is launched with programmatic stream serialisation and
+K1 releases its dependents as soon as its persistent CTAs are resident, so K2 runs in the SM
+resources K1 leaves free.  With ``use_graph=True`` the four launches are captured once into a
+CUDA graph and replayed (no per-launch host overhead, no tracing compiler — the kernels are the
+hand-written ones behind the C ABI).
 """
 from __future__ import annotations
 
@@ -37,7 +38,8 @@ class LabelPipeline:
         self.slot_class = torch.full((B, N), -1, dtype=i32, device=dev)
         self.records_in = torch.zeros((B, recs_per_frame, _lib.BBOX3D_RECORD_BYTES), dtype=u8, device=dev)
         self.cam = torch.zeros((B, CAM_STRIDE), dtype=f64, device=dev)
-        self.scan = torch.empty((B, N, SCAN_FIELDS), dtype=i32, device=dev)
+        # scan table starts as "no instance seen" (what cspe_mask_scan's init writes); K4 restores it per batch
+        self.scan = torch.tensor([0, width, height, -1, -1], dtype=i32, device=dev).repeat(B, N, 1).contiguous()
         self.uv = torch.empty((B, N, 8, 2), dtype=f64, device=dev)
         self.z = torch.empty((B, N, 8), dtype=f64, device=dev)
         self.pose = torch.empty((B, N, POSE_STRIDE), dtype=f64, device=dev)
@@ -46,33 +48,30 @@ class LabelPipeline:
         self.records = torch.empty((B, N, RECORD_DTYPE.itemsize), dtype=u8, device=dev)
         self.n_out = torch.empty((B,), dtype=i32, device=dev)
         self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=dev)
-        self.launches_per_run = 4  # scan_init + mask_scan + project_objects + emit
-        with torch.cuda.device(dev):
-            self.side = torch.cuda.Stream(device=dev)
+        self.launches_per_run = 3  # mask_scan (accumulate) + project_objects + emit (which re-initialises the scan table)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = use_graph
 
     # ---------------------------------------------------------------- enqueue
     def _enqueue(self) -> None:
+        """scan -> project -> emit on ONE stream, 3 launches.  The scan table is initialised once
+        (constructor) and re-initialised by K4 as it reads it, so K1 runs in accumulate mode with no
+        init launch.  K2 is launched with programmatic stream serialisation and the scan releases its
+        dependents as soon as its CTAs are resident, so K2 runs beside the scan (it does not read the
+        scan's output) and K4 still sees both done."""
         lib, chk = self.lib, _lib.check
-        main = torch.cuda.current_stream(self.device)
-        fork, join = torch.cuda.Event(), torch.cuda.Event()
-        fork.record(main)
-        self.side.wait_event(fork)
-        chk("cspe_project_objects", lib.cspe_project_objects(
+        main = torch.cuda.current_stream(self.device).cuda_stream
+        chk("cspe_mask_scan_accumulate", lib.cspe_mask_scan_accumulate(
+            self.mask.data_ptr(), self.B, self.H, self.W, self.lut.data_ptr(), self.L, self.lut_stride, self.N,
+            self.scan.data_ptr(), main))
+        chk("cspe_project_objects_overlapped", lib.cspe_project_objects_overlapped(
             self.records_in.data_ptr(), _lib.BBOX3D_RECORD_BYTES, self.R, self.obj_record.data_ptr(),
             self.cam.data_ptr(), self.B, self.N, self.uv.data_ptr(), self.z.data_ptr(), self.pose.data_ptr(),
-            self.loose.data_ptr(), self.flags.data_ptr(), self.side.cuda_stream))
-        join.record(self.side)
-        chk("cspe_mask_scan", lib.cspe_mask_scan(
-            self.mask.data_ptr(), self.B, self.H, self.W, self.lut.data_ptr(), self.L, self.lut_stride, self.N,
-            self.scan.data_ptr(), main.cuda_stream))
-        main.wait_event(join)
-        chk("cspe_emit", lib.cspe_emit(
+            self.loose.data_ptr(), self.flags.data_ptr(), main))
+        chk("cspe_emit_reset_scan", lib.cspe_emit_reset_scan(
             self.scan.data_ptr(), self.uv.data_ptr(), self.z.data_ptr(), self.pose.data_ptr(), self.loose.data_ptr(),
             self.flags.data_ptr(), self.slot_class.data_ptr(), self.B, self.N, self.H, self.W, self.min_pixels,
-            self.frame_base, self.records.data_ptr(), self.n_out.data_ptr(), self.class_hist.data_ptr(),
-            main.cuda_stream))
+            self.frame_base, self.records.data_ptr(), self.n_out.data_ptr(), self.class_hist.data_ptr(), main))
 
     def run(self) -> None:
         """Enqueue one batch on the current stream (graph replay when enabled)."""

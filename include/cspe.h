@@ -161,6 +161,16 @@ int cspe_project_objects(const void* records, int rec_stride, int recs_per_frame
                          double* uv, double* z, double* pose, double* loose, uint8_t* flags,
                          void* stream);
 
+/* K2 for pipelines: identical results, but the grid may START while the kernel queued before it
+ * in `stream` is still running, provided that kernel releases its dependents early (the mask
+ * scan does: programmatic dependent launch); it still COMPLETES after it, so whatever is queued
+ * next sees both done.  Contract: none of this call's inputs is written by that previous kernel.
+ * (cspe_project_objects itself makes no such assumption.) */
+int cspe_project_objects_overlapped(const void* records, int rec_stride, int recs_per_frame,
+                                    const int32_t* obj_record, const double* cam, int B, int N,
+                                    double* uv, double* z, double* pose, double* loose, uint8_t* flags,
+                                    void* stream);
+
 /* ---- K3: skeleton keypoint projection + depth-buffer visibility ([SPEC]; "skelroot" is
  * only a class keyword in the reference, gcd.py:105) ----------------------------------------
  * joints  float32 [B][P][J][3] world positions (Replicator skeleton_data globalTranslations)
@@ -183,6 +193,14 @@ int cspe_emit(const int32_t* scan, const double* uv, const double* z, const doub
               const double* loose, const uint8_t* flags, const int32_t* slot_class,
               int B, int N, int H, int W, int min_pixels, int frame_base,
               cspe_record* records, int32_t* n_out, int64_t* class_hist, void* stream);
+
+/* K4 for steady-state pipelines: same records, and every scan entry is re-initialised to the
+ * absent-instance identity {0, W, H, -1, -1} once read, so the next batch can go through
+ * cspe_mask_scan_accumulate on the same `scan` buffer without an initialisation launch. */
+int cspe_emit_reset_scan(int32_t* scan, const double* uv, const double* z, const double* pose,
+                         const double* loose, const uint8_t* flags, const int32_t* slot_class,
+                         int B, int N, int H, int W, int min_pixels, int frame_base,
+                         cspe_record* records, int32_t* n_out, int64_t* class_hist, void* stream);
 
 /* ---- next rows ------------------------------------------------------------- */
 
