@@ -60,6 +60,8 @@ class BatchLabels:
     _vis_host: Optional[torch.Tensor] = None
     person_slots: Optional[List[List[int]]] = None
     device_outputs: Dict[str, torch.Tensor] = field(default_factory=dict)
+    _depth_stats_host: Optional[torch.Tensor] = None
+    _depth_viz_host: Optional[torch.Tensor] = None
     _synced: bool = False
 
     def synchronize(self) -> "BatchLabels":
@@ -93,6 +95,26 @@ class BatchLabels:
         return {slot: formats.coco_keypoint_block(kp[p], vis[p])
                 for p, slot in enumerate(self.person_slots[f]) if slot >= 0 and p < kp.shape[0]}
 
+    def depth_quality(self, f: int) -> Optional[Dict[str, object]]:
+        """The dict the reference's DataQualityLogger.log_depth stores per frame (gcd.py:333-342)."""
+        if self._depth_stats_host is None:
+            return None
+        self.synchronize()
+        st = self._depth_stats_host[f].numpy().view(_lib.DEPTH_STATS_DTYPE)[0]
+        valid, total = int(st["valid_pixels"]), int(st["total_pixels"])
+        mean = float(np.float32(st["depth_sum"] / valid)) if valid else 0.0
+        return {"status": "valid", "valid_pixels": valid, "total_pixels": total,
+                "valid_ratio": float(valid / total) if total else 0.0, "zero_pixels": int(st["zero_pixels"]),
+                "inf_pixels": int(st["inf_pixels"]), "depth_range": [float(st["depth_min"]), float(st["depth_max"])],
+                "depth_mean": mean}
+
+    def depth_image(self, f: int) -> Optional[np.ndarray]:
+        """JET visualisation of the depth map, uint8 BGR [H,W,3] (gcd.py:1691-1709); needs "depth_png" in formats."""
+        if self._depth_viz_host is None:
+            return None
+        self.synchronize()
+        return self._depth_viz_host[f].numpy()
+
     def reference_label(self, f: int) -> Dict[str, object]:
         return formats.reference_label(self.frame_ids[f], self.camera_poses[f], self.camera_params[f], self.height,
                                        self.width, self.records(f), self.tables[f].objects,
@@ -122,7 +144,9 @@ class ConstructionLabelWriter:
     (``labels/`` as gcd.py:40), clipping range (gcd.py:1437), and the run-time crane part map
     (gcd.py:124).  ``formats`` selects what ``write`` serialises: ``"json"`` (reference schema),
     ``"yolo"``, ``"coco"``, ``"mask"`` (the real instance mask instead of the reference's -1
-    placeholder, gcd.py:2066-2069).
+    placeholder, gcd.py:2066-2069), ``"depth_png"`` (JET depth image, gcd.py:1691-1709).  When a
+    frame carries ``distance_to_image_plane`` the depth-quality statistics of the reference's
+    logger (gcd.py:314-359) are computed on the GPU and returned by ``BatchLabels.depth_quality``.
     """
 
     annotators = ["instance_segmentation", "distance_to_image_plane", "bounding_box_3d", "camera_params",
@@ -152,6 +176,8 @@ class ConstructionLabelWriter:
         self._coco_images: List[Dict] = []
         self._coco_annotations: List[Dict] = []
         self.frames_written = 0
+        self.objects_total = 0
+        self.depth_quality_log: List[Dict[str, object]] = []
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
             self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=self.device)
@@ -204,6 +230,10 @@ class ConstructionLabelWriter:
         hist = self.gather_class_histogram()
         summary = {
             "frames": self.frames_written,
+            # the reference logger's object counter (gcd.py:361-372, 392-394)
+            "object_count": {"total": self.objects_total,
+                             "per_frame_avg": self.objects_total / self.frames_written if self.frames_written else 0},
+            "depth_quality": self.depth_quality_log,
             "rank": self.rank,
             "world_size": self.world_size,
             "class_histogram": {CLASS_NAMES[i]: int(hist["total"][i]) for i in range(NUM_CLASSES)},
@@ -314,7 +344,7 @@ class ConstructionLabelWriter:
             uv, z, pose, loose, flags = ops.project_objects(d_rec, d_obj_record, d_cam)
             kp_host = vis_host = None
             person_slots = None
-            d_kp = d_vis = None
+            d_kp = d_vis = d_depth = None
             joints_list = [self._joints_of(fr) for fr in frames]
             depth_list = [_payload(fr.get("distance_to_image_plane")) for fr in frames]
             if all(j is not None and j.shape[0] > 0 for j in joints_list) and all(d is not None for d in depth_list) \
@@ -323,6 +353,17 @@ class ConstructionLabelWriter:
                 d_joints = self._stack_to_device(joints_list, torch.float32)
                 d_kp, _kz, d_vis = ops.keypoints(d_joints, d_depth, d_cam, self.keypoint_tolerance)
                 person_slots = [self._person_slots(t, joints_list[i].shape[0]) for i, t in enumerate(tables)]
+            stats_host = viz_host = None
+            if all(d is not None for d in depth_list):
+                if d_depth is None:
+                    d_depth = self._stack_to_device(depth_list, torch.float32)
+                d_stats = ops.depth_stats(d_depth)                                  # f2, gcd.py:314-359
+                stats_host = torch.empty(d_stats.shape, dtype=torch.uint8, pin_memory=True)
+                stats_host.copy_(d_stats, non_blocking=True)
+                if "depth_png" in self.formats:
+                    d_viz = ops.depth_colormap(d_depth, self._jet_lut(), d_stats)   # f4, gcd.py:1691-1709
+                    viz_host = torch.empty(d_viz.shape, dtype=torch.uint8, pin_memory=True)
+                    viz_host.copy_(d_viz, non_blocking=True)
             if contiguous_ids:
                 rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels,
                                              frame_base, class_hist=self.class_hist)
@@ -344,7 +385,7 @@ class ConstructionLabelWriter:
         labels = BatchLabels(frame_ids, tables, H, W, poses, params_list, rec_host, nout_host, event, kp_host,
                              vis_host, person_slots,
                              {"scan": scan, "uv": uv, "z": z, "pose": pose, "loose": loose, "flags": flags,
-                              "records": rec_dev, "n_out": n_out})
+                              "records": rec_dev, "n_out": n_out}, stats_host, viz_host)
         if not contiguous_ids:
             labels.synchronize()
             for f in range(B):  # frame field was written relative to 0
@@ -377,6 +418,17 @@ class ConstructionLabelWriter:
             out[i].copy_(src, non_blocking=True)
         return out
 
+    def _jet_lut(self) -> torch.Tensor:
+        """cv2.COLORMAP_JET as a [256,3] BGR table on the device (the table the reference applies, gcd.py:1702)."""
+        lut = getattr(self, "_jet_lut_dev", None)
+        if lut is None:
+            import cv2
+
+            table = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(-1, 1), cv2.COLORMAP_JET).reshape(256, 3)
+            lut = torch.from_numpy(np.ascontiguousarray(table)).to(self.device)
+            self._jet_lut_dev = lut
+        return lut
+
     @staticmethod
     def _joints_of(fr: Mapping) -> Optional[np.ndarray]:
         sk = fr.get("skeleton_data")
@@ -406,6 +458,12 @@ class ConstructionLabelWriter:
                 if "yolo" in self.formats:
                     with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
                         fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))
+                if "depth_png" in self.formats and labels.depth_image(f) is not None:
+                    import cv2
+
+                    ddir = os.path.join(self.output_dir, "depth")
+                    os.makedirs(ddir, exist_ok=True)
+                    cv2.imwrite(os.path.join(ddir, f"depth_{fid:06d}.png"), labels.depth_image(f))   # gcd.py:1703-1704
                 if "mask" in self.formats and masks is not None:
                     m = masks[f]
                     m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
@@ -414,4 +472,8 @@ class ConstructionLabelWriter:
                 self._coco_images.append(formats.coco_image(fid, labels.width, labels.height, f"rgb_{fid:06d}.png"))
                 self._coco_annotations += formats.coco_annotations(recs, fid, len(self._coco_annotations) + 1,
                                                                    labels.keypoints_by_slot(f))
+            dq = labels.depth_quality(f)
+            if dq is not None:
+                self.depth_quality_log.append({"frame_id": fid, "depth": dq})
+            self.objects_total += len(recs)
             self.frames_written += 1

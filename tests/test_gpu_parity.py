@@ -426,7 +426,7 @@ def test_writer_end_to_end(T, ops, tmp_path):
     from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
     frames = synthetic.make_batch(synthetic.SceneSpec(1280, 720, 20, 4, 17, config_id=1), 3)
     o = helpers.oracle_pipeline(frames)
-    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "yolo", "coco", "mask"), split_people=True)
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "yolo", "coco", "mask", "depth_png"), split_people=True)
     labels = w.write_batch(frames)
     summary = w.on_final_frame()
     assert np.array_equal(labels.n_out, o["n_out"])
@@ -441,8 +441,17 @@ def test_writer_end_to_end(T, ops, tmp_path):
         assert list(lab["objects"][0])[:7] == ["inst_idx", "class_id", "class_name", "center", "size", "rotation",
                                                "prim_path"]                          # gcd.py:1938-1946
         assert np.load(tmp_path / "labels" / f"instance_mask_{f:06d}.npy").shape == (720, 1280)
+        dq, ref = labels.depth_quality(f), O.depth_stats(frames[f]["distance_to_image_plane"])   # gcd.py:333-342
+        assert list(dq) == list(ref)
+        for k in ("status", "valid_pixels", "total_pixels", "valid_ratio", "zero_pixels", "inf_pixels", "depth_range"):
+            assert dq[k] == ref[k], k
+        assert abs(dq["depth_mean"] - ref["depth_mean"]) <= 1e-5 * ref["depth_mean"]
+        import cv2
+        png = cv2.imread(str(tmp_path / "depth" / f"depth_{f:06d}.png"))
+        assert np.array_equal(png, O.depth_colormap(frames[f]["distance_to_image_plane"]))           # gcd.py:1691-1704
         assert len((tmp_path / "labels" / f"label_{f:06d}.txt").read_text().splitlines()) == int(o["n_out"][f])
     assert sum(summary["class_histogram"].values()) == int(o["n_out"].sum())
+    assert summary["object_count"]["total"] == int(o["n_out"].sum()) and len(summary["depth_quality"]) == 3
     assert np.array_equal(np.asarray(summary["class_histogram_per_rank"])[0], o["hist"])
     coco = json.loads((tmp_path / "coco_rank00.json").read_text())
     assert len(coco["annotations"]) == int(o["n_out"].sum()) and len(coco["images"]) == 3
