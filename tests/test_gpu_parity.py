@@ -568,3 +568,30 @@ def test_sweep_frame_range_and_histogram(T, ops, tmp_path):
     files = sorted((tmp_path / "labels").glob("label_*.txt"))
     assert len(files) == 150 and files[-1].name == "label_000149.txt"
     assert len(files[17].read_text().splitlines()) == int(o["n_out"][1])
+
+
+def test_scan_random_shapes_property(T, ops):
+    """Hypothesis sweep over shapes / id ranges / LUT layouts against the C restatement of the oracle:
+    odd widths (non-TMA producer), widths around the 32/128-pixel box and tile edges, heights around the
+    64-row tile edge, shared and per-frame LUTs, ids beyond the LUT."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    from oracle import c_oracle
+
+    if not c_oracle.available():
+        pytest.skip("C oracle could not be built")
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+    @given(B=st.integers(1, 3), H=st.sampled_from([1, 2, 31, 63, 64, 65, 127, 130]),
+           W=st.sampled_from([1, 3, 4, 31, 32, 33, 36, 127, 128, 129, 132, 255, 256, 260, 515]),
+           n_ids=st.integers(1, 40), N=st.integers(1, 12), per_frame=st.booleans(), noise=st.booleans(),
+           seed=st.integers(0, 2**16))
+    def run(B, H, W, n_ids, N, per_frame, noise, seed):
+        rng = np.random.default_rng(seed)
+        mask = _random_mask(rng, B, H, W, n_ids, noise)
+        if rng.uniform() < 0.3:
+            mask[rng.uniform(size=mask.shape) < 0.05] = n_ids + 5 + int(rng.integers(0, 1 << 30))   # ids beyond the LUT
+        lut = rng.integers(-1, N + 1, size=(B, n_ids + 2) if per_frame else (n_ids + 2,)).astype(np.int32)
+        got = _scan_gpu(T, ops, mask, lut, N)
+        assert np.array_equal(got, c_oracle.mask_scan(mask, lut, N))
+
+    run()
