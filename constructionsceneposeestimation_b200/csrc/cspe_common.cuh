@@ -69,7 +69,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
-// ---- device: mbarrier + bulk async copy (TMA 1D, SASS UBLKCP) ---------------------------
+// ---- device: mbarrier helpers for the TMA ring ---------------------------------------------
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -112,17 +112,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
-}
-
-// global -> shared bulk copy, completion counted in bytes on `bar`.
-// dst, src 16-byte aligned; bytes a multiple of 16.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
-                                         uint64_t* bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
-      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
 }
 
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

@@ -458,6 +458,29 @@ def test_writer_end_to_end(T, ops, tmp_path):
     assert any("keypoints" in a for a in coco["annotations"])
 
 
+def test_writer_accepts_device_resident_annotators(T, ops):
+    """Annotators created with device="cuda" arrive as CUDA tensors: same labels, no host copy of the pixels."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(640, 360, 18, 3, 17, config_id=13), 2)
+    o = helpers.oracle_pipeline(frames)
+    dev_frames = []
+    for fr in frames:
+        d = dict(fr)
+        d["instance_segmentation"] = {"data": T.from_numpy(fr["instance_segmentation"]["data"].view(np.int32)).cuda(),
+                                      "info": fr["instance_segmentation"]["info"]}
+        d["distance_to_image_plane"] = T.from_numpy(fr["distance_to_image_plane"]).cuda()
+        dev_frames.append(d)
+    w = ConstructionLabelWriter(None, split_people=True)
+    labels = w.annotate_batch(dev_frames)
+    assert np.array_equal(labels.n_out, o["n_out"])
+    for f in range(2):
+        helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
+        assert np.array_equal(labels.keypoints(f)[1], o["vis"][f])
+    single = w.annotate_batch(dev_frames[:1])          # one device frame: used in place, no stacking copy
+    helpers.assert_records_equal(single.records(0), o["recs"][0, : o["n_out"][0]])
+
+
 def test_writer_tolerates_empty_annotators(T, ops):
     """gcd.py:1682/1788/1919: None or empty annotators never raise; the frame just has no objects."""
     from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
