@@ -202,6 +202,8 @@ def run_ours(args) -> int:
     if uniq < BATCH:
         frames = [frames[i % uniq] for i in range(BATCH)]
     lut, obj_record, slot_class, records, cam, _objs = helpers.host_tables(frames)
+    if lut.shape[1] % 4:  # 16-byte LUT rows, like the writer builds them
+        lut = np.pad(lut, ((0, 0), (0, 4 - lut.shape[1] % 4)), constant_values=-1)
     H, W = frames[0]["instance_segmentation"]["data"].shape
     N = obj_record.shape[1]
     mask_host = torch.empty((BATCH, H, W), dtype=torch.int32, pin_memory=True)

@@ -10,7 +10,10 @@ from pathlib import Path
 
 import numpy as np
 
-LIB_PATH = Path(__file__).resolve().parent / "libcspe.so"
+import os
+
+# CSPE_LIB points at an alternative build of the same ABI (used to A/B kernel variants on the GPU box)
+LIB_PATH = Path(os.environ.get("CSPE_LIB") or Path(__file__).resolve().parent / "libcspe.so")
 
 ABI_VERSION = 1
 CAM_STRIDE = 24

@@ -19,7 +19,8 @@ from ._lib import CAM_STRIDE, NUM_CLASSES, POSE_STRIDE, RECORD_DTYPE, SCAN_FIELD
 
 class LabelPipeline:
     def __init__(self, batch: int, height: int, width: int, num_slots: int, recs_per_frame: int, lut_len: int,
-                 device: torch.device, per_frame_lut: bool = True, min_pixels: int = 1, use_graph: bool = True,
+                 device: torch.device, per_frame_lut: bool = True,  # lut_len: use a multiple of 4 (16-byte rows)
+                 min_pixels: int = 1, use_graph: bool = True,
                  mask: Optional[torch.Tensor] = None):
         self.lib = _lib.load()
         self.B, self.H, self.W, self.N, self.R, self.L = batch, height, width, num_slots, recs_per_frame, lut_len

@@ -36,6 +36,7 @@ def _host_tables(frames, split_people=True):
     N = max(1, max(len(p[0]) for p in per))
     R = max(1, max(len(fr["bounding_box_3d"]["data"]) for fr in frames))
     L = max(1, max((max(p[2]) if p[2] else 0) for p in per) + 1)
+    L = (L + 3) & ~3  # 16-byte LUT rows (K1 stages each frame's LUT with a bulk copy)
     lut = np.full((B, L), -1, dtype=np.int32)
     obj_record = np.full((B, N), -1, dtype=np.int32)
     slot_class = np.full((B, N), -1, dtype=np.int32)

@@ -320,6 +320,7 @@ class ConstructionLabelWriter:
         R = max(1, max((len(r) for r in rec_arrays if r is not None), default=1))
         same_tables = all(t is tables[0] for t in tables)
         L = max(1, max(t.max_id for t in tables) + 1)
+        L = (L + 3) & ~3  # 16-byte LUT rows: K1 then carries each frame's LUT through its TMA ring
         lut = np.full((1 if same_tables else B, L), -1, dtype=np.int32)
         obj_record = np.full((B, N), -1, dtype=np.int32)
         slot_class = np.full((B, N), -1, dtype=np.int32)

@@ -9,6 +9,7 @@ from tests import helpers
 dev = torch.device("cuda")
 frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 8)
 lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
+lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
 B = 64; H, W = frames[0]["instance_segmentation"]["data"].shape; N = obj_record.shape[1]
 pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], dev, use_graph=False)
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)

@@ -39,6 +39,7 @@ def out(**kw):
 
 def build_pipeline(frames, B):
     lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
+    lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
     u = len(frames)
     rep = (B + u - 1) // u
     H, W = frames[0]["instance_segmentation"]["data"].shape

@@ -12,6 +12,8 @@ dev = torch.device("cuda")
 PEAK = 6454.3
 
 def timeit(mask, lut, N, label):
+    if lut.shape[-1] % 4:   # 16-byte LUT rows: the per-stage bulk copy of the LUT needs them
+        lut = torch.nn.functional.pad(lut, (0, 4 - lut.shape[-1] % 4), value=-1).contiguous()
     out = ops.mask_scan(mask, lut, N)
     for _ in range(3):
         ops.mask_scan(mask, lut, N, out=out, accumulate=True)
@@ -30,10 +32,12 @@ if "zeros" in which:
     timeit(m, torch.full((128,), -1, dtype=torch.int32, device=dev), 100, "zeros 64x1080p")
     del m
 if "c2" in which:
-    frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 16)
+    import os
+    uniq = int(os.environ.get("CSPE_MICRO_UNIQUE", "16"))
+    frames = synthetic.make_batch(synthetic.CONFIGS["c2"], uniq)
     lut, obj_record, *_ = helpers.host_tables(frames)
-    m = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(4, 1, 1)
-    l = torch.from_numpy(lut).to(dev).repeat(4, 1)
+    m = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(64 // uniq, 1, 1)
+    l = torch.from_numpy(lut).to(dev).repeat(64 // uniq, 1)
     timeit(m, l, obj_record.shape[1], "synthetic c2 64x1080p")
     del m
 if "noise16" in which:
