@@ -105,6 +105,7 @@ PROTOTYPES = {
     "cspe_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "cspe_mask_scan": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
     "cspe_mask_scan_accumulate": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
+    "cspe_mask_scan_accumulate_overlapped": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
     "cspe_mask_scan_depth_stats": (_I, [_P, _P, _I, _I, _I, _P, _I, _I64, _I, _P, _P, _P]),
     "cspe_project_objects": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cspe_project_objects_overlapped": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),

@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(kEmitThreads)
   const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
+  // let whatever is queued behind K4 get placed while K4 runs (the next batch's mask scan in
+  // overlapped mode streams its mask meanwhile and waits for us before it merges into `scan`)
+  pdl_launch_dependents();
   if (tid < CSPE_NUM_CLASSES) hist_s[tid] = 0;
   if (tid == 0) base_s = 0;
   __syncthreads();

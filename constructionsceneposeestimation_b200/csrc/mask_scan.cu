@@ -80,6 +80,7 @@ struct ScanParams {
   int stride;    // pass permutation inside a frame: q -> (q * stride) % ppf, gcd(stride, ppf) = 1
   int tma;       // 1: tensor-map TMA (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
   int smem_lut;  // 1: the frame's LUT is staged in shared memory
+  int lazy_wait; // 1: wait for the previous kernel only before the first merge into `out` (overlapped mode)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar,
@@ -302,9 +303,12 @@ __global__ void __maxnreg__(80)
   // running together).  A no-op when nothing was launched that way.
   pdl_launch_dependents();
   // ... and this kernel is itself launched that way: block placement and the set-up above overlap
-  // the tail of the previous kernel (scan_init_kernel); its writes — and the mask, if a kernel
-  // produced it — are visible after this
-  pdl_wait();
+  // the tail of the previous kernel; its writes — and the mask, if a kernel produced it — are
+  // visible after this.  In overlapped mode the caller promises that only `out` can still be in
+  // use by the previous kernel (K4 of the previous batch reading and resetting it), so the wait
+  // moves to just before this CTA's first merge into `out` and the streaming starts right away.
+  const bool lazy = kSmemTable && p.lazy_wait;
+  if (!lazy) pdl_wait();
 
   // virtual pass index v -> (frame, q); the tile is pq = (q * stride) % ppf -> (row block, segment)
   int frame = static_cast<int>(p_begin / p.ppf);
@@ -369,6 +373,7 @@ __global__ void __maxnreg__(80)
   entry_reset(e1, 0u);
 
   int cur_frame = frame;
+  bool waited = false;
   const int32_t* lut = nullptr;
   int32_t* tab = nullptr;
 
@@ -390,6 +395,10 @@ __global__ void __maxnreg__(80)
     entry_reset(e0, 0u);
     entry_reset(e1, 0u);
     if (kSmemTable || p.smem_lut) named_bar_sync(1, kConsumers);  // all flushes landed / LUT no longer read
+    if (lazy && !waited) {
+      pdl_wait();
+      waited = true;
+    }
     if (kSmemTable) {
       int32_t* gout = p.out + static_cast<long long>(cur_frame) * p.N * CSPE_SCAN_FIELDS;
       for (int i = tid; i < p.N * CSPE_SCAN_FIELDS; i += kConsumers) {
@@ -585,8 +594,8 @@ TensorMapEncodeFn tensor_map_encoder() {
 }
 
 template <int kBoxes>
-int launch_scan_geo(const uint32_t* mask, int B, int H, int W,
-                    const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
+int launch_scan_geo(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot, int lut_len, int64_t lut_stride,
+                    int N, int32_t* out, cudaStream_t st, int lazy_wait) {
   using G = Geo<kBoxes>;
   const int sms = sm_count();
   CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_mask_scan: no CUDA device");
@@ -601,6 +610,7 @@ int launch_scan_geo(const uint32_t* mask, int B, int H, int W,
   p.W = W;
   p.N = N;
   p.lut_len = lut_len;
+  p.lazy_wait = lazy_wait;
   p.nseg = (W + G::kTileCols - 1) / G::kTileCols;
   p.nrb = (H + kTileRows - 1) / kTileRows;
   const long long ppf = static_cast<long long>(p.nseg) * p.nrb;
@@ -669,15 +679,15 @@ int scan_boxes() {
   return v;
 }
 
-int launch_scan(const uint32_t* mask, int B, int H, int W,
-                const int32_t* id2slot, int lut_len, int64_t lut_stride, int N, int32_t* out, cudaStream_t st) {
+int launch_scan(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot, int lut_len, int64_t lut_stride, int N,
+                int32_t* out, cudaStream_t st, int lazy_wait = 0) {
   switch (scan_boxes()) {
     case 8:
-      return launch_scan_geo<8>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+      return launch_scan_geo<8>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st, lazy_wait);
     case 2:
-      return launch_scan_geo<2>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+      return launch_scan_geo<2>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st, lazy_wait);
     default:
-      return launch_scan_geo<4>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st);
+      return launch_scan_geo<4>(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, st, lazy_wait);
   }
 }
 
@@ -702,6 +712,14 @@ extern "C" int cspe_mask_scan_accumulate(const uint32_t* mask, int B, int H, int
   if (c <= 0) return c;
   return launch_scan(mask, B, H, W, id2slot, lut_len, lut_stride, N, out,
                             static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int cspe_mask_scan_accumulate_overlapped(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot,
+                                                    int lut_len, int64_t lut_stride, int N, int32_t* out,
+                                                    void* stream) {
+  const int c = check_common(mask, B, H, W, id2slot, lut_len, lut_stride, N, out);
+  if (c <= 0) return c;
+  return launch_scan(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, static_cast<cudaStream_t>(stream), 1);
 }
 
 extern "C" int cspe_mask_scan(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot, int lut_len,

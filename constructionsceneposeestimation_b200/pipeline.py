@@ -41,52 +41,88 @@ class LabelPipeline:
         self.cam = torch.zeros((B, CAM_STRIDE), dtype=f64, device=dev)
         # scan table starts as "no instance seen" (what cspe_mask_scan's init writes); K4 restores it per batch
         self.scan = torch.tensor([0, width, height, -1, -1], dtype=i32, device=dev).repeat(B, N, 1).contiguous()
-        self.uv = torch.empty((B, N, 8, 2), dtype=f64, device=dev)
-        self.z = torch.empty((B, N, 8), dtype=f64, device=dev)
-        self.pose = torch.empty((B, N, POSE_STRIDE), dtype=f64, device=dev)
-        self.loose = torch.empty((B, N, 4), dtype=f64, device=dev)
-        self.flags = torch.empty((B, N), dtype=u8, device=dev)
+        # K2's outputs are double-buffered: batch i+1's K2 starts beside batch i+1's scan, which itself
+        # overlaps batch i's K4 — K4(i) must still be able to read batch i's projections
+        self._k2 = [dict(uv=torch.empty((B, N, 8, 2), dtype=f64, device=dev),
+                         z=torch.empty((B, N, 8), dtype=f64, device=dev),
+                         pose=torch.empty((B, N, POSE_STRIDE), dtype=f64, device=dev),
+                         loose=torch.empty((B, N, 4), dtype=f64, device=dev),
+                         flags=torch.empty((B, N), dtype=u8, device=dev)) for _ in range(2)]
+        self._parity = 0
         self.records = torch.empty((B, N, RECORD_DTYPE.itemsize), dtype=u8, device=dev)
         self.n_out = torch.empty((B,), dtype=i32, device=dev)
         self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=dev)
         self.launches_per_run = 3  # mask_scan (accumulate) + project_objects + emit (which re-initialises the scan table)
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graphs = [None, None]  # one captured graph per K2 buffer parity
         self.use_graph = use_graph
 
+    # K2 outputs of the most recent run()
+    @property
+    def uv(self) -> torch.Tensor:
+        return self._k2[self._parity ^ 1]["uv"]
+
+    @property
+    def z(self) -> torch.Tensor:
+        return self._k2[self._parity ^ 1]["z"]
+
+    @property
+    def pose(self) -> torch.Tensor:
+        return self._k2[self._parity ^ 1]["pose"]
+
+    @property
+    def loose(self) -> torch.Tensor:
+        return self._k2[self._parity ^ 1]["loose"]
+
+    @property
+    def flags(self) -> torch.Tensor:
+        return self._k2[self._parity ^ 1]["flags"]
+
     # ---------------------------------------------------------------- enqueue
-    def _enqueue(self) -> None:
-        """scan -> project -> emit on ONE stream, 3 launches.  The scan table is initialised once
-        (constructor) and re-initialised by K4 as it reads it, so K1 runs in accumulate mode with no
-        init launch.  K2 is launched with programmatic stream serialisation and the scan releases its
-        dependents as soon as its CTAs are resident, so K2 runs beside the scan (it does not read the
-        scan's output) and K4 still sees both done."""
+    def _enqueue(self, parity: int) -> None:
+        """scan -> project -> emit on ONE stream, 3 launches, all chained by programmatic dependent
+        launch.  The scan table is initialised once (constructor) and re-initialised by K4 as it
+        reads it, so K1 runs in accumulate mode with no init launch.
+          * K1 (overlapped) may start while the PREVIOUS batch's K4 is still running — K4 releases
+            its dependents at entry — and waits for it only before its first merge into the table;
+          * K2 (overlapped) starts as soon as K1's CTAs are resident and runs in the SM resources
+            K1 leaves free; it completes only after K1 does;
+          * K4 waits for K2 (hence K1) and reads this batch's K2 buffers (double-buffered)."""
         lib, chk = self.lib, _lib.check
+        k2 = self._k2[parity]
         main = torch.cuda.current_stream(self.device).cuda_stream
-        chk("cspe_mask_scan_accumulate", lib.cspe_mask_scan_accumulate(
+        chk("cspe_mask_scan_accumulate_overlapped", lib.cspe_mask_scan_accumulate_overlapped(
             self.mask.data_ptr(), self.B, self.H, self.W, self.lut.data_ptr(), self.L, self.lut_stride, self.N,
             self.scan.data_ptr(), main))
         chk("cspe_project_objects_overlapped", lib.cspe_project_objects_overlapped(
             self.records_in.data_ptr(), _lib.BBOX3D_RECORD_BYTES, self.R, self.obj_record.data_ptr(),
-            self.cam.data_ptr(), self.B, self.N, self.uv.data_ptr(), self.z.data_ptr(), self.pose.data_ptr(),
-            self.loose.data_ptr(), self.flags.data_ptr(), main))
+            self.cam.data_ptr(), self.B, self.N, k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
+            k2["loose"].data_ptr(), k2["flags"].data_ptr(), main))
         chk("cspe_emit_reset_scan", lib.cspe_emit_reset_scan(
-            self.scan.data_ptr(), self.uv.data_ptr(), self.z.data_ptr(), self.pose.data_ptr(), self.loose.data_ptr(),
-            self.flags.data_ptr(), self.slot_class.data_ptr(), self.B, self.N, self.H, self.W, self.min_pixels,
-            self.frame_base, self.records.data_ptr(), self.n_out.data_ptr(), self.class_hist.data_ptr(), main))
+            self.scan.data_ptr(), k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
+            k2["loose"].data_ptr(), k2["flags"].data_ptr(), self.slot_class.data_ptr(), self.B, self.N, self.H, self.W,
+            self.min_pixels, self.frame_base, self.records.data_ptr(), self.n_out.data_ptr(),
+            self.class_hist.data_ptr(), main))
 
     def run(self) -> None:
-        """Enqueue one batch on the current stream (graph replay when enabled)."""
+        """Enqueue one batch on the current stream (graph replay when enabled).
+
+        Inputs (mask, lut, obj_record, slot_class, records_in, cam) must not be rewritten by a kernel
+        queued directly before run(): the overlapped launches read them without waiting for it.
+        Rewrite them with copies / from another stream's event, or synchronise first."""
+        parity = self._parity
+        self._parity ^= 1
         with torch.cuda.device(self.device):
             if not self.use_graph:
-                self._enqueue()
+                self._enqueue(parity)
                 return
-            if self.graph is None:
+            if self.graphs[parity] is None:
                 saved = self.class_hist.clone()
-                self._enqueue()  # warm-up outside capture (function attributes, lazy module load)
+                self._enqueue(parity)  # warm-up outside capture (function attributes, lazy module load)
                 torch.cuda.current_stream(self.device).synchronize()
                 self.class_hist.copy_(saved)  # one run() = one accumulation, also on the capturing call
+                # the warm-up consumed the table reset of this parity's emit; nothing else to restore
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    self._enqueue()
-                self.graph = g
-            self.graph.replay()
+                    self._enqueue(parity)
+                self.graphs[parity] = g
+            self.graphs[parity].replay()

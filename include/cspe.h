@@ -140,6 +140,15 @@ int cspe_mask_scan_accumulate(const uint32_t* mask, int B, int H, int W,
                               const int32_t* id2slot, int lut_len, int64_t lut_stride,
                               int N, int32_t* out, void* stream);
 
+/* K1 (accumulate) for steady-state pipelines: may START streaming the mask while the kernel
+ * queued before it in `stream` is still running (programmatic dependent launch; cspe_emit
+ * releases its dependents early) and only waits for it before its first merge into `out`.
+ * Contract: of this call's buffers, only `out` may be read or written by that previous kernel
+ * (K4 of the previous batch reading and resetting the table) — mask and id2slot must be stable. */
+int cspe_mask_scan_accumulate_overlapped(const uint32_t* mask, int B, int H, int W,
+                                         const int32_t* id2slot, int lut_len, int64_t lut_stride,
+                                         int N, int32_t* out, void* stream);
+
 /* K1 plus the depth-quality statistics of gcd.py:314-359 in one call (two HBM-bound launches on
  * `stream`; a fused kernel measured slower).
  * depth float32 [B][H][W]; stats cspe_depth_stats_t[B], fully overwritten. */

@@ -618,3 +618,35 @@ def test_scan_random_shapes_property(T, ops):
         assert np.array_equal(got, c_oracle.mask_scan(mask, lut, N))
 
     run()
+
+
+def test_pipeline_overlap_stress(T, ops):
+    """200 back-to-back batches through the PDL-overlapped pipeline (next scan streaming while the
+    previous K4 still reads and resets the scan table): the table hand-over must never lose or double a
+    pixel — the last batch's records equal the oracle and the histogram is exactly 200x one batch."""
+    from constructionsceneposeestimation_b200 import synthetic, _lib
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
+    frames = synthetic.make_batch(synthetic.SceneSpec(1280, 720, 40, 3, 17, config_id=14), 6)
+    o = helpers.oracle_pipeline(frames, min_pixels=1)
+    N, R = o["obj_record"].shape[1], o["records"].shape[1]
+    lut = np.pad(o["lut"], ((0, 0), (0, (-o["lut"].shape[1]) % 4)), constant_values=-1)
+    pipe = LabelPipeline(6, 720, 1280, N, R, lut.shape[1], T.device("cuda"), use_graph=False)
+    pipe.mask.copy_(T.from_numpy(o["mask"].view(np.int32)))
+    pipe.lut.copy_(T.from_numpy(lut))
+    pipe.obj_record.copy_(T.from_numpy(o["obj_record"]))
+    pipe.slot_class.copy_(T.from_numpy(o["slot_class"]))
+    pipe.records_in.copy_(T.from_numpy(o["records"].view(np.uint8).reshape(6, R, -1)))
+    pipe.cam.copy_(T.from_numpy(o["cam"]))
+    T.cuda.synchronize()
+    for _ in range(200):
+        pipe.run()
+    T.cuda.synchronize()
+    rec = pipe.records.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(6, N)
+    n_out = pipe.n_out.cpu().numpy()
+    assert np.array_equal(n_out, o["n_out"])
+    for f in range(6):
+        helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
+    assert np.array_equal(pipe.class_hist.cpu().numpy(), 200 * o["hist"])
+    # the table is back to "nothing seen" after the last K4
+    scan = pipe.scan.cpu().numpy()
+    assert np.array_equal(scan, np.tile(np.array([0, 1280, 720, -1, -1], dtype=np.int32), (6, N, 1)))
