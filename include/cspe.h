@@ -19,7 +19,11 @@
  *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*) and never
  *     synchronises, so calls are CUDA-graph capturable;
  *   - re-entrant per stream; no global state besides the thread-local error string and a
- *     per-device cache of immutable device attributes.
+ *     per-device cache of immutable device attributes;
+ *   - stream semantics: the kernels are launched with programmatic stream serialisation, but every
+ *     plain entry point waits for the previous kernel in `stream` before it reads or writes memory,
+ *     i.e. it behaves like an ordinary stream-ordered launch.  The `*_overlapped` variants relax
+ *     that for steady-state pipelines (each states what the caller must guarantee in return).
  */
 #ifndef CSPE_H_
 #define CSPE_H_
