@@ -194,6 +194,9 @@ def run_ours(args) -> int:
     dev = torch.device("cuda", local_rank)
     _lib.load()
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: each rank owns its own frame range (weak scaling: 64 frames per GPU) -------
