@@ -17,7 +17,7 @@ static_assert(sizeof(cspe_record) == 408, "cspe_record layout changed: update th
 namespace cspe {
 namespace {
 
-constexpr int kEmitThreads = 256;
+constexpr int kEmitChunk = 256;   // slots decided per pass (= header staging capacity)
 constexpr int kHdrWords = 22;                                   // 88-byte integer/float header of cspe_record
 constexpr int kRecWords = sizeof(cspe_record) / 4;              // 102
 static_assert(offsetof(cspe_record, uv) == kHdrWords * 4, "header size");
@@ -28,17 +28,20 @@ static_assert(offsetof(cspe_record, pose) == offsetof(cspe_record, z) + 64, "z b
 // and its stable rank (ballot + prefix).  Phase 2: each warp writes its kept records
 // cooperatively — 102 coalesced 4-byte words per record (header from shared memory, the 40
 // doubles straight from K2's arrays) instead of one thread issuing ~100 serial stores.
-__global__ void __launch_bounds__(kEmitThreads)
+// kThreads = 256 for frames of up to 256 slots, 1024 beyond: the first 256 threads decide, ALL
+// threads stream the records (that copy is what takes time when a frame holds hundreds of objects)
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
     emit_kernel(const int32_t* scan, int32_t* scan_reset, const double* __restrict__ uv, const double* __restrict__ z,
                 const double* __restrict__ pose, const double* __restrict__ loose, const uint8_t* __restrict__ flags,
                 const int32_t* __restrict__ slot_class, int N, int H, int W, int min_pixels, int frame_base,
                 cspe_record* __restrict__ records, int32_t* __restrict__ n_out,
                 unsigned long long* __restrict__ class_hist) {
-  __shared__ int warp_sums[kEmitThreads / 32];
+  __shared__ int warp_sums[kEmitChunk / 32];
   __shared__ int base_s;
   __shared__ int hist_s[CSPE_NUM_CLASSES];
-  __shared__ int32_t hdr_s[kEmitThreads][kHdrWords + 1];  // +1: odd pitch, conflict-free column writes
-  __shared__ int kept_s[kEmitThreads];                    // rank within the chunk -> thread (slot - n0)
+  __shared__ int32_t hdr_s[kEmitChunk][kHdrWords + 1];  // +1: odd pitch, conflict-free column writes
+  __shared__ int kept_s[kEmitChunk];                      // rank within the chunk -> thread (slot - n0)
   const int f = blockIdx.x;
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
@@ -56,8 +59,8 @@ __global__ void __launch_bounds__(kEmitThreads)
   const int32_t* z32 = reinterpret_cast<const int32_t*>(z);
   const int32_t* pose32 = reinterpret_cast<const int32_t*>(pose);
 
-  for (int n0 = 0; n0 < N; n0 += kEmitThreads) {
-    const int n = n0 + tid;
+  for (int n0 = 0; n0 < N; n0 += kEmitChunk) {
+    const int n = tid < kEmitChunk ? n0 + tid : N;  // threads beyond the chunk only help with the copy
     const long long o = static_cast<long long>(f) * N + n;
     bool keep = false;
     int cls = -1, cnt = 0, x0 = 0, y0 = 0, x1 = -1, y1 = -1;
@@ -84,7 +87,7 @@ __global__ void __launch_bounds__(kEmitThreads)
     // stable rank = exclusive prefix sum of keep flags
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const int in_warp = __popc(bal & ((1u << lane) - 1u));
-    if (lane == 0) warp_sums[wid] = __popc(bal);
+    if (lane == 0 && wid < kEmitChunk / 32) warp_sums[wid] = __popc(bal);
 
     if (keep) {
       cspe_record h;  // only the header fields are filled; lives in registers
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(kEmitThreads)
     int before = 0;
     int chunk_total = 0;
 #pragma unroll
-    for (int w = 0; w < kEmitThreads / 32; ++w) {
+    for (int w = 0; w < kEmitChunk / 32; ++w) {
       const int s = warp_sums[w];
       if (w < wid) before += s;
       chunk_total += s;
@@ -178,8 +181,8 @@ __global__ void __launch_bounds__(kEmitThreads)
       const int chunk_base = base_s;
       int32_t* dst = reinterpret_cast<int32_t*>(records + static_cast<long long>(f) * N + chunk_base);
       const int words = chunk_total * kRecWords;
-#pragma unroll 4
-      for (int w = tid; w < words; w += kEmitThreads) {
+#pragma unroll 8
+      for (int w = tid; w < words; w += kThreads) {
         const int r = w / kRecWords, k = w - r * kRecWords;
         const int t = kept_s[r];
         const long long so = static_cast<long long>(f) * N + n0 + t;
@@ -217,10 +220,17 @@ static int emit_impl(const int32_t* scan, int32_t* scan_reset, const double* uv,
                CSPE_ERR_INVALID_ARGUMENT, "cspe_emit: null pointer");
   CSPE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 7) == 0 && (reinterpret_cast<uintptr_t>(class_hist) & 7) == 0,
                CSPE_ERR_INVALID_ARGUMENT, "cspe_emit: records/class_hist must be 8-byte aligned");
-  CSPE_CUDA_OK(launch_pdl(emit_kernel, dim3(static_cast<unsigned>(B)), dim3(kEmitThreads), 0,
-                          static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class, N,
-                          H, W, min_pixels, frame_base, records, n_out,
-                          reinterpret_cast<unsigned long long*>(class_hist)));
+  if (N <= kEmitChunk) {
+    CSPE_CUDA_OK(launch_pdl(emit_kernel<256>, dim3(static_cast<unsigned>(B)), dim3(256), 0,
+                            static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class,
+                            N, H, W, min_pixels, frame_base, records, n_out,
+                            reinterpret_cast<unsigned long long*>(class_hist)));
+  } else {
+    CSPE_CUDA_OK(launch_pdl(emit_kernel<1024>, dim3(static_cast<unsigned>(B)), dim3(1024), 0,
+                            static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class,
+                            N, H, W, min_pixels, frame_base, records, n_out,
+                            reinterpret_cast<unsigned long long*>(class_hist)));
+  }
   return CSPE_OK;
 }
 

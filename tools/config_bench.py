@@ -37,14 +37,14 @@ def out(**kw):
     print(json.dumps(kw), flush=True)
 
 
-def build_pipeline(frames, B):
+def build_pipeline(frames, B, use_graph=False):
     lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
     lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
     u = len(frames)
     rep = (B + u - 1) // u
     H, W = frames[0]["instance_segmentation"]["data"].shape
     N = obj_record.shape[1]
-    pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], dev)
+    pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], dev, use_graph=use_graph)
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     tile = lambda a: t(a).repeat((rep,) + (1,) * (a.ndim - 1))[:B]
     pipe.mask.copy_(tile(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)))
@@ -58,10 +58,11 @@ def build_pipeline(frames, B):
 
 # ---- c1: single 1280x720 frame, ~20 instances: latency of one graph replay ----------------------
 frames = synthetic.make_batch(synthetic.CONFIGS["c1"], 1)
-pipe, (H, W, N) = build_pipeline(frames, 1)
-ms = timed(pipe.run, n=200)
-out(case="c1 single 720p frame, 20 instances (graph replay latency)", ms=round(ms, 4), frames_per_s=round(1000 / ms, 1),
-    note="3.7 MB fits L2: latency-bound, not a roofline case")
+for g in (True, False):
+    pipe, (H, W, N) = build_pipeline(frames, 1, use_graph=g)
+    ms = timed(pipe.run, n=200)
+    out(case=f"c1 single 720p frame, 20 instances ({'CUDA-graph replay' if g else 'eager PDL chain'}, back-to-back)",
+        ms=round(ms, 4), frames_per_s=round(1000 / ms, 1), note="3.7 MB fits L2: latency-bound, not a roofline case")
 
 # ---- c4: 4-camera 3840x2160 rig, 500 instances: 16 rig-camera frames per GPU ----------------------
 frames = synthetic.make_batch(synthetic.CONFIGS["c4"], 4)
