@@ -110,6 +110,7 @@ PROTOTYPES = {
     "cspe_project_objects": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cspe_project_objects_overlapped": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cspe_keypoints": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, C.c_double, _P, _P, _P, _P]),
+    "cspe_keypoints_overlapped": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, C.c_double, _P, _P, _P, _P]),
     "cspe_emit": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_emit_reset_scan": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),

@@ -14,12 +14,30 @@
 namespace cspe {
 namespace {
 
+__device__ __forceinline__ void keypoint_one(const float* __restrict__ joints, long long i, int per_frame,
+                                             const float* __restrict__ depth, int H, int W,
+                                             const double* __restrict__ cam, double tol, double* __restrict__ kp,
+                                             double* __restrict__ kz, uint8_t* __restrict__ vis);
+
 __global__ void __launch_bounds__(256)
     keypoints_kernel(const float* __restrict__ joints, long long total, int per_frame, const float* __restrict__ depth,
                      int H, int W, const double* __restrict__ cam, double tol, double* __restrict__ kp,
-                     double* __restrict__ kz, uint8_t* __restrict__ vis) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+                     double* __restrict__ kz, uint8_t* __restrict__ vis, int overlap_previous) {
+  // programmatic dependent launch, same protocol as K2 (project.cu): release whatever is queued
+  // next, then either behave like a serialised launch (wait now) or — overlapped mode, inputs not
+  // written by the previous kernel — run beside it and wait only before exiting
+  pdl_launch_dependents();
+  if (!overlap_previous) pdl_wait();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride)
+    keypoint_one(joints, i, per_frame, depth, H, W, cam, tol, kp, kz, vis);
+  if (overlap_previous) pdl_wait();
+}
+
+__device__ __forceinline__ void keypoint_one(const float* __restrict__ joints, long long i, int per_frame,
+                                             const float* __restrict__ depth, int H, int W,
+                                             const double* __restrict__ cam, double tol, double* __restrict__ kp,
+                                             double* __restrict__ kz, uint8_t* __restrict__ vis) {
   const int frame = static_cast<int>(i / per_frame);
   const double* cm = cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE;
   const double d0 = static_cast<double>(__ldg(joints + i * 3 + 0)) - cm[0];
@@ -53,8 +71,8 @@ __global__ void __launch_bounds__(256)
 
 using namespace cspe;
 
-extern "C" int cspe_keypoints(const float* joints, int B, int P, int J, const float* depth, int H, int W,
-                              const double* cam, double tol, double* kp, double* kz, uint8_t* vis, void* stream) {
+static int keypoints_impl(const float* joints, int B, int P, int J, const float* depth, int H, int W, const double* cam,
+                          double tol, double* kp, double* kz, uint8_t* vis, void* stream, int overlap_previous) {
   CSPE_REQUIRE(B >= 0 && P >= 0 && J >= 0 && H >= 0 && W >= 0, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_keypoints: negative size (B=%d P=%d J=%d H=%d W=%d)", B, P, J, H, W);
   const long long per_frame = static_cast<long long>(P) * J;
@@ -63,10 +81,32 @@ extern "C" int cspe_keypoints(const float* joints, int B, int P, int J, const fl
   CSPE_REQUIRE(per_frame < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_keypoints: P*J too large");
   CSPE_REQUIRE(joints && cam && kp && kz && vis, CSPE_ERR_INVALID_ARGUMENT, "cspe_keypoints: null pointer");
   CSPE_REQUIRE(depth != nullptr || H == 0 || W == 0, CSPE_ERR_INVALID_ARGUMENT, "cspe_keypoints: depth is null");
-  const long long blocks = (total + 255) / 256;
+  // standalone: one joint per thread.  Overlapped: one small block per SM with a grid-stride loop —
+  // its blocks stay resident beside the mask scan until that finishes (wait-at-exit), so they must
+  // all fit in the few registers the scan leaves free; the loop is hidden behind the scan anyway.
+  long long blocks = (total + 255) / 256;
+  int threads = 256;
+  if (overlap_previous) {
+    const int sms = sm_count();
+    CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_keypoints: no CUDA device");
+    threads = 64;
+    blocks = (total + threads - 1) / threads;
+    if (blocks > sms) blocks = sms;
+  }
   CSPE_REQUIRE(blocks < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_keypoints: too many joints");
-  keypoints_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      joints, total, static_cast<int>(per_frame), depth, H, W, cam, tol, kp, kz, vis);
-  CSPE_LAUNCH_OK("keypoints_kernel");
+  CSPE_CUDA_OK(launch_pdl(keypoints_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0,
+                          static_cast<cudaStream_t>(stream), joints, total, static_cast<int>(per_frame), depth, H, W, cam,
+                          tol, kp, kz, vis, overlap_previous));
   return CSPE_OK;
+}
+
+extern "C" int cspe_keypoints(const float* joints, int B, int P, int J, const float* depth, int H, int W,
+                              const double* cam, double tol, double* kp, double* kz, uint8_t* vis, void* stream) {
+  return keypoints_impl(joints, B, P, J, depth, H, W, cam, tol, kp, kz, vis, stream, 0);
+}
+
+extern "C" int cspe_keypoints_overlapped(const float* joints, int B, int P, int J, const float* depth, int H, int W,
+                                         const double* cam, double tol, double* kp, double* kz, uint8_t* vis,
+                                         void* stream) {
+  return keypoints_impl(joints, B, P, J, depth, H, W, cam, tol, kp, kz, vis, stream, 1);
 }

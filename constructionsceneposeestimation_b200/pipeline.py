@@ -21,7 +21,8 @@ class LabelPipeline:
     def __init__(self, batch: int, height: int, width: int, num_slots: int, recs_per_frame: int, lut_len: int,
                  device: torch.device, per_frame_lut: bool = True,  # lut_len: use a multiple of 4 (16-byte rows)
                  min_pixels: int = 1, use_graph: bool = True,
-                 mask: Optional[torch.Tensor] = None):
+                 mask: Optional[torch.Tensor] = None, num_people: int = 0, num_joints: int = 0,
+                 keypoint_tolerance: float = 0.15):
         self.lib = _lib.load()
         self.B, self.H, self.W, self.N, self.R, self.L = batch, height, width, num_slots, recs_per_frame, lut_len
         self.device = torch.device(device)
@@ -49,10 +50,21 @@ class LabelPipeline:
                          loose=torch.empty((B, N, 4), dtype=f64, device=dev),
                          flags=torch.empty((B, N), dtype=u8, device=dev)) for _ in range(2)]
         self._parity = 0
+        # optional K3 stage (config 3: skeleton keypoints + depth-buffer visibility)
+        self.P, self.J, self.keypoint_tolerance = int(num_people), int(num_joints), float(keypoint_tolerance)
+        self.joints = self.depth = None
+        self._k3 = None
+        if self.P > 0 and self.J > 0:
+            self.joints = torch.zeros((B, self.P, self.J, 3), dtype=torch.float32, device=dev)
+            self.depth = torch.full((B, height, width), float("inf"), dtype=torch.float32, device=dev)
+            self._k3 = [dict(kp=torch.empty((B, self.P, self.J, 2), dtype=f64, device=dev),
+                             kz=torch.empty((B, self.P, self.J), dtype=f64, device=dev),
+                             vis=torch.empty((B, self.P, self.J), dtype=u8, device=dev)) for _ in range(2)]
         self.records = torch.empty((B, N, RECORD_DTYPE.itemsize), dtype=u8, device=dev)
         self.n_out = torch.empty((B,), dtype=i32, device=dev)
         self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=dev)
-        self.launches_per_run = 3  # mask_scan (accumulate) + project_objects + emit (which re-initialises the scan table)
+        # mask_scan (accumulate) + project_objects [+ keypoints] + emit (which re-initialises the scan table)
+        self.launches_per_run = 3 + (1 if num_people > 0 and num_joints > 0 else 0)
         self.graphs = [None, None]  # one captured graph per K2 buffer parity
         self.use_graph = use_graph
 
@@ -77,6 +89,14 @@ class LabelPipeline:
     def flags(self) -> torch.Tensor:
         return self._k2[self._parity ^ 1]["flags"]
 
+    @property
+    def keypoints(self):
+        """(kp [B,P,J,2], kz [B,P,J], vis [B,P,J]) of the most recent run(), or None without a K3 stage."""
+        if self._k3 is None:
+            return None
+        k3 = self._k3[self._parity ^ 1]
+        return k3["kp"], k3["kz"], k3["vis"]
+
     # ---------------------------------------------------------------- enqueue
     def _enqueue(self, parity: int) -> None:
         """scan -> project -> emit on ONE stream, 3 launches, all chained by programmatic dependent
@@ -97,6 +117,12 @@ class LabelPipeline:
             self.records_in.data_ptr(), _lib.BBOX3D_RECORD_BYTES, self.R, self.obj_record.data_ptr(),
             self.cam.data_ptr(), self.B, self.N, k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
             k2["loose"].data_ptr(), k2["flags"].data_ptr(), main))
+        if self._k3 is not None:  # K3 rides the same chain: beside the scan, done before K4
+            k3 = self._k3[parity]
+            chk("cspe_keypoints_overlapped", lib.cspe_keypoints_overlapped(
+                self.joints.data_ptr(), self.B, self.P, self.J, self.depth.data_ptr(), self.H, self.W,
+                self.cam.data_ptr(), self.keypoint_tolerance, k3["kp"].data_ptr(), k3["kz"].data_ptr(),
+                k3["vis"].data_ptr(), main))
         chk("cspe_emit_reset_scan", lib.cspe_emit_reset_scan(
             self.scan.data_ptr(), k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
             k2["loose"].data_ptr(), k2["flags"].data_ptr(), self.slot_class.data_ptr(), self.B, self.N, self.H, self.W,

@@ -193,6 +193,13 @@ int cspe_keypoints(const float* joints, int B, int P, int J,
                    const float* depth, int H, int W, const double* cam, double tol,
                    double* kp, double* kz, uint8_t* vis, void* stream);
 
+/* K3 for pipelines: same contract as cspe_project_objects_overlapped — may start while the kernel
+ * queued before it is still running (if that kernel releases its dependents early), completes
+ * after it; none of this call's inputs may be written by that kernel. */
+int cspe_keypoints_overlapped(const float* joints, int B, int P, int J,
+                              const float* depth, int H, int W, const double* cam, double tol,
+                              double* kp, double* kz, uint8_t* vis, void* stream);
+
 /* ---- K4: occlusion ratios, order-preserving compaction, record emission and class
  * histogram  (replaces pose_list assembly gcd.py:1938-1946 and generalises the object
  * counter gcd.py:361-372) -------------------------------------------------------------------

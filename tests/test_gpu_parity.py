@@ -650,3 +650,37 @@ def test_pipeline_overlap_stress(T, ops):
     # the table is back to "nothing seen" after the last K4
     scan = pipe.scan.cpu().numpy()
     assert np.array_equal(scan, np.tile(np.array([0, 1280, 720, -1, -1], dtype=np.int32), (6, N, 1)))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_pipeline_with_keypoint_stage(T, ops, use_graph):
+    """Config-3 pipeline: K3 (overlapped) rides the same PDL chain; keypoints and records equal the oracle."""
+    from constructionsceneposeestimation_b200 import synthetic, _lib
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
+    frames = synthetic.make_batch(synthetic.SceneSpec(960, 540, 30, 12, 17, config_id=15), 3)
+    o = helpers.oracle_pipeline(frames)
+    N, R = o["obj_record"].shape[1], o["records"].shape[1]
+    lut = np.pad(o["lut"], ((0, 0), (0, (-o["lut"].shape[1]) % 4)), constant_values=-1)
+    pipe = LabelPipeline(3, 540, 960, N, R, lut.shape[1], T.device("cuda"), use_graph=use_graph, num_people=12,
+                         num_joints=17)
+    pipe.mask.copy_(T.from_numpy(o["mask"].view(np.int32)))
+    pipe.lut.copy_(T.from_numpy(lut))
+    pipe.obj_record.copy_(T.from_numpy(o["obj_record"]))
+    pipe.slot_class.copy_(T.from_numpy(o["slot_class"]))
+    pipe.records_in.copy_(T.from_numpy(o["records"].view(np.uint8).reshape(3, R, -1)))
+    pipe.cam.copy_(T.from_numpy(o["cam"]))
+    pipe.joints.copy_(T.from_numpy(o["joints"]))
+    pipe.depth.copy_(T.from_numpy(o["depth"]))
+    T.cuda.synchronize()
+    for _ in range(5):
+        pipe.run()
+    T.cuda.synchronize()
+    kp, kz, vis = pipe.keypoints
+    assert np.array_equal(vis.cpu().numpy(), o["vis"]) and np.array_equal(kp.cpu().numpy(), o["kp"])
+    assert np.array_equal(kz.cpu().numpy(), o["kz"])
+    rec = pipe.records.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(3, N)
+    n_out = pipe.n_out.cpu().numpy()
+    assert np.array_equal(n_out, o["n_out"])
+    for f in range(3):
+        helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
+    assert np.array_equal(pipe.class_hist.cpu().numpy(), 5 * o["hist"])
