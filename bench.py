@@ -204,9 +204,11 @@ def run_ours(args) -> int:
     frames = make_frames(uniq, first=rank * BATCH)
     if uniq < BATCH:
         frames = [frames[i % uniq] for i in range(BATCH)]
-    lut, obj_record, slot_class, records, cam, _objs = helpers.host_tables(frames)
-    if lut.shape[1] % 4:  # 16-byte LUT rows, like the writer builds them
-        lut = np.pad(lut, ((0, 0), (0, 4 - lut.shape[1] % 4)), constant_values=-1)
+    # input tables come from the PRODUCT's host logic (classes.py / camera.py); the oracle is only
+    # used below as the checker of one frame and as the CPU baseline
+    from constructionsceneposeestimation_b200.sweep import build_host_tables
+
+    lut, obj_record, slot_class, records, cam, _objs = build_host_tables(frames)
     H, W = frames[0]["instance_segmentation"]["data"].shape
     N = obj_record.shape[1]
     mask_host = torch.empty((BATCH, H, W), dtype=torch.int32, pin_memory=True)
@@ -221,7 +223,7 @@ def run_ours(args) -> int:
     pipe.lut.copy_(torch.from_numpy(lut))
     pipe.obj_record.copy_(torch.from_numpy(obj_record))
     pipe.slot_class.copy_(torch.from_numpy(slot_class))
-    pipe.records_in.copy_(torch.from_numpy(np.ascontiguousarray(records).view(np.uint8).reshape(BATCH, records.shape[1], -1)))
+    pipe.records_in.copy_(torch.from_numpy(records))
     pipe.cam.copy_(torch.from_numpy(cam))
     d_mask, d_lut, scan, rec_out, n_out, class_hist = pipe.mask, pipe.lut, pipe.scan, pipe.records, pipe.n_out, pipe.class_hist
     torch.cuda.synchronize()

@@ -24,7 +24,7 @@ from .camera import pack_camera
 from .pipeline import LabelPipeline
 
 
-def _host_tables(frames, split_people=True):
+def build_host_tables(frames, split_people=True):
     res = classes.ObjectRootResolver(split_people=split_people)
     per = []
     for fr in frames:
@@ -61,7 +61,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
     lo, hi = sharding.frame_range(rank, world, num_frames)
     spec = synthetic.CONFIGS[config]
     pool = synthetic.make_batch(spec, pool_frames, first_frame=rank * pool_frames)
-    lut, obj_record, slot_class, records, cam, objects = _host_tables(pool)
+    lut, obj_record, slot_class, records, cam, objects = build_host_tables(pool)
     H, W = pool[0]["instance_segmentation"]["data"].shape
     B, N = pool_frames, obj_record.shape[1]
     with torch.cuda.device(device):
