@@ -5,25 +5,65 @@
 // colour LUT (the reference uses cv2.COLORMAP_JET; the caller passes the table so the kernel does
 // not hard-code OpenCV's values).  min / max come from cspe_depth_stats (gcd.py:1693-1694 takes
 // them from the same valid set).  No valid pixel -> black image (gcd.py:1705-1709).
-// HBM-bound elementwise pass: 4 B read, 3 B written per pixel.
+//
+// Both kernels are HBM-bound elementwise passes (4 B read + 3 B written per pixel).  Fast path: a
+// block takes 4096 pixels per step — warp-contiguous 16-byte loads, the 24-bit pixels packed with
+// byte permutes into a shared-memory stage, warp-contiguous 16-byte streaming stores — when the
+// frame geometry keeps every access 16-byte aligned; otherwise a scalar path.
 #include "cspe_common.cuh"
 
 namespace cspe {
 namespace {
 
+constexpr int kVizThreads = 256;
+
 __device__ __forceinline__ unsigned depth_bin(float d, float mn, float den) {
-  const bool valid = (d > 0.0f) && (fabsf(d) != __int_as_float(0x7f800000));
-  if (!valid) return 0u;
+  const unsigned b = __float_as_uint(d);
+  if (!((b - 1u) < 0x7f7fffffu)) return 0u;  // not (finite and > 0)
   const float t = ((d - mn) / den) * 255.0f;
   return min(__float2uint_rz(t), 255u);
 }
 
-// 4 pixels per thread when the frame base is 16-byte aligned: one LDG.128 in, three STG.32 out
-__global__ void __launch_bounds__(256)
+// four 24-bit pixels c0..c3 (colour in the low 3 bytes) -> three packed 32-bit words
+__device__ __forceinline__ void pack4(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned& w0, unsigned& w1,
+                                      unsigned& w2) {
+  w0 = __byte_perm(c0, c1, 0x4210);
+  w1 = __byte_perm(c1, c2, 0x5421);
+  w2 = __byte_perm(c2, c3, 0x6542);
+}
+
+__device__ __forceinline__ void st_stream(uint4* p, const uint4 v) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+constexpr int kVizChunkPx = kVizThreads * 16;         // pixels per block iteration (4096)
+constexpr int kVizChunkWords = kVizChunkPx * 3 / 4;    // packed BGR words per iteration (3072)
+
+// The block's packed output for one 4096-pixel chunk sits in shared memory; stream it out with
+// warp-contiguous 16-byte stores.  (Storing each thread's 12 / 48 bytes directly is 3x the sector
+// traffic: the lanes of one store instruction land 12 or 48 bytes apart.)
+__device__ __forceinline__ void flush_chunk(const unsigned* stage, uint8_t* dst) {
+  __syncthreads();
+  const uint4* s4 = reinterpret_cast<const uint4*>(stage);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int j = 0; j < kVizChunkWords / 4 / kVizThreads; ++j) st_stream(d4 + threadIdx.x + j * kVizThreads, s4[threadIdx.x + j * kVizThreads]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kVizThreads)
     depth_colormap_kernel(const float* __restrict__ depth, long long hw, const cspe_depth_stats_t* __restrict__ stats,
                           const uint8_t* __restrict__ lut, uint8_t* __restrict__ out, int vec_ok) {
-  __shared__ uint8_t lut_s[768];
-  for (int i = threadIdx.x; i < 768; i += blockDim.x) lut_s[i] = lut[i];
+  __shared__ unsigned lut_s[256];  // BGR in the low three bytes
+  __shared__ __align__(16) unsigned stage[kVizChunkWords];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x)
+    lut_s[i] = lut[i * 3] | (lut[i * 3 + 1] << 8) | (static_cast<unsigned>(lut[i * 3 + 2]) << 16);
   __syncthreads();
   const int b = blockIdx.y;
   const cspe_depth_stats_t st = stats[b];
@@ -32,37 +72,106 @@ __global__ void __launch_bounds__(256)
   const bool any_valid = st.valid_pixels > 0;
   const float* d = depth + static_cast<long long>(b) * hw;
   uint8_t* o = out + static_cast<long long>(b) * hw * 3;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long long n4 = vec_ok ? hw / 4 : 0;
-  for (long long i = gtid; i < n4; i += stride) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(d) + i);
-    unsigned char px[12];
-    const float vals[4] = {v.x, v.y, v.z, v.w};
+  const long long nchunks = vec_ok ? hw / kVizChunkPx : 0;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(d + ch * kVizChunkPx);
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld_stream(src + threadIdx.x + k * kVizThreads);   // warp-contiguous loads
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const unsigned bin = any_valid ? depth_bin(vals[k], mn, den) : 0u;
+      unsigned c[4];
+      const float f[4] = {__uint_as_float(v[k].x), __uint_as_float(v[k].y), __uint_as_float(v[k].z),
+                          __uint_as_float(v[k].w)};
 #pragma unroll
-      for (int c = 0; c < 3; ++c) px[k * 3 + c] = any_valid ? lut_s[bin * 3 + c] : 0;
+      for (int j = 0; j < 4; ++j) c[j] = any_valid ? lut_s[depth_bin(f[j], mn, den)] : 0u;
+      unsigned w0, w1, w2;
+      pack4(c[0], c[1], c[2], c[3], w0, w1, w2);
+      unsigned* sp = stage + (threadIdx.x + k * kVizThreads) * 3;   // 3-word stride: bank-conflict free
+      sp[0] = w0;
+      sp[1] = w1;
+      sp[2] = w2;
     }
-    uint32_t w[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-      w[k] = px[4 * k] | (px[4 * k + 1] << 8) | (px[4 * k + 2] << 16) | (static_cast<uint32_t>(px[4 * k + 3]) << 24);
-    uint32_t* o32 = reinterpret_cast<uint32_t*>(o + i * 12);
-    o32[0] = w[0];
-    o32[1] = w[1];
-    o32[2] = w[2];
+    flush_chunk(stage, o + ch * (kVizChunkPx * 3));
   }
-  for (long long i = n4 * 4 + gtid; i < hw; i += stride) {
-    const unsigned bin = any_valid ? depth_bin(d[i], mn, den) : 0u;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) o[i * 3 + c] = any_valid ? lut_s[bin * 3 + c] : 0;
+  // leftover pixels (and every pixel when the geometry is not 16-byte friendly)
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = nchunks * kVizChunkPx + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < hw;
+       i += stride) {
+    const unsigned c = any_valid ? lut_s[depth_bin(d[i], mn, den)] : 0u;
+    o[i * 3 + 0] = static_cast<uint8_t>(c);
+    o[i * 3 + 1] = static_cast<uint8_t>(c >> 8);
+    o[i * 3 + 2] = static_cast<uint8_t>(c >> 16);
   }
 }
 
-__global__ void __launch_bounds__(256)
-    rgb_to_bgr_kernel(const uint8_t* __restrict__ rgb, int channels, long long n, uint8_t* __restrict__ bgr) {
+// RGBA (4 channels): 4096 pixels = 16 KB in, 12 KB out per block iteration
+__global__ void __launch_bounds__(kVizThreads)
+    rgba_to_bgr_kernel(const uint8_t* __restrict__ rgb, long long n, uint8_t* __restrict__ bgr) {
+  __shared__ __align__(16) unsigned stage[kVizChunkWords];
+  const long long nchunks = n / kVizChunkPx;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(rgb + ch * (kVizChunkPx * 4));
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld_stream(src + threadIdx.x + k * kVizThreads);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // 0xAABBGGRR -> colour with B, G, R in bytes 0, 1, 2
+      const unsigned c0 = __byte_perm(v[k].x, 0u, 0x4012), c1 = __byte_perm(v[k].y, 0u, 0x4012);
+      const unsigned c2 = __byte_perm(v[k].z, 0u, 0x4012), c3 = __byte_perm(v[k].w, 0u, 0x4012);
+      unsigned w0, w1, w2;
+      pack4(c0, c1, c2, c3, w0, w1, w2);
+      unsigned* sp = stage + (threadIdx.x + k * kVizThreads) * 3;
+      sp[0] = w0;
+      sp[1] = w1;
+      sp[2] = w2;
+    }
+    flush_chunk(stage, bgr + ch * (kVizChunkPx * 3));
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = nchunks * kVizChunkPx + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    bgr[i * 3 + 0] = rgb[i * 4 + 2];
+    bgr[i * 3 + 1] = rgb[i * 4 + 1];
+    bgr[i * 3 + 2] = rgb[i * 4 + 0];
+  }
+}
+
+// packed RGB (3 channels): same bytes in and out, R and B of every triple swapped; 12 bytes (4 pixels)
+// per thread step keeps loads and stores warp-contiguous without staging
+__global__ void __launch_bounds__(kVizThreads)
+    rgb3_to_bgr_kernel(const uint8_t* __restrict__ rgb, long long n, uint8_t* __restrict__ bgr) {
+  __shared__ __align__(16) unsigned stage[kVizChunkWords];
+  const long long nchunks = n / kVizChunkPx;
+  for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const uint4* src = reinterpret_cast<const uint4*>(rgb + ch * (kVizChunkPx * 3));
+    uint4* s4 = reinterpret_cast<uint4*>(stage);
+#pragma unroll
+    for (int j = 0; j < kVizChunkWords / 4 / kVizThreads; ++j) s4[threadIdx.x + j * kVizThreads] = ld_stream(src + threadIdx.x + j * kVizThreads);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // each thread swaps four 12-byte groups in place (3-word stride: conflict free)
+      unsigned* sp = stage + (threadIdx.x + k * kVizThreads) * 3;
+      const unsigned w0 = sp[0], w1 = sp[1], w2 = sp[2];
+      sp[0] = __byte_perm(w0, w1, 0x5012);
+      sp[1] = __byte_perm(__byte_perm(w1, w0, 0x3070), w2, 0x3410);
+      sp[2] = __byte_perm(w1, w2, 0x5672);
+    }
+    flush_chunk(stage, bgr + ch * (kVizChunkPx * 3));
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = nchunks * kVizChunkPx + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += stride) {
+    bgr[i * 3 + 0] = rgb[i * 3 + 2];
+    bgr[i * 3 + 1] = rgb[i * 3 + 1];
+    bgr[i * 3 + 2] = rgb[i * 3 + 0];
+  }
+}
+
+// any other layout (more than 4 channels, unaligned buffers)
+__global__ void __launch_bounds__(kVizThreads)
+    rgb_to_bgr_generic_kernel(const uint8_t* __restrict__ rgb, int channels, long long n, uint8_t* __restrict__ bgr) {
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const uint8_t* s = rgb + i * channels;
@@ -70,6 +179,12 @@ __global__ void __launch_bounds__(256)
     bgr[i * 3 + 1] = s[1];
     bgr[i * 3 + 2] = s[0];
   }
+}
+
+int resident_blocks(const void* kernel, int threads) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0) != cudaSuccess || occ < 1) occ = 4;
+  return occ;
 }
 
 }  // namespace
@@ -86,15 +201,18 @@ extern "C" int cspe_depth_colormap(const float* depth, int B, int H, int W, cons
   CSPE_REQUIRE(B <= 65535, CSPE_ERR_UNSUPPORTED, "cspe_depth_colormap: B > 65535");
   const int sms = sm_count();
   CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_depth_colormap: no CUDA device");
-  long long per_frame = (hw / 4 + 256 * 4 - 1) / (256 * 4);
+  // one wave of resident blocks over the batch
+  static const int occ = resident_blocks(reinterpret_cast<const void*>(depth_colormap_kernel), kVizThreads);
+  long long per_frame = (static_cast<long long>(sms) * occ) / B;
+  const long long max_useful = (hw + kVizChunkPx - 1) / kVizChunkPx;
+  if (per_frame > max_useful) per_frame = max_useful;
   if (per_frame < 1) per_frame = 1;
-  const long long want = (static_cast<long long>(sms) * 16 + B - 1) / B;
-  if (per_frame > want) per_frame = want;
+  // 16-pixel path: every frame base must keep 16-byte alignment for loads (hw % 4) and stores (3*hw % 16)
+  const int vec_ok = (reinterpret_cast<uintptr_t>(depth) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
+                     (B == 1 || hw % 16 == 0);
   dim3 grid(static_cast<unsigned>(per_frame), static_cast<unsigned>(B));
-  // vector path: every frame base must be 16-byte aligned for the loads and 4-byte aligned for the stores
-  const int vec_ok = (reinterpret_cast<uintptr_t>(depth) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 4 == 0) &&
-                     (B == 1 || hw % 4 == 0);
-  depth_colormap_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(depth, hw, stats, lut_bgr, out, vec_ok);
+  depth_colormap_kernel<<<grid, kVizThreads, 0, static_cast<cudaStream_t>(stream)>>>(depth, hw, stats, lut_bgr, out,
+                                                                                    vec_ok);
   CSPE_LAUNCH_OK("depth_colormap_kernel");
   return CSPE_OK;
 }
@@ -106,10 +224,23 @@ extern "C" int cspe_rgb_to_bgr(const uint8_t* rgb, int channels, int64_t num_pix
   CSPE_REQUIRE(rgb && bgr, CSPE_ERR_INVALID_ARGUMENT, "cspe_rgb_to_bgr: null pointer");
   const int sms = sm_count();
   CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_rgb_to_bgr: no CUDA device");
-  long long blocks = (num_pixels + 256 * 8 - 1) / (256 * 8);
-  if (blocks > static_cast<long long>(sms) * 16) blocks = static_cast<long long>(sms) * 16;
-  rgb_to_bgr_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(rgb, channels,
-                                                                                                 num_pixels, bgr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool aligned = (reinterpret_cast<uintptr_t>(rgb) % 16 == 0) && (reinterpret_cast<uintptr_t>(bgr) % 16 == 0);
+  long long blocks = (num_pixels + kVizChunkPx - 1) / kVizChunkPx;
+  if (blocks < 1) blocks = 1;
+  if (aligned && channels == 4) {
+    static const int occ = resident_blocks(reinterpret_cast<const void*>(rgba_to_bgr_kernel), kVizThreads);
+    if (blocks > static_cast<long long>(sms) * occ) blocks = static_cast<long long>(sms) * occ;
+    rgba_to_bgr_kernel<<<static_cast<unsigned>(blocks), kVizThreads, 0, st>>>(rgb, num_pixels, bgr);
+  } else if (aligned && channels == 3) {
+    static const int occ = resident_blocks(reinterpret_cast<const void*>(rgb3_to_bgr_kernel), kVizThreads);
+    if (blocks > static_cast<long long>(sms) * occ) blocks = static_cast<long long>(sms) * occ;
+    rgb3_to_bgr_kernel<<<static_cast<unsigned>(blocks), kVizThreads, 0, st>>>(rgb, num_pixels, bgr);
+  } else {
+    blocks = (num_pixels + kVizThreads * 8 - 1) / (kVizThreads * 8);
+    if (blocks > static_cast<long long>(sms) * 16) blocks = static_cast<long long>(sms) * 16;
+    rgb_to_bgr_generic_kernel<<<static_cast<unsigned>(blocks), kVizThreads, 0, st>>>(rgb, channels, num_pixels, bgr);
+  }
   CSPE_LAUNCH_OK("rgb_to_bgr_kernel");
   return CSPE_OK;
 }

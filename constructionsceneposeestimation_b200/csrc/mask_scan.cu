@@ -166,74 +166,6 @@ __device__ __forceinline__ int table_identity(int field) {
   return field == CSPE_SCAN_COUNT ? 0 : (field <= CSPE_SCAN_YMIN ? INT_MAX : -1);
 }
 
-struct DepthAcc {
-  int valid, zero, inf;
-  float mn, mx;
-  double sum;
-};
-
-__device__ __forceinline__ void depth_acc_reset(DepthAcc& a) {
-  a.valid = a.zero = a.inf = 0;
-  a.mn = __int_as_float(0x7f800000);
-  a.mx = 0.0f;
-  a.sum = 0.0;
-}
-
-// gcd.py:317-321: valid = isfinite & > 0, zero = == 0, inf = isinf
-__device__ __forceinline__ void depth_acc_add(DepthAcc& a, float v, float& part) {
-  const bool isinf_ = fabsf(v) == __int_as_float(0x7f800000);
-  const bool valid = (v > 0.0f) && !isinf_;  // NaN fails v > 0
-  a.valid += valid;
-  a.zero += (v == 0.0f);
-  a.inf += isinf_;
-  if (valid) {
-    a.mn = fminf(a.mn, v);
-    a.mx = fmaxf(a.mx, v);
-    part += v;
-  }
-}
-
-__device__ __forceinline__ void depth_acc_add4(DepthAcc& a, const float4 v) {
-  float part = 0.0f;
-  depth_acc_add(a, v.x, part);
-  depth_acc_add(a, v.y, part);
-  depth_acc_add(a, v.z, part);
-  depth_acc_add(a, v.w, part);
-  a.sum += static_cast<double>(part);
-}
-
-// warp-reduce and merge into stats[frame]; valid depths are > 0 so their float order equals
-// the order of their bit patterns as signed ints.
-__device__ __forceinline__ void depth_acc_flush(DepthAcc& a, cspe_depth_stats_t* st) {
-  const unsigned full = 0xffffffffu;
-  int valid = __reduce_add_sync(full, a.valid);
-  int zero = __reduce_add_sync(full, a.zero);
-  int inf = __reduce_add_sync(full, a.inf);
-  int mn = __reduce_min_sync(full, __float_as_int(a.mn));
-  int mx = __reduce_max_sync(full, __float_as_int(a.mx));
-  double sum = a.sum;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(full, sum, o);
-  if ((threadIdx.x & 31) == 0 && (valid | zero | inf)) {
-    atomicAdd(reinterpret_cast<unsigned long long*>(&st->valid_pixels), static_cast<unsigned long long>(valid));
-    atomicAdd(reinterpret_cast<unsigned long long*>(&st->zero_pixels), static_cast<unsigned long long>(zero));
-    atomicAdd(reinterpret_cast<unsigned long long*>(&st->inf_pixels), static_cast<unsigned long long>(inf));
-    if (valid) {
-      atomicMin(reinterpret_cast<int*>(&st->depth_min), mn);
-      atomicMax(reinterpret_cast<int*>(&st->depth_max), mx);
-      atomicAdd(&st->depth_sum, sum);
-    }
-  }
-  depth_acc_reset(a);
-}
-
-__device__ __forceinline__ float4 ldg_stream_f4(const float4* p) {
-  float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-               : "l"(p));
-  return r;
-}
 
 
 
@@ -507,59 +439,6 @@ __global__ void scan_init_kernel(int32_t* out, long long n_entries, int W, int H
   out[i] = f == CSPE_SCAN_COUNT ? 0 : f == CSPE_SCAN_XMIN ? W : f == CSPE_SCAN_YMIN ? H : -1;
 }
 
-__global__ void stats_init_kernel(cspe_depth_stats_t* st, int B, long long total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  st[i].valid_pixels = 0;
-  st[i].zero_pixels = 0;
-  st[i].inf_pixels = 0;
-  st[i].total_pixels = total;
-  st[i].depth_min = __int_as_float(0x7f800000);
-  st[i].depth_max = 0.0f;
-  st[i].depth_sum = 0.0;
-}
-
-// gcd.py:329: no valid pixel -> min = max = mean = 0
-__global__ void stats_finalize_kernel(cspe_depth_stats_t* st, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B) return;
-  if (st[i].valid_pixels == 0) {
-    st[i].depth_min = 0.0f;
-    st[i].depth_max = 0.0f;
-    st[i].depth_sum = 0.0;
-  }
-}
-
-// standalone depth statistics: grid (chunks, B), float4 streaming loads + scalar edges
-__global__ void __launch_bounds__(256) depth_stats_kernel(const float* __restrict__ depth, long long hw,
-                                                         cspe_depth_stats_t* st) {
-  const float* d = depth + static_cast<long long>(blockIdx.y) * hw;
-  DepthAcc a;
-  depth_acc_reset(a);
-  const long long gthreads = static_cast<long long>(gridDim.x) * blockDim.x;
-  const long long gtid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  // align to 16 bytes
-  const long long head = min(hw, static_cast<long long>((4 - ((reinterpret_cast<uintptr_t>(d) >> 2) & 3)) & 3));
-  const long long n4 = (hw - head) / 4;
-  const float4* d4 = reinterpret_cast<const float4*>(d + head);
-  long long i = gtid;
-  for (; i + 3 * gthreads < n4; i += 4 * gthreads) {  // four 16-byte loads in flight per thread
-    const float4 v0 = ldg_stream_f4(d4 + i), v1 = ldg_stream_f4(d4 + i + gthreads);
-    const float4 v2 = ldg_stream_f4(d4 + i + 2 * gthreads), v3 = ldg_stream_f4(d4 + i + 3 * gthreads);
-    depth_acc_add4(a, v0);
-    depth_acc_add4(a, v1);
-    depth_acc_add4(a, v2);
-    depth_acc_add4(a, v3);
-  }
-  for (; i < n4; i += gthreads) depth_acc_add4(a, ldg_stream_f4(d4 + i));
-  const long long tail0 = head + n4 * 4;
-  float part = 0.0f;
-  for (long long i = gtid; i < head; i += gthreads) depth_acc_add(a, d[i], part);
-  for (long long i = tail0 + gtid; i < hw; i += gthreads) depth_acc_add(a, d[i], part);
-  a.sum += static_cast<double>(part);
-  depth_acc_flush(a, st + blockIdx.y);
-}
-
 int check_common(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot, int lut_len, int64_t lut_stride,
                  int N, int32_t* out) {
   CSPE_REQUIRE(B >= 0 && H >= 0 && W >= 0 && N >= 0 && lut_len >= 0 && lut_stride >= 0, CSPE_ERR_INVALID_ARGUMENT,
@@ -733,42 +612,3 @@ extern "C" int cspe_mask_scan(const uint32_t* mask, int B, int H, int W, const i
                             static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int cspe_depth_stats(const float* depth, int B, int H, int W, cspe_depth_stats_t* stats, void* stream) {
-  CSPE_REQUIRE(B >= 0 && H >= 0 && W >= 0, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_stats: negative size");
-  if (B == 0) return CSPE_OK;
-  CSPE_REQUIRE(stats != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_stats: stats is null");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const long long hw = static_cast<long long>(H) * W;
-  stats_init_kernel<<<(B + 127) / 128, 128, 0, st>>>(stats, B, hw);
-  CSPE_LAUNCH_OK("stats_init_kernel");
-  if (hw > 0) {
-    CSPE_REQUIRE(depth != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_stats: depth is null");
-    CSPE_REQUIRE((reinterpret_cast<uintptr_t>(depth) & 3) == 0, CSPE_ERR_INVALID_ARGUMENT,
-                 "cspe_depth_stats: depth must be 4-byte aligned");
-    const int sms = sm_count();
-    CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_depth_stats: no CUDA device");
-    long long per_frame = (hw / 4 + 256 * 8 - 1) / (256 * 8);
-    long long want = (static_cast<long long>(sms) * 8 + B - 1) / B;
-    if (per_frame > want) per_frame = want;
-    if (per_frame < 1) per_frame = 1;
-    CSPE_REQUIRE(B <= 65535, CSPE_ERR_UNSUPPORTED, "cspe_depth_stats: B > 65535");
-    dim3 grid(static_cast<unsigned>(per_frame), static_cast<unsigned>(B));
-    depth_stats_kernel<<<grid, 256, 0, st>>>(depth, hw, stats);
-    CSPE_LAUNCH_OK("depth_stats_kernel");
-  }
-  stats_finalize_kernel<<<(B + 127) / 128, 128, 0, st>>>(stats, B);
-  CSPE_LAUNCH_OK("stats_finalize_kernel");
-  return CSPE_OK;
-}
-
-extern "C" int cspe_mask_scan_depth_stats(const uint32_t* mask, const float* depth, int B, int H, int W,
-                                          const int32_t* id2slot, int lut_len, int64_t lut_stride, int N,
-                                          int32_t* out, cspe_depth_stats_t* stats, void* stream) {
-  // Both passes are HBM-bound and read disjoint buffers, so a fused kernel can save at most the
-  // launch gap.  A fused variant (consumers streaming the depth tile with LDG next to the TMA-fed
-  // mask ring) measured SLOWER than the two launches (0.262 vs 0.200 ms on 64 x 1080p) and was
-  // removed; the entry point keeps the one-call convenience.
-  const int rc = cspe_mask_scan(mask, B, H, W, id2slot, lut_len, lut_stride, N, out, stream);
-  if (rc != CSPE_OK) return rc;
-  return cspe_depth_stats(depth, B, H, W, stats, stream);
-}

@@ -536,6 +536,17 @@ def test_depth_colormap_and_bgr(T, ops):
     assert not got[1].any() and got[0].any()
     flat = np.full((1, 9, 13), 3.5, dtype=np.float32)          # max == min: everything lands in bin 0
     assert np.array_equal(ops.depth_colormap(T.from_numpy(flat).cuda(), lut).cpu().numpy()[0], O.depth_colormap(flat[0]))
+    # odd geometry (scalar path, frames not 16-byte aligned) and a 5-channel image (generic path)
+    rng = np.random.default_rng(9)
+    odd = rng.uniform(-1, 200, size=(3, 37, 45)).astype(np.float32)
+    odd[rng.uniform(size=odd.shape) < 0.2] = np.inf
+    got_odd = ops.depth_colormap(T.from_numpy(odd).cuda(), lut).cpu().numpy()
+    for b in range(3):
+        assert np.array_equal(got_odd[b], O.depth_colormap(odd[b])), b
+    five = rng.integers(0, 256, size=(19, 23, 5), dtype=np.uint8)
+    assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(five).cuda()).cpu().numpy(), O.rgb_to_bgr(five))
+    tiny = rng.integers(0, 256, size=(7, 9, 4), dtype=np.uint8)          # fewer than 16 pixels per thread chunk + tail
+    assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(tiny).cuda()).cpu().numpy(), O.rgb_to_bgr(tiny))
     rgb = frames[0]["rgb"]
     assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(rgb).cuda()).cpu().numpy(), O.rgb_to_bgr(rgb))
     assert np.array_equal(ops.rgb_to_bgr(T.from_numpy(np.ascontiguousarray(rgb[..., :3])).cuda()).cpu().numpy(),
