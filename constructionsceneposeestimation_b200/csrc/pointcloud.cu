@@ -7,9 +7,15 @@
 // RGB gather with the "max <= 1 -> x255" rule (gcd.py:691-696); ROW-MAJOR STABLE compaction
 // into (N, 6) float64.
 //
-// Three launches: (1) per-tile valid counts + max RGB over valid pixels, (2) one-CTA exclusive
-// scan of tile counts, (3) recompute validity, in-tile ranks, write.  HBM-bound: reads
-// 4*HW (depth) twice + C*HW (rgb), writes 48 B per point.
+// HBM-bound on the OUTPUT: 48 bytes written per valid pixel against 4 (depth, read twice) + C
+// (rgb) bytes read.  Four launches chained by programmatic dependent launch:
+//   1. per-tile (1024 px) valid counts;
+//   2. one-CTA exclusive scan of the tile counts -> tile offsets, total;
+//   3. per tile: recompute validity, in-tile ranks, build the tile's points in shared memory and
+//      stream them out as one contiguous run of 16-byte stores (a thread writing its own 48-byte
+//      points directly costs ~6x the sector traffic); colours are written as they are and the
+//      maximum colour over valid pixels is reduced on the side;
+//   4. only if that maximum is <= 1 (the reference's [0,1]-image rule): scale the colours by 255.
 #include <math.h>
 
 #include "cspe_common.cuh"
@@ -20,64 +26,64 @@ namespace {
 constexpr int kPcThreads = 256;
 constexpr int kPcPerThread = 4;
 constexpr int kPcTile = kPcThreads * kPcPerThread;  // 1024 pixels
+constexpr int kPcStageBytes = kPcTile * 48;          // a tile's points, 48 KB
 
 struct PcWorkspace {  // layout of the caller-provided scratch
   unsigned int rgb_max;
   unsigned int pad;
   long long total;
-  // followed by: int32 tile_count[tiles]; int64 tile_offset[tiles]
+  // followed by: int64 tile_offset[tiles]; int32 tile_count[tiles]
 };
 
 __device__ __forceinline__ bool pc_valid(float d) {
   return (d > 0.0f) && (d < 250.0f);  // finite follows from < 250; NaN fails both
 }
 
-__global__ void __launch_bounds__(kPcThreads)
-    pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw,
-                    PcWorkspace* ws, int32_t* tile_count) {
-  __shared__ int s_cnt[kPcThreads / 32];
-  __shared__ unsigned s_max[kPcThreads / 32];
-  const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
-  int cnt = 0;
-  unsigned mx = 0;
+__device__ __forceinline__ void load4(const float* __restrict__ depth, long long base, long long hw, bool vec, float* d) {
+  if (vec && base + 3 < hw) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(depth + base));
+    d[0] = v.x;
+    d[1] = v.y;
+    d[2] = v.z;
+    d[3] = v.w;
+  } else {
 #pragma unroll
-  for (int k = 0; k < kPcPerThread; ++k) {
-    const long long i = base + k;
-    if (i < hw && pc_valid(__ldg(depth + i))) {
-      ++cnt;
-      if (rgb) {
-        const uint8_t* c = rgb + i * C;
-        mx = max(mx, max(static_cast<unsigned>(c[0]), max(static_cast<unsigned>(c[1]), static_cast<unsigned>(c[2]))));
-      }
-    }
+    for (int k = 0; k < kPcPerThread; ++k) d[k] = base + k < hw ? __ldg(depth + base + k) : 0.0f;
   }
+}
+
+__global__ void __launch_bounds__(kPcThreads)
+    pc_count_kernel(const float* __restrict__ depth, long long hw, int vec, int32_t* tile_count) {
+  pdl_launch_dependents();
+  __shared__ int s_cnt[kPcThreads / 32];
+  const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
+  float d[kPcPerThread];
+  load4(depth, base, hw, vec, d);
+  int cnt = 0;
+#pragma unroll
+  for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
   cnt = __reduce_add_sync(0xffffffffu, cnt);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (lane == 0) {
-    s_cnt[wid] = cnt;
-    s_max[wid] = mx;
-  }
+  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
-    unsigned m = 0;
 #pragma unroll
-    for (int w = 0; w < kPcThreads / 32; ++w) {
-      t += s_cnt[w];
-      m = max(m, s_max[w]);
-    }
+    for (int w = 0; w < kPcThreads / 32; ++w) t += s_cnt[w];
     tile_count[blockIdx.x] = t;
-    if (m) atomicMax(&ws->rgb_max, m);
   }
 }
 
 __global__ void __launch_bounds__(1024) pc_scan_kernel(const int32_t* __restrict__ tile_count, long long* tile_offset,
                                                       int tiles, PcWorkspace* ws, long long* n_points) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ long long s_warp[32];
   __shared__ long long s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) s_base = 0;
+  if (tid == 0) {
+    s_base = 0;
+    ws->rgb_max = 0;
+  }
   __syncthreads();
   for (int t0 = 0; t0 < tiles; t0 += 1024) {
     const int t = t0 + tid;
@@ -113,19 +119,19 @@ __global__ void __launch_bounds__(1024) pc_scan_kernel(const int32_t* __restrict
 }
 
 __global__ void __launch_bounds__(kPcThreads)
-    pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw,
-                    const double* __restrict__ cam, const PcWorkspace* __restrict__ ws,
-                    const long long* __restrict__ tile_offset, double* __restrict__ out, long long capacity) {
+    pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
+                    const double* __restrict__ cam, PcWorkspace* ws, const long long* __restrict__ tile_offset,
+                    double* __restrict__ out, long long capacity) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) double stage[];  // [points in this tile][6]
   __shared__ int s_warp[kPcThreads / 32];
+  __shared__ unsigned s_max[kPcThreads / 32];
   const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
   float d[kPcPerThread];
+  load4(depth, base, hw, vec, d);   // depth is an input: no need to wait for the scan yet
   int cnt = 0;
 #pragma unroll
-  for (int k = 0; k < kPcPerThread; ++k) {
-    const long long i = base + k;
-    d[k] = i < hw ? __ldg(depth + i) : 0.0f;
-    cnt += pc_valid(d[k]);
-  }
+  for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = cnt;
 #pragma unroll
@@ -135,39 +141,83 @@ __global__ void __launch_bounds__(kPcThreads)
   }
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
-  int before = inc - cnt;
-  for (int w = 0; w < wid; ++w) before += s_warp[w];
-  if (cnt == 0) return;
+  int before = inc - cnt, tile_total = 0;
+#pragma unroll
+  for (int w = 0; w < kPcThreads / 32; ++w) {
+    if (w < wid) before += s_warp[w];
+    tile_total += s_warp[w];
+  }
 
   const double t0 = cam[0], t1 = cam[1], t2 = cam[2];
   const double fx = cam[12], fy = cam[13], cx = cam[14], cy = cam[15];
-  const bool scale255 = ws->rgb_max <= 1u;  // gcd.py:693
-  long long rank = tile_offset[blockIdx.x] + before;
+  unsigned mx = 0;
+  int r = before;
 #pragma unroll
   for (int k = 0; k < kPcPerThread; ++k) {
     if (!pc_valid(d[k])) continue;
     const long long i = base + k;
-    if (rank < capacity) {
-      const int v = static_cast<int>(i / W);
-      const int u = static_cast<int>(i - static_cast<long long>(v) * W);
-      const double zc = static_cast<double>(d[k]);
-      const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
-      const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
-      double* o = out + rank * 6;
-      o[0] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
-      o[1] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
-      o[2] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
-      if (rgb) {
-        const uint8_t* c = rgb + i * C;
-        const unsigned m = scale255 ? 255u : 1u;
-        o[3] = static_cast<double>((c[0] * m) & 0xffu);
-        o[4] = static_cast<double>((c[1] * m) & 0xffu);
-        o[5] = static_cast<double>((c[2] * m) & 0xffu);
-      } else {
-        o[3] = o[4] = o[5] = 255.0;  // gcd.py:698-700
-      }
+    const int v = static_cast<int>(i / W);
+    const int u = static_cast<int>(i - static_cast<long long>(v) * W);
+    const double zc = static_cast<double>(d[k]);
+    const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
+    const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
+    double* o = stage + r * 6;
+    o[0] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
+    o[1] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
+    o[2] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
+    if (rgb) {
+      const uint8_t* c = rgb + i * C;
+      const unsigned c0 = c[0], c1 = c[1], c2 = c[2];
+      mx = max(mx, max(c0, max(c1, c2)));
+      o[3] = static_cast<double>(c0);
+      o[4] = static_cast<double>(c1);
+      o[5] = static_cast<double>(c2);
+    } else {
+      o[3] = o[4] = o[5] = 255.0;  // gcd.py:698-700
     }
-    ++rank;
+    ++r;
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) s_max[wid] = mx;
+  __syncthreads();  // stage and s_max complete
+
+  pdl_wait();       // tile offsets and the zeroed rgb_max come from the scan kernel
+  if (threadIdx.x == 0) {
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; ++w) m = max(m, s_max[w]);
+    if (m) atomicMax(&ws->rgb_max, m);
+  }
+  // stream the tile's points out: ranks are consecutive, so it is one contiguous run
+  const long long first = tile_offset[blockIdx.x];
+  long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
+  if (keep > tile_total) keep = tile_total;
+  if (keep <= 0) return;
+  const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs
+  double* dst = out + first * 6;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(stage);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (int j = threadIdx.x; j < n2; j += kPcThreads) {
+      const double2 vv = s2[j];
+      asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
+    }
+  } else {
+    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) dst[j] = stage[j];
+  }
+}
+
+// gcd.py:693: rgb.max() <= 1.0 over the valid pixels -> colours were a [0,1] image: x255
+__global__ void __launch_bounds__(256) pc_fixup_kernel(const PcWorkspace* __restrict__ ws, double* __restrict__ out,
+                                                       long long capacity) {
+  pdl_wait();
+  if (ws->rgb_max > 1u) return;
+  long long n = ws->total;
+  if (n > capacity) n = capacity;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * 3; i += stride) {
+    const long long p = i / 3, c = i - p * 3;
+    out[p * 6 + 3 + c] *= 255.0;
   }
 }
 
@@ -197,8 +247,8 @@ extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long hw = static_cast<long long>(H) * W;
   PcWorkspace* ws = static_cast<PcWorkspace*>(workspace);
-  CSPE_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(PcWorkspace), st));
   if (hw == 0) {
+    CSPE_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(PcWorkspace), st));
     CSPE_CUDA_OK(cudaMemsetAsync(n_points, 0, sizeof(int64_t), st));
     return CSPE_OK;
   }
@@ -208,13 +258,22 @@ extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, 
   CSPE_REQUIRE(tiles < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: frame too large");
   long long* tile_offset = reinterpret_cast<long long*>(ws + 1);
   int32_t* tile_count = reinterpret_cast<int32_t*>(tile_offset + tiles);
-  pc_count_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, ws, tile_count);
+  const int vec = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  static const cudaError_t smem_attr =
+      cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
+  (void)smem_attr;
+  // plain launch first (serialised behind whatever produced depth / rgb), then a PDL chain
+  pc_count_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, hw, vec, tile_count);
   CSPE_LAUNCH_OK("pc_count_kernel");
-  pc_scan_kernel<<<1, 1024, 0, st>>>(tile_count, tile_offset, static_cast<int>(tiles), ws,
-                                     reinterpret_cast<long long*>(n_points));
-  CSPE_LAUNCH_OK("pc_scan_kernel");
-  pc_write_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, rgb, rgb_channels, W, hw, cam, ws,
-                                                                      tile_offset, out, capacity);
-  CSPE_LAUNCH_OK("pc_write_kernel");
+  CSPE_CUDA_OK(launch_pdl(pc_scan_kernel, dim3(1), dim3(1024), 0, st, tile_count, tile_offset, static_cast<int>(tiles), ws,
+                          reinterpret_cast<long long*>(n_points)));
+  CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kPcThreads), kPcStageBytes, st, depth,
+                          rgb, rgb_channels, W, hw, vec, cam, ws, tile_offset, out, static_cast<long long>(capacity)));
+  if (rgb != nullptr && capacity > 0) {
+    const int sms = sm_count();
+    CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_depth_to_pointcloud: no CUDA device");
+    CSPE_CUDA_OK(launch_pdl(pc_fixup_kernel, dim3(static_cast<unsigned>(sms) * 4), dim3(256), 0, st,
+                            static_cast<const PcWorkspace*>(ws), out, static_cast<long long>(capacity)));
+  }
   return CSPE_OK;
 }
