@@ -695,3 +695,76 @@ def test_pipeline_with_keypoint_stage(T, ops, use_graph):
     for f in range(3):
         helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
     assert np.array_equal(pipe.class_hist.cpu().numpy(), 5 * o["hist"])
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_project_and_keypoints_random_cameras(T, ops, seed):
+    """Random camera orientations / positions, boxes anywhere (in front, behind, straddling the near
+    plane), non-uniform scales and shear, mirrored and degenerate transforms; joints everywhere: flags
+    and visibility exact, projections identical, poses within 1e-5."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(100 + seed)
+    B, R, P, J, H, W = 3, 80, 6, 11, 270, 480
+    recs = np.zeros((B, R), dtype=O.BBOX3D_DTYPE)
+    for b in range(B):
+        for i in range(R):
+            lo = rng.uniform(-4, 0, 3)
+            hi = lo + rng.uniform(0.01, 8, 3)
+            m = np.eye(4)
+            lin = Rotation.random(random_state=int(rng.integers(1 << 31))).as_matrix() @ np.diag(rng.uniform(0.2, 3, 3))
+            if i % 7 == 0:
+                lin = lin @ (np.eye(3) + rng.normal(0, 0.2, (3, 3)))      # shear
+            if i % 11 == 0:
+                lin[:, 0] *= -1                                            # mirrored
+            if i % 29 == 0:
+                lin[:, 1] = 0                                              # singular
+            m[:3, :3] = lin.T
+            m[3, :3] = rng.uniform(-40, 40, 3)
+            r = recs[b, i]
+            r["x_min"], r["y_min"], r["z_min"] = lo
+            r["x_max"], r["y_max"], r["z_max"] = hi
+            r["transform"] = m.astype(np.float32)
+    cam = np.stack([O.pack_camera(list(rng.uniform(-30, 30, 3)) + list(Rotation.random(random_state=int(rng.integers(1 << 31))).as_quat()),
+                                  {"focal_length": rng.uniform(8, 30), "horizontal_aperture": 25.0,
+                                   "vertical_aperture": 25.0 * H / W, "width": W, "height": H}) for _ in range(B)])
+    obj_record = rng.integers(-1, R + 2, size=(B, R + 5)).astype(np.int32)      # incl. -1 and out-of-range indices
+    uv, z, pose, loose, flags = _project_gpu(T, ops, recs, obj_record, cam)
+    want = O.project_objects(recs, obj_record, cam)
+    assert np.array_equal(flags, want[4])
+    assert np.array_equal(uv, want[0], equal_nan=True) and np.array_equal(z, want[1], equal_nan=True)
+    assert np.array_equal(loose, want[3], equal_nan=True)
+    helpers.assert_pose_close(pose, want[2], (want[4] & O.OBJ_POSE_VALID) != 0)
+    assert len(np.unique(flags)) >= 4                                            # the case mixes outcomes
+
+    joints = rng.uniform(-45, 45, size=(B, P, J, 3)).astype(np.float32)
+    depth = rng.uniform(0.5, 80, size=(B, H, W)).astype(np.float32)
+    depth[rng.uniform(size=depth.shape) < 0.3] = np.inf
+    kp, kz, vis = ops.keypoints(T.from_numpy(joints).cuda(), T.from_numpy(depth).cuda(), T.from_numpy(cam).cuda(), 0.15)
+    T.cuda.synchronize()
+    wkp, wkz, wvis = O.keypoints(joints, depth, cam, 0.15)
+    assert np.array_equal(vis.cpu().numpy(), wvis)
+    assert np.array_equal(kp.cpu().numpy(), wkp, equal_nan=True) and np.array_equal(kz.cpu().numpy(), wkz, equal_nan=True)
+
+
+def test_writer_single_frame_write_json_values(T, ops, tmp_path):
+    """Writer.write(data) (the Replicator signature, one frame): the JSON's numbers are the oracle's."""
+    import json
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    fr = synthetic.make_frame(synthetic.SceneSpec(640, 360, 16, 2, 17, config_id=16), 7)
+    o = helpers.oracle_pipeline([fr], frame_base=7)
+    w = ConstructionLabelWriter(str(tmp_path), split_people=True)
+    w.write(fr)
+    w.on_final_frame()
+    lab = json.loads((tmp_path / "labels" / "label_000007.json").read_text())
+    recs = o["recs"][0, : o["n_out"][0]]
+    assert lab["frame_id"] == 7 and lab["num_objects"] == len(recs)
+    assert lab["camera_pose"] == fr["camera_pose"] and lab["camera_params"] == fr["camera_params"]
+    for obj, r in zip(lab["objects"], recs):
+        assert obj["inst_idx"] == r["inst_idx"] and obj["class_id"] == r["class_id"]
+        assert obj["prim_path"] == o["objects"][0][r["inst_idx"]].prim_path
+        assert obj["bbox_2d_tight"] == [int(r["x_min"]), int(r["y_min"]), int(r["x_max"]), int(r["y_max"])]
+        assert obj["pixel_count"] == r["count"]
+        assert np.allclose(obj["center"], r["pose"][7:10], rtol=1e-9) and np.allclose(obj["size"], r["pose"][10:13], rtol=1e-9)
+        assert np.allclose(obj["bbox_3d_projected"], r["uv"], rtol=0, atol=helpers.PX_ATOL)
+        assert abs(obj["occlusion"] - float(r["occlusion"])) <= 1e-6
