@@ -193,10 +193,12 @@ def run_ours(args) -> int:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()
+    # keep stdout to the one JSON line: libraries (NCCL's version banner) write to fd 1 from C, so
+    # point fd 1 at stderr until the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner there at VERSION level
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: each rank owns its own frame range (weak scaling: 64 frames per GPU) -------
@@ -358,6 +360,8 @@ def run_ours(args) -> int:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -172,8 +172,6 @@ def main() -> int:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     res = run_sweep(args.frames, rank, world, torch.device("cuda", local), args.pool, args.config,
                     None if args.emit == "none" else args.emit, args.out)
