@@ -6,26 +6,33 @@
 // per frame); everything else stays on chip.
 //
 // Design (B200 / sm_100a):
-//   * persistent grid, one CTA per SM, warp-specialised: 1 producer warp + 16 consumer warps;
-//   * the batch is one 2-D tensor [B*H rows][W] behind a TMA tensor map; a tile is 8 boxes of
-//     32 px x 64 rows (128-byte rows, SWIZZLE_128B) = 256 px x 64 rows = 64 KB, streamed into a
+//   * persistent grid, two CTAs per SM (296 on a B200), each warp-specialised: 1 producer warp +
+//     8 consumer warps, capped at 80 registers so that small kernels can run beside it;
+//   * the batch is one 2-D tensor [B*H rows][W] behind a TMA tensor map; a tile is 4 boxes of
+//     32 px x 64 rows (128-byte rows, SWIZZLE_128B) = 128 px x 64 rows = 32 KB, streamed into a
 //     3-stage shared-memory ring by cp.async.bulk.tensor.2d (SASS UTMALDG) signalled on
-//     mbarriers, L2 evict_first.  (Measured: this geometry streams at 6.6 TB/s; one 1-D bulk
-//     copy per row segment capped at 4.3 TB/s because every bulk op costs ~85 cycles of TMA.)
-//   * consumer warp w owns box (w & 7) and row half (w >> 3) of the tile: a 32-pixel column
-//     strip whose LANES RUN DOWN THE ROWS (lane l = row l).  Object silhouettes are dominated by
-//     near-vertical edges, so either all lanes of a warp see a uniform strip (fast path:
-//     8 LDS.128 + 16 LOP3) or all of them cross the same edge together (slow path, every lane
-//     active) — the warp does not diverge on edges the way a lanes-along-x mapping does.  The
-//     128-byte swizzle makes both paths' LDS.128 bank-conflict free;
+//     mbarriers, L2 evict_first.  (Measured: tensor-map boxes stream at 6.4-6.9 TB/s whatever the
+//     geometry; one 1-D bulk copy per row segment capped at 4.3 TB/s because every bulk op costs
+//     ~85 cycles of TMA.)  Two CTAs per SM = two independent rings per SM: a slow warp only holds
+//     back its own ring;
+//   * consumer warp w owns box (w & 3) and row half (w >> 2) of the tile: a 32-pixel column
+//     strip whose LANES RUN DOWN THE ROWS (lane l = row l).  Fast path (the strip is one id):
+//     8 LDS.128 + 16 LOP3.  Slow path: all lanes build a 32-bit run-start mask in lockstep, then
+//     walk their runs (one shared-memory load per run).  The 128-byte swizzle makes every
+//     LDS.128 bank-conflict free.  A lanes-along-x mapping left 10.8 of 32 lanes active, because
+//     every warp meets an object edge;
 //   * each thread keeps the two most recent ids with their partial {count, xmin, xmax, ymin,
 //     ymax} in registers and touches shared memory only when a third id shows up; evicted
-//     entries are reduced across the warp, then merged into a per-CTA shared-memory table with
-//     red.shared add/min/max through a shared-memory copy of the frame's id->slot LUT; the table
-//     merges into global memory with red.global once per (CTA, frame);
+//     entries are reduced across the warp (match.all + redux), then merged into a per-CTA
+//     shared-memory table with red.shared add/min/max through a shared-memory copy of the frame's
+//     id->slot LUT; the table merges into global memory with red.global once per (CTA, frame);
 //   * work is a contiguous range of passes per CTA, but the pass order inside a frame is
 //     stride-permuted so every CTA samples busy and empty image regions alike (a plain
-//     contiguous split left SMs idle 43 % of the time on instance-dense frames).
+//     contiguous split left SMs idle 43 % of the time on instance-dense frames);
+//   * programmatic dependent launch: the kernel releases its dependents right after set-up (K2 /
+//     K3 then run beside it) and waits for the kernel before it either at entry or — overlapped
+//     mode — only before its first merge into `out`, so it can stream while the previous batch's
+//     K4 is still reading that table;
 //   * masks whose rows are not 16-byte aligned (W % 4 != 0 or a misaligned base) cannot use
 //     TMA: the producer warp then fills the same swizzled layout with plain loads.
 //
@@ -50,8 +57,8 @@ constexpr int kDefaultBoxes = 4;  // measured best: 2 CTAs per SM (profiles/)
 
 // Geometry of one CTA: kBoxes TMA boxes side by side per tile, two consumer warps per box (row
 // halves) + one producer warp.  CTAs per SM = 8 / kBoxes, so an SM always runs 16 consumer warps
-// over 3 x 64 KB of ring; smaller CTAs mean more independent rings per SM (a slow warp only
-// holds back its own CTA's ring).
+// over 3 x 64 KB of ring.  kBoxes = 4 (2 CTAs per SM) measured best; 8 and 2 stay selectable with
+// CSPE_SCAN_BOXES for tuning on other parts.
 template <int kBoxes>
 struct Geo {
   static constexpr int kConsumerWarps = 2 * kBoxes;
