@@ -23,6 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib, formats, ops
+from .quality import FrameQualityLog, depth_quality_from_stats
 from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
 from .camera import DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, pack_camera
 from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot,
@@ -100,13 +101,7 @@ class BatchLabels:
         if self._depth_stats_host is None:
             return None
         self.synchronize()
-        st = self._depth_stats_host[f].numpy().view(_lib.DEPTH_STATS_DTYPE)[0]
-        valid, total = int(st["valid_pixels"]), int(st["total_pixels"])
-        mean = float(np.float32(st["depth_sum"] / valid)) if valid else 0.0
-        return {"status": "valid", "valid_pixels": valid, "total_pixels": total,
-                "valid_ratio": float(valid / total) if total else 0.0, "zero_pixels": int(st["zero_pixels"]),
-                "inf_pixels": int(st["inf_pixels"]), "depth_range": [float(st["depth_min"]), float(st["depth_max"])],
-                "depth_mean": mean}
+        return depth_quality_from_stats(self._depth_stats_host[f].numpy().view(_lib.DEPTH_STATS_DTYPE)[0])
 
     def depth_image(self, f: int) -> Optional[np.ndarray]:
         """JET visualisation of the depth map, uint8 BGR [H,W,3] (gcd.py:1691-1709); needs "depth_png" in formats."""
@@ -156,7 +151,7 @@ class ConstructionLabelWriter:
                  formats: Sequence[str] = ("json",), min_pixels: int = 1, keypoint_tolerance: float = 0.15,
                  near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, split_people: bool = False,
                  record_fallback: str = "first_mesh", crane_part_map: Optional[Mapping] = None,
-                 rank: int = 0, world_size: int = 1, max_pending: int = 2):
+                 rank: int = 0, world_size: int = 1, max_pending: int = 2, quality_log: bool = True):
         _lib.load()  # fail loudly right here if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.CspeLibraryError("ConstructionLabelWriter needs a CUDA device (no CPU fallback exists)")
@@ -178,6 +173,10 @@ class ConstructionLabelWriter:
         self.frames_written = 0
         self.objects_total = 0
         self.depth_quality_log: List[Dict[str, object]] = []
+        # the reference's DataQualityLogger (gcd.py:236-464): logs/generation_summary.json
+        self.quality: Optional[FrameQualityLog] = None
+        if quality_log:
+            self.quality = FrameQualityLog(os.path.join(output_dir, "logs") if output_dir is not None else None)
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
             self.class_hist = torch.zeros((NUM_CLASSES,), dtype=torch.int64, device=self.device)
@@ -248,6 +247,12 @@ class ConstructionLabelWriter:
             if self.rank == 0:
                 with open(os.path.join(self.output_dir, "label_summary.json"), "w", encoding="utf-8") as f:
                     json.dump(summary, f, indent=2)
+            if self.quality is not None:   # gcd.py:2090; one file per rank beyond rank 0
+                name = "generation_summary.json" if self.world_size == 1 else f"generation_summary_rank{self.rank:02d}.json"
+                os.makedirs(self.quality.log_dir, exist_ok=True)
+                self.quality.save_summary(os.path.join(self.quality.log_dir, name))
+        if self.quality is not None:
+            summary["quality"] = self.quality.summary()["statistics"]
         return summary
 
     def gather_class_histogram(self) -> Dict[str, np.ndarray]:
@@ -483,5 +488,10 @@ class ConstructionLabelWriter:
             dq = labels.depth_quality(f)
             if dq is not None:
                 self.depth_quality_log.append({"frame_id": fid, "depth": dq})
+            if self.quality is not None:   # the events of gcd.py:1567, 1684 / 1711, 2075, 2078
+                self.quality.frame_start(fid, list(labels.camera_poses[f][:3]))
+                self.quality.depth(dq, reason="annotator返回None或空")
+                self.quality.labels(len(recs))
+                self.quality.frame_end(True)
             self.objects_total += len(recs)
             self.frames_written += 1

@@ -167,6 +167,47 @@ def make_depth_stats(ref):
     return list(results)
 
 
+# events replayed through the reference's DataQualityLogger and, in the tests, through FrameQualityLog;
+# "depth" names a case of depth_stats.npz (None = annotator returned nothing)
+QUALITY_EVENTS = [
+    {"frame": 0, "cam": [1.0, 2.0, 3.0], "cloud": [True, 5000, ""], "rgb": [True, ""], "depth": "mixed", "labels": 7, "ok": True},
+    {"frame": 1, "cam": [0.0, 0.0, 9.5], "retry": 1, "cloud": [False, 0, "annotator返回None"], "ok": False},
+    {"frame": 1, "cam": [0.0, 0.0, 9.5], "retry": 2, "cloud": [False, 40, "少于阈值 100"], "rgb": [False, "camera.get_rgba()返回None或空"],
+     "depth": "all_zero", "labels": 0, "ok": True},
+    {"frame": 2, "cam": [-4.0, 2.5, 3.0], "rgb": [True, ""], "depth": "all_inf", "labels": 3, "ok": True},
+    {"frame": 3, "cam": [-4.0, 2.5, 3.0], "rgb": [True, ""], "depth": None, "labels": 12, "ok": True},
+    {"frame": 4, "cam": [8.0, 8.0, 1.0], "cloud": [True, 123456, ""], "depth": "big", "labels": 1, "ok": True},
+]
+
+
+def make_quality_log(ref):
+    cases = np.load(HERE / "depth_stats.npz")
+    with tempfile.TemporaryDirectory() as tmp:
+        logger = ref.DataQualityLogger(tmp)
+        for ev in QUALITY_EVENTS:
+            logger.log_frame_start(ev["frame"], np.asarray(ev["cam"]))
+            if "retry" in ev:
+                logger.log_retry(ev["retry"])
+            if "cloud" in ev:
+                logger.log_pointcloud(*ev["cloud"])
+            if "rgb" in ev:
+                logger.log_rgb(*ev["rgb"])
+            if "depth" in ev:
+                if ev["depth"] is None:
+                    logger.log_depth(False, reason="annotator返回None或空")
+                else:
+                    logger.log_depth(True, cases[ev["depth"]])
+            if "labels" in ev:
+                logger.log_labels(ev["labels"])
+            logger.log_frame_end(ev["ok"])
+        report = logger.save_summary()
+        summary = json.loads((Path(tmp) / "generation_summary.json").read_text(encoding="utf-8"))
+    issue_lines = [ln.strip() for ln in report.split("常见问题:\n")[1].splitlines() if ln.strip()]
+    (HERE / "quality_log.json").write_text(json.dumps({"events": QUALITY_EVENTS, "summary": summary,
+                                                       "issue_lines": issue_lines}, ensure_ascii=False, indent=1))
+    return len(summary["frame_logs"])
+
+
 def make_label_json(ref):
     label = {
         "frame_id": 7, "camera_pose": [1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 1.0],
@@ -195,9 +236,10 @@ def main():
         pc_shape = make_pointcloud(ref)
         stats = make_depth_stats(ref)
         n_text = make_label_json(ref)
+        n_quality = make_quality_log(ref)
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "paths": n_paths, "records": n_recs,
             "mirrored_transform_raises": raised, "pointcloud_shape": list(pc_shape), "depth_cases": stats,
-            "label_text_bytes": n_text, "source": str(reference_extract.REFERENCE_SCRIPT)}
+            "label_text_bytes": n_text, "quality_frames": n_quality, "source": str(reference_extract.REFERENCE_SCRIPT)}
     (HERE / "META.json").write_text(json.dumps(meta, indent=1))
     print(json.dumps(meta, indent=1))
 

@@ -456,6 +456,14 @@ def test_writer_end_to_end(T, ops, tmp_path):
     coco = json.loads((tmp_path / "coco_rank00.json").read_text())
     assert len(coco["annotations"]) == int(o["n_out"].sum()) and len(coco["images"]) == 3
     assert any("keypoints" in a for a in coco["annotations"])
+    # f3: the reference logger's run summary (gcd.py:389-418), fed from the device statistics
+    q = json.loads((tmp_path / "logs" / "generation_summary.json").read_text(encoding="utf-8"))
+    assert q["statistics"]["successful_frames"] == 3 and q["statistics"]["depth_stats"]["valid"] == 3
+    assert q["statistics"]["object_count"]["total"] == int(o["n_out"].sum())
+    assert q["statistics"]["object_count"]["per_frame_avg"] == int(o["n_out"].sum()) / 3
+    assert [fl["labels"]["object_count"] for fl in q["frame_logs"]] == [int(n) for n in o["n_out"]]
+    assert q["frame_logs"][1]["depth"]["valid_pixels"] == O.depth_stats(frames[1]["distance_to_image_plane"])["valid_pixels"]
+    assert summary["quality"] == q["statistics"]
 
 
 def test_writer_accepts_device_resident_annotators(T, ops):

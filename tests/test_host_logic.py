@@ -2,6 +2,7 @@
 import json
 import os
 import socket
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -9,6 +10,8 @@ import pytest
 from constructionsceneposeestimation_b200 import classes, formats, sharding, synthetic
 from oracle import labels as O
 from tests import helpers
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
 
 
 # ------------------------------------------------------------------ synthetic annotator frames
@@ -206,3 +209,61 @@ def test_native_yolo_formatter_matches_python(libcspe_path):
     from constructionsceneposeestimation_b200 import _lib
     with pytest.raises(_lib.CspeError):
         formats.yolo_text_batch(bad, n_out)
+
+
+# ------------------------------------------------------------------ f3: quality log (gcd.py:236-464)
+def _replay_quality(events, depth_dict_of):
+    from constructionsceneposeestimation_b200.quality import FrameQualityLog
+
+    log = FrameQualityLog()
+    for ev in events:
+        log.frame_start(ev["frame"], np.asarray(ev["cam"]))
+        if "retry" in ev:
+            log.retry(ev["retry"])
+        if "cloud" in ev:
+            log.pointcloud(*ev["cloud"])
+        if "rgb" in ev:
+            log.rgb(*ev["rgb"])
+        if "depth" in ev:
+            log.depth(None if ev["depth"] is None else depth_dict_of(ev["depth"]), reason="annotator返回None或空")
+        if "labels" in ev:
+            log.labels(ev["labels"])
+        log.frame_end(ev["ok"])
+    return log
+
+
+def test_quality_log_matches_reference_logger(tmp_path):
+    """Same events -> the generation_summary.json the reference's DataQualityLogger wrote (golden)."""
+    gold = json.loads((GOLDEN / "quality_log.json").read_text(encoding="utf-8"))
+    cases = np.load(GOLDEN / "depth_stats.npz")
+    log = _replay_quality(gold["events"], lambda name: O.depth_stats(cases[name]))
+    log.log_dir = str(tmp_path / "logs")
+    data = log.save_summary()
+    assert data == gold["summary"]
+    on_disk = json.loads((tmp_path / "logs" / "generation_summary.json").read_text(encoding="utf-8"))
+    assert on_disk == gold["summary"]
+    assert list(on_disk["statistics"]) == list(gold["summary"]["statistics"])       # key order too
+    assert [f"{k}: {v} 次" for k, v in log.issue_counts().items()] == gold["issue_lines"]   # gcd.py:447-455
+
+
+def test_depth_quality_from_device_record_layout():
+    """cspe_depth_stats_t -> the reference's depth dict (host conversion only; the kernel is a GPU test)."""
+    from constructionsceneposeestimation_b200 import _lib
+    from constructionsceneposeestimation_b200.quality import depth_quality_from_stats
+
+    cases = np.load(GOLDEN / "depth_stats.npz")
+    want = json.loads(str(cases["results"]))
+    for name, ref in want.items():
+        d = cases[name]
+        ok = np.isfinite(d) & (d > 0)
+        st = np.zeros(1, dtype=_lib.DEPTH_STATS_DTYPE)[0]
+        st["valid_pixels"], st["zero_pixels"], st["inf_pixels"], st["total_pixels"] = ok.sum(), (d == 0).sum(), np.isinf(d).sum(), d.size
+        if ok.any():
+            st["depth_min"], st["depth_max"], st["depth_sum"] = d[ok].min(), d[ok].max(), d[ok].astype(np.float64).sum()
+        got = depth_quality_from_stats(st)
+        assert list(got) == list(ref)
+        for k in ref:
+            if k == "depth_mean":
+                assert abs(got[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k]))
+            else:
+                assert got[k] == ref[k], (name, k)
