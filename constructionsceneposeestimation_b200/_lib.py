@@ -118,6 +118,8 @@ PROTOTYPES = {
     "cspe_depth_stats": (_I, [_P, _I, _I, _I, _P, _P]),
     "cspe_depth_colormap": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_rgb_to_bgr": (_I, [_P, _I, _I64, _P, _P]),
+    "cspe_text_workspace_bytes": (C.c_size_t, [_I64, _I]),
+    "cspe_format_fixed6": (_I, [_P, _I, _I64, _P, _I, C.c_char_p, _P, _I64, _P, _I64, _P, _P, _P]),
     "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
 }
 

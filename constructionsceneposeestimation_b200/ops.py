@@ -222,6 +222,59 @@ def depth_to_pointcloud(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: t
     return out, n
 
 
+def format_fixed6(values: torch.Tensor, n_rows: Optional[torch.Tensor] = None, header: Optional[str] = None,
+                  split_rows: int = 0, capacity: Optional[int] = None, out: Optional[torch.Tensor] = None):
+    """f3: the bytes ``np.savetxt(f, values, fmt='%.6f', delimiter=' ', header=header, comments='')`` writes
+    (gcd.py:1688, 1752), formatted on the device.
+
+    values f32 / f64 [rows, cols]; n_rows int64 [1] on the device = live rows (None = all);
+    split_rows > 0 additionally returns the byte offset of every ``split_rows``-th row.
+    Returns (text u8 [capacity], n_bytes int64 [1], split_offsets int64 [ceil(rows/split_rows)] or None);
+    ``n_bytes`` is the size of the complete text — more than ``capacity`` means it was cut (call again with
+    that capacity), -1 means a finite value of magnitude >= 2^128 was met."""
+    lib = _lib.load()
+    if values.dim() != 2:
+        raise ValueError(f"values must be [rows, cols], got {tuple(values.shape)}")
+    if values.dtype not in (torch.float32, torch.float64):
+        raise TypeError(f"values must be float32 or float64, got {values.dtype}")
+    _dev(values, values.dtype, "values")
+    rows, cols = values.shape
+    if n_rows is not None:
+        _dev(n_rows, torch.int64, "n_rows")
+    dev = values.device
+    if out is not None:
+        _dev(out, torch.uint8, "out")
+        capacity = out.numel()
+    elif capacity is None:
+        # typical line: "-123.456789 " = 12 bytes per value; the caller retries with n_bytes if that was short
+        capacity = rows * cols * 14 + 64
+    if out is None:
+        out = torch.empty((capacity,), dtype=torch.uint8, device=dev)
+    n_bytes = torch.empty((1,), dtype=torch.int64, device=dev)
+    split = None
+    if split_rows > 0:
+        split = torch.zeros(((rows + split_rows - 1) // split_rows,), dtype=torch.int64, device=dev)
+    ws_bytes = lib.cspe_text_workspace_bytes(rows, cols)
+    ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cspe_format_fixed6(values.data_ptr(), 1 if values.dtype == torch.float64 else 0, rows, _ptr(n_rows),
+                                    cols, header.encode("utf-8") if header is not None else None, out.data_ptr(),
+                                    capacity, n_bytes.data_ptr(), split_rows, _ptr(split), ws.data_ptr(), _stream_ptr())
+    _lib.check("cspe_format_fixed6", rc)
+    return out, n_bytes, split
+
+
+def savetxt_bytes(values: torch.Tensor, n_rows: Optional[torch.Tensor] = None, header: Optional[str] = None) -> bytes:
+    """Complete ``np.savetxt(fmt='%.6f', delimiter=' ')`` text of a device matrix as host bytes (synchronises)."""
+    text, n_bytes, _ = format_fixed6(values, n_rows, header)
+    need = int(n_bytes.item())
+    if need < 0:
+        raise ValueError("format_fixed6: a finite value of magnitude >= 2^128 cannot be formatted")
+    if need > text.numel():
+        text, n_bytes, _ = format_fixed6(values, n_rows, header, capacity=need)
+    return text[:need].cpu().numpy().tobytes()
+
+
 def depth_colormap(depth: torch.Tensor, lut_bgr: torch.Tensor, stats: Optional[torch.Tensor] = None) -> torch.Tensor:
     """f4: depth f32 [B,H,W] + colour LUT u8 [256,3] (BGR) -> u8 [B,H,W,3]; stats from depth_stats if not given."""
     lib = _lib.load()

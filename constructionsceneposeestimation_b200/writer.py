@@ -64,6 +64,7 @@ class BatchLabels:
     _depth_stats_host: Optional[torch.Tensor] = None
     _depth_viz_host: Optional[torch.Tensor] = None
     _synced: bool = False
+    rgb_images: Optional[List[Optional[ArrayLike]]] = None   # per-frame RGB(A) for the point-cloud file
 
     def synchronize(self) -> "BatchLabels":
         if not self._synced:
@@ -139,7 +140,10 @@ class ConstructionLabelWriter:
     (``labels/`` as gcd.py:40), clipping range (gcd.py:1437), and the run-time crane part map
     (gcd.py:124).  ``formats`` selects what ``write`` serialises: ``"json"`` (reference schema),
     ``"yolo"``, ``"coco"``, ``"mask"`` (the real instance mask instead of the reference's -1
-    placeholder, gcd.py:2066-2069), ``"depth_png"`` (JET depth image, gcd.py:1691-1709).  When a
+    placeholder, gcd.py:2066-2069), ``"depth_png"`` (JET depth image, gcd.py:1691-1709), ``"depth_csv"``
+    (``depth/depth_%06d.csv``, the np.savetxt text of gcd.py:1688) and ``"pointcloud"``
+    (``pointcloud/pointcloud_%06d.txt`` from depth + ``data["rgb"]``, gcd.py:1729-1759) — both texts are
+    formatted on the GPU (``cspe_format_fixed6``) and only their bytes cross PCIe.  When a
     frame carries ``distance_to_image_plane`` the depth-quality statistics of the reference's
     logger (gcd.py:314-359) are computed on the GPU and returned by ``BatchLabels.depth_quality``.
     """
@@ -214,6 +218,8 @@ class ConstructionLabelWriter:
         masks = None
         if "mask" in self.formats and self.output_dir is not None:
             masks = [_payload(fr.get("instance_segmentation")) for fr in frames]
+        if "pointcloud" in self.formats and self.output_dir is not None:
+            labels.rgb_images = [_payload(fr.get("rgb")) for fr in frames]
         self._pending.append((labels, masks))
         while len(self._pending) > self.max_pending:
             self._serialise(*self._pending.pop(0))
@@ -398,7 +404,9 @@ class ConstructionLabelWriter:
         labels = BatchLabels(frame_ids, tables, H, W, poses, params_list, rec_host, nout_host, event, kp_host,
                              vis_host, person_slots,
                              {"scan": scan, "uv": uv, "z": z, "pose": pose, "loose": loose, "flags": flags,
-                              "records": rec_dev, "n_out": n_out}, stats_host, viz_host)
+                              "records": rec_dev, "n_out": n_out, "cam": d_cam,
+                              **({"depth": d_depth} if d_depth is not None and
+                                 {"depth_csv", "pointcloud"} & set(self.formats) else {})}, stats_host, viz_host)
         if not contiguous_ids:
             labels.synchronize()
             for f in range(B):  # frame field was written relative to 0
@@ -459,8 +467,68 @@ class ConstructionLabelWriter:
         humans = [o.inst_idx for o in t.objects if o.class_name == "human"]
         return [humans[p] if p < len(humans) else -1 for p in range(num_people)]
 
+    # ------------------------------------------------------------------ device-formatted text files
+    def _host_bytes(self, text: torch.Tensor, begin: int, end: int) -> memoryview:
+        """text[begin:end] (device u8) through a grow-only pinned buffer; valid until the next call."""
+        n = end - begin
+        buf = getattr(self, "_text_host", None)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty((max(n, 1 << 20),), dtype=torch.uint8, pin_memory=True)
+            self._text_host = buf
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            buf[:n].copy_(text[begin:end], non_blocking=True)
+            self.stream.synchronize()
+        return memoryview(buf.numpy())[:n]
+
+    def _write_depth_csv(self, labels: BatchLabels, chunk: int = 8) -> None:
+        """gcd.py:1687-1688: depth/depth_%06d.csv, a few frames per formatting call."""
+        depth = labels.device_outputs.get("depth")
+        if depth is None:
+            return
+        ddir = os.path.join(self.output_dir, "depth")
+        os.makedirs(ddir, exist_ok=True)
+        B, H, W = depth.shape
+        for f0 in range(0, B, chunk):
+            nb = min(chunk, B - f0)
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                text, n_bytes, split = ops.format_fixed6(depth[f0:f0 + nb].reshape(nb * H, W), split_rows=H)
+                total = int(n_bytes.item())
+                offs = split.cpu().tolist() + [total]
+            if total > text.numel():
+                raise RuntimeError(f"depth CSV text of {total} bytes exceeds the {text.numel()} byte estimate")
+            for k in range(nb):
+                with open(os.path.join(ddir, f"depth_{labels.frame_ids[f0 + k]:06d}.csv"), "wb") as fh:
+                    fh.write(self._host_bytes(text, offs[k], offs[k + 1]))
+
+    def _write_pointcloud(self, labels: BatchLabels, f: int) -> Optional[int]:
+        """gcd.py:1729-1759: pointcloud/pointcloud_%06d.txt from the depth map and the RGB image; returns the
+        number of points (None when the frame has no depth)."""
+        depth = labels.device_outputs.get("depth")
+        if depth is None:
+            return None
+        rgb = labels.rgb_images[f] if labels.rgb_images is not None else None
+        pdir = os.path.join(self.output_dir, "pointcloud")
+        os.makedirs(pdir, exist_ok=True)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            d_rgb = None
+            if rgb is not None:
+                d_rgb = rgb if isinstance(rgb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rgb))
+                d_rgb = d_rgb.to(self.device, non_blocking=True).contiguous()
+            pts, n = ops.depth_to_pointcloud(depth[f], d_rgb, labels.device_outputs["cam"][f])
+            text, n_bytes, _ = ops.format_fixed6(pts, n_rows=n, header="x y z r g b")
+            total, points = int(n_bytes.item()), int(n.item())
+            if total > text.numel():
+                text, n_bytes, _ = ops.format_fixed6(pts, n_rows=n, header="x y z r g b", capacity=total)
+        if points == 0:   # the reference saves nothing for an empty cloud (gcd.py:1749)
+            return 0
+        with open(os.path.join(pdir, f"pointcloud_{labels.frame_ids[f]:06d}.txt"), "wb") as fh:
+            fh.write(self._host_bytes(text, 0, total))
+        return points
+
     def _serialise(self, labels: BatchLabels, masks: Optional[List[ArrayLike]]) -> None:
         labels.synchronize()
+        if "depth_csv" in self.formats and self.output_dir is not None:
+            self._write_depth_csv(labels)
         for f in range(len(labels)):
             fid = labels.frame_ids[f]
             recs = labels.records(f)
@@ -481,6 +549,9 @@ class ConstructionLabelWriter:
                     m = masks[f]
                     m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
                     np.save(os.path.join(ldir, f"instance_mask_{fid:06d}.npy"), m.astype(np.int32, copy=False))
+            points = None
+            if "pointcloud" in self.formats and self.output_dir is not None:
+                points = self._write_pointcloud(labels, f)
             if "coco" in self.formats:
                 self._coco_images.append(formats.coco_image(fid, labels.width, labels.height, f"rgb_{fid:06d}.png"))
                 self._coco_annotations += formats.coco_annotations(recs, fid, len(self._coco_annotations) + 1,
@@ -491,6 +562,8 @@ class ConstructionLabelWriter:
             if self.quality is not None:   # the events of gcd.py:1567, 1684 / 1711, 2075, 2078
                 self.quality.frame_start(fid, list(labels.camera_poses[f][:3]))
                 self.quality.depth(dq, reason="annotator返回None或空")
+                if points is not None:   # gcd.py:1754
+                    self.quality.pointcloud(points > 0, points, "no valid depth pixel")
                 self.quality.labels(len(recs))
                 self.quality.frame_end(True)
             self.objects_total += len(recs)

@@ -251,6 +251,26 @@ int cspe_depth_colormap(const float* depth, int B, int H, int W, const cspe_dept
  * rgb uint8 [num_pixels][channels >= 3], bgr uint8 [num_pixels][3]. */
 int cspe_rgb_to_bgr(const uint8_t* rgb, int channels, int64_t num_pixels, uint8_t* bgr, void* stream);
 
+/* f3: "%.6f" text of a matrix, formatted on the device — the byte stream of
+ *   np.savetxt(path, depth_data, delimiter=' ', fmt='%.6f')                              gcd.py:1688
+ *   np.savetxt(path, xyzrgb, fmt='%.6f', delimiter=' ', header='x y z r g b', comments='') gcd.py:1752
+ * values: float32 or float64 [max_rows][cols] (dtype = CSPE_DTYPE_F32 / CSPE_DTYPE_F64);
+ * n_rows: device int64[1] = live rows (e.g. n_points of cspe_depth_to_pointcloud), or NULL = max_rows;
+ * header: HOST string of < 63 bytes without '\n', written first followed by '\n', or NULL;
+ * text: device char[capacity]; n_bytes: device int64[1] = size of the complete text (bytes past
+ *   capacity are dropped but counted; -1 = a finite |value| >= 2^128 was met, text undefined);
+ * split_rows > 0: split_offsets[k] (device int64[ceil(rows / split_rows)]) = byte offset of row
+ *   k * split_rows, so a [B*H][W] batch of depth maps is cut into B files;
+ * scratch: cspe_text_workspace_bytes(max_rows, cols) bytes, 8-byte aligned.
+ * Every finite value is rounded exactly (ties to even) like printf / Python; nan, inf, -inf are
+ * written as Python writes them. */
+#define CSPE_DTYPE_F32 0
+#define CSPE_DTYPE_F64 1
+size_t cspe_text_workspace_bytes(int64_t max_rows, int cols);
+int cspe_format_fixed6(const void* values, int dtype, int64_t max_rows, const int64_t* n_rows, int cols,
+                       const char* header, char* text, int64_t capacity, int64_t* n_bytes,
+                       int64_t split_rows, int64_t* split_offsets, void* workspace, void* stream);
+
 /* f3: host-side YOLO serialisation of a D2H record buffer (no CUDA; all pointers are HOST
  * pointers).  Formats the first `frames` frames of records_host [B][N] / n_out_host [B] as
  * "class cx cy w h\n" lines with six decimals — byte-identical to Python's

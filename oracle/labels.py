@@ -388,6 +388,23 @@ def depth_stats(depth_data: np.ndarray) -> Dict[str, object]:
 
 
 # ------------------------------------------------------------------------------------------
+# f3: the text files of the depth map and the point cloud  (gcd.py:1688, 1752-1753)
+# ------------------------------------------------------------------------------------------
+def savetxt_fixed6(values: np.ndarray, header: Optional[str] = None) -> bytes:
+    """The bytes the reference's own call writes: ``np.savetxt(path, depth_data, delimiter=' ', fmt='%.6f')``
+    (gcd.py:1688) and, with ``header='x y z r g b', comments=''``, the point-cloud file (gcd.py:1752-1753).
+    numpy is the implementation here exactly as it is in the reference, so this row needs no restatement."""
+    import io
+
+    buf = io.BytesIO()
+    if header is None:
+        np.savetxt(buf, values, delimiter=" ", fmt="%.6f")
+    else:
+        np.savetxt(buf, values, fmt="%.6f", delimiter=" ", header=header, comments="")
+    return buf.getvalue()
+
+
+# ------------------------------------------------------------------------------------------
 # f4: depth visualisation  (gcd.py:1691-1709) and RGB -> BGR (gcd.py:1671)
 # ------------------------------------------------------------------------------------------
 def jet_lut_bgr() -> np.ndarray:

@@ -776,3 +776,118 @@ def test_writer_single_frame_write_json_values(T, ops, tmp_path):
         assert np.allclose(obj["center"], r["pose"][7:10], rtol=1e-9) and np.allclose(obj["size"], r["pose"][10:13], rtol=1e-9)
         assert np.allclose(obj["bbox_3d_projected"], r["uv"], rtol=0, atol=helpers.PX_ATOL)
         assert abs(obj["occlusion"] - float(r["occlusion"])) <= 1e-6
+
+
+# ------------------------------------------------------------------ f3: "%.6f" text on the device
+def _nasty_doubles(rng, n):
+    """Values that exercise every branch of the decimal rounding: ties, carries, signs, huge, tiny, specials."""
+    base = [0.0, -0.0, 1 / 128, 3 / 128, -5 / 128, 0.9999995, 0.9999994999, 9.9999996, 99999.9999995, 1e-7, -1e-9,
+            5e-7, 4.9999999e-7, 1e15, 2.0 ** 52, 2.0 ** 53 + 2, 2.0 ** 63, 2.0 ** 64, 2.0 ** 100, -1.5 * 2.0 ** 127,
+            123456789.1234565, 5e-324, np.inf, -np.inf, np.nan, 255.0, 249.999999, 1e19, 9.5, 10.0 - 2 ** -40]
+    ties = rng.integers(-10 ** 7, 10 ** 7, n // 4) / 128.0 / (2.0 ** rng.integers(0, 7, n // 4))
+    bits = rng.integers(0, 2 ** 63, n // 4, dtype=np.uint64) | (rng.integers(0, 2, n // 4, dtype=np.uint64) << np.uint64(63))
+    anyd = bits.view(np.float64)
+    anyd = np.where(np.isfinite(anyd) & (np.abs(anyd) >= 2.0 ** 128), 1.0 / anyd, anyd)   # keep the supported range
+    coords = rng.uniform(-300, 300, n - len(base) - 2 * (n // 4))
+    return np.concatenate([np.asarray(base), ties, anyd, coords])
+
+
+@pytest.mark.parametrize("cols", [1, 6, 7])
+def test_format_fixed6_f64_matches_numpy_savetxt(T, ops, cols):
+    """Byte-exact against the reference's own call np.savetxt(fmt='%.6f', delimiter=' ', header=…, comments='')."""
+    rng = np.random.default_rng(60 + cols)
+    rows = 3001
+    v = _nasty_doubles(rng, rows * cols)
+    rng.shuffle(v)
+    v = v.reshape(rows, cols)
+    want = O.savetxt_fixed6(v, "x y z r g b")
+    got = ops.savetxt_bytes(T.from_numpy(v).cuda(), header="x y z r g b")
+    assert got == want
+    # live row count from the device, no header, misaligned destination
+    n = T.tensor([1234], dtype=T.int64, device="cuda")
+    buf = T.zeros((len(want) + 64,), dtype=T.uint8, device="cuda")
+    text, n_bytes, _ = ops.format_fixed6(T.from_numpy(v).cuda(), n_rows=n, out=buf[5:])
+    want2 = O.savetxt_fixed6(v[:1234])
+    assert int(n_bytes.item()) == len(want2)
+    assert text[: len(want2)].cpu().numpy().tobytes() == want2
+    assert int(buf[:5].sum().item()) == 0 and int(buf[5 + len(want2):].sum().item()) == 0   # nothing outside the text
+
+
+def test_format_fixed6_depth_csv_batch(T, ops):
+    """gcd.py:1688: the depth CSV (f32 with inf holes); a [B*H][W] batch is cut into per-frame texts."""
+    from constructionsceneposeestimation_b200 import synthetic
+    frames = synthetic.make_batch(synthetic.SceneSpec(320, 180, 10, 0, 0, config_id=31), 3)
+    depth = np.stack([f["distance_to_image_plane"] for f in frames])
+    depth[1, 3, 4], depth[2, 0, 0], depth[0, 179, 319] = np.nan, 0.0, -np.inf
+    B, H, W = depth.shape
+    text, n_bytes, split = ops.format_fixed6(T.from_numpy(depth).cuda().view(B * H, W), split_rows=H)
+    total = int(n_bytes.item())
+    assert total <= text.numel()
+    host = text[:total].cpu().numpy().tobytes()
+    offs = split.cpu().numpy().tolist() + [total]
+    for f in range(B):
+        assert host[offs[f]: offs[f + 1]] == O.savetxt_fixed6(depth[f]), f
+
+
+def test_format_fixed6_edges(T, ops):
+    """Empty matrix, zero live rows, short capacity (size query + retry), unsupported magnitude."""
+    z = T.zeros((0, 6), dtype=T.float64, device="cuda")
+    assert ops.savetxt_bytes(z, header="x y z r g b") == O.savetxt_fixed6(np.zeros((0, 6)), "x y z r g b")
+    assert ops.savetxt_bytes(z) == b""
+    v = np.arange(24, dtype=np.float64).reshape(4, 6) * 1.000001
+    d = T.from_numpy(v).cuda()
+    assert ops.savetxt_bytes(d, n_rows=T.zeros((1,), dtype=T.int64, device="cuda"), header="h") == b"h\n"
+    want = O.savetxt_fixed6(v)
+    text, n_bytes, _ = ops.format_fixed6(d, capacity=10)
+    assert int(n_bytes.item()) == len(want) and text.cpu().numpy().tobytes() == want[:10]   # cut, but counted
+    big = T.tensor([[1.0, 2.0 ** 128]], dtype=T.float64, device="cuda")
+    _, n_bytes, _ = ops.format_fixed6(big)
+    assert int(n_bytes.item()) == -1
+    with pytest.raises(ValueError):
+        ops.savetxt_bytes(big)
+    f32 = T.tensor([[3.4028235e38, -1e-45, 0.1]], dtype=T.float32, device="cuda")       # every finite f32 is supported
+    assert ops.savetxt_bytes(f32) == O.savetxt_fixed6(f32.cpu().numpy())
+
+
+def test_pointcloud_text_file(T, ops):
+    """gcd.py:1752-1753: the point-cloud text = savetxt of the device points, count taken from the device."""
+    from constructionsceneposeestimation_b200 import synthetic, camera
+    fr = synthetic.make_frame(synthetic.SceneSpec(320, 180, 12, 2, 17, config_id=6, with_rgb=True), 1)
+    cam = T.from_numpy(camera.pack_camera(fr["camera_pose"], fr["camera_params"])).cuda()
+    pts, n = ops.depth_to_pointcloud(T.from_numpy(fr["distance_to_image_plane"]).cuda(), T.from_numpy(fr["rgb"]).cuda(), cam)
+    got = ops.savetxt_bytes(pts, n_rows=n, header="x y z r g b")
+    host = pts[: int(n.item())].cpu().numpy()
+    assert got == O.savetxt_fixed6(host, "x y z r g b")
+
+
+def test_writer_depth_csv_and_pointcloud_files(T, ops, tmp_path):
+    """depth/depth_%06d.csv (gcd.py:1688) and pointcloud/pointcloud_%06d.txt (gcd.py:1752-1753) written from
+    device-formatted text; the quality summary counts the clouds (gcd.py:1754)."""
+    import json
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(320, 180, 12, 2, 17, config_id=6, with_rgb=True), 3, first_frame=40)
+    frames[2] = dict(frames[2])
+    frames[2]["distance_to_image_plane"] = np.full((180, 320), np.inf, dtype=np.float32)     # nothing valid: no cloud file
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "depth_csv", "pointcloud"), split_people=True)
+    w.write_batch(frames)
+    summary = w.on_final_frame()
+    for k, fr in enumerate(frames):
+        fid = fr["frame_id"]
+        assert (tmp_path / "depth" / f"depth_{fid:06d}.csv").read_bytes() == O.savetxt_fixed6(fr["distance_to_image_plane"])
+        pc_file = tmp_path / "pointcloud" / f"pointcloud_{fid:06d}.txt"
+        want = O.depth_to_pointcloud(fr["distance_to_image_plane"], fr["rgb"], fr["camera_params"], fr["camera_pose"])
+        if k == 2:
+            assert len(want) == 0 and not pc_file.exists()
+            continue
+        text = pc_file.read_bytes()
+        assert text.startswith(b"x y z r g b\n") and text.count(b"\n") == len(want) + 1
+        got = np.loadtxt(pc_file, skiprows=1).reshape(-1, 6)
+        assert np.array_equal(got[:, 3:], want[:, 3:])
+        assert np.allclose(got[:, :3], want[:, :3], rtol=helpers.REL_TOL, atol=1e-6)     # six decimals
+    q = summary["quality"]
+    assert q["pointcloud_stats"] == {"valid": 2, "empty": 1, "insufficient": 0}
+    assert q["depth_stats"]["all_inf"] == 1 and q["depth_stats"]["valid"] == 2
+    logs = json.loads((tmp_path / "logs" / "generation_summary.json").read_text(encoding="utf-8"))["frame_logs"]
+    assert logs[0]["pointcloud"]["points"] == len(O.depth_to_pointcloud(frames[0]["distance_to_image_plane"], frames[0]["rgb"],
+                                                                        frames[0]["camera_params"], frames[0]["camera_pose"]))

@@ -44,3 +44,29 @@ ms = timed(lambda: lib.cspe_depth_to_pointcloud(d0.data_ptr(), rgb0.data_ptr(), 
 npts = int(n.item()); byts = H * W * 4 + H * W * 4 + npts * 48   # depth + rgba read once, points written
 print(json.dumps({"case": "f1 depth_to_pointcloud one 1080p frame", "ms": round(ms, 4), "points": npts,
                   "algorithmic_GB/s": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / PEAK, 3)}))
+# ---- f3: "%.6f" text of the point cloud and of the depth map (gcd.py:1752, 1688) --------------------
+import time
+tws = torch.empty((lib.cspe_text_workspace_bytes(H * W, 6) + 7) // 8, dtype=torch.int64, device=dev)
+text = torch.empty((npts * 6 * 14 + 64,), dtype=torch.uint8, device=dev); nb = torch.empty(1, dtype=torch.int64, device=dev)
+ms = timed(lambda: lib.cspe_format_fixed6(out.data_ptr(), 1, H * W, n.data_ptr(), 6, b"x y z r g b", text.data_ptr(), text.numel(),
+                                          nb.data_ptr(), 0, None, tws.data_ptr(), s))
+size = int(nb.item())
+sample = out[:20000].cpu().numpy()
+t0 = time.perf_counter(); ref = O.savetxt_fixed6(sample, "x y z r g b"); cpu_s = (time.perf_counter() - t0) * npts / len(sample)
+assert text[: len(ref)].cpu().numpy().tobytes() == ref
+print(json.dumps({"case": "f3 point-cloud text, one 1080p frame (np.savetxt bytes)", "ms": round(ms, 4), "points": npts,
+                  "text_MB": round(size / 1e6, 1), "text_GB/s": round(size / ms / 1e6, 1),
+                  "values_per_s": round(npts * 6 / ms * 1e3), "numpy_savetxt_s_per_frame_extrapolated": round(cpu_s, 2)}))
+Bc = 8
+dcsv = depth[:Bc].contiguous().view(Bc * H, W)
+tws2 = torch.empty((lib.cspe_text_workspace_bytes(Bc * H, W) + 7) // 8, dtype=torch.int64, device=dev)
+text2 = torch.empty((Bc * H * W * 14 + 64,), dtype=torch.uint8, device=dev)
+split = torch.empty((Bc,), dtype=torch.int64, device=dev)
+ms = timed(lambda: lib.cspe_format_fixed6(dcsv.data_ptr(), 0, Bc * H, None, W, None, text2.data_ptr(), text2.numel(), nb.data_ptr(),
+                                          H, split.data_ptr(), tws2.data_ptr(), s))
+size = int(nb.item())
+t0 = time.perf_counter(); ref = O.savetxt_fixed6(depth[0, :64].cpu().numpy()); cpu_s = (time.perf_counter() - t0) * H / 64
+assert text2[: len(ref)].cpu().numpy().tobytes() == ref
+print(json.dumps({"case": f"f3 depth CSV text, {Bc} x 1080p frames in one call", "ms": round(ms, 4), "ms_per_frame": round(ms / Bc, 4),
+                  "text_MB_per_frame": round(size / Bc / 1e6, 1), "text_GB/s": round(size / ms / 1e6, 1),
+                  "values_per_s": round(Bc * H * W / ms * 1e3), "numpy_savetxt_s_per_frame_extrapolated": round(cpu_s, 2)}))
