@@ -51,19 +51,44 @@ enum : int { kFinite = 0, kWide = 1, kNan = 2, kInf = 3, kTooLarge = 4 };
 
 struct Fixed6 {
   unsigned long long ip;  // integer part (kFinite)
-  unsigned int frac;      // six decimals, 0..999999
+  unsigned long long fm;  // fraction = fm / 2^s (before rounding)
+  unsigned int frac;      // six decimals, 0..999999 (after round_fixed6)
+  int s;
   int kind;
   bool neg;
 };
 
-// Exact decimal rounding of a double to six places: x = m * 2^E with integer m < 2^53; the
-// integer part is a shift, the six decimals are round-half-even((m mod 2^s) * 10^6 / 2^s).
-__device__ __forceinline__ Fixed6 decode_fixed6(double x) {
+__constant__ unsigned long long kPow10[20] = {1ull,
+                                              10ull,
+                                              100ull,
+                                              1000ull,
+                                              10000ull,
+                                              100000ull,
+                                              1000000ull,
+                                              10000000ull,
+                                              100000000ull,
+                                              1000000000ull,
+                                              10000000000ull,
+                                              100000000000ull,
+                                              1000000000000ull,
+                                              10000000000000ull,
+                                              100000000000000ull,
+                                              1000000000000000ull,
+                                              10000000000000000ull,
+                                              100000000000000000ull,
+                                              1000000000000000000ull,
+                                              10000000000000000000ull};
+
+// x = m * 2^E with integer m < 2^53: the integer part is a shift, the fraction is the s = -E low
+// bits of m.  No rounding yet.
+__device__ __forceinline__ Fixed6 split_fixed6(double x) {
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(x));
   Fixed6 r;
   r.neg = (bits >> 63) != 0;
   r.ip = 0;
+  r.fm = 0;
   r.frac = 0;
+  r.s = 0;
   r.kind = kFinite;
   const int be = static_cast<int>((bits >> 52) & 0x7ffu);
   unsigned long long m = bits & ((1ull << 52) - 1);
@@ -84,33 +109,60 @@ __device__ __forceinline__ Fixed6 decode_fixed6(double x) {
       r.kind = E <= 75 ? kWide : kTooLarge;
     return r;
   }
-  const int s = -E;  // 1..1074 fraction bits
-  unsigned long long fm = m;
-  if (s < 64) {
-    r.ip = m >> s;
-    fm = m & ((1ull << s) - 1);
+  r.s = -E;  // 1..1074 fraction bits
+  r.fm = m;
+  if (r.s < 64) {
+    r.ip = m >> r.s;
+    r.fm = m & ((1ull << r.s) - 1);
   }
-  if (s >= 75 || fm == 0) return r;  // fm * 10^6 < 2^73: the fraction rounds to .000000
+  return r;
+}
+
+// round-half-even(fm * 10^6 / 2^s) for 64 <= s < 75 (128-bit product; rare, kept out of line)
+__device__ __noinline__ unsigned long long round_tiny(unsigned long long fm, int s) {
+  const u128 P = static_cast<u128>(fm) * 1000000u;
+  const u128 qq = P >> s;
+  const u128 rem = P - (qq << s), half = static_cast<u128>(1) << (s - 1);
+  const unsigned long long q = static_cast<unsigned long long>(qq);
+  return q + ((rem > half || (rem == half && (q & 1))) ? 1 : 0);
+}
+
+// Six decimals of fm / 2^s, exactly rounded (ties to even); returns true when the fraction rounds up to
+// 1.000000, i.e. carries into the integer part.  Integer arithmetic only.
+__device__ __forceinline__ bool round_fixed6(unsigned long long fm, int s, unsigned int* frac) {
+  *frac = 0;
+  if (fm == 0) return false;
+  const int tz = __ffsll(static_cast<long long>(fm)) - 1;  // strip trailing zeros: float32 inputs lose 29 bits here
+  fm >>= tz;
+  s -= tz;
+  if (s >= 75) return false;  // fm * 10^6 < 2^73: rounds to .000000
   unsigned long long q;
   bool up;
-  if (s <= 44) {  // fm < 2^44: the product fits 64 bits
-    const unsigned long long P = fm * 1000000ull;
-    q = P >> s;
-    const unsigned long long rem = P & ((1ull << s) - 1), half = 1ull << (s - 1);
+  if (s <= 50) {
+    // one 64-bit product: fm * 10^6 < 2^64 for s <= 44, else fm * 15625 / 2^(s-6) (10^6 = 2^6 * 15625)
+    const int sh = s <= 44 ? s : s - 6;
+    const unsigned long long P = fm * (s <= 44 ? 1000000ull : 15625ull);
+    q = P >> sh;
+    const unsigned long long rem = P & ((1ull << sh) - 1), half = 1ull << (sh - 1);
+    up = rem > half || (rem == half && (q & 1));
+  } else if (s <= 63) {
+    const unsigned long long lo = fm * 1000000ull, hi = __umul64hi(fm, 1000000ull);
+    q = (hi << (64 - s)) | (lo >> s);
+    const unsigned long long rem = lo & ((1ull << s) - 1), half = 1ull << (s - 1);
     up = rem > half || (rem == half && (q & 1));
   } else {
-    const u128 P = static_cast<u128>(fm) * 1000000u;
-    const u128 qq = P >> s;
-    const u128 rem = P - (qq << s), half = static_cast<u128>(1) << (s - 1);
-    q = static_cast<unsigned long long>(qq);
-    up = rem > half || (rem == half && (q & 1));
+    q = round_tiny(fm, s);  // |x| < 2^-11
+    up = false;
   }
   q += up;
-  if (q == 1000000ull) {
-    q = 0;
-    ++r.ip;  // ip < 2^53: cannot overflow
-  }
-  r.frac = static_cast<unsigned int>(q);
+  if (q == 1000000ull) return true;
+  *frac = static_cast<unsigned int>(q);
+  return false;
+}
+
+__device__ __forceinline__ Fixed6 decode_fixed6(double x) {
+  Fixed6 r = split_fixed6(x);
+  if (r.kind == kFinite && round_fixed6(r.fm, r.s, &r.frac)) ++r.ip;  // ip < 2^53: cannot overflow
   return r;
 }
 
@@ -122,16 +174,31 @@ __device__ __noinline__ u128 wide_integer(double x) {
   return static_cast<u128>(m) << (be - 1075);
 }
 
-__device__ __forceinline__ int digits_u64(unsigned long long v) {
+__device__ __forceinline__ int digits_u32(unsigned int v) {
   int n = 1;
-  while (v >= 10000ull) {
-    v /= 10000ull;
+  if (v >= 100000000u) {
+    v /= 100000000u;
+    n += 8;
+  }
+  if (v >= 10000u) {
+    v /= 10000u;
     n += 4;
   }
-  if (v >= 1000ull) return n + 3;
-  if (v >= 100ull) return n + 2;
-  if (v >= 10ull) return n + 1;
-  return n;
+  if (v >= 100u) {
+    v /= 100u;
+    n += 2;
+  }
+  return n + (v >= 10u);
+}
+
+__device__ __forceinline__ int digits_u64(unsigned long long v) {
+  if ((v >> 32) == 0) return digits_u32(static_cast<unsigned int>(v));  // coordinates, depths, colours
+  int n = 0;
+  while (v >> 32) {
+    v /= 100000000ull;
+    n += 8;
+  }
+  return n + digits_u32(static_cast<unsigned int>(v));
 }
 
 __device__ __noinline__ int digits_u128(u128 v) {
@@ -144,18 +211,61 @@ __device__ __noinline__ int digits_u128(u128 v) {
   return n + digits_u64(static_cast<unsigned long long>(v));
 }
 
+__device__ __noinline__ int special_length(int kind, bool neg, double x) {
+  if (kind == kNan) return 3;
+  if (kind == kInf) return 3 + static_cast<int>(neg);
+  if (kind == kWide) return static_cast<int>(neg) + digits_u128(wide_integer(x)) + 7;
+  return 1;  // kTooLarge: the whole call is flagged; one '?' keeps the layout consistent
+}
+
 // length of the text of one value without its delimiter
 __device__ __forceinline__ int fixed6_length(const Fixed6& r, double x) {
   if (r.kind == kFinite) return static_cast<int>(r.neg) + digits_u64(r.ip) + 7;
-  if (r.kind == kNan) return 3;
-  if (r.kind == kInf) return 3 + static_cast<int>(r.neg);
-  if (r.kind == kWide) return static_cast<int>(r.neg) + digits_u128(wide_integer(x)) + 7;
-  return 1;  // kTooLarge: the whole call is flagged; one '?' keeps the layout consistent
+  return special_length(r.kind, r.neg, x);
+}
+
+// pass 1: the length needs the rounding only when a carry could add a digit (integer part 9, 99, 999 ...)
+__device__ __forceinline__ int fixed6_length_only(double x, bool* too_large) {
+  const Fixed6 r = split_fixed6(x);
+  if (r.kind == kFinite) {
+    int n = digits_u64(r.ip);
+    if (r.ip + 1 == kPow10[n]) {
+      unsigned int frac;
+      n += round_fixed6(r.fm, r.s, &frac);
+    }
+    return static_cast<int>(r.neg) + n + 7;
+  }
+  *too_large |= r.kind == kTooLarge;
+  return fixed6_length(r, x);
+}
+
+__device__ __noinline__ void special_put(char* p, int kind, bool neg, unsigned int frac, double x, int len) {
+  if (kind == kWide) {
+    char* e = p + len;
+    for (int i = 0; i < 6; ++i) {
+      *--e = static_cast<char>('0' + frac % 10u);
+      frac /= 10u;
+    }
+    *--e = '.';
+    u128 v = wide_integer(x);
+    do {
+      *--e = static_cast<char>('0' + static_cast<unsigned int>(v % 10u));
+      v /= 10u;
+    } while (v);
+    if (neg) *--e = '-';
+  } else if (kind == kNan) {
+    p[0] = 'n', p[1] = 'a', p[2] = 'n';
+  } else if (kind == kInf) {
+    if (neg) *p++ = '-';
+    p[0] = 'i', p[1] = 'n', p[2] = 'f';
+  } else {
+    p[0] = '?';
+  }
 }
 
 // write the text of one value (len characters, as fixed6_length says) at p
 __device__ __forceinline__ void fixed6_put(char* p, const Fixed6& r, double x, int len) {
-  if (r.kind == kFinite || r.kind == kWide) {
+  if (r.kind == kFinite) {
     char* e = p + len;  // write backwards
     unsigned int f = r.frac;
 #pragma unroll
@@ -164,30 +274,25 @@ __device__ __forceinline__ void fixed6_put(char* p, const Fixed6& r, double x, i
       f /= 10u;
     }
     *--e = '.';
-    if (r.kind == kFinite) {
-      unsigned long long v = r.ip;
-      do {
-        *--e = static_cast<char>('0' + static_cast<unsigned int>(v % 10ull));
-        v /= 10ull;
-      } while (v);
-    } else {
-      u128 v = wide_integer(x);
-      do {
-        *--e = static_cast<char>('0' + static_cast<unsigned int>(v % 10u));
-        v /= 10u;
-      } while (v);
+    unsigned long long v = r.ip;
+    while (v >> 32) {  // rare: peel eight digits at a time down to 32 bits
+      unsigned int lo = static_cast<unsigned int>(v % 100000000ull);
+      v /= 100000000ull;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        *--e = static_cast<char>('0' + lo % 10u);
+        lo /= 10u;
+      }
     }
+    unsigned int w = static_cast<unsigned int>(v);
+    do {
+      *--e = static_cast<char>('0' + w % 10u);
+      w /= 10u;
+    } while (w);
     if (r.neg) *--e = '-';
     return;
   }
-  if (r.kind == kNan) {
-    p[0] = 'n', p[1] = 'a', p[2] = 'n';
-  } else if (r.kind == kInf) {
-    if (r.neg) *p++ = '-';
-    p[0] = 'i', p[1] = 'n', p[2] = 'f';
-  } else {
-    p[0] = '?';
-  }
+  special_put(p, r.kind, r.neg, r.frac, x, len);
 }
 
 template <bool kF64>
@@ -217,11 +322,7 @@ __global__ void __launch_bounds__(kTxThreads)
   bool too_large = false;
 #pragma unroll
   for (int k = 0; k < kTxPerThread; ++k) {
-    if (base + k >= total) break;
-    const double x = load_value<kF64>(values, base + k);
-    const Fixed6 r = decode_fixed6(x);
-    too_large |= r.kind == kTooLarge;
-    len += fixed6_length(r, x) + 1;  // + ' ' or '\n'
+    if (base + k < total) len += fixed6_length_only(load_value<kF64>(values, base + k), &too_large) + 1;  // + ' ' or '\n'
   }
   if (too_large) atomicOr(&ws->flags, 1u);
   len = __reduce_add_sync(0xffffffffu, len);

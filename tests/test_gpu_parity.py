@@ -787,7 +787,8 @@ def _nasty_doubles(rng, n):
     ties = rng.integers(-10 ** 7, 10 ** 7, n // 4) / 128.0 / (2.0 ** rng.integers(0, 7, n // 4))
     bits = rng.integers(0, 2 ** 63, n // 4, dtype=np.uint64) | (rng.integers(0, 2, n // 4, dtype=np.uint64) << np.uint64(63))
     anyd = bits.view(np.float64)
-    anyd = np.where(np.isfinite(anyd) & (np.abs(anyd) >= 2.0 ** 128), 1.0 / anyd, anyd)   # keep the supported range
+    with np.errstate(over="ignore"):
+        anyd = np.where(np.isfinite(anyd) & (np.abs(anyd) >= 2.0 ** 128), 1.0 / anyd, anyd)   # keep the supported range
     coords = rng.uniform(-300, 300, n - len(base) - 2 * (n // 4))
     return np.concatenate([np.asarray(base), ties, anyd, coords])
 
@@ -878,7 +879,7 @@ def test_writer_depth_csv_and_pointcloud_files(T, ops, tmp_path):
         pc_file = tmp_path / "pointcloud" / f"pointcloud_{fid:06d}.txt"
         want = O.depth_to_pointcloud(fr["distance_to_image_plane"], fr["rgb"], fr["camera_params"], fr["camera_pose"])
         if k == 2:
-            assert len(want) == 0 and not pc_file.exists()
+            assert want is None and not pc_file.exists()          # the reference returns None / saves nothing
             continue
         text = pc_file.read_bytes()
         assert text.startswith(b"x y z r g b\n") and text.count(b"\n") == len(want) + 1
