@@ -892,3 +892,50 @@ def test_writer_depth_csv_and_pointcloud_files(T, ops, tmp_path):
     logs = json.loads((tmp_path / "logs" / "generation_summary.json").read_text(encoding="utf-8"))["frame_logs"]
     assert logs[0]["pointcloud"]["points"] == len(O.depth_to_pointcloud(frames[0]["distance_to_image_plane"], frames[0]["rgb"],
                                                                         frames[0]["camera_params"], frames[0]["camera_pose"]))
+
+
+# ------------------------------------------------------------------ kernels against the reference's own outputs
+GOLD = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+
+
+def test_kernels_against_reference_goldens(T, ops):
+    """No oracle in between: the fixtures under tests/golden were written by the reference's own functions
+    (bboxDict_to_transform gcd.py:553-584, depth_to_pointcloud_with_rgb gcd.py:616-711, DataQualityLogger.log_depth
+    gcd.py:314-359) executed by tests/golden/make_golden.py."""
+    import json
+    from constructionsceneposeestimation_b200 import _lib, camera
+    from constructionsceneposeestimation_b200.quality import depth_quality_from_stats
+    # R3 inside K2
+    g = np.load(GOLD / "bbox_to_transform.npz")
+    recs = g["records"][None]
+    cam = camera.pack_camera([1, 2, 3, 0.1, 0.2, 0.3, 0.9], camera.camera_params(1280, 720))[None]
+    _, _, pose, _, flags = _project_gpu(T, ops, recs, np.arange(recs.shape[1], dtype=np.int32)[None], cam)
+    assert np.all(flags[0] & _lib.OBJ_POSE_VALID)
+    assert np.allclose(pose[0, :, 7:10], g["center"], rtol=1e-6, atol=1e-9)
+    assert np.allclose(pose[0, :, 10:13], g["size"], rtol=1e-6, atol=1e-9)
+    de = np.abs(pose[0, :, 13:16] - g["euler"])
+    assert np.all(np.minimum(de, 360 - de) <= 1e-3)          # the reference's SVD runs in float32
+    # f1
+    g = np.load(GOLD / "pointcloud.npz")
+    params, pose7 = json.loads(str(g["params"])), list(g["pose"])
+    H, W = g["depth"].shape
+    for rgb, key, prm in ((g["rgb"], "out", params), (g["dark"], "out_dark", params), (g["rgb"], "out_defaults", {})):
+        # {} = the script's fallback aperture / focal length with the image size taken from the depth map (gcd.py:639-644)
+        d_cam = T.from_numpy(camera.pack_camera(pose7, prm or {"width": W, "height": H})).cuda()
+        pts, n = ops.depth_to_pointcloud(T.from_numpy(g["depth"]).cuda(), T.from_numpy(rgb).cuda(), d_cam)
+        got = pts[: int(n.item())].cpu().numpy()
+        assert got.shape == g[key].shape, key
+        assert np.array_equal(got[:, 3:], g[key][:, 3:]), key
+        assert np.allclose(got[:, :3], g[key][:, :3], rtol=helpers.REL_TOL, atol=1e-9), key
+    # f2
+    g = np.load(GOLD / "depth_stats.npz")
+    want = json.loads(str(g["results"]))
+    for name, ref in want.items():
+        st = ops.depth_stats(T.from_numpy(g[name]).cuda()[None]).cpu().numpy().view(_lib.DEPTH_STATS_DTYPE)[0]
+        got = depth_quality_from_stats(st)
+        assert list(got) == list(ref), name
+        for k in ref:
+            if k == "depth_mean":
+                assert abs(got[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k])), name
+            else:
+                assert got[k] == ref[k], (name, k)
