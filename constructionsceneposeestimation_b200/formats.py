@@ -80,6 +80,67 @@ def dump_label_json(label: Mapping, path) -> None:
         json.dump(label, f, indent=2, ensure_ascii=False)
 
 
+def nested_json(value, level: int = 1) -> bytes:
+    """``value`` as json.dump(indent=2, ensure_ascii=False) writes it ``level`` containers deep."""
+    text = json.dumps(value, indent=2, ensure_ascii=False)
+    return text.replace("\n", "\n" + "  " * level).encode("utf-8")
+
+
+_CLASS_MAPPING_JSON = None
+
+
+def slot_string_table(objects: Sequence[SceneObject]):
+    """(blob, int32 offsets [2 * N + 1]): per slot the JSON literals of class_name and prim_path."""
+    parts: List[bytes] = []
+    offsets = [0]
+    for o in objects:
+        for text in (o.class_name, o.prim_path):
+            parts.append(json.dumps(text, ensure_ascii=False).encode("utf-8"))
+            offsets.append(offsets[-1] + len(parts[-1]))
+    return b"".join(parts), np.asarray(offsets, dtype=np.int32)
+
+
+def label_json_bytes(frame_id: int, camera_pose: Sequence[float], camera_params: Mapping, height: int, width: int,
+                     records: np.ndarray, objects: Sequence[SceneObject], slot_strings=None,
+                     keypoints: Optional[np.ndarray] = None, visibility: Optional[np.ndarray] = None,
+                     person_slots: Optional[Sequence[int]] = None) -> bytes:
+    """Native formatter (libcspe ``cspe_format_label_json_host``): the UTF-8 text
+    ``json.dumps(reference_label(...), indent=2, ensure_ascii=False)`` gives, byte for byte, straight from
+    the D2H record buffer.  ``slot_strings`` caches ``slot_string_table(objects)``; ``keypoints`` f64 [P,J,2] /
+    ``visibility`` u8 [P,J] / ``person_slots`` (slot of person p, -1 = none) add the keypoint blocks."""
+    global _CLASS_MAPPING_JSON
+    from . import _lib
+
+    lib = _lib.load()
+    if _CLASS_MAPPING_JSON is None:
+        _CLASS_MAPPING_JSON = nested_json(dict(CLASS_TABLE))
+    blob, offsets = slot_strings if slot_strings is not None else slot_string_table(objects)
+    records = np.ascontiguousarray(records)
+    pose = np.ascontiguousarray(camera_pose, dtype=np.float64)
+    if pose.shape != (7,):
+        raise ValueError(f"camera_pose must have 7 entries, got shape {pose.shape}")
+    n, num_slots = len(records), len(objects)
+    kp_ptr = vis_ptr = pos_ptr = None
+    P = J = 0
+    if keypoints is not None and person_slots is not None:
+        keypoints = np.ascontiguousarray(keypoints, dtype=np.float64)
+        visibility = np.ascontiguousarray(visibility, dtype=np.uint8)
+        P, J = visibility.shape
+        person_of_slot = np.full(max(num_slots, 1), -1, dtype=np.int32)
+        for p_idx in range(min(P, len(person_slots))):
+            if 0 <= person_slots[p_idx] < num_slots:
+                person_of_slot[person_slots[p_idx]] = p_idx
+        kp_ptr, vis_ptr, pos_ptr = keypoints.ctypes.data, visibility.ctypes.data, person_of_slot.ctypes.data
+    cap = 4096 + len(_CLASS_MAPPING_JSON) + n * (2600 + 100 * J) + int(offsets[-1])
+    buf = np.empty(cap, dtype=np.uint8)
+    rc = lib.cspe_format_label_json_host(records.ctypes.data if n else None, n, int(frame_id), pose.ctypes.data,
+                                         nested_json(dict(camera_params)), _CLASS_MAPPING_JSON, blob,
+                                         offsets.ctypes.data, num_slots, int(height), int(width), kp_ptr, vis_ptr,
+                                         pos_ptr, P, J, buf.ctypes.data, cap)
+    _lib.check("cspe_format_label_json_host", rc)
+    return buf[:rc].tobytes()
+
+
 def yolo_lines(records: np.ndarray) -> List[str]:
     """``class cx cy w h`` normalised to the image, one line per kept object."""
     return [

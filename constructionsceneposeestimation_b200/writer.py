@@ -43,6 +43,7 @@ class FrameTables:
     lut_ids: np.ndarray         # int64 [K] instance ids that map to a slot
     lut_slots: np.ndarray       # int32 [K]
     max_id: int
+    slot_strings: Optional[Tuple[bytes, np.ndarray]] = None   # JSON literals of class_name / prim_path per slot (lazy)
 
 
 @dataclass
@@ -115,6 +116,18 @@ class BatchLabels:
         return formats.reference_label(self.frame_ids[f], self.camera_poses[f], self.camera_params[f], self.height,
                                        self.width, self.records(f), self.tables[f].objects,
                                        self.keypoints_by_slot(f))
+
+    def label_json(self, f: int) -> bytes:
+        """The text of ``label_%06d.json`` (= json.dumps(self.reference_label(f), indent=2, ensure_ascii=False)),
+        formatted natively from the D2H record buffer."""
+        t = self.tables[f]
+        if t.slot_strings is None:
+            t.slot_strings = formats.slot_string_table(t.objects)
+        kv = self.keypoints(f) if self.person_slots is not None else None
+        kp, vis = kv if kv is not None else (None, None)
+        return formats.label_json_bytes(self.frame_ids[f], self.camera_poses[f], self.camera_params[f], self.height,
+                                        self.width, self.records(f), t.objects, t.slot_strings, kp, vis,
+                                        self.person_slots[f] if kv is not None else None)
 
     def __len__(self) -> int:
         return len(self.frame_ids)
@@ -534,8 +547,9 @@ class ConstructionLabelWriter:
             recs = labels.records(f)
             if self.output_dir is not None:
                 ldir = os.path.join(self.output_dir, "labels")
-                if "json" in self.formats:
-                    formats.dump_label_json(labels.reference_label(f), os.path.join(ldir, f"label_{fid:06d}.json"))
+                if "json" in self.formats:   # gcd.py:2071-2072
+                    with open(os.path.join(ldir, f"label_{fid:06d}.json"), "wb") as fh:
+                        fh.write(labels.label_json(f))
                 if "yolo" in self.formats:
                     with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
                         fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))

@@ -280,6 +280,27 @@ int cspe_format_fixed6(const void* values, int dtype, int64_t max_rows, const in
 int64_t cspe_format_yolo_host(const cspe_record* records_host, const int32_t* n_out_host, int B, int N,
                               int frames, char* out_host, int64_t capacity, int64_t* offsets_host);
 
+/* f3: host-side label JSON of ONE frame (no CUDA; all pointers are HOST pointers) — the text
+ * json.dump(label, f, indent=2, ensure_ascii=False) writes (gcd.py:608-613) for the frame dict of
+ * gcd.py:2056-2064 with the object dicts of gcd.py:1938-1946 plus the added fields
+ * (formats.reference_label is the Python statement of the same layout).
+ * records_host[n]: the frame's kept records in inst_idx order (D2H buffer of cspe_emit);
+ * camera_params_json / class_mapping_json: the already serialised values of those two keys (nested
+ *   one level: continuation lines indented by two more spaces);
+ * slot_strings + slot_string_offsets[2 * num_slots + 1]: per slot the JSON string literals (quotes
+ *   and escapes included) of class_name, then prim_path;
+ * keypoints double [num_people][num_joints][2], visibility uint8 [num_people][num_joints],
+ *   person_of_slot int32 [num_slots] (-1 = no skeleton) — all three NULL when the frame has none.
+ * Floats are written as Python's repr(); non-finite label values as null where the Python path maps
+ * them to None.  Returns the number of bytes written or a negative CSPE_ERR_*. */
+int64_t cspe_format_label_json_host(const cspe_record* records_host, int n, int64_t frame_id,
+                                    const double* camera_pose7, const char* camera_params_json,
+                                    const char* class_mapping_json, const char* slot_strings,
+                                    const int32_t* slot_string_offsets, int num_slots, int height, int width,
+                                    const double* keypoints, const uint8_t* visibility,
+                                    const int32_t* person_of_slot, int num_people, int num_joints,
+                                    char* out_host, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -434,7 +434,9 @@ def test_writer_end_to_end(T, ops, tmp_path):
         helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
         kp, vis = labels.keypoints(f)
         assert np.array_equal(vis, o["vis"][f]) and np.allclose(kp, o["kp"][f], rtol=helpers.REL_TOL, atol=helpers.PX_ATOL)
-        lab = json.loads((tmp_path / "labels" / f"label_{f:06d}.json").read_text())
+        raw = (tmp_path / "labels" / f"label_{f:06d}.json").read_bytes()          # written by the native formatter
+        assert raw == json.dumps(labels.reference_label(f), indent=2, ensure_ascii=False).encode("utf-8")   # gcd.py:613
+        lab = json.loads(raw)
         assert list(lab)[:7] == ["frame_id", "camera_pose", "camera_params", "objects", "instance_mask_shape",
                                  "num_objects", "class_mapping"]                      # gcd.py:2056-2064
         assert lab["num_objects"] == int(o["n_out"][f]) == len(lab["objects"])

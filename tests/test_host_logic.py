@@ -267,3 +267,88 @@ def test_depth_quality_from_device_record_layout():
                 assert abs(got[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k]))
             else:
                 assert got[k] == ref[k], (name, k)
+
+
+# ------------------------------------------------------------------ f3: native label JSON (gcd.py:608-613, 2056-2064)
+def _random_records(rng, n, num_slots):
+    from constructionsceneposeestimation_b200 import _lib
+
+    recs = np.zeros(n, dtype=_lib.RECORD_DTYPE)
+    recs["inst_idx"] = np.sort(rng.choice(num_slots, n, replace=False))
+    recs["class_id"] = rng.integers(0, 10, n)
+    recs["count"] = rng.integers(0, 10 ** 6, n)
+    for k in ("x_min", "y_min", "x_max", "y_max"):
+        recs[k] = rng.integers(-1, 4000, n)
+    recs["loose"] = rng.integers(-5, 4000, (n, 4))
+    recs["flags"] = rng.integers(0, 16, n)
+    for k in ("occlusion", "fill", "truncation"):
+        recs[k] = rng.uniform(size=n).astype(np.float32)
+    # magnitudes across Python's fixed / exponent repr switch (1e-4, 1e16), integers, negative zero, specials
+    mag = 10.0 ** rng.integers(-12, 22, (n, 16))
+    recs["pose"] = rng.normal(size=(n, 16)) * mag
+    recs["uv"] = rng.uniform(-100, 4000, (n, 8, 2))
+    recs["z"] = np.round(rng.uniform(-5, 300, (n, 8)), 1)
+    if n > 8:
+        recs["pose"][0, :8] = [0.0, -0.0, 1e16, 9999999999999998.0, 1e-4, 0.00009999, 5e-324, 1.7976931348623157e308]
+        recs["pose"][1, 7], recs["pose"][1, 14], recs["uv"][2, 3, 0], recs["z"][3, 7] = np.nan, np.inf, -np.inf, np.nan
+        recs["pose"][4, :3] = [100.0, 123456.0, 1e15]
+        recs["occlusion"][5], recs["truncation"][6], recs["fill"][7] = np.nan, np.inf, 1.0
+    return recs
+
+
+def test_native_label_json_matches_python_json_dump(libcspe_path):
+    """cspe_format_label_json_host == json.dumps(reference_label(...), indent=2, ensure_ascii=False), byte for byte."""
+    from constructionsceneposeestimation_b200.classes import SceneObject
+
+    rng = np.random.default_rng(2026)
+    names = ["fence", "tree", 'we"ird\\name', "吊车\ttab", "ctl\x01\n", "human"]
+    objects = [SceneObject(inst_idx=i, class_id=i % 10, class_name=names[i % len(names)],
+                           prim_path=f"/World/锥/obj_{i:03d}/\"q\"") for i in range(40)]
+    pose = [1.5, -2.0, 3.25, 0.1, 0.2, 0.3, 0.9]
+    params = {"horizontal_aperture": 25.0, "vertical_aperture": 14.0625, "focal_length": 12.0, "width": 1280, "height": 720}
+    for n in (0, 1, 17, 40):
+        recs = _random_records(rng, n, 40)
+        want = json.dumps(formats.reference_label(7, pose, params, 720, 1280, recs, objects), indent=2, ensure_ascii=False)
+        assert formats.label_json_bytes(7, pose, params, 720, 1280, recs, objects) == want.encode("utf-8"), n
+    # keypoint blocks, unusual camera dicts and non-finite camera poses
+    recs = _random_records(rng, 12, 40)
+    P, J = 3, 5
+    kp = rng.uniform(-50, 2000, (P, J, 2))
+    vis = rng.integers(0, 3, (P, J)).astype(np.uint8)
+    kp[0, 1, 0], kp[2, 4, 1] = np.nan, np.inf
+    person_slots = [int(recs["inst_idx"][2]), -1, int(recs["inst_idx"][9])]
+    blocks = {s: formats.coco_keypoint_block(kp[p], vis[p]) for p, s in enumerate(person_slots) if s >= 0}
+    for prm, cam in ((params, pose), ({}, [np.nan, np.inf, -np.inf, 0, 0, 0, 1]), ({"k": [1, {"a": None}], "ü": "é"}, pose)):
+        want = json.dumps(formats.reference_label(123456, cam, prm, 2160, 3840, recs, objects, blocks), indent=2,
+                          ensure_ascii=False)
+        got = formats.label_json_bytes(123456, cam, prm, 2160, 3840, recs, objects, None, kp, vis, person_slots)
+        assert got == want.encode("utf-8")
+    with pytest.raises(Exception):
+        bad = recs.copy()
+        bad["inst_idx"][0] = 99
+        formats.label_json_bytes(0, pose, params, 720, 1280, bad, objects)
+
+
+def test_native_label_json_reproduces_reference_file():
+    """The golden text was written by the reference's own save_label_json (gcd.py:608-613)."""
+    from constructionsceneposeestimation_b200 import _lib
+    from constructionsceneposeestimation_b200.classes import SceneObject
+
+    gold = json.loads((GOLDEN / "label_schema.json").read_text(encoding="utf-8"))
+    lab, obj = gold["label"], gold["label"]["objects"][0]
+    rec = np.zeros(1, dtype=_lib.RECORD_DTYPE)
+    rec["inst_idx"], rec["class_id"], rec["flags"] = obj["inst_idx"], obj["class_id"], 15
+    rec["pose"][0, 7:10], rec["pose"][0, 10:13], rec["pose"][0, 13:16] = obj["center"], obj["size"], obj["rotation"]
+    objects = [SceneObject(inst_idx=0, class_id=obj["class_id"], class_name=obj["class_name"], prim_path=obj["prim_path"])]
+    ours = json.loads(formats.label_json_bytes(lab["frame_id"], lab["camera_pose"], lab["camera_params"],
+                                               *lab["instance_mask_shape"], rec, objects).decode("utf-8"))
+    # reference keys, in the reference's order, with the reference's values; our extra keys come after
+    assert list(ours)[:7] == list(lab)
+    for k in lab:
+        if k != "objects":
+            assert ours[k] == lab[k], k
+    assert list(ours["objects"][0])[:7] == list(obj) and all(ours["objects"][0][k] == obj[k] for k in obj)
+    # and the layout (indent=2, one element per line) is the reference file's: strip our added keys and compare text
+    trimmed = dict(ours)
+    trimmed["objects"] = [{k: ours["objects"][0][k] for k in obj}]
+    assert json.dumps(trimmed, indent=2, ensure_ascii=False) == gold["text"]
