@@ -24,24 +24,28 @@ void set_error(const char* fmt, ...);
 
 namespace {
 
+// Bounds are checked per object (see `room`), not per character: one record needs at most
+// kRecordBytes plus its two strings plus kJointBytes per joint.
+constexpr int64_t kFrameBytes = 4096;   // frame-level keys, camera pose, mask shape
+constexpr int64_t kRecordBytes = 4096;  // ~65 numbers of <= 40 bytes per line + ~20 keys
+constexpr int64_t kJointBytes = 128;    // three lines per joint
+const char kSpaces[] = "                                ";
+
 struct Out {
   char* p;
   char* end;
-  bool overflow = false;
 
+  bool room(int64_t n) const { return end - p >= n; }
   void raw(const char* s, size_t n) {
-    if (static_cast<size_t>(end - p) < n) {
-      overflow = true;
-      return;
-    }
     memcpy(p, s, n);
     p += n;
   }
   void lit(const char* s) { raw(s, strlen(s)); }
-  void ch(char c) { raw(&c, 1); }
+  void ch(char c) { *p++ = c; }
   void newline(int level) {
-    ch('\n');
-    for (int i = 0; i < level; ++i) raw("  ", 2);
+    *p++ = '\n';
+    memcpy(p, kSpaces, 16);  // level <= 5: at most ten spaces are kept
+    p += 2 * level;
   }
   void integer(long long v) {
     char b[24];
@@ -129,6 +133,13 @@ struct Out {
   }
 };
 
+int64_t too_small(int64_t capacity) {
+  cspe::set_error("cspe_format_label_json_host: output buffer of %lld bytes is too small (needs 4096 + fragments + "
+                  "per record 4096 + strings + 128 per joint)",
+                  static_cast<long long>(capacity));
+  return CSPE_ERR_INVALID_ARGUMENT;
+}
+
 }  // namespace
 
 extern "C" int64_t cspe_format_label_json_host(const cspe_record* records_host, int n, int64_t frame_id,
@@ -144,7 +155,9 @@ extern "C" int64_t cspe_format_label_json_host(const cspe_record* records_host, 
     cspe::set_error("cspe_format_label_json_host: invalid argument");
     return CSPE_ERR_INVALID_ARGUMENT;
   }
+  const int64_t fragments = static_cast<int64_t>(strlen(camera_params_json) + strlen(class_mapping_json));
   Out o{out_host, out_host + capacity};
+  if (!o.room(kFrameBytes + fragments)) return too_small(capacity);
   o.ch('{');
   o.key(1, "frame_id", true);
   o.integer(frame_id);
@@ -173,6 +186,12 @@ extern "C" int64_t cspe_format_label_json_host(const cspe_record* records_host, 
       }
       const bool valid = (r.flags & CSPE_OBJ_POSE_VALID) != 0;
       const int32_t* so = slot_string_offsets + 2 * r.inst_idx;
+      if (so[2] < so[1] || so[1] < so[0]) {
+        cspe::set_error("cspe_format_label_json_host: slot_string_offsets not ascending at slot %d", r.inst_idx);
+        return CSPE_ERR_INVALID_ARGUMENT;
+      }
+      if (!o.room(kFrameBytes + fragments + kRecordBytes + (so[2] - so[0]) + kJointBytes * num_joints))
+        return too_small(capacity);
       if (i) o.ch(',');
       o.newline(2);
       o.ch('{');
@@ -279,10 +298,5 @@ extern "C" int64_t cspe_format_label_json_host(const cspe_record* records_host, 
   o.lit(class_mapping_json);
   o.newline(0);
   o.ch('}');
-  if (o.overflow) {
-    cspe::set_error("cspe_format_label_json_host: output buffer of %lld bytes is too small",
-                    static_cast<long long>(capacity));
-    return CSPE_ERR_INVALID_ARGUMENT;
-  }
   return o.p - out_host;
 }

@@ -131,10 +131,12 @@ def label_json_bytes(frame_id: int, camera_pose: Sequence[float], camera_params:
             if 0 <= person_slots[p_idx] < num_slots:
                 person_of_slot[person_slots[p_idx]] = p_idx
         kp_ptr, vis_ptr, pos_ptr = keypoints.ctypes.data, visibility.ctypes.data, person_of_slot.ctypes.data
-    cap = 4096 + len(_CLASS_MAPPING_JSON) + n * (2600 + 100 * J) + int(offsets[-1])
+    params_json = nested_json(dict(camera_params))
+    # the bound the library checks: frame part + fragments + per record 4096 + its strings + 128 per joint
+    cap = 2 * 4096 + len(_CLASS_MAPPING_JSON) + len(params_json) + n * (4096 + 128 * J) + int(offsets[-1])
     buf = np.empty(cap, dtype=np.uint8)
     rc = lib.cspe_format_label_json_host(records.ctypes.data if n else None, n, int(frame_id), pose.ctypes.data,
-                                         nested_json(dict(camera_params)), _CLASS_MAPPING_JSON, blob,
+                                         params_json, _CLASS_MAPPING_JSON, blob,
                                          offsets.ctypes.data, num_slots, int(height), int(width), kp_ptr, vis_ptr,
                                          pos_ptr, P, J, buf.ctypes.data, cap)
     _lib.check("cspe_format_label_json_host", rc)

@@ -168,7 +168,8 @@ class ConstructionLabelWriter:
                  formats: Sequence[str] = ("json",), min_pixels: int = 1, keypoint_tolerance: float = 0.15,
                  near: float = DEFAULT_NEAR, far: float = DEFAULT_FAR, split_people: bool = False,
                  record_fallback: str = "first_mesh", crane_part_map: Optional[Mapping] = None,
-                 rank: int = 0, world_size: int = 1, max_pending: int = 2, quality_log: bool = True):
+                 rank: int = 0, world_size: int = 1, max_pending: int = 2, quality_log: bool = True,
+                 io_threads: Optional[int] = None):
         _lib.load()  # fail loudly right here if the CUDA library is missing
         if not torch.cuda.is_available():
             raise _lib.CspeLibraryError("ConstructionLabelWriter needs a CUDA device (no CPU fallback exists)")
@@ -182,6 +183,9 @@ class ConstructionLabelWriter:
         self.resolver = ObjectRootResolver(crane_part_map, split_people=split_people)
         self.rank, self.world_size = rank, world_size
         self.max_pending = max_pending
+        # per-frame files of a batch are formatted and written by a small thread pool
+        self.io_threads = min(16, os.cpu_count() or 1) if io_threads is None else max(1, int(io_threads))
+        self._io_pool = None
         self._tables_cache: Dict[Tuple, FrameTables] = {}
         self._next_frame_id = 0
         self._pending: List[Tuple[BatchLabels, Optional[List[np.ndarray]]]] = []
@@ -245,6 +249,9 @@ class ConstructionLabelWriter:
     def on_final_frame(self) -> Dict[str, object]:
         """Flush pending frames, gather the per-class histogram across ranks and write the summary."""
         self.flush()
+        if self._io_pool is not None:
+            self._io_pool.shutdown()
+            self._io_pool = None
         hist = self.gather_class_histogram()
         summary = {
             "frames": self.frames_written,
@@ -538,31 +545,49 @@ class ConstructionLabelWriter:
             fh.write(self._host_bytes(text, 0, total))
         return points
 
+    def _write_frame_files(self, labels: BatchLabels, f: int, masks: Optional[List[ArrayLike]]) -> None:
+        """The per-frame label files; runs on a worker thread (the native formatters, cv2.imwrite, np.save and
+        file writes all release the GIL)."""
+        fid = labels.frame_ids[f]
+        ldir = os.path.join(self.output_dir, "labels")
+        if "json" in self.formats:   # gcd.py:2071-2072
+            with open(os.path.join(ldir, f"label_{fid:06d}.json"), "wb") as fh:
+                fh.write(labels.label_json(f))
+        if "yolo" in self.formats:
+            recs = labels.records(f)
+            with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
+                fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))
+        if "depth_png" in self.formats and labels.depth_image(f) is not None:
+            import cv2
+
+            cv2.imwrite(os.path.join(self.output_dir, "depth", f"depth_{fid:06d}.png"), labels.depth_image(f))   # gcd.py:1703-1704
+        if "mask" in self.formats and masks is not None:
+            m = masks[f]
+            m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+            np.save(os.path.join(ldir, f"instance_mask_{fid:06d}.npy"), m.astype(np.int32, copy=False))
+
     def _serialise(self, labels: BatchLabels, masks: Optional[List[ArrayLike]]) -> None:
         labels.synchronize()
-        if "depth_csv" in self.formats and self.output_dir is not None:
-            self._write_depth_csv(labels)
-        for f in range(len(labels)):
+        B = len(labels)
+        if self.output_dir is not None:
+            if "depth_png" in self.formats:
+                os.makedirs(os.path.join(self.output_dir, "depth"), exist_ok=True)
+            if "depth_csv" in self.formats:
+                self._write_depth_csv(labels)
+            if self.io_threads > 1 and B > 1:
+                if self._io_pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+
+                    self._io_pool = ThreadPoolExecutor(max_workers=self.io_threads, thread_name_prefix="cspe-io")
+                for fut in [self._io_pool.submit(self._write_frame_files, labels, f, masks) for f in range(B)]:
+                    fut.result()   # re-raises a worker's exception here
+            else:
+                for f in range(B):
+                    self._write_frame_files(labels, f, masks)
+        # bookkeeping stays on the caller's thread, in frame order
+        for f in range(B):
             fid = labels.frame_ids[f]
             recs = labels.records(f)
-            if self.output_dir is not None:
-                ldir = os.path.join(self.output_dir, "labels")
-                if "json" in self.formats:   # gcd.py:2071-2072
-                    with open(os.path.join(ldir, f"label_{fid:06d}.json"), "wb") as fh:
-                        fh.write(labels.label_json(f))
-                if "yolo" in self.formats:
-                    with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
-                        fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))
-                if "depth_png" in self.formats and labels.depth_image(f) is not None:
-                    import cv2
-
-                    ddir = os.path.join(self.output_dir, "depth")
-                    os.makedirs(ddir, exist_ok=True)
-                    cv2.imwrite(os.path.join(ddir, f"depth_{fid:06d}.png"), labels.depth_image(f))   # gcd.py:1703-1704
-                if "mask" in self.formats and masks is not None:
-                    m = masks[f]
-                    m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
-                    np.save(os.path.join(ldir, f"instance_mask_{fid:06d}.npy"), m.astype(np.int32, copy=False))
             points = None
             if "pointcloud" in self.formats and self.output_dir is not None:
                 points = self._write_pointcloud(labels, f)
