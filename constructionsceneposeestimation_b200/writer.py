@@ -66,6 +66,7 @@ class BatchLabels:
     _depth_viz_host: Optional[torch.Tensor] = None
     _synced: bool = False
     rgb_images: Optional[List[Optional[ArrayLike]]] = None   # per-frame RGB(A) for the point-cloud file
+    _yolo: Optional[Tuple[np.ndarray, np.ndarray]] = None
 
     def synchronize(self) -> "BatchLabels":
         if not self._synced:
@@ -116,6 +117,16 @@ class BatchLabels:
         return formats.reference_label(self.frame_ids[f], self.camera_poses[f], self.camera_params[f], self.height,
                                        self.width, self.records(f), self.tables[f].objects,
                                        self.keypoints_by_slot(f))
+
+    def yolo_text(self, f: int) -> memoryview:
+        """``class cx cy w h`` lines of frame ``f`` (native formatter, one call per batch, cached)."""
+        if self._yolo is None:
+            self.synchronize()
+            B, N = self._rec_host.shape[0], self._rec_host.shape[1]
+            recs = self._rec_host.numpy().view(RECORD_DTYPE).reshape(B, N)
+            self._yolo = formats.yolo_text_batch(recs, self._nout_host.numpy())
+        buf, offsets = self._yolo
+        return memoryview(buf)[int(offsets[f]): int(offsets[f + 1])]
 
     def label_json(self, f: int) -> bytes:
         """The text of ``label_%06d.json`` (= json.dumps(self.reference_label(f), indent=2, ensure_ascii=False)),
@@ -554,9 +565,8 @@ class ConstructionLabelWriter:
             with open(os.path.join(ldir, f"label_{fid:06d}.json"), "wb") as fh:
                 fh.write(labels.label_json(f))
         if "yolo" in self.formats:
-            recs = labels.records(f)
-            with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "w", encoding="utf-8") as fh:
-                fh.write("\n".join(formats.yolo_lines(recs)) + ("\n" if len(recs) else ""))
+            with open(os.path.join(ldir, f"label_{fid:06d}.txt"), "wb") as fh:
+                fh.write(labels.yolo_text(f))
         if "depth_png" in self.formats and labels.depth_image(f) is not None:
             import cv2
 
@@ -574,6 +584,8 @@ class ConstructionLabelWriter:
                 os.makedirs(os.path.join(self.output_dir, "depth"), exist_ok=True)
             if "depth_csv" in self.formats:
                 self._write_depth_csv(labels)
+            if "yolo" in self.formats:
+                labels.yolo_text(0)   # format the whole batch once, before the workers slice it
             if self.io_threads > 1 and B > 1:
                 if self._io_pool is None:
                     from concurrent.futures import ThreadPoolExecutor

@@ -451,7 +451,9 @@ def test_writer_end_to_end(T, ops, tmp_path):
         import cv2
         png = cv2.imread(str(tmp_path / "depth" / f"depth_{f:06d}.png"))
         assert np.array_equal(png, O.depth_colormap(frames[f]["distance_to_image_plane"]))           # gcd.py:1691-1704
-        assert len((tmp_path / "labels" / f"label_{f:06d}.txt").read_text().splitlines()) == int(o["n_out"][f])
+        from constructionsceneposeestimation_b200 import formats as F
+        assert (tmp_path / "labels" / f"label_{f:06d}.txt").read_text().splitlines() == F.yolo_lines(labels.records(f))
+        assert len(F.yolo_lines(labels.records(f))) == int(o["n_out"][f])
     assert sum(summary["class_histogram"].values()) == int(o["n_out"].sum())
     assert summary["object_count"]["total"] == int(o["n_out"].sum()) and len(summary["depth_quality"]) == 3
     assert np.array_equal(np.asarray(summary["class_histogram_per_rank"])[0], o["hist"])
