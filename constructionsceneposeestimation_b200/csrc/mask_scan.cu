@@ -173,9 +173,6 @@ __device__ __forceinline__ int table_identity(int field) {
   return field == CSPE_SCAN_COUNT ? 0 : (field <= CSPE_SCAN_YMIN ? INT_MAX : -1);
 }
 
-
-
-
 // make `V` the MRU entry e0 (swap with e1, or evict e1)
 #define CSPE_SWITCH(V)                                                                  \
   do {                                                                                  \
