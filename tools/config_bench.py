@@ -7,13 +7,13 @@ import sys
 from pathlib import Path
 
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import cv2
 import numpy as np
 import torch
 
 from constructionsceneposeestimation_b200 import _lib, camera, ops, synthetic
 from constructionsceneposeestimation_b200.pipeline import LabelPipeline
-from oracle import labels as O
-from tests import helpers
+from constructionsceneposeestimation_b200.sweep import build_host_tables
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 dev = torch.device("cuda")
@@ -38,7 +38,7 @@ def out(**kw):
 
 
 def build_pipeline(frames, B, use_graph=False):
-    lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
+    lut, obj_record, slot_class, records, cam, _ = build_host_tables(frames)
     lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
     u = len(frames)
     rep = (B + u - 1) // u
@@ -78,7 +78,7 @@ del pipe
 for J in (17, 101):
     spec = synthetic.SceneSpec(1920, 1080, 60, 50, J, config_id=3)
     frames = synthetic.make_batch(spec, 8)
-    lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
+    lut, obj_record, slot_class, records, cam, _ = build_host_tables(frames)
     lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
     H, W = frames[0]["instance_segmentation"]["data"].shape
     N = obj_record.shape[1]
@@ -99,7 +99,7 @@ for J in (17, 101):
 
 # ---- next rows on c2-shaped data ------------------------------------------------------------------
 frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 8)
-lut, obj_record, *_ = helpers.host_tables(frames)
+lut, obj_record, *_ = build_host_tables(frames)
 N = obj_record.shape[1]
 mask = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(8, 1, 1)
 depth = torch.from_numpy(np.stack([f["distance_to_image_plane"] for f in frames])).to(dev).repeat(8, 1, 1)
@@ -111,7 +111,7 @@ fused_ms = timed(lambda: ops.mask_scan_depth_stats(mask, depth, lut_d, N))
 out(case="f2 depth statistics, 64 x 1080p", scan_ms=round(scan_ms, 4), depth_stats_alone_ms=round(stats_ms, 4),
     depth_stats_GBs=round(B * H * W * 4 / stats_ms / 1e6, 1), fused_scan_plus_stats_ms=round(fused_ms, 4),
     fused_GBs=round(2 * B * H * W * 4 / fused_ms / 1e6, 1), fused_frac=round(2 * B * H * W * 4 / fused_ms / 1e6 / PEAK, 3))
-lut_bgr = torch.from_numpy(np.ascontiguousarray(O.jet_lut_bgr())).to(dev)
+lut_bgr = torch.from_numpy(np.ascontiguousarray(cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(-1, 1), cv2.COLORMAP_JET).reshape(256, 3))).to(dev)
 st = ops.depth_stats(depth)
 cm_ms = timed(lambda: ops.depth_colormap(depth, lut_bgr, st))
 out(case="f4 depth colormap, 64 x 1080p", ms=round(cm_ms, 4), GBs=round(B * H * W * 7 / cm_ms / 1e6, 1))

@@ -5,10 +5,10 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 from constructionsceneposeestimation_b200 import synthetic, _lib
 from constructionsceneposeestimation_b200.pipeline import LabelPipeline
-from tests import helpers
+from constructionsceneposeestimation_b200.sweep import build_host_tables
 dev = torch.device("cuda")
 frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 8)
-lut, obj_record, slot_class, records, cam, _ = helpers.host_tables(frames)
+lut, obj_record, slot_class, records, cam, _ = build_host_tables(frames)
 lut = np.pad(lut, ((0, 0), (0, (-lut.shape[1]) % 4)), constant_values=-1)
 B = 64; H, W = frames[0]["instance_segmentation"]["data"].shape; N = obj_record.shape[1]
 pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], dev, use_graph=False)

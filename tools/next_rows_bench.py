@@ -5,7 +5,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 from constructionsceneposeestimation_b200 import _lib, camera, synthetic
-from oracle import labels as O
+import cv2, io
 dev = torch.device("cuda"); PEAK = 6454.3
 lib = _lib.load()
 frames = synthetic.make_batch(synthetic.CONFIGS["c2"], 8)
@@ -24,7 +24,7 @@ stats = torch.empty((B, 48), dtype=torch.uint8, device=dev)
 ms = timed(lambda: lib.cspe_depth_stats(depth.data_ptr(), B, H, W, stats.data_ptr(), s))
 print(json.dumps({"case": "f2 depth_stats 64x1080p (3 launches: init, reduce, finalize)", "ms": round(ms, 4),
                   "GB/s": round(B * H * W * 4 / ms / 1e6, 1), "frac": round(B * H * W * 4 / ms / 1e6 / PEAK, 3)}))
-lut = torch.from_numpy(np.ascontiguousarray(O.jet_lut_bgr())).to(dev)
+lut = torch.from_numpy(np.ascontiguousarray(cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(-1, 1), cv2.COLORMAP_JET).reshape(256, 3))).to(dev)
 img = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev)
 ms = timed(lambda: lib.cspe_depth_colormap(depth.data_ptr(), B, H, W, stats.data_ptr(), lut.data_ptr(), img.data_ptr(), s))
 print(json.dumps({"case": "f4 depth_colormap 64x1080p", "ms": round(ms, 4), "GB/s": round(B * H * W * 7 / ms / 1e6, 1),
@@ -52,7 +52,11 @@ ms = timed(lambda: lib.cspe_format_fixed6(out.data_ptr(), 1, H * W, n.data_ptr()
                                           nb.data_ptr(), 0, None, tws.data_ptr(), s))
 size = int(nb.item())
 sample = out[:20000].cpu().numpy()
-t0 = time.perf_counter(); ref = O.savetxt_fixed6(sample, "x y z r g b"); cpu_s = (time.perf_counter() - t0) * npts / len(sample)
+def savetxt(a, header=None):   # the reference's own calls, gcd.py:1688 / 1752
+    b = io.BytesIO()
+    np.savetxt(b, a, delimiter=" ", fmt="%.6f") if header is None else np.savetxt(b, a, fmt="%.6f", delimiter=" ", header=header, comments="")
+    return b.getvalue()
+t0 = time.perf_counter(); ref = savetxt(sample, "x y z r g b"); cpu_s = (time.perf_counter() - t0) * npts / len(sample)
 assert text[: len(ref)].cpu().numpy().tobytes() == ref
 print(json.dumps({"case": "f3 point-cloud text, one 1080p frame (np.savetxt bytes)", "ms": round(ms, 4), "points": npts,
                   "text_MB": round(size / 1e6, 1), "text_GB/s": round(size / ms / 1e6, 1),
@@ -65,7 +69,7 @@ split = torch.empty((Bc,), dtype=torch.int64, device=dev)
 ms = timed(lambda: lib.cspe_format_fixed6(dcsv.data_ptr(), 0, Bc * H, None, W, None, text2.data_ptr(), text2.numel(), nb.data_ptr(),
                                           H, split.data_ptr(), tws2.data_ptr(), s))
 size = int(nb.item())
-t0 = time.perf_counter(); ref = O.savetxt_fixed6(depth[0, :64].cpu().numpy()); cpu_s = (time.perf_counter() - t0) * H / 64
+t0 = time.perf_counter(); ref = savetxt(depth[0, :64].cpu().numpy()); cpu_s = (time.perf_counter() - t0) * H / 64
 assert text2[: len(ref)].cpu().numpy().tobytes() == ref
 print(json.dumps({"case": f"f3 depth CSV text, {Bc} x 1080p frames in one call", "ms": round(ms, 4), "ms_per_frame": round(ms / Bc, 4),
                   "text_MB_per_frame": round(size / Bc / 1e6, 1), "text_GB/s": round(size / ms / 1e6, 1),

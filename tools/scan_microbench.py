@@ -4,7 +4,7 @@ from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import numpy as np, torch
 from constructionsceneposeestimation_b200 import ops, synthetic
-from tests import helpers
+from constructionsceneposeestimation_b200.sweep import build_host_tables
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 which = sys.argv[2].split(",") if len(sys.argv) > 2 else ["zeros", "c2", "noise16", "c4"]
@@ -35,7 +35,7 @@ if "c2" in which:
     import os
     uniq = int(os.environ.get("CSPE_MICRO_UNIQUE", "16"))
     frames = synthetic.make_batch(synthetic.CONFIGS["c2"], uniq)
-    lut, obj_record, *_ = helpers.host_tables(frames)
+    lut, obj_record, *_ = build_host_tables(frames)
     m = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(64 // uniq, 1, 1)
     l = torch.from_numpy(lut).to(dev).repeat(64 // uniq, 1)
     timeit(m, l, obj_record.shape[1], "synthetic c2 64x1080p")
@@ -49,7 +49,7 @@ if "noise16" in which:
     del m, g
 if "c4" in which:
     frames = synthetic.make_batch(synthetic.CONFIGS["c4"], 4)
-    lut, obj_record, *_ = helpers.host_tables(frames)
+    lut, obj_record, *_ = build_host_tables(frames)
     m = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(4, 1, 1)
     l = torch.from_numpy(lut).to(dev).repeat(4, 1)
     timeit(m, l, obj_record.shape[1], "synthetic c4 16x2160p")
