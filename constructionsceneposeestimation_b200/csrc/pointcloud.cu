@@ -7,15 +7,15 @@
 // RGB gather with the "max <= 1 -> x255" rule (gcd.py:691-696); ROW-MAJOR STABLE compaction
 // into (N, 6) float64.
 //
-// HBM-bound on the OUTPUT: 48 bytes written per valid pixel against 4 (depth, read twice) + C
-// (rgb) bytes read.  Four launches chained by programmatic dependent launch:
-//   1. per-tile (1024 px) valid counts;
-//   2. one-CTA exclusive scan of the tile counts -> tile offsets, total;
-//   3. per tile: recompute validity, in-tile ranks, build the tile's points in shared memory and
+// HBM-bound on the OUTPUT: 48 bytes written per valid pixel against 4 (depth) + C (rgb) bytes read,
+// both read twice.  Two launches chained by programmatic dependent launch (a single 1080p frame is
+// latency-bound, every launch costs):
+//   1. per tile (1024 px): valid count and the maximum colour over valid pixels; the LAST CTA to
+//      finish (atomic ticket) scans the tile counts into tile offsets and the total;
+//   2. per tile: recompute validity, in-tile ranks, build the tile's points in shared memory and
 //      stream them out as one contiguous run of 16-byte stores (a thread writing its own 48-byte
-//      points directly costs ~6x the sector traffic); colours are written as they are and the
-//      maximum colour over valid pixels is reduced on the side;
-//   4. only if that maximum is <= 1 (the reference's [0,1]-image rule): scale the colours by 255.
+//      points directly costs ~6x the sector traffic); colours are scaled by 255 when the maximum
+//      found by pass 1 is <= 1 (the reference's [0,1]-image rule, gcd.py:693).
 #include <math.h>
 
 #include "cspe_common.cuh"
@@ -29,8 +29,8 @@ constexpr int kPcTile = kPcThreads * kPcPerThread;  // 1024 pixels
 constexpr int kPcStageBytes = kPcTile * 48;          // a tile's points, 48 KB
 
 struct PcWorkspace {  // layout of the caller-provided scratch
-  unsigned int rgb_max;
-  unsigned int pad;
+  unsigned int rgb_max;  // maximum colour byte over valid pixels
+  unsigned int done;     // CTAs of pass 1 that have published their count (ticket for the last-CTA scan)
   long long total;
   // followed by: int64 tile_offset[tiles]; int32 tile_count[tiles]
 };
@@ -52,86 +52,118 @@ __device__ __forceinline__ void load4(const float* __restrict__ depth, long long
   }
 }
 
+// colours of the thread's four pixels: one 16-byte load for RGBA, byte loads otherwise
+__device__ __forceinline__ void load_rgb4(const uint8_t* __restrict__ rgb, int C, long long base, long long hw, bool vec,
+                                          uint32_t* px) {
+  if (vec && base + 3 < hw) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rgb + base * 4));
+    px[0] = v.x, px[1] = v.y, px[2] = v.z, px[3] = v.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) {
+      px[k] = 0;
+      if (base + k < hw) {
+        const uint8_t* c = rgb + (base + k) * C;
+        px[k] = static_cast<uint32_t>(c[0]) | (static_cast<uint32_t>(c[1]) << 8) | (static_cast<uint32_t>(c[2]) << 16);
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kPcThreads)
-    pc_count_kernel(const float* __restrict__ depth, long long hw, int vec, int32_t* tile_count) {
+    pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw, int vec,
+                    int rgb_vec, int32_t* tile_count, long long* tile_offset, int tiles, PcWorkspace* ws,
+                    long long* n_points) {
   pdl_launch_dependents();
   __shared__ int s_cnt[kPcThreads / 32];
+  __shared__ unsigned s_max[kPcThreads / 32];
+  __shared__ long long s_scan[kPcThreads / 32];
+  __shared__ long long s_base;
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
   float d[kPcPerThread];
   load4(depth, base, hw, vec, d);
   int cnt = 0;
+  unsigned mx = 0;
 #pragma unroll
   for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
+  if (rgb != nullptr && cnt) {
+    uint32_t px[kPcPerThread];
+    load_rgb4(rgb, C, base, hw, rgb_vec, px);
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k)
+      if (pc_valid(d[k])) mx = max(mx, max(px[k] & 255u, max((px[k] >> 8) & 255u, (px[k] >> 16) & 255u)));
+  }
   cnt = __reduce_add_sync(0xffffffffu, cnt);
-  if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = cnt;
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) {
+    s_cnt[wid] = cnt;
+    s_max[wid] = mx;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     int t = 0;
+    unsigned m = 0;
 #pragma unroll
-    for (int w = 0; w < kPcThreads / 32; ++w) t += s_cnt[w];
+    for (int w = 0; w < kPcThreads / 32; ++w) {
+      t += s_cnt[w];
+      m = max(m, s_max[w]);
+    }
     tile_count[blockIdx.x] = t;
-  }
-}
-
-__global__ void __launch_bounds__(1024) pc_scan_kernel(const int32_t* __restrict__ tile_count, long long* tile_offset,
-                                                      int tiles, PcWorkspace* ws, long long* n_points) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ long long s_warp[32];
-  __shared__ long long s_base;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid == 0) {
+    if (m) atomicMax(&ws->rgb_max, m);
+    __threadfence();  // publish the count before taking the ticket
+    s_last = atomicAdd(&ws->done, 1u) == gridDim.x - 1;
     s_base = 0;
-    ws->rgb_max = 0;
   }
   __syncthreads();
-  for (int t0 = 0; t0 < tiles; t0 += 1024) {
-    const int t = t0 + tid;
-    const long long v = t < tiles ? tile_count[t] : 0;
+  if (!s_last) return;
+  // ---- last CTA: exclusive scan of every tile's count (all of them are published) ----
+  __threadfence();
+  for (int t0 = 0; t0 < tiles; t0 += kPcThreads) {
+    const int t = t0 + threadIdx.x;
+    const long long v = t < tiles ? __ldcg(tile_count + t) : 0;
     long long inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const long long n = __shfl_up_sync(0xffffffffu, inc, o);
       if (lane >= o) inc += n;
     }
-    if (lane == 31) s_warp[wid] = inc;
+    if (lane == 31) s_scan[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-      long long w = s_warp[lane];
+    long long before = s_base + inc - v, chunk = 0;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long n = __shfl_up_sync(0xffffffffu, w, o);
-        if (lane >= o) w += n;
-      }
-      s_warp[lane] = w;
+    for (int w = 0; w < kPcThreads / 32; ++w) {
+      if (w < wid) before += s_scan[w];
+      chunk += s_scan[w];
     }
-    __syncthreads();
-    const long long before = s_base + (wid ? s_warp[wid - 1] : 0) + inc - v;
     if (t < tiles) tile_offset[t] = before;
     __syncthreads();
-    if (tid == 0) s_base += s_warp[31];
+    if (threadIdx.x == 0) s_base += chunk;
     __syncthreads();
   }
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     ws->total = s_base;
     *n_points = s_base;
+    ws->done = 0;  // ready for the next call on this workspace
   }
 }
 
 __global__ void __launch_bounds__(kPcThreads)
     pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
-                    const double* __restrict__ cam, PcWorkspace* ws, const long long* __restrict__ tile_offset,
-                    double* __restrict__ out, long long capacity) {
+                    int rgb_vec, const double* __restrict__ cam, const PcWorkspace* __restrict__ ws,
+                    const long long* __restrict__ tile_offset, double* __restrict__ out, long long capacity) {
   pdl_launch_dependents();
   extern __shared__ __align__(16) double stage[];  // [points in this tile][6]
   __shared__ int s_warp[kPcThreads / 32];
-  __shared__ unsigned s_max[kPcThreads / 32];
   const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
   float d[kPcPerThread];
-  load4(depth, base, hw, vec, d);   // depth is an input: no need to wait for the scan yet
+  load4(depth, base, hw, vec, d);   // depth / rgb are inputs of the chain: no need to wait for pass 1 yet
   int cnt = 0;
 #pragma unroll
   for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
+  uint32_t px[kPcPerThread] = {0, 0, 0, 0};
+  if (rgb != nullptr && cnt) load_rgb4(rgb, C, base, hw, rgb_vec, px);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int inc = cnt;
 #pragma unroll
@@ -150,7 +182,6 @@ __global__ void __launch_bounds__(kPcThreads)
 
   const double t0 = cam[0], t1 = cam[1], t2 = cam[2];
   const double fx = cam[12], fy = cam[13], cx = cam[14], cy = cam[15];
-  unsigned mx = 0;
   int r = before;
 #pragma unroll
   for (int k = 0; k < kPcPerThread; ++k) {
@@ -166,58 +197,40 @@ __global__ void __launch_bounds__(kPcThreads)
     o[1] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
     o[2] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
     if (rgb) {
-      const uint8_t* c = rgb + i * C;
-      const unsigned c0 = c[0], c1 = c[1], c2 = c[2];
-      mx = max(mx, max(c0, max(c1, c2)));
-      o[3] = static_cast<double>(c0);
-      o[4] = static_cast<double>(c1);
-      o[5] = static_cast<double>(c2);
+      o[3] = static_cast<double>(px[k] & 255u);
+      o[4] = static_cast<double>((px[k] >> 8) & 255u);
+      o[5] = static_cast<double>((px[k] >> 16) & 255u);
     } else {
       o[3] = o[4] = o[5] = 255.0;  // gcd.py:698-700
     }
     ++r;
   }
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) s_max[wid] = mx;
-  __syncthreads();  // stage and s_max complete
+  __syncthreads();  // stage complete
 
-  pdl_wait();       // tile offsets and the zeroed rgb_max come from the scan kernel
-  if (threadIdx.x == 0) {
-    unsigned m = 0;
-#pragma unroll
-    for (int w = 0; w < kPcThreads / 32; ++w) m = max(m, s_max[w]);
-    if (m) atomicMax(&ws->rgb_max, m);
-  }
+  pdl_wait();       // tile offsets and the colour maximum come from pass 1
+  // gcd.py:693: rgb.max() <= 1.0 over the valid pixels -> the colours were a [0,1] image: x255
+  const bool scale = rgb != nullptr && ws->rgb_max <= 1u;
   // stream the tile's points out: ranks are consecutive, so it is one contiguous run
   const long long first = tile_offset[blockIdx.x];
   long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
   if (keep > tile_total) keep = tile_total;
   if (keep <= 0) return;
-  const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs
+  const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs: (x,y) (z,r) (g,b)
   double* dst = out + first * 6;
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const double2* s2 = reinterpret_cast<const double2*>(stage);
     double2* d2 = reinterpret_cast<double2*>(dst);
     for (int j = threadIdx.x; j < n2; j += kPcThreads) {
-      const double2 vv = s2[j];
+      double2 vv = s2[j];
+      if (scale) {
+        const int m = j % 3;
+        if (m == 2) vv.x *= 255.0;
+        if (m >= 1) vv.y *= 255.0;
+      }
       asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
     }
   } else {
-    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) dst[j] = stage[j];
-  }
-}
-
-// gcd.py:693: rgb.max() <= 1.0 over the valid pixels -> colours were a [0,1] image: x255
-__global__ void __launch_bounds__(256) pc_fixup_kernel(const PcWorkspace* __restrict__ ws, double* __restrict__ out,
-                                                       long long capacity) {
-  pdl_wait();
-  if (ws->rgb_max > 1u) return;
-  long long n = ws->total;
-  if (n > capacity) n = capacity;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * 3; i += stride) {
-    const long long p = i / 3, c = i - p * 3;
-    out[p * 6 + 3 + c] *= 255.0;
+    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) dst[j] = (scale && j % 6 >= 3) ? stage[j] * 255.0 : stage[j];
   }
 }
 
@@ -262,18 +275,16 @@ extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, 
   static const cudaError_t smem_attr =
       cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
   (void)smem_attr;
-  // plain launch first (serialised behind whatever produced depth / rgb), then a PDL chain
-  pc_count_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, hw, vec, tile_count);
+  const int rgb_vec = rgb != nullptr && rgb_channels == 4 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
+  CSPE_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(PcWorkspace), st));
+  // plain launch first (serialised behind whatever produced depth / rgb), then the PDL-chained writer
+  pc_count_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, tile_count,
+                                                                      tile_offset, static_cast<int>(tiles), ws,
+                                                                      reinterpret_cast<long long*>(n_points));
   CSPE_LAUNCH_OK("pc_count_kernel");
-  CSPE_CUDA_OK(launch_pdl(pc_scan_kernel, dim3(1), dim3(1024), 0, st, tile_count, tile_offset, static_cast<int>(tiles), ws,
-                          reinterpret_cast<long long*>(n_points)));
-  CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kPcThreads), kPcStageBytes, st, depth,
-                          rgb, rgb_channels, W, hw, vec, cam, ws, tile_offset, out, static_cast<long long>(capacity)));
-  if (rgb != nullptr && capacity > 0) {
-    const int sms = sm_count();
-    CSPE_REQUIRE(sms > 0, CSPE_ERR_NO_DEVICE, "cspe_depth_to_pointcloud: no CUDA device");
-    CSPE_CUDA_OK(launch_pdl(pc_fixup_kernel, dim3(static_cast<unsigned>(sms) * 4), dim3(256), 0, st,
-                            static_cast<const PcWorkspace*>(ws), out, static_cast<long long>(capacity)));
-  }
+  if (capacity > 0)
+    CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kPcThreads), kPcStageBytes, st, depth,
+                            rgb, rgb_channels, W, hw, vec, rgb_vec, cam, static_cast<const PcWorkspace*>(ws),
+                            static_cast<const long long*>(tile_offset), out, static_cast<long long>(capacity)));
   return CSPE_OK;
 }
