@@ -26,7 +26,7 @@ namespace {
 constexpr int kPcThreads = 256;
 constexpr int kPcPerThread = 4;
 constexpr int kPcTile = kPcThreads * kPcPerThread;  // 1024 pixels
-constexpr int kPcStageBytes = kPcTile * 48;          // a tile's points, 48 KB
+constexpr int kPcStageBytes = kPcTile * (3 * 8 + 4);  // a tile's points as x[], y[], z[] (f64) + packed colour: 28 KB
 
 struct PcWorkspace {  // layout of the caller-provided scratch
   unsigned int rgb_max;  // maximum colour byte over valid pixels
@@ -154,7 +154,13 @@ __global__ void __launch_bounds__(kPcThreads)
                     int rgb_vec, const double* __restrict__ cam, const PcWorkspace* __restrict__ ws,
                     const long long* __restrict__ tile_offset, double* __restrict__ out, long long capacity) {
   pdl_launch_dependents();
-  extern __shared__ __align__(16) double stage[];  // [points in this tile][6]
+  // structure of arrays: 28 bytes per point instead of 48 doubles the resident CTAs per SM, and
+  // consecutive ranks hit consecutive banks
+  extern __shared__ __align__(16) double stage[];
+  double* sx = stage;
+  double* sy = stage + kPcTile;
+  double* sz = stage + 2 * kPcTile;
+  uint32_t* sc = reinterpret_cast<uint32_t*>(stage + 3 * kPcTile);
   __shared__ int s_warp[kPcThreads / 32];
   const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
   float d[kPcPerThread];
@@ -192,17 +198,10 @@ __global__ void __launch_bounds__(kPcThreads)
     const double zc = static_cast<double>(d[k]);
     const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
     const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
-    double* o = stage + r * 6;
-    o[0] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
-    o[1] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
-    o[2] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
-    if (rgb) {
-      o[3] = static_cast<double>(px[k] & 255u);
-      o[4] = static_cast<double>((px[k] >> 8) & 255u);
-      o[5] = static_cast<double>((px[k] >> 16) & 255u);
-    } else {
-      o[3] = o[4] = o[5] = 255.0;  // gcd.py:698-700
-    }
+    sx[r] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
+    sy[r] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
+    sz[r] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
+    sc[r] = rgb ? px[k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
     ++r;
   }
   __syncthreads();  // stage complete
@@ -215,22 +214,32 @@ __global__ void __launch_bounds__(kPcThreads)
   long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
   if (keep > tile_total) keep = tile_total;
   if (keep <= 0) return;
+  const double cs = scale ? 255.0 : 1.0;
   const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs: (x,y) (z,r) (g,b)
   double* dst = out + first * 6;
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    const double2* s2 = reinterpret_cast<const double2*>(stage);
     double2* d2 = reinterpret_cast<double2*>(dst);
     for (int j = threadIdx.x; j < n2; j += kPcThreads) {
-      double2 vv = s2[j];
-      if (scale) {
-        const int m = j % 3;
-        if (m == 2) vv.x *= 255.0;
-        if (m >= 1) vv.y *= 255.0;
+      const int pt = j / 3, m = j - pt * 3;
+      const uint32_t c = sc[pt];
+      double2 vv;
+      if (m == 0) {
+        vv.x = sx[pt];
+        vv.y = sy[pt];
+      } else if (m == 1) {
+        vv.x = sz[pt];
+        vv.y = static_cast<double>(c & 255u) * cs;
+      } else {
+        vv.x = static_cast<double>((c >> 8) & 255u) * cs;
+        vv.y = static_cast<double>((c >> 16) & 255u) * cs;
       }
       asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
     }
   } else {
-    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) dst[j] = (scale && j % 6 >= 3) ? stage[j] * 255.0 : stage[j];
+    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) {
+      const int pt = j / 6, m = j - pt * 6;
+      dst[j] = m == 0 ? sx[pt] : m == 1 ? sy[pt] : m == 2 ? sz[pt] : static_cast<double>((sc[pt] >> (8 * (m - 3))) & 255u) * cs;
+    }
   }
 }
 
