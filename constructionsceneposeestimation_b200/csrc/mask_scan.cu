@@ -10,8 +10,9 @@
 //     8 consumer warps, capped at 80 registers so that small kernels can run beside it;
 //   * the batch is one 2-D tensor [B*H rows][W] behind a TMA tensor map; a tile is 4 boxes of
 //     32 px x 64 rows (128-byte rows, SWIZZLE_128B) = 128 px x 64 rows = 32 KB, streamed into a
-//     3-stage shared-memory ring by cp.async.bulk.tensor.2d (SASS UTMALDG) signalled on
-//     mbarriers, L2 evict_first.  (Measured: tensor-map boxes stream at 6.4-6.9 TB/s whatever the
+//     3-stage shared-memory ring by cp.async.bulk.tensor (SASS UTMALDG) signalled on mbarriers,
+//     L2 evict_first — one 3-D box {32 px, 64 rows, 4 strips} per tile when W % 32 == 0 (the mask
+//     seen as [W/32 strips][B*H rows][32 px]), else one 2-D box per strip.  (Measured: tensor-map boxes stream at 6.4-6.9 TB/s whatever the
 //     geometry; one 1-D bulk copy per row segment capped at 4.3 TB/s because every bulk op costs
 //     ~85 cycles of TMA.)  Two CTAs per SM = two independent rings per SM: a slow warp only holds
 //     back its own ring;
@@ -85,7 +86,8 @@ struct ScanParams {
   int nrb;       // 64-row blocks per frame
   int ppf;       // passes per frame = nseg * nrb
   int stride;    // pass permutation inside a frame: q -> (q * stride) % ppf, gcd(stride, ppf) = 1
-  int tma;       // 1: tensor-map TMA (W % 4 == 0, 16 B aligned base), 0: producer-warp copy
+  int tma;       // 2: one 3-D TMA box per tile (W % 32 == 0), 1: one 2-D TMA box per strip (W % 4 == 0, 16 B
+                 // aligned base), 0: producer-warp copy
   int smem_lut;  // 1: the frame's LUT is staged in shared memory
   int lazy_wait; // 1: wait for the previous kernel only before the first merge into `out` (overlapped mode)
 };
@@ -96,6 +98,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
       "[%0], [%1, {%2, %3}], [%4], %5;" ::"r"(smem_u32(dst)),
       "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar,
+                                            uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%2, %3, %4}], [%5], %6;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
 
@@ -202,7 +213,7 @@ __device__ __forceinline__ int table_identity(int field) {
   } while (0)
 
 template <bool kSmemTable, int kBoxes>
-// 80 registers (no spills): leaves ~19 K registers per SM beside the two resident scan CTAs for
+// 80 registers (one 4-byte spill): leaves ~19 K registers per SM beside the two resident scan CTAs for
 // the small kernels that overlap with it
 __global__ void __maxnreg__(80)
     mask_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap tmap) {
@@ -265,7 +276,13 @@ __global__ void __maxnreg__(80)
       const int col0 = seg * kTileCols;
       unsigned char* dst = smem + stage * kStageBytes;
       mbar_wait(&empty_bar[stage], parity ^ 1);
-      if (p.tma) {
+      if (p.tma == 2) {
+        // the whole tile in ONE instruction: the mask seen as [W/32 strips][B*H rows][32 px], box =
+        // {32 px, 64 rows, kBoxes strips} lands exactly like kBoxes 2-D boxes side by side (measured
+        // +2.7 % on the load side: tools/tma_stream_probe.cu); strips past the last one are zero fill
+        mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kStageBytes));
+        tma_load_3d(dst, &tmap, 0, frame * p.H + row0, col0 / kStripPx, &full_bar[stage], policy);
+      } else if (p.tma) {
         // boxes that start beyond W are skipped; a box is always written in full (zero fill
         // past the tensor edge), so the byte count is whole boxes
         const int nbox = min(kBoxesPerTile, (p.W - col0 + kStripPx - 1) / kStripPx);
@@ -476,6 +493,15 @@ TensorMapEncodeFn tensor_map_encoder() {
   return fn;
 }
 
+// CSPE_SCAN_TMA_DIMS=2 keeps the one-2-D-box-per-strip producer (for A/B runs); default 3
+int scan_tma_dims() {
+  static int v = []() {
+    const char* e = getenv("CSPE_SCAN_TMA_DIMS");
+    return (e && atoi(e) == 2) ? 2 : 3;
+  }();
+  return v;
+}
+
 template <int kBoxes>
 int launch_scan_geo(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot, int lut_len, int64_t lut_stride,
                     int N, int32_t* out, cudaStream_t st, int lazy_wait) {
@@ -519,6 +545,20 @@ int launch_scan_geo(const uint32_t* mask, int B, int H, int W, const int32_t* id
                               estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     p.tma = (r == CUDA_SUCCESS) ? 1 : 0;
+    if (p.tma && W % kStripPx == 0 && scan_tma_dims() == 3) {
+      // same bytes, viewed as [W/32 strips][B*H rows][32 px] (strip stride 128 B): one box per tile
+      CUtensorMap tmap3;
+      const cuuint64_t gdim3[3] = {kStripPx, static_cast<cuuint64_t>(B) * H, static_cast<cuuint64_t>(W / kStripPx)};
+      const cuuint64_t gstride3[2] = {static_cast<cuuint64_t>(W) * 4, kStripPx * 4};
+      const cuuint32_t box3[3] = {kStripPx, kBoxRows, static_cast<cuuint32_t>(kBoxes)};
+      const cuuint32_t estride3[3] = {1, 1, 1};
+      if (encode(&tmap3, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint32_t*>(mask), gdim3, gstride3, box3, estride3,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+        tmap = tmap3;
+        p.tma = 2;
+      }
+    }
   }
 
   // pass permutation: when several CTAs share a frame, stride the tile order so each CTA's

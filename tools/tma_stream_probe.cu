@@ -23,9 +23,16 @@ __device__ __forceinline__ void tma2d(void* dst, const CUtensorMap* map, int x, 
                ::"r"(s32(dst)), "l"(map), "r"(x), "r"(y), "r"(s32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void tma3d(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(s32(dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(s32(bar)) : "memory");
+}
+
 // tile = bx boxes side by side (each box_w x box_h); tiles enumerate (row block, column block)
-__global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorMap map, int W, int rows, int box_w,
-                                               int box_h, int bx, int stages, long long* sink) {
+// three_d: ONE 3-D box {32 px, box_h rows, bx strips} per tile over the view [W/32 strips][rows][32 px]
+// (strip stride 128 B): same shared-memory layout as bx 2-D boxes of 32 x box_h, a single TMA instruction
+__global__ void __launch_bounds__(64, 2) probe(const __grid_constant__ CUtensorMap map, int W, int rows, int box_w,
+                                               int box_h, int bx, int stages, int three_d, long long* sink) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int box_bytes = box_w * box_h * 4;
   const int tile_bytes = box_bytes * bx;
@@ -47,8 +54,11 @@ __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorM
       mbar_wait(&empty[s], ph ^ 1);
       const int ty = (int)(t / tiles_x), tx = (int)(t % tiles_x);
       mbar_expect(&full[s], tile_bytes);
-      for (int b = 0; b < bx; ++b)
-        tma2d(smem + (size_t)s * tile_bytes + (size_t)b * box_bytes, &map, (tx * bx + b) * box_w, ty * box_h, &full[s]);
+      if (three_d)
+        tma3d(smem + (size_t)s * tile_bytes, &map, 0, ty * box_h, tx * bx, &full[s]);
+      else
+        for (int b = 0; b < bx; ++b)
+          tma2d(smem + (size_t)s * tile_bytes + (size_t)b * box_bytes, &map, (tx * bx + b) * box_w, ty * box_h, &full[s]);
     }
   } else if (threadIdx.x == 0) {  // consumer
     int it = 0; long long acc = 0;
@@ -75,32 +85,47 @@ int main() {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
   EncodeFn encode = (EncodeFn)fn;
   int sms; CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
-  struct Cfg { int box_w, box_h, bx, stages, swz; } cfgs[] = {
-      {32, 32, 16, 3, 1}, {32, 64, 8, 3, 1}, {32, 128, 4, 3, 1}, {32, 256, 2, 3, 1}, {32, 64, 4, 6, 1},
-      {256, 32, 1, 4, 0}, {256, 64, 1, 3, 0}, {256, 16, 1, 8, 0}, {128, 64, 2, 3, 0}, {64, 64, 4, 3, 0},
-      {32, 64, 8, 3, 0}, {256, 40, 1, 4, 0}, {192, 64, 1, 4, 0}, {240, 32, 2, 3, 0}, {160, 64, 1, 5, 0}};
+  struct Cfg { int box_w, box_h, bx, stages, swz, three_d, ctas; } cfgs[] = {
+      {32, 32, 16, 3, 1, 0, 1}, {32, 64, 8, 3, 1, 0, 1}, {32, 128, 4, 3, 1, 0, 1}, {32, 256, 2, 3, 1, 0, 1},
+      {32, 64, 4, 6, 1, 0, 1}, {256, 32, 1, 4, 0, 0, 1}, {256, 64, 1, 3, 0, 0, 1}, {256, 16, 1, 8, 0, 0, 1},
+      {128, 64, 2, 3, 0, 0, 1}, {64, 64, 4, 3, 0, 0, 1}, {32, 64, 8, 3, 0, 0, 1}, {256, 40, 1, 4, 0, 0, 1},
+      {192, 64, 1, 4, 0, 0, 1}, {240, 32, 2, 3, 0, 0, 1}, {160, 64, 1, 5, 0, 0, 1},
+      // the shipped geometry (2 CTAs per SM, 4 boxes of 32 x 64, 3 stages) and its single-instruction 3-D forms
+      {32, 64, 4, 3, 1, 0, 2}, {32, 64, 4, 3, 1, 1, 2}, {32, 64, 8, 3, 1, 1, 1}, {32, 64, 8, 3, 1, 0, 1},
+      {32, 128, 2, 3, 1, 1, 2}, {32, 32, 8, 3, 1, 1, 2}, {32, 64, 4, 3, 1, 0, 2}, {32, 64, 4, 3, 1, 1, 2}};
   for (auto c : cfgs) {
     CUtensorMap map;
-    cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)W * 4};
-    cuuint32_t box[2] = {(cuuint32_t)c.box_w, (cuuint32_t)c.box_h};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        c.swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { printf("encode failed %d for box %dx%d\n", (int)r, c.box_w, c.box_h); continue; }
+    CUresult r;
+    if (c.three_d) {
+      cuuint64_t gdim[3] = {32, (cuuint64_t)rows, (cuuint64_t)(W / 32)};
+      cuuint64_t gstr[2] = {(cuuint64_t)W * 4, 128};
+      cuuint32_t box[3] = {32, (cuuint32_t)c.box_h, (cuuint32_t)c.bx};
+      cuuint32_t estr[3] = {1, 1, 1};
+      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t gdim[2] = {(cuuint64_t)W, (cuuint64_t)rows};
+      cuuint64_t gstr[1] = {(cuuint64_t)W * 4};
+      cuuint32_t box[2] = {(cuuint32_t)c.box_w, (cuuint32_t)c.box_h};
+      cuuint32_t estr[2] = {1, 1};
+      r = encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 c.swz ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) { printf("encode failed %d for box %dx%d (3-D %d)\n", (int)r, c.box_w, c.box_h, c.three_d); continue; }
     const size_t smem = (size_t)c.stages * c.box_w * c.box_h * 4 * c.bx + 256;
     CK(cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    for (int i = 0; i < 3; ++i) probe<<<sms, 64, smem>>>(map, W, (int)rows, c.box_w, c.box_h, c.bx, c.stages, sink);
+    for (int i = 0; i < 3; ++i) probe<<<sms * c.ctas, 64, smem>>>(map, W, (int)rows, c.box_w, c.box_h, c.bx, c.stages, c.three_d, sink);
     CK(cudaDeviceSynchronize());
     const int reps = 10;
     CK(cudaEventRecord(e0));
-    for (int i = 0; i < reps; ++i) probe<<<sms, 64, smem>>>(map, W, (int)rows, c.box_w, c.box_h, c.bx, c.stages, sink);
+    for (int i = 0; i < reps; ++i) probe<<<sms * c.ctas, 64, smem>>>(map, W, (int)rows, c.box_w, c.box_h, c.bx, c.stages, c.three_d, sink);
     CK(cudaEventRecord(e1)); CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= reps;
-    printf("box %3d px x %3d rows, %2d boxes/tile (%6.1f KB tile), %d stages, swz %d: %.4f ms  %.0f GB/s\n", c.box_w,
-           c.box_h, c.bx, c.box_w * c.box_h * 4 * c.bx / 1024.0, c.stages, c.swz, ms, rows * W * 4.0 / ms / 1e6);
+    printf("box %3d px x %3d rows, %2d boxes/tile (%6.1f KB tile), %d stages, swz %d, %s, %d CTA/SM: %.4f ms  %.0f GB/s\n",
+           c.box_w, c.box_h, c.bx, c.box_w * c.box_h * 4 * c.bx / 1024.0, c.stages, c.swz,
+           c.three_d ? "one 3-D box" : "2-D boxes", c.ctas, ms, rows * W * 4.0 / ms / 1e6);
   }
   return 0;
 }
