@@ -82,6 +82,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             os.makedirs(label_dir, exist_ok=True)
         coco_imgs: List[dict] = []
         coco_anns: List[dict] = []
+        slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
+        io_pool = None
+        if emit == "json":
+            from concurrent.futures import ThreadPoolExecutor
+
+            io_pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1), thread_name_prefix="cspe-io")
         emitted = 0
         hist_host = np.zeros(_lib.NUM_CLASSES, dtype=np.int64)
         batches = sharding.batches(lo, hi, B)
@@ -113,17 +119,23 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                         with open(os.path.join(label_dir, f"label_{s + j:06d}.txt"), "wb") as fh:
                             fh.write(raw[off[j]:off[j + 1]])
                 return
+            if emit == "json":   # native formatter (libcspe, f3) on the I/O threads: label_%06d.json, gcd.py:2071
+                def one(j: int) -> int:
+                    text = formats.label_json_bytes(s + j, pool[j]["camera_pose"], pool[j]["camera_params"], H, W,
+                                                    recs_all[j, : n_all[j]], objects[j], slot_strings[j])
+                    if label_dir is not None:
+                        with open(os.path.join(label_dir, f"label_{s + j:06d}.json"), "wb") as fh:
+                            fh.write(text)
+                    return len(text)
+
+                sum(io_pool.map(one, range(nf)))
+                return
             for j in range(nf):
                 fid = s + j                       # global frame id; pipeline frames are batch-relative
                 recs = recs_all[j, : n_all[j]]
                 if emit == "coco":
                     coco_imgs.append(formats.coco_image(fid, W, H, f"rgb_{fid:06d}.png"))
                     coco_anns.extend(formats.coco_annotations(recs, fid, len(coco_anns) + 1))
-                elif emit == "json":
-                    lab = formats.reference_label(fid, pool[j]["camera_pose"], pool[j]["camera_params"], H, W, recs,
-                                                  objects[j])
-                    if label_dir is not None:
-                        formats.dump_label_json(lab, os.path.join(label_dir, f"label_{fid:06d}.json"))
 
         # The device histogram (K4) counts every frame of every launched batch; a trailing partial
         # batch still runs the whole pool, so the frames this rank OWNS are counted on the host from
@@ -137,6 +149,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             consume(len(batches) - 1)
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
+        if io_pool is not None:
+            io_pool.shutdown()
         if batches and all(e - s == B for s, e in batches):
             dev_hist = pipe.class_hist.cpu().numpy()
             if not np.array_equal(dev_hist, hist_host):

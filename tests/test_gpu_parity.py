@@ -614,6 +614,17 @@ def test_sweep_frame_range_and_histogram(T, ops, tmp_path):
     files = sorted((tmp_path / "labels").glob("label_*.txt"))
     assert len(files) == 150 and files[-1].name == "label_000149.txt"
     assert len(files[17].read_text().splitlines()) == int(o["n_out"][1])
+    # the same sweep emitting label_%06d.json through the native formatter
+    import json
+    synthetic.CONFIGS["_t"] = spec
+    try:
+        res = sweep.run_sweep(40, 0, 1, T.device("cuda"), pool_frames=16, config="_t", emit="json", out_dir=str(tmp_path / "j"))
+    finally:
+        del synthetic.CONFIGS["_t"]
+    lab = json.loads((tmp_path / "j" / "labels" / "label_000035.json").read_text())
+    assert lab["frame_id"] == 35 and lab["num_objects"] == int(o["n_out"][3]) == len(lab["objects"])
+    assert [ob["pixel_count"] for ob in lab["objects"]] == [int(c) for c in o["recs"][3, : o["n_out"][3]]["count"]]
+    assert len(list((tmp_path / "j" / "labels").glob("label_*.json"))) == 40
 
 
 def test_scan_random_shapes_property(T, ops):
