@@ -121,6 +121,7 @@ PROTOTYPES = {
     "cspe_text_workspace_bytes": (C.c_size_t, [_I64, _I]),
     "cspe_format_fixed6": (_I, [_P, _I, _I64, _P, _I, C.c_char_p, _P, _I64, _P, _I64, _P, _P, _P]),
     "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
+    "cspe_format_coco_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P, _P, _P, _I, _I, _P, _I64]),
     "cspe_format_label_json_host": (_I64, [_P, _I, _I64, _P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _P, _P, _P, _I,
                                            _I, _P, _I64]),
 }

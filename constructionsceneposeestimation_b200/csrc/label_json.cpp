@@ -300,3 +300,87 @@ extern "C" int64_t cspe_format_label_json_host(const cspe_record* records_host, 
   o.ch('}');
   return o.p - out_host;
 }
+
+// COCO annotations of a batch: for every kept record of frames [0, frames) one
+//   {"id": i, "image_id": f, "category_id": c, "bbox": [x, y, w, h], "area": a, "iscrowd": 0,
+//    "occlusion": o, "truncation": t[, "keypoints": [x, y, v, ...], "num_keypoints": k]}
+// joined by ", " — the text json.dump(list_of_annotations) puts between its brackets (default
+// separators), byte for byte what formats.coco_annotations + json.dump produce.
+extern "C" int64_t cspe_format_coco_host(const cspe_record* records_host, const int32_t* n_out_host, int B, int N,
+                                         int frames, const int64_t* image_ids, int64_t first_annotation_id,
+                                         const double* keypoints, const uint8_t* visibility,
+                                         const int32_t* person_of_slot, int num_people, int num_joints,
+                                         char* out_host, int64_t capacity) {
+  if (B < 0 || N < 0 || frames < 0 || frames > B || capacity < 0 || (frames > 0 && (!records_host || !n_out_host || !image_ids)) ||
+      (capacity > 0 && !out_host) || (person_of_slot && (!keypoints || !visibility || num_people < 0 || num_joints < 0))) {
+    cspe::set_error("cspe_format_coco_host: invalid argument");
+    return CSPE_ERR_INVALID_ARGUMENT;
+  }
+  Out o{out_host, out_host + capacity};
+  int64_t ann_id = first_annotation_id;
+  bool first = true;
+  for (int f = 0; f < frames; ++f) {
+    const int n = n_out_host[f];
+    if (n < 0 || n > N) {
+      cspe::set_error("cspe_format_coco_host: n_out[%d] = %d outside [0, %d]", f, n, N);
+      return CSPE_ERR_INVALID_ARGUMENT;
+    }
+    const cspe_record* r = records_host + static_cast<int64_t>(f) * N;
+    for (int i = 0; i < n; ++i, ++r, ++ann_id) {
+      if (!o.room(512 + kJointBytes * num_joints)) {
+        cspe::set_error("cspe_format_coco_host: output buffer of %lld bytes is too small (512 + 128 per joint per record)",
+                        static_cast<long long>(capacity));
+        return CSPE_ERR_INVALID_ARGUMENT;
+      }
+      if (!first) o.raw(", ", 2);
+      first = false;
+      o.lit("{\"id\": ");
+      o.integer(ann_id);
+      o.lit(", \"image_id\": ");
+      o.integer(image_ids[f]);
+      o.lit(", \"category_id\": ");
+      o.integer(r->class_id);
+      o.lit(", \"bbox\": [");
+      if (r->count > 0) {
+        o.integer(r->x_min);
+        o.raw(", ", 2);
+        o.integer(r->y_min);
+        o.raw(", ", 2);
+        o.integer(static_cast<long long>(r->x_max) - r->x_min + 1);
+        o.raw(", ", 2);
+        o.integer(static_cast<long long>(r->y_max) - r->y_min + 1);
+      } else {
+        o.lit("0, 0, 0, 0");
+      }
+      o.lit("], \"area\": ");
+      o.integer(r->count);
+      o.lit(", \"iscrowd\": 0, \"occlusion\": ");
+      o.repr(static_cast<double>(r->occlusion));
+      o.lit(", \"truncation\": ");
+      o.repr(static_cast<double>(r->truncation));
+      int person = -1;
+      if (person_of_slot && r->inst_idx >= 0 && r->inst_idx < N)
+        person = person_of_slot[static_cast<int64_t>(f) * N + r->inst_idx];
+      if (person >= 0 && person < num_people) {
+        const double* kp = keypoints + (static_cast<int64_t>(f) * num_people + person) * num_joints * 2;
+        const uint8_t* vis = visibility + (static_cast<int64_t>(f) * num_people + person) * num_joints;
+        o.lit(", \"keypoints\": [");
+        int seen = 0;
+        for (int j = 0; j < num_joints; ++j) {
+          const bool shown = vis[j] != 0 && std::isfinite(kp[2 * j]) && std::isfinite(kp[2 * j + 1]);
+          seen += vis[j] > 0;
+          if (j) o.raw(", ", 2);
+          o.repr(shown ? kp[2 * j] : 0.0);
+          o.raw(", ", 2);
+          o.repr(shown ? kp[2 * j + 1] : 0.0);
+          o.raw(", ", 2);
+          o.integer(shown ? vis[j] : 0);
+        }
+        o.lit("], \"num_keypoints\": ");
+        o.integer(seen);
+      }
+      o.ch('}');
+    }
+  }
+  return o.p - out_host;
+}

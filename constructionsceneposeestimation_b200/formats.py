@@ -201,6 +201,51 @@ def coco_annotations(records: np.ndarray, image_id: int, first_ann_id: int,
     return anns
 
 
+def coco_annotations_text(records: np.ndarray, n_out: np.ndarray, image_ids: Sequence[int], first_ann_id: int,
+                          keypoints: Optional[np.ndarray] = None, visibility: Optional[np.ndarray] = None,
+                          person_slots: Optional[Sequence[Sequence[int]]] = None):
+    """Native formatter (libcspe ``cspe_format_coco_host``): the annotations of a whole batch as the text
+    ``json.dumps([...])`` puts between its brackets — byte-identical to dumping ``coco_annotations`` frame by
+    frame.  records RECORD_DTYPE [B,N], n_out int32 [B], image_ids per frame; keypoints f64 [B,P,J,2] /
+    visibility u8 [B,P,J] / person_slots[f][p] = slot of person p (or -1).  Returns (bytes, number of annotations)."""
+    from . import _lib
+
+    lib = _lib.load()
+    records = np.ascontiguousarray(records)
+    n_out = np.ascontiguousarray(n_out, dtype=np.int32)
+    B, N = records.shape
+    frames = len(image_ids)
+    ids = np.ascontiguousarray(image_ids, dtype=np.int64)
+    kp_ptr = vis_ptr = pos_ptr = None
+    P = J = 0
+    if keypoints is not None and person_slots is not None:
+        keypoints = np.ascontiguousarray(keypoints, dtype=np.float64)
+        visibility = np.ascontiguousarray(visibility, dtype=np.uint8)
+        _, P, J = visibility.shape
+        person_of_slot = np.full((B, max(N, 1)), -1, dtype=np.int32)
+        for f in range(min(frames, len(person_slots))):
+            for p_idx, slot in enumerate(person_slots[f][:P]):
+                if 0 <= slot < N:
+                    person_of_slot[f, slot] = p_idx
+        kp_ptr, vis_ptr, pos_ptr = keypoints.ctypes.data, visibility.ctypes.data, person_of_slot.ctypes.data
+    total = int(n_out[:frames].sum())
+    cap = 64 + total * (512 + 128 * J)
+    buf = np.empty(cap, dtype=np.uint8)
+    rc = lib.cspe_format_coco_host(records.ctypes.data, n_out.ctypes.data, B, N, frames, ids.ctypes.data,
+                                   int(first_ann_id), kp_ptr, vis_ptr, pos_ptr, P, J, buf.ctypes.data, cap)
+    _lib.check("cspe_format_coco_host", rc)
+    return buf[:rc].tobytes(), total
+
+
+def write_coco_file(path, images: Sequence[Mapping], annotation_chunks: Sequence[bytes]) -> None:
+    """The bytes json.dump({"images": [...], "annotations": [...], "categories": [...]}, f) writes, with the
+    annotations given as natively formatted chunks (``coco_annotations_text``)."""
+    with open(path, "wb") as f:
+        f.write(b'{"images": ' + json.dumps(list(images)).encode("ascii") + b', "annotations": [')
+        f.write(b", ".join(c for c in annotation_chunks if c))
+        f.write(b'], "categories": ' + json.dumps(coco_categories()).encode("ascii") + b"}")
+
+
 def coco_keypoint_block(kp: np.ndarray, vis: np.ndarray) -> Dict[str, object]:
     """kp f64 [J,2], vis u8 [J] -> {"keypoints": [x,y,v]*J, "num_keypoints": n} (x,y zeroed when v == 0)."""
     flat: List[float] = []

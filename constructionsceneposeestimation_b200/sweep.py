@@ -81,7 +81,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             label_dir = os.path.join(out_dir, "labels")
             os.makedirs(label_dir, exist_ok=True)
         coco_imgs: List[dict] = []
-        coco_anns: List[dict] = []
+        coco_anns: List[bytes] = []
+        coco_count = 0
         slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
         io_pool = None
         if emit == "json":
@@ -101,7 +102,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             ev.record()
 
         def consume(k: int) -> None:
-            nonlocal emitted, hist_host
+            nonlocal emitted, hist_host, coco_count
             rec_h, n_h, ev = host[k % 2]
             ev.synchronize()
             s, e = batches[k]
@@ -130,12 +131,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
 
                 sum(io_pool.map(one, range(nf)))
                 return
-            for j in range(nf):
-                fid = s + j                       # global frame id; pipeline frames are batch-relative
-                recs = recs_all[j, : n_all[j]]
-                if emit == "coco":
-                    coco_imgs.append(formats.coco_image(fid, W, H, f"rgb_{fid:06d}.png"))
-                    coco_anns.extend(formats.coco_annotations(recs, fid, len(coco_anns) + 1))
+            if emit == "coco":   # native formatter, one call per batch
+                ids = list(range(s, e))               # global frame ids; pipeline frames are batch-relative
+                coco_imgs.extend(formats.coco_image(fid, W, H, f"rgb_{fid:06d}.png") for fid in ids)
+                text, count = formats.coco_annotations_text(recs_all, n_all, ids, coco_count + 1)
+                coco_anns.append(text)
+                coco_count += count
 
         # The device histogram (K4) counts every frame of every launched batch; a trailing partial
         # batch still runs the whole pool, so the frames this rank OWNS are counted on the host from
@@ -164,8 +165,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         else:
             gathered = hist_host.reshape(1, -1)
         if emit == "coco" and out_dir is not None:
-            with open(os.path.join(out_dir, f"coco_rank{rank:02d}.json"), "w") as fh:
-                json.dump({"images": coco_imgs, "annotations": coco_anns, "categories": formats.coco_categories()}, fh)
+            formats.write_coco_file(os.path.join(out_dir, f"coco_rank{rank:02d}.json"), coco_imgs, coco_anns)
     return {"rank": rank, "world": world, "frames": hi - lo, "frame_range": [lo, hi], "records": emitted,
             "seconds": dt, "frames_per_s": (hi - lo) / dt if dt > 0 else 0.0, "class_hist_rank": hist_host.tolist(),
             "class_hist_total": gathered.sum(axis=0).tolist(), "class_hist_per_rank": gathered.tolist()}

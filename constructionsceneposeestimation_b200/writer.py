@@ -128,6 +128,17 @@ class BatchLabels:
         buf, offsets = self._yolo
         return memoryview(buf)[int(offsets[f]): int(offsets[f + 1])]
 
+    def coco_text(self, first_annotation_id: int) -> Tuple[bytes, int]:
+        """COCO annotation objects of the whole batch, ", "-joined (native formatter); returns (text, count)."""
+        self.synchronize()
+        B, N = self._rec_host.shape[0], self._rec_host.shape[1]
+        recs = self._rec_host.numpy().view(RECORD_DTYPE).reshape(B, N)
+        kp = vis = None
+        if self._kp_host is not None and self.person_slots is not None:
+            kp, vis = self._kp_host.numpy(), self._vis_host.numpy()
+        return formats.coco_annotations_text(recs, self._nout_host.numpy(), self.frame_ids, first_annotation_id, kp, vis,
+                                             self.person_slots if kp is not None else None)
+
     def label_json(self, f: int) -> bytes:
         """The text of ``label_%06d.json`` (= json.dumps(self.reference_label(f), indent=2, ensure_ascii=False)),
         formatted natively from the D2H record buffer."""
@@ -201,7 +212,8 @@ class ConstructionLabelWriter:
         self._next_frame_id = 0
         self._pending: List[Tuple[BatchLabels, Optional[List[np.ndarray]]]] = []
         self._coco_images: List[Dict] = []
-        self._coco_annotations: List[Dict] = []
+        self._coco_annotation_text: List[bytes] = []   # natively formatted, one chunk per batch
+        self._coco_annotation_count = 0
         self.frames_written = 0
         self.objects_total = 0
         self.depth_quality_log: List[Dict[str, object]] = []
@@ -277,10 +289,8 @@ class ConstructionLabelWriter:
         }
         if self.output_dir is not None:
             if "coco" in self.formats:
-                coco = {"images": self._coco_images, "annotations": self._coco_annotations,
-                        "categories": formats.coco_categories()}
-                with open(os.path.join(self.output_dir, f"coco_rank{self.rank:02d}.json"), "w", encoding="utf-8") as f:
-                    json.dump(coco, f)
+                formats.write_coco_file(os.path.join(self.output_dir, f"coco_rank{self.rank:02d}.json"),
+                                        self._coco_images, self._coco_annotation_text)
             if self.rank == 0:
                 with open(os.path.join(self.output_dir, "label_summary.json"), "w", encoding="utf-8") as f:
                     json.dump(summary, f, indent=2)
@@ -596,6 +606,11 @@ class ConstructionLabelWriter:
             else:
                 for f in range(B):
                     self._write_frame_files(labels, f, masks)
+        if "coco" in self.formats:   # all annotations of the batch in one native call
+            text, count = labels.coco_text(self._coco_annotation_count + 1)
+            if count:
+                self._coco_annotation_text.append(text)
+                self._coco_annotation_count += count
         # bookkeeping stays on the caller's thread, in frame order
         for f in range(B):
             fid = labels.frame_ids[f]
@@ -605,8 +620,6 @@ class ConstructionLabelWriter:
                 points = self._write_pointcloud(labels, f)
             if "coco" in self.formats:
                 self._coco_images.append(formats.coco_image(fid, labels.width, labels.height, f"rgb_{fid:06d}.png"))
-                self._coco_annotations += formats.coco_annotations(recs, fid, len(self._coco_annotations) + 1,
-                                                                   labels.keypoints_by_slot(f))
             dq = labels.depth_quality(f)
             if dq is not None:
                 self.depth_quality_log.append({"frame_id": fid, "depth": dq})

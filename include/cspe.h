@@ -301,6 +301,19 @@ int64_t cspe_format_label_json_host(const cspe_record* records_host, int n, int6
                                     const int32_t* person_of_slot, int num_people, int num_joints,
                                     char* out_host, int64_t capacity);
 
+/* f3 / S6: host-side COCO annotations of a batch (no CUDA; HOST pointers).  For every kept record of
+ * frames [0, frames) of records_host [B][N] / n_out_host [B] one object
+ *   {"id", "image_id", "category_id", "bbox": [x_min, y_min, w, h], "area": count, "iscrowd": 0,
+ *    "occlusion", "truncation"[, "keypoints": [x, y, v]*J, "num_keypoints"]}
+ * joined by ", " — what json.dump(list) writes between its brackets.  image_ids int64 [frames];
+ * annotation ids count up from first_annotation_id; keypoints double [B][P][J][2], visibility uint8
+ * [B][P][J], person_of_slot int32 [B][N] (-1 = none), all three NULL without skeletons.
+ * Returns the number of bytes written or a negative CSPE_ERR_*. */
+int64_t cspe_format_coco_host(const cspe_record* records_host, const int32_t* n_out_host, int B, int N, int frames,
+                              const int64_t* image_ids, int64_t first_annotation_id, const double* keypoints,
+                              const uint8_t* visibility, const int32_t* person_of_slot, int num_people,
+                              int num_joints, char* out_host, int64_t capacity);
+
 #ifdef __cplusplus
 }
 #endif

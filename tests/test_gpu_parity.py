@@ -458,6 +458,13 @@ def test_writer_end_to_end(T, ops, tmp_path):
     assert summary["object_count"]["total"] == int(o["n_out"].sum()) and len(summary["depth_quality"]) == 3
     assert np.array_equal(np.asarray(summary["class_histogram_per_rank"])[0], o["hist"])
     coco = json.loads((tmp_path / "coco_rank00.json").read_text())
+    from constructionsceneposeestimation_b200 import formats as F
+    py_anns = []
+    for f in range(3):                                                   # the Python statement of the same annotations
+        py_anns += F.coco_annotations(labels.records(f), f, len(py_anns) + 1, labels.keypoints_by_slot(f))
+    assert coco["annotations"] == py_anns
+    assert (tmp_path / "coco_rank00.json").read_text() == json.dumps(
+        {"images": coco["images"], "annotations": py_anns, "categories": F.coco_categories()})
     assert len(coco["annotations"]) == int(o["n_out"].sum()) and len(coco["images"]) == 3
     assert any("keypoints" in a for a in coco["annotations"])
     # f3: the reference logger's run summary (gcd.py:389-418), fed from the device statistics

@@ -352,3 +352,36 @@ def test_native_label_json_reproduces_reference_file():
     trimmed = dict(ours)
     trimmed["objects"] = [{k: ours["objects"][0][k] for k in obj}]
     assert json.dumps(trimmed, indent=2, ensure_ascii=False) == gold["text"]
+
+
+def test_native_coco_annotations_match_python_json_dump(libcspe_path):
+    """cspe_format_coco_host == the inside of json.dumps(coco_annotations(...) of every frame)."""
+    from constructionsceneposeestimation_b200 import _lib
+
+    rng = np.random.default_rng(77)
+    B, N, P, J = 4, 24, 3, 5
+    recs = np.zeros((B, N), dtype=_lib.RECORD_DTYPE)
+    n_out = np.array([24, 0, 7, 13], dtype=np.int32)
+    for f in range(B):
+        r = _random_records(rng, int(n_out[f]), N) if n_out[f] else recs[f, :0]
+        recs[f, : n_out[f]] = r
+    recs["count"][0, 3] = 0          # empty box -> [0, 0, 0, 0]
+    image_ids = [100, 101, 205, 206]
+    kp = rng.uniform(-50, 2000, (B, P, J, 2))
+    vis = rng.integers(0, 3, (B, P, J)).astype(np.uint8)
+    kp[0, 1, 2, 0], kp[3, 0, 4, 1] = np.nan, np.inf
+    person_slots = [[int(recs["inst_idx"][f, 0]) if n_out[f] else -1, -1, int(recs["inst_idx"][f, 2]) if n_out[f] > 2 else -1]
+                    for f in range(B)]
+    for with_kp in (False, True):
+        anns = []
+        for f in range(B):
+            blocks = None
+            if with_kp:
+                blocks = {s: formats.coco_keypoint_block(kp[f, p], vis[f, p]) for p, s in enumerate(person_slots[f]) if s >= 0}
+            anns += formats.coco_annotations(recs[f, : n_out[f]], image_ids[f], len(anns) + 11, blocks)
+        want = json.dumps(anns)
+        text, count = formats.coco_annotations_text(recs, n_out, image_ids, 11, *((kp, vis, person_slots) if with_kp else ()))
+        assert count == len(anns) == int(n_out.sum())
+        assert b"[" + text + b"]" == want.encode("ascii")
+    text, count = formats.coco_annotations_text(recs, np.zeros(B, dtype=np.int32), image_ids, 1)
+    assert text == b"" and count == 0
