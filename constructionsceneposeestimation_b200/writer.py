@@ -532,11 +532,12 @@ class ConstructionLabelWriter:
         for f0 in range(0, B, chunk):
             nb = min(chunk, B - f0)
             with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-                text, n_bytes, split = ops.format_fixed6(depth[f0:f0 + nb].reshape(nb * H, W), split_rows=H)
+                chunk_depth = depth[f0:f0 + nb].reshape(nb * H, W)
+                text, n_bytes, split = ops.format_fixed6(chunk_depth, split_rows=H)
                 total = int(n_bytes.item())
+                if total > text.numel():   # the 14-bytes-per-number estimate was short: format again into `total` bytes
+                    text, n_bytes, split = ops.format_fixed6(chunk_depth, split_rows=H, capacity=total)
                 offs = split.cpu().tolist() + [total]
-            if total > text.numel():
-                raise RuntimeError(f"depth CSV text of {total} bytes exceeds the {text.numel()} byte estimate")
             for k in range(nb):
                 with open(os.path.join(ddir, f"depth_{labels.frame_ids[f0 + k]:06d}.csv"), "wb") as fh:
                     fh.write(self._host_bytes(text, offs[k], offs[k + 1]))
