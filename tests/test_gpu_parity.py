@@ -961,3 +961,19 @@ def test_kernels_against_reference_goldens(T, ops):
                 assert abs(got[k] - ref[k]) <= 1e-5 * max(1.0, abs(ref[k])), name
             else:
                 assert got[k] == ref[k], (name, k)
+
+
+def test_writer_depth_csv_long_numbers(T, ops, tmp_path):
+    """A depth map of astronomic values overflows the text-size estimate: the writer formats again with the exact size."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(160, 90, 6, 0, 0, config_id=33), 2)
+    for fr in frames:
+        fr["distance_to_image_plane"] = np.full((90, 160), 3.0e38, dtype=np.float32)
+    frames[1]["distance_to_image_plane"][::2] = -1.5e-7
+    w = ConstructionLabelWriter(str(tmp_path), formats=("depth_csv",))
+    w.write_batch(frames)
+    w.on_final_frame()
+    for fr in frames:
+        got = (tmp_path / "depth" / f"depth_{fr['frame_id']:06d}.csv").read_bytes()
+        assert got == O.savetxt_fixed6(fr["distance_to_image_plane"])
