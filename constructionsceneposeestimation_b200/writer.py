@@ -178,7 +178,9 @@ class ConstructionLabelWriter:
     placeholder, gcd.py:2066-2069), ``"depth_png"`` (JET depth image, gcd.py:1691-1709), ``"depth_csv"``
     (``depth/depth_%06d.csv``, the np.savetxt text of gcd.py:1688) and ``"pointcloud"``
     (``pointcloud/pointcloud_%06d.txt`` from depth + ``data["rgb"]``, gcd.py:1729-1759) — both texts are
-    formatted on the GPU (``cspe_format_fixed6``) and only their bytes cross PCIe.  When a
+    formatted on the GPU (``cspe_format_fixed6``) and only their bytes cross PCIe — and ``"rgb_png"``
+    (``rgb/rgb_%06d.png`` from ``data["rgb"]``, gcd.py:1669-1674; the RGB(A) -> BGR conversion runs on the GPU
+    when the annotator is device-resident, PNG encoding is cv2's as in the reference).  When a
     frame carries ``distance_to_image_plane`` the depth-quality statistics of the reference's
     logger (gcd.py:314-359) are computed on the GPU and returned by ``BatchLabels.depth_quality``.
     """
@@ -258,7 +260,7 @@ class ConstructionLabelWriter:
         masks = None
         if "mask" in self.formats and self.output_dir is not None:
             masks = [_payload(fr.get("instance_segmentation")) for fr in frames]
-        if "pointcloud" in self.formats and self.output_dir is not None:
+        if {"pointcloud", "rgb_png"} & set(self.formats) and self.output_dir is not None:
             labels.rgb_images = [_payload(fr.get("rgb")) for fr in frames]
         self._pending.append((labels, masks))
         while len(self._pending) > self.max_pending:
@@ -508,6 +510,18 @@ class ConstructionLabelWriter:
         humans = [o.inst_idx for o in t.objects if o.class_name == "human"]
         return [humans[p] if p < len(humans) else -1 for p in range(num_people)]
 
+    def _io_stream(self) -> torch.cuda.Stream:
+        """One CUDA stream per I/O worker thread (device work issued from the file writers)."""
+        import threading
+
+        local = getattr(self, "_io_local", None)
+        if local is None:
+            local = self._io_local = threading.local()
+        st = getattr(local, "stream", None)
+        if st is None:
+            st = local.stream = torch.cuda.Stream(device=self.device)
+        return st
+
     # ------------------------------------------------------------------ device-formatted text files
     def _host_bytes(self, text: torch.Tensor, begin: int, end: int) -> memoryview:
         """text[begin:end] (device u8) through a grow-only pinned buffer; valid until the next call."""
@@ -582,6 +596,17 @@ class ConstructionLabelWriter:
             import cv2
 
             cv2.imwrite(os.path.join(self.output_dir, "depth", f"depth_{fid:06d}.png"), labels.depth_image(f))   # gcd.py:1703-1704
+        if "rgb_png" in self.formats and labels.rgb_images is not None and labels.rgb_images[f] is not None:
+            import cv2
+
+            rgb = labels.rgb_images[f]
+            if isinstance(rgb, torch.Tensor) and rgb.is_cuda:   # device-resident annotator: f4 kernel, then D2H of 3 bytes/px
+                with torch.cuda.device(self.device), torch.cuda.stream(self._io_stream()):
+                    bgr = ops.rgb_to_bgr(rgb.contiguous()).cpu().numpy()
+            else:                                               # host image: the reference's own call, gcd.py:1671
+                rgb = rgb.numpy() if isinstance(rgb, torch.Tensor) else np.asarray(rgb)
+                bgr = cv2.cvtColor(np.ascontiguousarray(rgb[..., :3]), cv2.COLOR_RGB2BGR)
+            cv2.imwrite(os.path.join(self.output_dir, "rgb", f"rgb_{fid:06d}.png"), bgr)   # gcd.py:1672-1673
         if "mask" in self.formats and masks is not None:
             m = masks[f]
             m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
@@ -593,6 +618,8 @@ class ConstructionLabelWriter:
         if self.output_dir is not None:
             if "depth_png" in self.formats:
                 os.makedirs(os.path.join(self.output_dir, "depth"), exist_ok=True)
+            if "rgb_png" in self.formats:
+                os.makedirs(os.path.join(self.output_dir, "rgb"), exist_ok=True)
             if "depth_csv" in self.formats:
                 self._write_depth_csv(labels)
             if "yolo" in self.formats:

@@ -977,3 +977,21 @@ def test_writer_depth_csv_long_numbers(T, ops, tmp_path):
     for fr in frames:
         got = (tmp_path / "depth" / f"depth_{fr['frame_id']:06d}.csv").read_bytes()
         assert got == O.savetxt_fixed6(fr["distance_to_image_plane"])
+
+
+def test_writer_rgb_png(T, ops, tmp_path):
+    """rgb/rgb_%06d.png (gcd.py:1669-1674): cv2.COLOR_RGB2BGR of rgb[..., :3], from a host image and from a
+    device-resident one (f4 kernel)."""
+    import cv2
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(320, 180, 8, 0, 0, config_id=41, with_rgb=True), 2)
+    want = [cv2.cvtColor(np.ascontiguousarray(fr["rgb"][..., :3]), cv2.COLOR_RGB2BGR) for fr in frames]
+    frames[1] = dict(frames[1])
+    frames[1]["rgb"] = T.from_numpy(frames[1]["rgb"]).cuda()
+    w = ConstructionLabelWriter(str(tmp_path), formats=("rgb_png",))
+    w.write_batch(frames)
+    w.on_final_frame()
+    for fr, ref in zip(frames, want):
+        got = cv2.imread(str(tmp_path / "rgb" / f"rgb_{fr['frame_id']:06d}.png"), cv2.IMREAD_COLOR)
+        assert np.array_equal(got, ref)
