@@ -995,3 +995,26 @@ def test_writer_rgb_png(T, ops, tmp_path):
     for fr, ref in zip(frames, want):
         got = cv2.imread(str(tmp_path / "rgb" / f"rgb_{fr['frame_id']:06d}.png"), cv2.IMREAD_COLOR)
         assert np.array_equal(got, ref)
+
+
+def test_format_fixed6_bit_pattern_property(T, ops):
+    """Hypothesis: any float64 / float32 bit pattern inside the supported range formats like Python's '%.6f'."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.lists(st.integers(0, 2 ** 64 - 1), min_size=1, max_size=300), st.integers(1, 9), st.booleans())
+    def run(bits, cols, as_f32):
+        if as_f32:
+            v = (np.asarray(bits, dtype=np.uint64) & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+        else:
+            v = np.asarray(bits, dtype=np.uint64).view(np.float64)
+            big = np.isfinite(v) & (np.abs(v) >= 2.0 ** 128)
+            v = np.where(big, np.ldexp(np.frexp(v)[0], 100), v)      # same mantissa, exponent inside the range
+        n = (len(v) // cols) * cols
+        if n == 0:
+            return
+        v = v[:n].reshape(-1, cols)
+        want = "".join(" ".join("%.6f" % float(x) for x in row) + "\n" for row in v).encode("ascii")
+        assert ops.savetxt_bytes(T.from_numpy(v).cuda()) == want
+
+    run()
