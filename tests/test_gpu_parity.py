@@ -1018,3 +1018,35 @@ def test_format_fixed6_bit_pattern_property(T, ops):
         assert ops.savetxt_bytes(T.from_numpy(v).cuda()) == want
 
     run()
+
+
+def test_depth_colormap_bin_boundaries(T, ops):
+    """f4: the kernel replaces the reference's division (gcd.py:1698) by a multiply wherever that provably gives
+    the same bin; every float within a few ulps of every bin boundary must still land in numpy's bin."""
+    lut = T.from_numpy(np.ascontiguousarray(O.jet_lut_bgr())).cuda()
+    rng = np.random.default_rng(12)
+    frames = []
+    for mn, mx in ((0.5, 250.0), (1.0, 1.0000305), (3.25, 3.25 + 1e-6), (1e-3, 1e4), (17.0, 4.0e37), (2.0 ** -126, 1.0)):
+        mn32, mx32 = np.float32(mn), np.float32(mx)
+        den = np.float64(np.float32(np.float32(mx32 - mn32) + np.float32(1e-6)))
+        centres = (np.float64(mn32) + np.arange(257) * den / 255.0).astype(np.float32)
+        bits = centres.view(np.uint32).astype(np.int64)[:, None] + np.arange(-4, 5)[None, :]
+        v = np.clip(bits, 1, 0x7f7fffff).astype(np.uint32).view(np.float32).ravel()
+        v = np.concatenate([v, rng.uniform(mn, min(mx, 3e38), 1500).astype(np.float32), [mn32, mx32]])
+        v = np.clip(v, mn32, mx32)                       # the frame's own min / max stay mn, mx
+        img = np.full(64 * 64, mn32, dtype=np.float32)
+        img[: len(v)] = v
+        img[-5:] = [np.inf, 0.0, -1.0, np.nan, mx32]
+        frames.append(img.reshape(64, 64))
+    depth = np.stack(frames)
+    got = ops.depth_colormap(T.from_numpy(depth).cuda(), lut).cpu().numpy()
+    for b in range(len(frames)):
+        assert np.array_equal(got[b], O.depth_colormap(depth[b])), b
+    # statistics taken from another image (values above its max): still the reference's formula, bin by bin
+    st = ops.depth_stats(T.from_numpy(depth[:1]).cuda())          # min 0.5, max 250
+    other = rng.uniform(0.5, 900.0, (1, 64, 64)).astype(np.float32)
+    got = ops.depth_colormap(T.from_numpy(other).cuda(), lut, st).cpu().numpy()[0]
+    mn32, mx32 = np.float32(0.5), np.float32(250.0)
+    bins = ((other[0] - mn32) / (np.float32(mx32 - mn32) + np.float32(1e-6)) * np.float32(255.0))
+    bins = np.minimum(bins.astype(np.int64), 255).astype(np.uint8)            # the kernel clamps where numpy's cast wraps
+    assert np.array_equal(got, O.jet_lut_bgr()[bins])
