@@ -39,6 +39,8 @@ if "c2" in which:
     m = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in frames]).view(np.int32)).to(dev).repeat(64 // uniq, 1, 1)
     l = torch.from_numpy(lut).to(dev).repeat(64 // uniq, 1)
     timeit(m, l, obj_record.shape[1], "synthetic c2 64x1080p")
+    if "c2nolut" in which:   # same pixels, every id unmapped: the run decomposition without any table merge
+        timeit(m, torch.full_like(l, -1), obj_record.shape[1], "synthetic c2 64x1080p, all ids unmapped")
     del m
 if "noise16" in which:
     # 16x16-pixel blocks of random ids: many short runs
