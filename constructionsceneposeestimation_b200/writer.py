@@ -155,6 +155,65 @@ class BatchLabels:
         return len(self.frame_ids)
 
 
+class _FrameList(list):
+    """Per-frame dicts cut from a stacked batch dict; remembers the stacked pixel arrays so that they reach the
+    device in one copy (or none, when they already live there)."""
+    stacked: Dict[str, ArrayLike]
+
+
+def _unstack(data: Mapping) -> _FrameList:
+    """``{"instance_segmentation": {"data": [B,H,W], "info": ...}, ...}`` -> list of B frame dicts (views, no copy).
+    Every annotator may carry one ``info`` shared by the batch or a list of B; ``camera_pose`` is [B,7] (or one
+    pose), ``camera_params`` one dict or a list, ``frame_id`` a list or the id of the first frame."""
+    seg = data.get("instance_segmentation")
+    masks = _payload(seg)
+    if masks is None or masks.ndim != 3:
+        raise ValueError("stacked batch: instance_segmentation data must be [B,H,W]")
+    B = int(masks.shape[0])
+
+    def per_frame(value, i):
+        if isinstance(value, (list, tuple)) and len(value) == B:
+            return value[i]
+        return value
+
+    def cut(annot, i):
+        if annot is None:
+            return None
+        if isinstance(annot, Mapping):
+            payload = annot.get("data")
+            out = {"data": None if payload is None else payload[i]}
+            if "info" in annot:
+                out["info"] = per_frame(annot["info"], i)
+            return out
+        return annot[i]
+
+    frames = _FrameList()
+    fid = data.get("frame_id")
+    pose = data.get("camera_pose")
+    for i in range(B):
+        fr: Dict[str, object] = {}
+        for name in ("instance_segmentation", "distance_to_image_plane", "bounding_box_3d", "rgb"):
+            if data.get(name) is not None:
+                fr[name] = cut(data[name], i)
+        sk = data.get("skeleton_data")
+        if sk is not None:
+            j = sk.get("globalTranslations") if isinstance(sk, Mapping) else sk
+            fr["skeleton_data"] = {"globalTranslations": j[i]}
+        if pose is not None:
+            p = np.asarray(pose, dtype=np.float64)
+            fr["camera_pose"] = list(p[i] if p.ndim == 2 else p)
+        if data.get("camera_params") is not None:
+            fr["camera_params"] = per_frame(data["camera_params"], i)
+        if fid is not None:
+            fr["frame_id"] = int(fid[i]) if np.ndim(fid) else int(fid) + i
+        frames.append(fr)
+    frames.stacked = {"instance_segmentation": masks}
+    depth = _payload(data.get("distance_to_image_plane"))
+    if depth is not None and getattr(depth, "ndim", 0) == 3:
+        frames.stacked["distance_to_image_plane"] = depth
+    return frames
+
+
 def _info(annot) -> Mapping:
     if isinstance(annot, Mapping):
         info = annot.get("info")
@@ -254,8 +313,12 @@ class ConstructionLabelWriter:
         """One frame (Replicator ``Writer.write`` signature)."""
         self.write_batch([data])
 
-    def write_batch(self, frames: Sequence[Mapping]) -> BatchLabels:
-        """Annotate a list of frame dicts in one set of launches and queue them for serialisation."""
+    def write_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
+        """Annotate B frames in one set of launches and queue them for serialisation.  ``frames`` is a list of
+        frame dicts (what ``write`` takes) or ONE dict of stacked annotators (``[B,H,W]`` masks / depth, ``[B,R]``
+        records, ``[B,7]`` poses; see ``_unstack``) — stacked pixel arrays go to the device in a single copy."""
+        if isinstance(frames, Mapping):
+            frames = _unstack(frames)
         labels = self.annotate_batch(frames)
         masks = None
         if "mask" in self.formats and self.output_dir is not None:
@@ -339,7 +402,8 @@ class ConstructionLabelWriter:
             # device-resident annotators (device="cuda" in Replicator) were produced on the caller's stream
             self.stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(self.stream):
-                d_mask = self._stack_to_device(masks, torch.int32)
+                stacked = getattr(frames, "stacked", {})
+                d_mask = self._stack_to_device(masks, torch.int32, stacked.get("instance_segmentation"))
 
         # ---- host: per-frame tables ----------------------------------------------------
         tables: List[FrameTables] = []
@@ -411,14 +475,14 @@ class ConstructionLabelWriter:
             depth_list = [_payload(fr.get("distance_to_image_plane")) for fr in frames]
             if all(j is not None and j.shape[0] > 0 for j in joints_list) and all(d is not None for d in depth_list) \
                     and len({tuple(j.shape) for j in joints_list}) == 1:
-                d_depth = self._stack_to_device(depth_list, torch.float32)
+                d_depth = self._stack_to_device(depth_list, torch.float32, stacked.get("distance_to_image_plane"))
                 d_joints = self._stack_to_device(joints_list, torch.float32)
                 d_kp, _kz, d_vis = ops.keypoints(d_joints, d_depth, d_cam, self.keypoint_tolerance)
                 person_slots = [self._person_slots(t, joints_list[i].shape[0]) for i, t in enumerate(tables)]
             stats_host = viz_host = None
             if all(d is not None for d in depth_list):
                 if d_depth is None:
-                    d_depth = self._stack_to_device(depth_list, torch.float32)
+                    d_depth = self._stack_to_device(depth_list, torch.float32, stacked.get("distance_to_image_plane"))
                 d_stats = ops.depth_stats(d_depth)                                  # f2, gcd.py:314-359
                 stats_host = torch.empty(d_stats.shape, dtype=torch.uint8, pin_memory=True)
                 stats_host.copy_(d_stats, non_blocking=True)
@@ -457,8 +521,18 @@ class ConstructionLabelWriter:
         return labels
 
     # ------------------------------------------------------------------ helpers
-    def _stack_to_device(self, arrays: Sequence[ArrayLike], dtype: torch.dtype) -> torch.Tensor:
-        """[B, ...] device tensor from per-frame host arrays / device tensors (async copies)."""
+    def _stack_to_device(self, arrays: Sequence[ArrayLike], dtype: torch.dtype,
+                         stacked: Optional[ArrayLike] = None) -> torch.Tensor:
+        """[B, ...] device tensor from per-frame host arrays / device tensors (async copies); ``stacked`` is the
+        same data as one [B, ...] array when the caller has it (one copy, or none if it is on the device)."""
+        if stacked is not None:
+            if isinstance(stacked, torch.Tensor):
+                t = stacked.view(torch.int32) if dtype == torch.int32 and stacked.dtype == torch.uint32 else stacked
+            else:
+                a = np.ascontiguousarray(stacked)
+                t = torch.from_numpy(a.view(np.int32) if dtype == torch.int32 and a.dtype == np.uint32 else a)
+            if t.dtype == dtype:
+                return t.to(self.device, non_blocking=True).contiguous()
         first = arrays[0]
         if len(arrays) == 1 and isinstance(first, torch.Tensor) and first.is_cuda:
             t = first if first.dtype == dtype or (dtype == torch.int32 and first.dtype == torch.uint32) else first.to(dtype)

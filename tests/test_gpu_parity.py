@@ -1050,3 +1050,36 @@ def test_depth_colormap_bin_boundaries(T, ops):
     bins = ((other[0] - mn32) / (np.float32(mx32 - mn32) + np.float32(1e-6)) * np.float32(255.0))
     bins = np.minimum(bins.astype(np.int64), 255).astype(np.uint8)            # the kernel clamps where numpy's cast wraps
     assert np.array_equal(got, O.jet_lut_bgr()[bins])
+
+
+def test_writer_stacked_batch(T, ops, tmp_path):
+    """write_batch(one dict of stacked annotators) == write_batch(list of frame dicts); host and device stacks."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(640, 360, 18, 3, 17, config_id=13), 3, first_frame=5)
+    o = helpers.oracle_pipeline(frames, frame_base=5)
+    stacked = {
+        "instance_segmentation": {"data": np.stack([f["instance_segmentation"]["data"] for f in frames]),
+                                  "info": [f["instance_segmentation"]["info"] for f in frames]},
+        "distance_to_image_plane": np.stack([f["distance_to_image_plane"] for f in frames]),
+        "bounding_box_3d": {"data": np.stack([f["bounding_box_3d"]["data"] for f in frames]),
+                            "info": [f["bounding_box_3d"]["info"] for f in frames]},
+        "skeleton_data": {"globalTranslations": np.stack([f["skeleton_data"]["globalTranslations"] for f in frames])},
+        "camera_pose": np.asarray([f["camera_pose"] for f in frames]),
+        "camera_params": frames[0]["camera_params"],
+        "frame_id": 5,
+    }
+    for variant in ("host", "device"):
+        data = dict(stacked)
+        if variant == "device":
+            data["instance_segmentation"] = {"data": T.from_numpy(stacked["instance_segmentation"]["data"].view(np.int32)).cuda(),
+                                             "info": stacked["instance_segmentation"]["info"]}
+            data["distance_to_image_plane"] = T.from_numpy(stacked["distance_to_image_plane"]).cuda()
+        w = ConstructionLabelWriter(str(tmp_path / variant), split_people=True)
+        labels = w.write_batch(data)
+        w.on_final_frame()
+        assert labels.frame_ids == [5, 6, 7] and np.array_equal(labels.n_out, o["n_out"])
+        for f in range(3):
+            helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
+            assert np.array_equal(labels.keypoints(f)[1], o["vis"][f])
+        assert (tmp_path / variant / "labels" / "label_000007.json").exists()
