@@ -380,7 +380,11 @@ class ConstructionLabelWriter:
         return {"per_rank": per_rank, "total": per_rank.sum(axis=0)}
 
     # ------------------------------------------------------------------ the hot path
-    def annotate_batch(self, frames: Sequence[Mapping]) -> BatchLabels:
+    def annotate_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
+        """Enqueue the whole path for B frames (list of frame dicts or one stacked dict, like ``write_batch``)
+        and return at once; the result is fenced by ``BatchLabels.synchronize()``."""
+        if isinstance(frames, Mapping):
+            frames = _unstack(frames)
         if len(frames) == 0:
             raise ValueError("annotate_batch needs at least one frame")
         B = len(frames)
