@@ -26,7 +26,7 @@ from . import _lib, formats, ops
 from .quality import FrameQualityLog, depth_quality_from_stats
 from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
 from .camera import DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, pack_camera
-from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot,
+from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot, label_path,
                       record_index_for)
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
@@ -214,6 +214,12 @@ def _unstack(data: Mapping) -> _FrameList:
     return frames
 
 
+def tables_cache_key(prim_paths: Sequence[str], id_to_labels: Mapping) -> Tuple:
+    """Hashable signature of a scene: the prim paths and (id, labelled path) pairs.  Replicator's idToLabels
+    values are strings or ``{"class": ...}`` dicts and its keys may be strings (gcd.py:1826-1837)."""
+    return tuple(prim_paths), tuple((str(k), label_path(v)) for k, v in id_to_labels.items())
+
+
 def _info(annot) -> Mapping:
     if isinstance(annot, Mapping):
         info = annot.get("info")
@@ -290,7 +296,7 @@ class ConstructionLabelWriter:
 
     # ------------------------------------------------------------------ host tables
     def frame_tables(self, prim_paths: Sequence[str], id_to_labels: Mapping) -> FrameTables:
-        key = (tuple(prim_paths), tuple(id_to_labels.items()))
+        key = tables_cache_key(prim_paths, id_to_labels)
         hit = self._tables_cache.get(key)
         if hit is not None:
             return hit

@@ -509,6 +509,16 @@ def test_writer_tolerates_empty_annotators(T, ops):
         labels = w.annotate_batch([{"instance_segmentation": {"data": mask, "info": {"idToLabels": {}}},
                                     "bounding_box_3d": bbox}])
         assert int(labels.n_out[0]) == 0 and len(labels.records(0)) == 0
+    # Replicator's idToLabels: string keys, semantic {"class": ...} dicts next to prim-path strings (gcd.py:1826-1837)
+    from constructionsceneposeestimation_b200 import synthetic
+    fr = synthetic.make_frame(synthetic.SceneSpec(320, 180, 8, 0, 0, config_id=21), 0)
+    want = w.annotate_batch([fr]).records(0).copy()
+    odd = dict(fr)
+    labels_str = {str(k): v for k, v in fr["instance_segmentation"]["info"]["idToLabels"].items()}
+    labels_str["999999"] = {"class": "fence"}
+    odd["instance_segmentation"] = {"data": fr["instance_segmentation"]["data"], "info": {"idToLabels": labels_str}}
+    got = w.annotate_batch([odd]).records(0)
+    assert len(got) == len(want) > 0 and np.array_equal(got["count"], want["count"])
 
 
 def test_pointcloud(T, ops):

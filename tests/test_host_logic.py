@@ -385,3 +385,14 @@ def test_native_coco_annotations_match_python_json_dump(libcspe_path):
         assert b"[" + text + b"]" == want.encode("ascii")
     text, count = formats.coco_annotations_text(recs, np.zeros(B, dtype=np.int32), image_ids, 1)
     assert text == b"" and count == 0
+
+
+def test_tables_cache_key_accepts_replicator_label_shapes():
+    """idToLabels as Replicator hands it over: string keys, prim-path strings or {"class": ...} dicts (gcd.py:1826-1837)."""
+    from constructionsceneposeestimation_b200.writer import tables_cache_key
+
+    labels = {"0": "BACKGROUND", "1": "UNLABELLED", "2": "/World/a/mesh", 3: {"class": "fence"}, 4: {"primPath": "/World/b"}, 5: None}
+    key = tables_cache_key(["/World/a/mesh", "/World/b"], labels)
+    assert hash(key) == hash(tables_cache_key(["/World/a/mesh", "/World/b"], dict(labels)))
+    assert key != tables_cache_key(["/World/a/mesh", "/World/b"], {**labels, "2": "/World/c/mesh"})
+    assert key[1][3] == ("3", None) and key[1][4] == ("4", "/World/b")
