@@ -244,8 +244,8 @@ class ConstructionLabelWriter:
     (``depth/depth_%06d.csv``, the np.savetxt text of gcd.py:1688) and ``"pointcloud"``
     (``pointcloud/pointcloud_%06d.txt`` from depth + ``data["rgb"]``, gcd.py:1729-1759) — both texts are
     formatted on the GPU (``cspe_format_fixed6``) and only their bytes cross PCIe — and ``"rgb_png"``
-    (``rgb/rgb_%06d.png`` from ``data["rgb"]``, gcd.py:1669-1674; the RGB(A) -> BGR conversion runs on the GPU
-    when the annotator is device-resident, PNG encoding is cv2's as in the reference).  When a
+    (``rgb/rgb_%06d.png`` from ``data["rgb"]``, gcd.py:1669-1674; the RGB(A) -> BGR conversion runs on the GPU,
+    PNG encoding is cv2's as in the reference).  When a
     frame carries ``distance_to_image_plane`` the depth-quality statistics of the reference's
     logger (gcd.py:314-359) are computed on the GPU and returned by ``BatchLabels.depth_quality``.
     """
@@ -684,12 +684,9 @@ class ConstructionLabelWriter:
             import cv2
 
             rgb = labels.rgb_images[f]
-            if isinstance(rgb, torch.Tensor) and rgb.is_cuda:   # device-resident annotator: f4 kernel, then D2H of 3 bytes/px
-                with torch.cuda.device(self.device), torch.cuda.stream(self._io_stream()):
-                    bgr = ops.rgb_to_bgr(rgb.contiguous()).cpu().numpy()
-            else:                                               # host image: the reference's own call, gcd.py:1671
-                rgb = rgb.numpy() if isinstance(rgb, torch.Tensor) else np.asarray(rgb)
-                bgr = cv2.cvtColor(np.ascontiguousarray(rgb[..., :3]), cv2.COLOR_RGB2BGR)
+            src = rgb if isinstance(rgb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rgb))
+            with torch.cuda.device(self.device), torch.cuda.stream(self._io_stream()):   # f4 kernel, gcd.py:1671
+                bgr = ops.rgb_to_bgr(src.to(self.device, non_blocking=True).contiguous()).cpu().numpy()
             cv2.imwrite(os.path.join(self.output_dir, "rgb", f"rgb_{fid:06d}.png"), bgr)   # gcd.py:1672-1673
         if "mask" in self.formats and masks is not None:
             m = masks[f]
