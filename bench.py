@@ -284,10 +284,11 @@ def run_ours(args) -> int:
     algo_bytes = 4.0 * H * W * BATCH + 20.0 * N * BATCH
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
     peaks_file = ROOT / "MEASURED_PEAKS.json"
-    if peaks_file.exists():
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
     traffic = None
     tfile = ROOT / "profiles" / "scan_traffic.json"
     if tfile.exists():
