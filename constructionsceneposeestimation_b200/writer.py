@@ -272,6 +272,7 @@ class ConstructionLabelWriter:
         self.resolver = ObjectRootResolver(crane_part_map, split_people=split_people)
         self.rank, self.world_size = rank, world_size
         self.max_pending = max_pending
+        self.max_lut_entries = 1 << 28     # 1 GiB of id -> slot table per batch
         # per-frame files of a batch are formatted and written by a small thread pool
         self.io_threads = min(16, os.cpu_count() or 1) if io_threads is None else max(1, int(io_threads))
         self._io_pool = None
@@ -448,8 +449,14 @@ class ConstructionLabelWriter:
         R = max(1, max((len(r) for r in rec_arrays if r is not None), default=1))
         same_tables = all(t is tables[0] for t in tables)
         L = max(1, max(t.max_id for t in tables) + 1)
-        L = (L + 3) & ~3  # 16-byte LUT rows: K1 then carries each frame's LUT through its TMA ring
-        lut = np.full((1 if same_tables else B, L), -1, dtype=np.int32)
+        L = (L + 3) & ~3  # 16-byte LUT rows
+        lut_rows = 1 if same_tables else B
+        if L * lut_rows > self.max_lut_entries:
+            # the id -> slot table is dense (4 bytes per possible id, per distinct scene in the batch); instance ids
+            # are prim indices in Replicator, so this only trips on ids that are not instance ids
+            raise ValueError(f"instance ids up to {L - 1} need a {L * lut_rows * 4 / 2**20:.0f} MiB id->slot table "
+                             f"(limit {self.max_lut_entries * 4 / 2**20:.0f} MiB, max_lut_entries)")
+        lut = np.full((lut_rows, L), -1, dtype=np.int32)
         obj_record = np.full((B, N), -1, dtype=np.int32)
         slot_class = np.full((B, N), -1, dtype=np.int32)
         rec_bytes = np.zeros((B, R, BBOX3D_DTYPE.itemsize), dtype=np.uint8)
