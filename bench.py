@@ -2,16 +2,29 @@
 """Benchmark of the per-frame annotation hot path (BASELINE.json metric: annotated frames/s at
 1080p / 100 instances; HBM GB/s of the mask-scan kernel vs the measured peak).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (1 process per GPU)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference-style numpy path on host cores
+    python bench.py --gpus N --steps K --warmup W [--config c2|c4]     # our arm (1 process per GPU)
+    python bench.py --impl reference --gpus N --steps K ...             # the reference-style numpy path on host cores
 
-A *step* is one pass of the hot path over one batch of synthetic annotator tensors of
-BASELINE config 2: 64 frames of 1920x1080, 100 instances — mask scan (K1) + per-object
-projection / pose (K2) + occlusion ratios, compaction, record emission and class histogram
-(K4).  ``value`` times K steps on the device with inputs resident in HBM (the 531 MB mask batch
-is 4x the L2, so every step streams from HBM); ``e2e`` times the same batch through the public
-``ConstructionLabelWriter.annotate_batch`` call with HOST (pinned) annotator arrays, i.e.
-including the host table build, the H2D copies and the D2H read of the records.
+A *step* is one pass of the hot path over one batch of synthetic annotator tensors — mask scan (K1)
++ per-object projection / pose (K2) + occlusion ratios, compaction, record emission and class
+histogram (K4):
+  * ``--config c2`` (default, the configuration BASELINE's metric is quoted on): 64 frames of
+    1920x1080, 100 instances, per GPU;
+  * ``--config c4``: the 4-camera 3840x2160 rig with 500 instances per frame; (rig frame, camera)
+    pairs are flattened and sharded over the ranks (``sharding.rig_frame_range``), 4 rig frames =
+    16 camera frames per GPU per step.
+Either batch is 531 MB of mask, 4x the L2, so every step streams from HBM.
+
+``value``: a WINDOW is K steps (one CUDA-graph launch whose kernel nodes keep their programmatic
+dependent-launch edges; ``--eager`` launches the same kernels one by one) followed, on N > 1 GPUs, by
+the path's one collective (all-gather of the int64[10] class histogram).  Windows are queued back to
+back between one barrier + synchronize on each side until at least 25 windows and 0.5 s of device
+time have run; every window is timed with CUDA events on the launching stream, the per-window times
+are MAX-reduced over the ranks, and ``value`` is the whole-job frames/s of the MEDIAN window
+(``ms_per_step`` = median window / K; min / max window and the length of the whole region are in
+``timing``).  ``e2e`` times the same batch through the public
+``ConstructionLabelWriter.annotate_batch`` call with HOST (pinned) annotator arrays, i.e. including
+the host table build, the H2D copies and the D2H read of the records.
 
 One JSON line is printed by rank 0.
 """
@@ -19,6 +32,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -32,20 +46,49 @@ if str(ROOT) not in sys.path:
 
 import numpy as np  # noqa: E402
 
-METRIC = "annotated frames/sec at 1080p/100 instances"
 UNIT = "frames/s"
-WORKLOAD = "c2: 64 x 1920x1080 frames, 100 instances, mask scan + 3D-box projection/pose + occlusion + emission"
-BATCH = 64
-CONFIG_KEY = "c2"
+DTYPE = "int32+f64"
+
+# workload table: synthetic config key, frames per GPU per step, metric wording
+WORKLOADS = {
+    "c2": {"key": "c2", "batch": 64, "cameras": 1,
+           "metric": "annotated frames/sec at 1080p/100 instances",
+           "workload": "c2: 64 x 1920x1080 frames, 100 instances, mask scan + 3D-box projection/pose + occlusion + emission"},
+    "c4": {"key": "c4", "batch": 16, "cameras": 4,
+           "metric": "annotated frames/sec at 2160p/500 instances (4-camera rig)",
+           "workload": "c4: 4-camera 3840x2160 rig, 500 instances/frame, 4 rig frames (16 camera frames) per GPU per step, "
+                       "mask scan + 3D-box projection/pose + occlusion + emission"},
+}
+MIN_WINDOWS = 25
+MIN_REGION_S = 0.5
+
+
+def bench_config(wl, spec) -> dict:
+    """The ``config`` object of the JSON line — the same keys and values in both arms."""
+    return {"workload": wl["workload"], "batch_frames_per_gpu": wl["batch"],
+            "resolution": f"{spec.width}x{spec.height}", "instances": spec.num_instances,
+            "cameras_per_rig": wl["cameras"]}
 
 
 # --------------------------------------------------------------------------------------------
 # synthetic batch
 # --------------------------------------------------------------------------------------------
-def make_frames(n: int, first: int = 0):
-    from constructionsceneposeestimation_b200 import synthetic
+def make_frames(wl, rank: int, world: int, n: int = None):
+    """This rank's frames of one step.  Frames (c4: (rig frame, camera) pairs) are numbered globally and
+    sharded in contiguous ranges; synthetic frame i is seeded by its global index."""
+    from constructionsceneposeestimation_b200 import sharding, synthetic
 
-    return synthetic.make_batch(synthetic.CONFIGS[CONFIG_KEY], n, first)
+    batch, cams = wl["batch"], wl["cameras"]
+    spec = synthetic.CONFIGS[wl["key"]]
+    if cams > 1:
+        pairs = sharding.rig_frame_range(rank, world, world * batch // cams, cams)
+        ids = [rf * cams + c for rf, c in pairs]
+    else:
+        lo, hi = sharding.frame_range(rank, world, world * batch)
+        ids = list(range(lo, hi))
+    if n is not None:
+        ids = ids[:n]
+    return [synthetic.make_frame(spec, i) for i in ids], ids
 
 
 # --------------------------------------------------------------------------------------------
@@ -88,15 +131,20 @@ def run_reference(args) -> int:
     sample of the workload's frames."""
     import multiprocessing as mp
 
+    from constructionsceneposeestimation_b200 import synthetic
+
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    wl = WORKLOADS[args.config]
+    spec = synthetic.CONFIGS[wl["key"]]
+    batch = wl["batch"]
     cores = os.cpu_count() or 1
-    sample = max(cores, min(BATCH, 2 * cores))
-    frames = make_frames(sample)
+    sample = min(batch, cores) if wl["key"] == "c4" else max(cores, min(batch, 2 * cores))
+    frames, _ = make_frames(wl, 0, 1, sample)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        for _ in range(max(1, args.warmup)):
+        for _ in range(max(1, min(args.warmup, 2))):
             pool.map(_cpu_frame, frames, chunksize=1)
         t0 = time.perf_counter()
         for _ in range(args.steps):
@@ -104,13 +152,13 @@ def run_reference(args) -> int:
         dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": 1000.0 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_frames": BATCH, "resolution": "1920x1080", "instances": 100,
-                   "frames_per_reference_step": sample},
+        "impl": "reference", "metric": wl["metric"], "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1000.0 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": bench_config(wl, spec),
+        "timing": {"frames_per_reference_step": sample, "timed_region_s": dt},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of the {BATCH} frames of one step per reference step, numpy oracle "
+                         "sample": f"{sample} of the {batch} frames of one step per reference step, numpy oracle "
                                    f"(bincount+find_objects scan, per-object projection, emission), "
                                    f"{cores} worker processes"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -175,11 +223,30 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
+def _scan_roofline(torch, ops, mask, lut, N, out, reps: int, windows: int = 5):
+    """Median over `windows` of the CUDA-event time of `reps` back-to-back scan launches (ms per launch)."""
+    for _ in range(3):
+        ops.mask_scan(mask, lut, N, out=out, accumulate=True)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(windows):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            ops.mask_scan(mask, lut, N, out=out, accumulate=True)   # the scan kernel only (no init launch)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / reps)
+    return float(np.median(times))
+
+
 def run_ours(args) -> int:
     import torch
     import torch.distributed as dist
 
-    from constructionsceneposeestimation_b200 import _lib, ops
+    from constructionsceneposeestimation_b200 import _lib, ops, synthetic
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline, graph_edge_kinds
+    from constructionsceneposeestimation_b200.sweep import build_host_tables
     from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,6 +259,11 @@ def run_ours(args) -> int:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.load()
+    wl = WORKLOADS[args.config]
+    spec = synthetic.CONFIGS[wl["key"]]
+    BATCH = wl["batch"]
+    K = args.steps
+    warmup = max(3, args.warmup)
     # keep stdout to the one JSON line: libraries (NCCL's version banner) write to fd 1 from C, so
     # point fd 1 at stderr until the line is printed
     sys.stdout.flush()
@@ -200,26 +272,20 @@ def run_ours(args) -> int:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- inputs: each rank owns its own frame range (weak scaling: 64 frames per GPU) -------
-    uniq = int(os.environ.get("CSPE_BENCH_UNIQUE", str(BATCH)))
-    frames = make_frames(uniq, first=rank * BATCH)
-    if uniq < BATCH:
-        frames = [frames[i % uniq] for i in range(BATCH)]
+    # ---- inputs: each rank owns its own frame range (weak scaling: BATCH frames per GPU) -----
+    frames, frame_ids = make_frames(wl, rank, world)
     # input tables come from the PRODUCT's host logic (classes.py / camera.py); the oracle is only
     # used below as the checker of one frame and as the CPU baseline
-    from constructionsceneposeestimation_b200.sweep import build_host_tables
-
     lut, obj_record, slot_class, records, cam, _objs = build_host_tables(frames)
     H, W = frames[0]["instance_segmentation"]["data"].shape
     N = obj_record.shape[1]
     mask_host = torch.empty((BATCH, H, W), dtype=torch.int32, pin_memory=True)
     for i, fr in enumerate(frames):
         mask_host[i].copy_(torch.from_numpy(fr["instance_segmentation"]["data"].view(np.int32)))
-    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
 
     pipe = LabelPipeline(BATCH, H, W, N, records.shape[1], lut.shape[1], dev, per_frame_lut=True, min_pixels=1,
-                         use_graph=args.graph)
-    pipe.frame_base = rank * BATCH
+                         use_graph=False)
+    pipe.frame_base = frame_ids[0]
     pipe.mask.copy_(mask_host, non_blocking=True)
     pipe.lut.copy_(torch.from_numpy(lut))
     pipe.obj_record.copy_(torch.from_numpy(obj_record))
@@ -228,10 +294,23 @@ def run_ours(args) -> int:
     pipe.cam.copy_(torch.from_numpy(cam))
     d_mask, d_lut, scan, rec_out, n_out, class_hist = pipe.mask, pipe.lut, pipe.scan, pipe.records, pipe.n_out, pipe.class_hist
     torch.cuda.synchronize()
-
-    def step():
-        pipe.run()   # mask_scan (accumulate) || project_objects -> emit (+ scan-table reset)
     launches_per_step = pipe.launches_per_run
+
+    graph_info = None
+    if args.eager:
+        def window():
+            for _ in range(K):
+                pipe.run()   # mask_scan (accumulate) || project_objects -> emit (+ scan-table reset), PDL-chained
+    else:
+        if K % 2:   # the K2 buffers alternate per step: an odd K needs one graph per starting parity
+            pipe.step_graph(K)
+            pipe._parity ^= 1
+            pipe.step_graph(K)
+            pipe._parity ^= 1
+        graph_info = graph_edge_kinds(pipe.step_graph(K))
+
+        def window():
+            pipe.run_steps(K)   # ONE graph launch: K x (K1 || K2 -> K4), programmatic edges inside
 
     def barrier():
         if world > 1:
@@ -241,46 +320,70 @@ def run_ours(args) -> int:
     sampler = ClockSampler(local_rank)   # samples clocks from the warm-up to the end of the e2e region
     if rank == 0:
         sampler.start()
-    for _ in range(max(3, args.warmup)):
-        step()
-    if world > 1:  # the histogram all-gather is part of the timed region: set its NCCL channels up here
-        warm = torch.empty((world, _lib.NUM_CLASSES), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(warm, class_hist)
+    gathered = torch.zeros((world, _lib.NUM_CLASSES), dtype=torch.int64, device=dev)
+    # ---- warm-up: W untimed steps, then two untimed windows (one timed, to size the region) -----
+    for _ in range(warmup):
+        pipe.run()
+    window()
+    if world > 1:  # the histogram all-gather is part of every timed window: set its NCCL channels up here
+        dist.all_gather_into_tensor(gathered, class_hist)
     barrier()
+    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0.record()
+    window()
+    w1.record()
+    torch.cuda.synchronize()
+    est = torch.tensor([w0.elapsed_time(w1) / 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(est, op=dist.ReduceOp.MIN)   # same window count on every rank
+    windows = args.windows if args.windows > 0 else max(MIN_WINDOWS, int(math.ceil(1.15 * MIN_REGION_S / max(float(est.item()), 1e-6))))
+    windows = min(windows, 20000)
 
-    # what the timed path produces for frame 0: compared with the oracle inside the CPU-baseline leg below
-    gpu_frame0 = rec_out[0].cpu().numpy().view(_lib.RECORD_DTYPE).reshape(-1)[: int(n_out[0])].copy() if rank == 0 else None
+    # what the timed path produces: frame 0 is compared with the oracle inside the CPU-baseline leg below,
+    # and the per-batch class histogram (from the emitted records) predicts the gathered histogram
+    rec_np = rec_out.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(BATCH, N)
+    n_np = n_out.cpu().numpy()
+    gpu_frame0 = rec_np[0, : int(n_np[0])].copy() if rank == 0 else None
+    kept = np.arange(N)[None, :] < n_np[:, None]
+    batch_hist = np.bincount(rec_np["class_id"][kept], minlength=_lib.NUM_CLASSES)[: _lib.NUM_CLASSES].astype(np.int64)
 
-    # ---- value: K steps, device-timed, inputs resident in HBM ---------------------------------
+    # ---- value: `windows` windows of K steps, device-timed, inputs resident in HBM ---------------
     class_hist.zero_()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    if world > 1:  # the path's one collective: all-gather of the per-class histogram at sweep end
-        gathered = torch.empty((world, _lib.NUM_CLASSES), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, class_hist)
-    ev1.record()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(windows)]
+    for a, b in ev:
+        a.record()
+        window()
+        if world > 1:  # the path's one collective: all-gather of the per-class histogram
+            dist.all_gather_into_tensor(gathered, class_hist)
+        b.record()
     barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    t = torch.tensor([a.elapsed_time(b) for a, b in ev] + [ev[0][0].elapsed_time(ev[-1][1])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    ms_per_step = ms_total / args.steps
-    value = world * BATCH * args.steps / (ms_total / 1000.0)
+    t = t.cpu().numpy()
+    win_ms, region_ms = t[:-1], float(t[-1])
+    med_ms = float(np.median(win_ms))
+    ms_per_step = med_ms / K
+    value = world * BATCH * K / (med_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel: the mask scan alone, K launches -----------------------
+    # the gathered histogram must be exactly (windows x K steps) x every rank's per-batch histogram
+    expect = torch.from_numpy(batch_hist * (windows * K)).to(dev)
+    expect_all = torch.empty((world, _lib.NUM_CLASSES), dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_gather_into_tensor(expect_all, expect)
+    else:
+        expect_all[0] = expect
+        gathered[0] = class_hist
+    if not torch.equal(gathered, expect_all):
+        raise SystemExit(f"rank {rank}: class histogram mismatch after the timed region: gathered "
+                         f"{gathered.tolist()} vs expected {expect_all.tolist()}")
+    hist_total = gathered.sum(dim=0).tolist()
+
+    # ---- roofline of the dominant kernel: the mask scan alone --------------------------------------
     barrier()
-    reps = max(args.steps, 10)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        ops.mask_scan(d_mask, d_lut, N, out=scan, accumulate=True)   # the scan kernel only (no init launch)
-    e1.record()
-    torch.cuda.synchronize()
-    scan_ms = e0.elapsed_time(e1) / reps
+    reps = max(K, 20)
+    scan_ms = _scan_roofline(torch, ops, d_mask, d_lut, N, scan, reps)
     algo_bytes = 4.0 * H * W * BATCH + 20.0 * N * BATCH
     achieved = algo_bytes / (scan_ms * 1e-3) / 1e9
     peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -289,64 +392,117 @@ def run_ours(args) -> int:
         peak, peak_src = float(json.loads(peaks_file.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     except (OSError, ValueError, KeyError, TypeError):
         pass
-    traffic = None
+    traffic, traffic_src = None, None
     tfile = ROOT / "profiles" / "scan_traffic.json"
     if tfile.exists():
         try:
-            traffic = json.loads(tfile.read_text()).get("dram_bytes_per_launch")
-        except (ValueError, OSError):
+            tj = json.loads(tfile.read_text())
+            traffic = tj.get("dram_bytes_per_launch", {}).get(wl["key"]) if isinstance(tj.get("dram_bytes_per_launch"), dict) \
+                else (tj.get("dram_bytes_per_launch") if wl["key"] == "c2" else None)
+            traffic_src = ("static: ncu --set full capture committed under profiles/ (" + str(tj.get("source", "scan_traffic.json"))
+                           + "), not measured in this run") if traffic is not None else None
+        except (ValueError, OSError, AttributeError):
             traffic = None
+
+    # ---- the same kernel on masks that live on its slow path (N = 1 only) ----------------------------
+    stress = None
+    if world == 1 and not args.no_stress and wl["key"] == "c2":
+        stress = {}
+        uniq = 16
+        for key in ("c2_dense", "c2_textured"):
+            sf = synthetic.make_batch(synthetic.CONFIGS[key], uniq)
+            s_lut, s_obj, *_ = build_host_tables(sf)
+            sm = torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in sf]).view(np.int32)).to(dev)
+            sm = sm.repeat(BATCH // uniq, 1, 1)
+            sl = torch.from_numpy(s_lut).to(dev).repeat(BATCH // uniq, 1)
+            s_out = ops.mask_scan(sm, sl, s_obj.shape[1])
+            ms = _scan_roofline(torch, ops, sm, sl, s_obj.shape[1], s_out, reps, 3)
+            stress[key] = {"ms_per_launch": ms, "frac": 4.0 * H * W * BATCH / (ms * 1e-3) / 1e9 / peak}
+            del sm, sl, s_out
+        flat_lut = torch.arange(-2, 126, dtype=torch.int32, device=dev).clamp(min=-1)
+        g = torch.randint(2, 102, (BATCH, (H + 15) // 16, (W + 15) // 16), device=dev, dtype=torch.int32)
+        cases = {"blocks16x16": g.repeat_interleave(16, 1).repeat_interleave(16, 2)[:, :H, :W].contiguous(),
+                 "noise_2_ids": torch.randint(4, 6, (BATCH, H, W), device=dev, dtype=torch.int32),
+                 "noise_100_ids": torch.randint(2, 102, (BATCH, H, W), device=dev, dtype=torch.int32)}
+        del g
+        for name, sm in cases.items():
+            s_out = ops.mask_scan(sm, flat_lut, 100)
+            ms = _scan_roofline(torch, ops, sm, flat_lut, 100, s_out, reps, 3)
+            stress[name] = {"ms_per_launch": ms, "frac": 4.0 * H * W * BATCH / (ms * 1e-3) / 1e9 / peak}
+        del cases
+        torch.cuda.empty_cache()
 
     # ---- e2e: the public Writer call with HOST annotator arrays ----------------------------------
     # one dict of stacked annotators, the batch form of the writer's input: the mask batch is ONE pinned
-    # [64,H,W] array (config 2 has no keypoint stage, so no skeleton / depth annotator)
-    host_frames = {
-        "instance_segmentation": {"data": mask_host, "info": [fr["instance_segmentation"]["info"] for fr in frames]},
-        "bounding_box_3d": {"data": [fr["bounding_box_3d"]["data"] for fr in frames],
-                            "info": [fr["bounding_box_3d"]["info"] for fr in frames]},
-        "camera_pose": np.asarray([fr["camera_pose"] for fr in frames], dtype=np.float64),
-        "camera_params": [fr["camera_params"] for fr in frames],
-        "frame_id": rank * BATCH,
-    }
+    # [B,H,W] array (these configs have no keypoint stage, so no skeleton / depth annotator)
+    def stacked(mask_array):
+        return {
+            "instance_segmentation": {"data": mask_array, "info": [fr["instance_segmentation"]["info"] for fr in frames]},
+            "bounding_box_3d": {"data": [fr["bounding_box_3d"]["data"] for fr in frames],
+                                "info": [fr["bounding_box_3d"]["info"] for fr in frames]},
+            "camera_pose": np.asarray([fr["camera_pose"] for fr in frames], dtype=np.float64),
+            "camera_params": [fr["camera_params"] for fr in frames],
+            "frame_id": list(frame_ids),
+        }
+
     writer = ConstructionLabelWriter(None, device=dev, split_people=True)
-    for _ in range(2):
-        writer.annotate_batch(host_frames).synchronize()
+    e2e_steps = max(1, min(K, 10))
+
+    def e2e_run(batch_dict):
+        for _ in range(2):
+            writer.annotate_batch(batch_dict).synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        # two batches in flight, like write_batch's queue (max_pending = 2): the host work of step k+1
+        # (tables, enqueueing the copies) overlaps the PCIe transfer of step k; every step still copies its
+        # inputs from pinned host memory and has its records read back on the host
+        in_flight, emitted = None, 0
+        for _ in range(e2e_steps):
+            labels = writer.annotate_batch(batch_dict)
+            if in_flight is not None:
+                emitted += int(in_flight.n_out.sum())          # synchronises on that batch's event
+            in_flight = labels
+            d2h = labels._rec_host.numel() + labels._nout_host.numel() * 4
+        emitted += int(in_flight.n_out.sum())
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if emitted != int(batch_hist.sum()) * e2e_steps:
+            raise SystemExit(f"rank {rank}: e2e emitted {emitted} records, expected {int(batch_hist.sum()) * e2e_steps}")
+        return float(dt.item()), d2h
+
+    e2e_s, d2h = e2e_run(stacked(mask_host))
+    e2e_value = world * BATCH * e2e_steps / e2e_s
+    small_h2d = lut.nbytes + obj_record.nbytes + slot_class.nbytes + records.nbytes + cam.nbytes
+    h2d = mask_host.numel() * 4 + small_h2d
+    # ceiling of that arm: a bare pinned -> device copy of the same mask batch, all ranks at once
     barrier()
-    e2e_steps = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
-    d2h = 0
-    # two batches in flight, like write_batch's queue (max_pending = 2): the host work of step k+1
-    # (tables, enqueueing the copies) overlaps the PCIe transfer of step k; every step still copies its
-    # inputs from pinned host memory and has its records read back on the host
-    in_flight = None
-    emitted = 0
-    for _ in range(e2e_steps):
-        labels = writer.annotate_batch(host_frames)
-        if in_flight is not None:
-            emitted += int(in_flight.n_out.sum())          # synchronises on that batch's event
-        in_flight = labels
-        d2h = labels._rec_host.numel() + labels._nout_host.numel() * 4
-    emitted += int(in_flight.n_out.sum())
+    for _ in range(5):
+        d_mask.copy_(mask_host, non_blocking=True)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    cp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * e2e_steps / float(te.item())
-    h2d = mask_host.numel() * 4 + lut.nbytes + obj_record.nbytes + slot_class.nbytes + records.nbytes + cam.nbytes
+        dist.all_reduce(cp, op=dist.ReduceOp.MAX)
+    pcie_gbs = 5 * mask_host.numel() * 4 / float(cp.item()) / 1e9
+    # ... and the same Writer call fed DEVICE-resident annotators (what device="cuda" annotators deliver): the
+    # Writer's own overhead without PCIe in front of it (only the small tables go up, the records come back)
+    dev_s, _ = e2e_run(stacked(d_mask))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- CPU baseline (rank 0, N = 1 only): numpy oracle on the host cores, bounded sample ---------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(cores, min(BATCH, 2 * cores))
+        sample = min(BATCH, cores) if wl["key"] == "c4" else max(cores, min(BATCH, 2 * cores))
         fps = cpu_throughput(frames[:sample], cores, reps=2)
-        fps1 = cpu_throughput(frames[:4], 1, reps=1)
+        fps1 = cpu_throughput(frames[:2 if wl["key"] == "c4" else 4], 1, reps=1)
         # the CPU leg doubles as the checker of the GPU arm: frame 0 of the timed batch, record for record
         from tests import helpers
 
-        want = helpers.oracle_pipeline(frames[:1], frame_base=0)
+        want = helpers.oracle_pipeline(frames[:1], frame_base=frame_ids[0])
         helpers.assert_records_equal(gpu_frame0, want["recs"][0, : want["n_out"][0]])
         cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{sample} of the step's {BATCH} frames through the numpy oracle pipeline "
@@ -355,22 +511,39 @@ def run_ours(args) -> int:
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_frames_per_gpu": BATCH, "resolution": f"{W}x{H}", "instances": N,
-                       "unique_frames": uniq, "l2": "inputs (531 MB mask batch per step) larger than the 126 MB L2",
-                       "parallelism": f"frames sharded, {world} rank(s), no data-path collective",
-                       "step": "CUDA graph replay" if args.graph else "3 eager launches per step (PDL-chained)"},
+            "metric": wl["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": bench_config(wl, spec),
+            "timing": {"windows": windows, "steps_per_window": K, "statistic": "median window, max over ranks per window",
+                       "window_ms_median": med_ms, "window_ms_min": float(win_ms.min()), "window_ms_max": float(win_ms.max()),
+                       "timed_region_s": region_ms / 1e3, "sum_of_windows_s": float(win_ms.sum()) / 1e3,
+                       "value_over_whole_region": world * BATCH * K * windows / (region_ms / 1e3),
+                       "step": "K steps per window, eager launches (PDL-chained)" if args.eager else
+                               "K steps per window as one CUDA graph launch (programmatic edges kept)",
+                       "graph": graph_info,
+                       "collective": "all_gather(int64[10]) once per window" if world > 1 else "none (1 rank)",
+                       "unique_frames_per_gpu": BATCH,
+                       "l2": f"inputs ({algo_bytes / 1e6:.0f} MB mask batch per step) larger than the 126 MB L2",
+                       "parallelism": f"frames sharded, {world} rank(s), no data-path collective"},
+            "class_histogram": {"total": hist_total, "checked": "gathered == windows x K x per-batch histogram of every rank"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "mask_scan_kernel", "ms_per_launch": scan_ms,
-                         "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "mask_scan_kernel",
+                         "ms_per_launch": scan_ms, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "ConstructionLabelWriter.annotate_batch(stacked host annotator dict), 2 batches in flight",
-                    "h2d_gbs_effective": h2d * e2e_steps / float(te.item()) / 1e9},
-            "gpu_launches": launches_per_step * args.steps,
+                    "h2d_gbs_effective": h2d * e2e_steps / e2e_s / 1e9,
+                    "pcie_ceiling_gbs": pcie_gbs, "frac_of_pcie": (h2d * e2e_steps / e2e_s / 1e9) / pcie_gbs,
+                    "pcie_ceiling_how": "bare pinned->device copy of the same mask batch, 5x, all ranks at once, per GPU",
+                    "device_resident": {"value": world * BATCH * e2e_steps / dev_s, "unit": UNIT,
+                                        "h2d_bytes_per_step": int(small_h2d), "d2h_bytes_per_step": int(d2h),
+                                        "api": "same call, mask batch already a CUDA tensor (device annotators)"}},
+            "gpu_launches": launches_per_step * K * windows,
             "clocks": clocks,
         }
+        if stress is not None:
+            line["roofline_stress"] = {"kernel": "mask_scan_kernel", "peak": peak, "cases": stress,
+                                       "what": "same launch shape (64 x 1080p) on masks that take the kernel's slow path"}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         sys.stdout.flush()
@@ -387,10 +560,12 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--windows", type=int, default=0, help="timed windows of K steps (default: >= 25 and >= 0.5 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--graph", action="store_true",
-                    help="replay the step as a CUDA graph (default: eager launches, which keep the programmatic "
-                         "dependent-launch overlap between the kernels and measured faster)")
+    ap.add_argument("--no-stress", action="store_true", help="skip the roofline_stress block (N = 1, c2 only)")
+    ap.add_argument("--eager", action="store_true",
+                    help="launch the kernels of a window one by one instead of replaying one CUDA graph per window")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

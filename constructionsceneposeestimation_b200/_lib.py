@@ -106,6 +106,7 @@ PROTOTYPES = {
     "cspe_mask_scan": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
     "cspe_mask_scan_accumulate": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
     "cspe_mask_scan_accumulate_overlapped": (_I, [_P, _I, _I, _I, _P, _I, _I64, _I, _P, _P]),
+    "cspe_mask_scan_fills_device": (_I, [_I, _I, _I]),
     "cspe_mask_scan_depth_stats": (_I, [_P, _P, _I, _I, _I, _P, _I, _I64, _I, _P, _P, _P]),
     "cspe_project_objects": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cspe_project_objects_overlapped": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
@@ -113,6 +114,10 @@ PROTOTYPES = {
     "cspe_keypoints_overlapped": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, C.c_double, _P, _P, _P, _P]),
     "cspe_emit": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_emit_reset_scan": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "cspe_emit_reset_scan_indirect": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "cspe_format_yolo": (_I, [_P, _P, _I, _I, _P, _I64, _P, _P]),
+    "cspe_memcpy_async": (_I, [_P, _P, C.c_size_t, _P]),
+    "cspe_graph_edge_kinds": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),
     "cspe_depth_to_pointcloud": (_I, [_P, _P, _I, _I, _I, _P, _P, _I64, _P, _P, _P]),
     "cspe_depth_stats": (_I, [_P, _I, _I, _I, _P, _P]),

@@ -49,3 +49,41 @@ extern "C" int cspe_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) *cc_minor = min;
   return CSPE_OK;
 }
+
+// Stream-ordered copy through the library's own runtime (cudaMemcpyDefault): lets a host driver put the D2H
+// read-back of a batch into a captured CUDA graph next to the kernels without going through a framework's
+// pinned-memory bookkeeping.  Host memory should be page-locked or the copy is not asynchronous.
+extern "C" int cspe_memcpy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return CSPE_OK;
+  CSPE_REQUIRE(dst != nullptr && src != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_memcpy_async: null pointer");
+  CSPE_CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return CSPE_OK;
+}
+
+// Diagnostics for captured step graphs: how many dependency edges the graph holds and how many of them are
+// PROGRAMMATIC (a kernel launched with programmatic stream serialisation behind another kernel keeps its
+// early-start edge through stream capture; anything else between two kernels turns it into a full edge).
+extern "C" int cspe_graph_edge_kinds(void* cuda_graph, int* num_nodes, int* num_edges, int* num_programmatic) {
+  CSPE_REQUIRE(cuda_graph != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_graph_edge_kinds: graph is null");
+  cudaGraph_t g = static_cast<cudaGraph_t>(cuda_graph);
+  size_t nn = 0, ne = 0;
+  CSPE_CUDA_OK(cudaGraphGetNodes(g, nullptr, &nn));
+  CSPE_CUDA_OK(cudaGraphGetEdges_v2(g, nullptr, nullptr, nullptr, &ne));
+  int prog = 0;
+  if (ne > 0) {
+    cudaGraphNode_t* from = new cudaGraphNode_t[ne];
+    cudaGraphNode_t* to = new cudaGraphNode_t[ne];
+    cudaGraphEdgeData* data = new cudaGraphEdgeData[ne];
+    const cudaError_t e = cudaGraphGetEdges_v2(g, from, to, data, &ne);
+    if (e == cudaSuccess)
+      for (size_t i = 0; i < ne; ++i) prog += data[i].type == cudaGraphDependencyTypeProgrammatic ? 1 : 0;
+    delete[] from;
+    delete[] to;
+    delete[] data;
+    CSPE_CUDA_OK(e);
+  }
+  if (num_nodes) *num_nodes = static_cast<int>(nn);
+  if (num_edges) *num_edges = static_cast<int>(ne);
+  if (num_programmatic) *num_programmatic = prog;
+  return CSPE_OK;
+}

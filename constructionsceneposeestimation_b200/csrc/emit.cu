@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads)
     emit_kernel(const int32_t* scan, int32_t* scan_reset, const double* __restrict__ uv, const double* __restrict__ z,
                 const double* __restrict__ pose, const double* __restrict__ loose, const uint8_t* __restrict__ flags,
                 const int32_t* __restrict__ slot_class, int N, int H, int W, int min_pixels, int frame_base,
-                cspe_record* __restrict__ records, int32_t* __restrict__ n_out,
+                const int32_t* __restrict__ frame_base_dev, cspe_record* __restrict__ records, int32_t* __restrict__ n_out,
                 unsigned long long* __restrict__ class_hist) {
   __shared__ int warp_sums[kEmitChunk / 32];
   __shared__ int base_s;
@@ -55,6 +55,8 @@ __global__ void __launch_bounds__(kThreads)
   // kernel before us; its results (and, transitively, the mask scan's) are complete after this
   pdl_wait();
 
+  // graph-replayable frame numbering: the id of the batch's first frame may come from device memory
+  if (frame_base_dev) frame_base += __ldg(frame_base_dev);
   const int32_t* uv32 = reinterpret_cast<const int32_t*>(uv);
   const int32_t* z32 = reinterpret_cast<const int32_t*>(z);
   const int32_t* pose32 = reinterpret_cast<const int32_t*>(pose);
@@ -210,8 +212,8 @@ using namespace cspe;
 
 static int emit_impl(const int32_t* scan, int32_t* scan_reset, const double* uv, const double* z, const double* pose,
                      const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N, int H, int W,
-                     int min_pixels, int frame_base, cspe_record* records, int32_t* n_out, int64_t* class_hist,
-                     void* stream) {
+                     int min_pixels, int frame_base, const int32_t* frame_base_dev, cspe_record* records,
+                     int32_t* n_out, int64_t* class_hist, void* stream) {
   CSPE_REQUIRE(B >= 0 && N >= 0 && H >= 0 && W >= 0, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_emit: negative size (B=%d N=%d H=%d W=%d)", B, N, H, W);
   if (B == 0) return CSPE_OK;
@@ -223,12 +225,12 @@ static int emit_impl(const int32_t* scan, int32_t* scan_reset, const double* uv,
   if (N <= kEmitChunk) {
     CSPE_CUDA_OK(launch_pdl(emit_kernel<256>, dim3(static_cast<unsigned>(B)), dim3(256), 0,
                             static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class,
-                            N, H, W, min_pixels, frame_base, records, n_out,
+                            N, H, W, min_pixels, frame_base, frame_base_dev, records, n_out,
                             reinterpret_cast<unsigned long long*>(class_hist)));
   } else {
     CSPE_CUDA_OK(launch_pdl(emit_kernel<1024>, dim3(static_cast<unsigned>(B)), dim3(1024), 0,
                             static_cast<cudaStream_t>(stream), scan, scan_reset, uv, z, pose, loose, flags, slot_class,
-                            N, H, W, min_pixels, frame_base, records, n_out,
+                            N, H, W, min_pixels, frame_base, frame_base_dev, records, n_out,
                             reinterpret_cast<unsigned long long*>(class_hist)));
   }
   return CSPE_OK;
@@ -238,14 +240,24 @@ extern "C" int cspe_emit(const int32_t* scan, const double* uv, const double* z,
                          const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N, int H,
                          int W, int min_pixels, int frame_base, cspe_record* records, int32_t* n_out,
                          int64_t* class_hist, void* stream) {
-  return emit_impl(scan, nullptr, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, records,
-                   n_out, class_hist, stream);
+  return emit_impl(scan, nullptr, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, nullptr,
+                   records, n_out, class_hist, stream);
 }
 
 extern "C" int cspe_emit_reset_scan(int32_t* scan, const double* uv, const double* z, const double* pose,
                                     const double* loose, const uint8_t* flags, const int32_t* slot_class, int B, int N,
                                     int H, int W, int min_pixels, int frame_base, cspe_record* records,
                                     int32_t* n_out, int64_t* class_hist, void* stream) {
-  return emit_impl(scan, scan, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, records,
-                   n_out, class_hist, stream);
+  return emit_impl(scan, scan, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base, nullptr,
+                   records, n_out, class_hist, stream);
+}
+
+extern "C" int cspe_emit_reset_scan_indirect(int32_t* scan, const double* uv, const double* z, const double* pose,
+                                             const double* loose, const uint8_t* flags, const int32_t* slot_class,
+                                             int B, int N, int H, int W, int min_pixels, int frame_base,
+                                             const int32_t* frame_base_dev, cspe_record* records, int32_t* n_out,
+                                             int64_t* class_hist, void* stream) {
+  CSPE_REQUIRE(frame_base_dev != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_emit_reset_scan_indirect: frame_base_dev is null");
+  return emit_impl(scan, scan, uv, z, pose, loose, flags, slot_class, B, N, H, W, min_pixels, frame_base,
+                   frame_base_dev, records, n_out, class_hist, stream);
 }

@@ -55,6 +55,8 @@ constexpr int kTileRows = kBoxRows;               // 64
 constexpr int kStages = 3;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kDefaultBoxes = 4;  // measured best: 2 CTAs per SM (profiles/)
+constexpr int kRunWalkMax = 4;    // rows with fewer run STARTS than this walk their runs (<= 4 runs)
+constexpr int kMaxDistinct = 3;   // ids accounted per equality mask before the run walk takes the rest
 
 // Geometry of one CTA: kBoxes TMA boxes side by side per tile, two consumer warps per box (row
 // halves) + one producer warp.  CTAs per SM = 8 / kBoxes, so an SM always runs 16 consumer warps
@@ -144,26 +146,49 @@ __device__ __forceinline__ void red_global_max(int32_t* p, int v) {
 }
 
 // Merge one evicted register entry into the CTA table (shared) or straight into `out`.
-template <bool kSmemTable>
+//
+// kFlush = 1 (default): the id goes through the LUT first — an ignored id (background, unlabelled,
+// unmapped) costs one shared-memory load and nothing else — then the lanes that are here are
+// grouped by SLOT with match.any and every group is reduced with redux before its leader issues
+// the five reds.  Lanes run down the rows of one strip, so a warp usually evicts one id at the
+// same moment (one group); where an object edge or a texture crosses the 32 rows it evicts a
+// few (one group each) — never 32 lanes x 5 same-address reds, which is what saturated the
+// shared-memory atomic unit on fragmented masks (16x16-pixel id blocks ran at 0.71 of peak).
+// kFlush = 0 keeps round 1's form (match.all on the id, else every lane on its own) for A/B runs.
+template <bool kSmemTable, int kFlush>
 __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx, int ymn, int ymx,
                                          const int32_t* lut, int lut_len, int N, int32_t* tab) {
-  // Lanes run down the rows of one strip, so a whole warp usually evicts the SAME id at the
-  // same moment: reduce across the converged lanes first and let one lane do the merge
-  // (otherwise the five reds below are 32-way same-address conflicts).
-  const unsigned active = __activemask();
-  int same;
-  __match_all_sync(active, id, &same);
-  if (same) {
-    cnt = __reduce_add_sync(active, cnt);
-    xmn = __reduce_min_sync(active, xmn);
-    xmx = __reduce_max_sync(active, xmx);
-    ymn = __reduce_min_sync(active, ymn);
-    ymx = __reduce_max_sync(active, ymx);
-    if ((threadIdx.x & 31) != __ffs(active) - 1) return;
+  int slot;
+  if (kFlush == 1) {
+    if (id >= static_cast<uint32_t>(lut_len)) return;
+    slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
+    if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
+    const unsigned active = __activemask();
+    const unsigned grp = __match_any_sync(active, slot);
+    if (grp & (grp - 1)) {  // more than one lane holds this slot: reduce inside the group
+      cnt = __reduce_add_sync(grp, cnt);
+      xmn = __reduce_min_sync(grp, xmn);
+      xmx = __reduce_max_sync(grp, xmx);
+      ymn = __reduce_min_sync(grp, ymn);
+      ymx = __reduce_max_sync(grp, ymx);
+      if ((threadIdx.x & 31) != __ffs(grp) - 1) return;
+    }
+  } else {
+    const unsigned active = __activemask();
+    int same;
+    __match_all_sync(active, id, &same);
+    if (same) {
+      cnt = __reduce_add_sync(active, cnt);
+      xmn = __reduce_min_sync(active, xmn);
+      xmx = __reduce_max_sync(active, xmx);
+      ymn = __reduce_min_sync(active, ymn);
+      ymx = __reduce_max_sync(active, ymx);
+      if ((threadIdx.x & 31) != __ffs(active) - 1) return;
+    }
+    if (id >= static_cast<uint32_t>(lut_len)) return;
+    slot = lut[id];
+    if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
   }
-  if (id >= static_cast<uint32_t>(lut_len)) return;
-  const int slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
-  if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
   int32_t* e = tab + slot * CSPE_SCAN_FIELDS;
   if (kSmemTable) {
     red_shared_add(e + CSPE_SCAN_COUNT, cnt);
@@ -195,7 +220,7 @@ __device__ __forceinline__ int table_identity(int field) {
         e1 = t__;                                                                       \
       } else {                                                                          \
         if (e1.cnt)                                                                     \
-          flush_entry<kSmemTable>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut,   \
+          flush_entry<kSmemTable, kFlush>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut,   \
                                   p.lut_len, p.N, tab);                                 \
         e1 = e0;                                                                        \
         entry_reset(e0, v__);                                                           \
@@ -212,7 +237,7 @@ __device__ __forceinline__ int table_identity(int field) {
     e0.ymx = max(e0.ymx, y);                                                            \
   } while (0)
 
-template <bool kSmemTable, int kBoxes>
+template <bool kSmemTable, int kBoxes, int kFlush, int kSlow>
 // 80 registers (one 4-byte spill): leaves ~19 K registers per SM beside the two resident scan CTAs for
 // the small kernels that overlap with it
 __global__ void __maxnreg__(80)
@@ -343,8 +368,8 @@ __global__ void __maxnreg__(80)
   };
 
   auto close_frame = [&]() {
-    if (e0.cnt) flush_entry<kSmemTable>(e0.id, e0.cnt, e0.xmn, e0.xmx, e0.ymn, e0.ymx, lut, p.lut_len, p.N, tab);
-    if (e1.cnt) flush_entry<kSmemTable>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut, p.lut_len, p.N, tab);
+    if (e0.cnt) flush_entry<kSmemTable, kFlush>(e0.id, e0.cnt, e0.xmn, e0.xmx, e0.ymn, e0.ymx, lut, p.lut_len, p.N, tab);
+    if (e1.cnt) flush_entry<kSmemTable, kFlush>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut, p.lut_len, p.N, tab);
     entry_reset(e0, 0u);
     entry_reset(e1, 0u);
     if (kSmemTable || p.smem_lut) named_bar_sync(1, kConsumers);  // all flushes landed / LUT no longer read
@@ -417,24 +442,56 @@ __global__ void __maxnreg__(80)
         CSPE_ACCUM(kStripPx, x0, x0 + kStripPx - 1);
       } else {
         // run decomposition: bit j of `bm` marks a run start (pixel j differs from pixel j-1);
-        // all lanes of the warp that are here build the mask in lockstep, then walk their runs
+        // all lanes of the warp that are here build the mask in lockstep
         const uint32_t v[kStripPx] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z,
                                       q2.w, q3.x, q3.y, q3.z, q3.w, q4.x, q4.y, q4.z, q4.w, q5.x, q5.y,
                                       q5.z, q5.w, q6.x, q6.y, q6.z, q6.w, q7.x, q7.y, q7.z, q7.w};
         uint32_t bm = 0;
 #pragma unroll
         for (int j = 1; j < kStripPx; ++j) bm |= (v[j] != v[j - 1]) ? (1u << j) : 0u;
-        if (len < kStripPx) bm &= (1u << len) - 1u;
-        int s0 = 0;
+        const uint32_t live = len < kStripPx ? (1u << len) - 1u : 0xffffffffu;
+        bm &= live;
+        // pixels not yet accounted for
+        uint32_t rem = live;
+        if (kSlow == 1 && __popc(bm) >= kRunWalkMax) {
+          // Many runs (a see-through texture: wire mesh, foliage, or an edge that zig-zags): the row
+          // usually still holds only two or three DISTINCT ids, so account for it per id instead of
+          // per run — equality bit mask of the id over the 32 pixels, count = popc, extent = ffs / clz.
+          // After kMaxDistinct ids whatever is left goes through the run walk below.
+          uint32_t id = a;
 #pragma unroll 1
-        while (s0 < len) {
-          const uint32_t t = bm & (0xfffffffeu << s0);
+          for (int k = 0; k < kMaxDistinct; ++k) {
+            // the row is re-read from shared memory (8 conflict-free LDS.128) instead of keeping 32
+            // pixel registers alive across the loop: the kernel is capped at 80 registers
+            uint32_t m = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 r = *reinterpret_cast<const uint4*>(base + ((c ^ sw) << 4));
+              m |= (r.x == id ? 1u : 0u) << (4 * c) | (r.y == id ? 2u : 0u) << (4 * c) |
+                   (r.z == id ? 4u : 0u) << (4 * c) | (r.w == id ? 8u : 0u) << (4 * c);
+            }
+            m &= rem;
+            CSPE_SWITCH(id);
+            CSPE_ACCUM(__popc(m), x0 + __ffs(m) - 1, x0 + 31 - __clz(m));
+            rem &= ~m;
+            if (rem == 0) break;
+            const int s = __ffs(rem) - 1;
+            id = *reinterpret_cast<const uint32_t*>(base + (((s >> 2) ^ sw) << 4) + ((s & 3) << 2));
+          }
+        }
+        // run walk over the pixels still in `rem` (all of them when the row has few runs): one
+        // iteration per run, one shared-memory load per run
+        const uint32_t stops = bm | ~rem;   // a run ends before the next run start or accounted pixel
+#pragma unroll 1
+        while (rem) {
+          const int s0 = __ffs(rem) - 1;
+          const uint32_t t = stops & (0xfffffffeu << s0);
           const int e = t ? __ffs(t) - 2 : len - 1;   // last pixel of the run starting at s0
           const uint32_t id =
               *reinterpret_cast<const uint32_t*>(base + (((s0 >> 2) ^ sw) << 4) + ((s0 & 3) << 2));
           CSPE_SWITCH(id);
           CSPE_ACCUM(e - s0 + 1, x0 + s0, x0 + e);
-          s0 = e + 1;
+          rem &= 0xfffffffeu << e;   // clears bits 0..e (everything below s0 is already clear)
         }
       }
     }
@@ -500,6 +557,13 @@ int scan_tma_dims() {
     return (e && atoi(e) == 2) ? 2 : 3;
   }();
   return v;
+}
+
+// CSPE_SCAN_FLUSH / CSPE_SCAN_SLOW = 0 select round 1's flush (match.all) / slow path (run walk only) for
+// same-box A/B runs; default 1 / 1
+int scan_variant(const char* name) {
+  const char* e = getenv(name);
+  return (e && atoi(e) == 0) ? 0 : 1;
 }
 
 template <int kBoxes>
@@ -586,7 +650,16 @@ int launch_scan_geo(const uint32_t* mask, int B, int H, int W, const int32_t* id
   p.smem_lut = lut_len > 0 && (smem_table ? table_bytes : 0) + lut_bytes <= static_cast<size_t>(G::kSmemFree);
   const size_t smem_bytes = G::kSmemFixed + (smem_table ? table_bytes : 0) + (p.smem_lut ? lut_bytes : 0);
 
-  auto kern = smem_table ? mask_scan_kernel<true, kBoxes> : mask_scan_kernel<false, kBoxes>;
+  const int flush_v = scan_variant("CSPE_SCAN_FLUSH"), slow_v = scan_variant("CSPE_SCAN_SLOW");  // read per launch
+  auto kern = smem_table ? mask_scan_kernel<true, kBoxes, 1, 1> : mask_scan_kernel<false, kBoxes, 1, 1>;
+  if constexpr (kBoxes == kDefaultBoxes) if (!(flush_v == 1 && slow_v == 1)) {   // A/B variants exist for the default geometry only
+    if (flush_v == 0 && slow_v == 0)
+      kern = smem_table ? mask_scan_kernel<true, kBoxes, 0, 0> : mask_scan_kernel<false, kBoxes, 0, 0>;
+    else if (flush_v == 0)
+      kern = smem_table ? mask_scan_kernel<true, kBoxes, 0, 1> : mask_scan_kernel<false, kBoxes, 0, 1>;
+    else
+      kern = smem_table ? mask_scan_kernel<true, kBoxes, 1, 0> : mask_scan_kernel<false, kBoxes, 1, 0>;
+  }
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   CSPE_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(G::kThreads), smem_bytes, st, p, tmap));
   return CSPE_OK;
@@ -628,6 +701,33 @@ int launch_init(int32_t* out, int B, int N, int W, int H, cudaStream_t st) {
 }  // namespace cspe
 
 using namespace cspe;
+
+// 1 when the scan of a [B][H][W] batch launches its full persistent grid (every SM holds its two CTAs and
+// is out of shared memory): only then is it impossible for the scan of batch i+2 to become resident before
+// the scan of batch i+1 has exited, which is what orders the double-buffered K2 / K3 outputs of an overlapped
+// pipeline behind the K4 that still reads them.
+extern "C" int cspe_mask_scan_fills_device(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  const int sms = sm_count();
+  if (sms <= 0) return 0;
+  switch (scan_boxes()) {
+    case 8: {
+      using G = Geo<8>;
+      const long long passes = static_cast<long long>((W + G::kTileCols - 1) / G::kTileCols) * ((H + kTileRows - 1) / kTileRows) * B;
+      return passes >= static_cast<long long>(sms) * G::kCtasPerSm;
+    }
+    case 2: {
+      using G = Geo<2>;
+      const long long passes = static_cast<long long>((W + G::kTileCols - 1) / G::kTileCols) * ((H + kTileRows - 1) / kTileRows) * B;
+      return passes >= static_cast<long long>(sms) * G::kCtasPerSm;
+    }
+    default: {
+      using G = Geo<4>;
+      const long long passes = static_cast<long long>((W + G::kTileCols - 1) / G::kTileCols) * ((H + kTileRows - 1) / kTileRows) * B;
+      return passes >= static_cast<long long>(sms) * G::kCtasPerSm;
+    }
+  }
+}
 
 extern "C" int cspe_mask_scan_accumulate(const uint32_t* mask, int B, int H, int W, const int32_t* id2slot,
                                          int lut_len, int64_t lut_stride, int N, int32_t* out, void* stream) {

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import json
 import math
-from typing import Dict, Iterable, List, Mapping, Optional, Sequence
+from typing import Union, Dict, Iterable, List, Mapping, Optional, Sequence
 
 import numpy as np
 
@@ -237,11 +237,23 @@ def coco_annotations_text(records: np.ndarray, n_out: np.ndarray, image_ids: Seq
     return buf[:rc].tobytes(), total
 
 
-def write_coco_file(path, images: Sequence[Mapping], annotation_chunks: Sequence[bytes]) -> None:
+def coco_images_text(image_ids: Sequence[int], width: int, height: int) -> bytes:
+    """The ``images`` entries of a run of frames as the text ``json.dumps([coco_image(...), ...])`` puts between
+    its brackets (a 100 k-frame sweep would otherwise build and dump 100 k dicts)."""
+    w, h = int(width), int(height)
+    return ", ".join(f'{{"id": {int(i)}, "width": {w}, "height": {h}, "file_name": "rgb_{int(i):06d}.png"}}'
+                     for i in image_ids).encode("ascii")
+
+
+def write_coco_file(path, images: Sequence[Union[Mapping, bytes]], annotation_chunks: Sequence[bytes]) -> None:
     """The bytes json.dump({"images": [...], "annotations": [...], "categories": [...]}, f) writes, with the
-    annotations given as natively formatted chunks (``coco_annotations_text``)."""
+    annotations given as natively formatted chunks (``coco_annotations_text``) and the images either as dicts
+    (``coco_image``) or as pre-formatted chunks (``coco_images_text``)."""
     with open(path, "wb") as f:
-        f.write(b'{"images": ' + json.dumps(list(images)).encode("ascii") + b', "annotations": [')
+        if images and isinstance(images[0], (bytes, bytearray)):
+            f.write(b'{"images": [' + b", ".join(c for c in images if c) + b'], "annotations": [')
+        else:
+            f.write(b'{"images": ' + json.dumps(list(images)).encode("ascii") + b', "annotations": [')
         f.write(b", ".join(c for c in annotation_chunks if c))
         f.write(b'], "categories": ' + json.dumps(coco_categories()).encode("ascii") + b"}")
 

@@ -195,6 +195,26 @@ def emit(scan, uv, z, pose, loose, flags, slot_class, H: int, W: int, min_pixels
     return records, n_out, class_hist
 
 
+def format_yolo(records: torch.Tensor, n_out: torch.Tensor, frame_stride: Optional[int] = None):
+    """S6 / f3 on the device: records u8 [B,N,408] + n_out int32 [B] (K4's outputs) -> (text u8 [B, frame_stride],
+    n_bytes int32 [B]); frame f's YOLO label file is ``text[f, :n_bytes[f]]`` (``class cx cy w h`` lines, six
+    decimals).  n_bytes[f] > frame_stride means the frame's text was cut, -1 an unprintable box value."""
+    lib = _lib.load()
+    _dev(records, torch.uint8, "records")
+    _dev(n_out, torch.int32, "n_out")
+    if records.dim() != 3 or records.shape[2] != _lib.RECORD_DTYPE.itemsize or records.shape[0] != n_out.shape[0]:
+        raise ValueError(f"records must be u8 [B,N,{_lib.RECORD_DTYPE.itemsize}] with B = len(n_out), got {tuple(records.shape)}")
+    B, N = records.shape[0], records.shape[1]
+    stride = 48 * N if frame_stride is None else int(frame_stride)
+    text = torch.empty((B, stride), dtype=torch.uint8, device=records.device)
+    n_bytes = torch.empty((B,), dtype=torch.int32, device=records.device)
+    with torch.cuda.device(records.device):
+        rc = lib.cspe_format_yolo(records.data_ptr(), n_out.data_ptr(), B, N, text.data_ptr(), stride,
+                                  n_bytes.data_ptr(), _stream_ptr())
+    _lib.check("cspe_format_yolo", rc)
+    return text, n_bytes
+
+
 def depth_to_pointcloud(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: torch.Tensor,
                         capacity: Optional[int] = None):
     """f1: depth f32 [H,W], rgb u8 [H,W,C>=3] or None, cam f64 [24] -> (points f64 [cap,6], n int64 [1])."""

@@ -3,10 +3,20 @@ emit YOLO / COCO labels and all-gather the per-class histogram at the end.
 
     torchrun --nproc-per-node 8 -m constructionsceneposeestimation_b200.sweep --frames 100000 --emit yolo --out DIR
 
-Each rank owns the contiguous global frame range ``sharding.frame_range(rank, world, frames)``
-and cycles a device-resident pool of synthetic annotator frames (>= 64 x 1080p = 531 MB, far
-beyond L2) so every batch streams from HBM.  Records come back through pinned host buffers,
-double-buffered: batch k+1 runs on the GPU while the host formats batch k.
+This is the loop the reference runs at gcd.py:1540-2081 (one frame per iteration, label emission at
+gcd.py:2055-2072) restated for a frame range per GPU:
+
+* rank r owns the contiguous global frame range ``sharding.frame_range(r, world, frames)``; frame g is
+  always the resident pool frame ``g % pool`` (the pool — >= 64 x 1080p = 531 MB, far beyond L2 — is
+  seeded identically on every rank), so the union of the ranks' outputs equals a one-rank sweep;
+* full batches run as CUDA graphs of ``group`` batches each (kernel nodes keep their programmatic
+  dependent-launch edges; the D2H read-back of every batch is a side branch of the same graph), two
+  graph instances with their own output buffers alternate, and the host consumes one group while the
+  GPU runs the next; the head / tail of the range that does not fill a batch runs eagerly;
+* ``--emit yolo``: the label text is formatted ON THE DEVICE (``cspe_format_yolo``), D2H carries ~2 KB
+  of text per frame instead of 26 KB of records; ``--emit coco`` / ``json``: records come back and the
+  native host formatters run on worker threads;
+* the per-class histogram is accumulated by K4 on the device and all-gathered once at the end (NCCL).
 """
 from __future__ import annotations
 
@@ -14,14 +24,17 @@ import argparse
 import json
 import os
 import time
-from typing import Dict, List, Optional
+from concurrent.futures import ThreadPoolExecutor
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
 
 from . import _lib, classes, formats, sharding, synthetic
 from .camera import pack_camera
-from .pipeline import LabelPipeline
+from .pipeline import LabelPipeline, graph_edge_kinds
+
+YOLO_BYTES_PER_SLOT = 48   # 38 bytes per line for class ids 0..9 and boxes inside the image
 
 
 def build_host_tables(frames, split_people=True):
@@ -53,122 +66,283 @@ def build_host_tables(frames, split_people=True):
     return lut, obj_record, slot_class, records, cam, [p[0] for p in per]
 
 
+def split_range(lo: int, hi: int, batch: int) -> Tuple[List[Tuple[int, int]], List[Tuple[int, int]], List[Tuple[int, int]]]:
+    """[lo, hi) cut at the global multiples of ``batch``: (head partial, full batches, tail partial) as
+    lists of (start, end).  A full batch always starts at pool frame 0."""
+    if hi <= lo:
+        return [], [], []
+    a = min(hi, -(-lo // batch) * batch)     # first multiple of batch >= lo
+    b = max(a, (hi // batch) * batch)        # last multiple of batch <= hi
+    head = [(lo, a)] if a > lo else []
+    full = [(s, s + batch) for s in range(a, b, batch)]
+    tail = [(b, hi)] if hi > b else []
+    return head, full, tail
+
+
+class _BatchOut:
+    """Device outputs of one batch slot and their pinned host mirrors."""
+
+    def __init__(self, pipe: LabelPipeline, want_records: bool, want_yolo: bool, records_dev: Optional[torch.Tensor]):
+        B, N, dev = pipe.B, pipe.N, pipe.device
+        self.n_out = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.n_out_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+        # with device-side YOLO text the records never leave the GPU: one buffer serves every slot (the
+        # kernel chain orders K4 of the next batch behind this batch's text kernel)
+        self.records = records_dev if records_dev is not None else \
+            torch.empty((B, N, _lib.RECORD_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+        self.records_h = torch.empty(self.records.shape, dtype=torch.uint8, pin_memory=True) if want_records else None
+        self.text = self.text_h = self.n_bytes = self.n_bytes_h = None
+        if want_yolo:
+            self.stride = YOLO_BYTES_PER_SLOT * N
+            self.text = torch.empty((B, self.stride), dtype=torch.uint8, device=dev)
+            self.text_h = torch.empty((B, self.stride), dtype=torch.uint8, pin_memory=True)
+            self.n_bytes = torch.empty((B,), dtype=torch.int32, device=dev)
+            self.n_bytes_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+
+    def enqueue_text(self, lib, nf: int, stream: int) -> None:
+        _lib.check("cspe_format_yolo", lib.cspe_format_yolo(
+            self.records.data_ptr(), self.n_out.data_ptr(), nf, self.records.shape[1], self.text.data_ptr(),
+            self.stride, self.n_bytes.data_ptr(), stream))
+
+    def enqueue_readback(self, lib, nf: int, stream: int) -> None:
+        def cp(dst, src, n):
+            _lib.check("cspe_memcpy_async", lib.cspe_memcpy_async(dst.data_ptr(), src.data_ptr(), n, stream))
+
+        cp(self.n_out_h, self.n_out, nf * 4)
+        if self.text is not None:
+            cp(self.n_bytes_h, self.n_bytes, nf * 4)
+            cp(self.text_h, self.text, nf * self.stride)
+        if self.records_h is not None:
+            cp(self.records_h, self.records, nf * self.records.shape[1] * self.records.shape[2])
+
+
+class _GroupGraph:
+    """One CUDA graph of ``group`` full batches: [frame-base upload] -> (K1 || K2 -> K4 [-> YOLO text]) x group on the
+    capture stream, the read-back of every batch on a side branch.  Replayed for any frame range by rewriting
+    ``frame_base_h`` (a pinned int32 the upload node reads at execution time)."""
+
+    def __init__(self, pipe: LabelPipeline, group: int, want_records: bool, want_yolo: bool):
+        lib = pipe.lib
+        dev = pipe.device
+        self.pipe, self.group = pipe, group
+        shared = torch.empty((pipe.B, pipe.N, _lib.RECORD_DTYPE.itemsize), dtype=torch.uint8, device=dev) \
+            if not want_records else None
+        self.slots = [_BatchOut(pipe, want_records, want_yolo, shared) for _ in range(group)]
+        self.frame_base_h = torch.zeros((1,), dtype=torch.int32, pin_memory=True)
+        self.frame_base_d = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.done = torch.cuda.Event()
+        self.busy = False
+        side = torch.cuda.Stream(device=dev)
+        p0 = pipe._parity
+
+        def body():
+            main = torch.cuda.current_stream(dev)
+            _lib.check("cspe_memcpy_async", lib.cspe_memcpy_async(self.frame_base_d.data_ptr(),
+                                                                  self.frame_base_h.data_ptr(), 4, main.cuda_stream))
+            for i, slot in enumerate(self.slots):
+                pipe.enqueue(p0 ^ (i & 1), records=slot.records, n_out=slot.n_out, frame_base=i * pipe.B,
+                             frame_base_dev=self.frame_base_d)
+                if want_yolo:
+                    slot.enqueue_text(lib, pipe.B, main.cuda_stream)
+                # fork: the copies of batch i run beside the kernels of batch i+1 (an event record / wait adds
+                # an edge, not a node, so the next kernel still follows a kernel: its programmatic edge stays)
+                side.wait_stream(main)
+                slot.enqueue_readback(lib, pipe.B, side.cuda_stream)
+            main.wait_stream(side)   # join
+
+        with torch.cuda.device(dev):
+            self.graph = pipe._capture(body)
+        if group & 1:
+            pipe._parity ^= 1      # the next instance (and the eager tail) continue with the other K2 buffers
+        self.edges = graph_edge_kinds(self.graph)
+
+    def launch(self, first_frame: int) -> None:
+        self.frame_base_h[0] = first_frame
+        self.graph.replay()
+        self.done.record()
+        self.busy = True
+
+
 def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[torch.device] = None,
               pool_frames: int = 64, config: str = "c2", emit: Optional[str] = "yolo", out_dir: Optional[str] = None,
-              use_graph: bool = True) -> Dict[str, object]:
+              use_graph: bool = True, group: int = 8, io_threads: Optional[int] = None) -> Dict[str, object]:
     """Annotate this rank's share of ``num_frames``; returns counters, timings and the histogram."""
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     lo, hi = sharding.frame_range(rank, world, num_frames)
     spec = synthetic.CONFIGS[config]
-    pool = synthetic.make_batch(spec, pool_frames, first_frame=rank * pool_frames)
+    pool = synthetic.make_batch(spec, pool_frames, first_frame=0)   # the same pool on every rank: frame g = pool[g % B]
     lut, obj_record, slot_class, records, cam, objects = build_host_tables(pool)
     H, W = pool[0]["instance_segmentation"]["data"].shape
     B, N = pool_frames, obj_record.shape[1]
+    want_yolo = emit == "yolo"
+    want_records = emit in ("coco", "json", "records")
+    lib = _lib.load()
     with torch.cuda.device(device):
-        pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], device, use_graph=use_graph)
+        pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], device, use_graph=False)
         pipe.mask.copy_(torch.from_numpy(np.stack([f["instance_segmentation"]["data"] for f in pool]).view(np.int32)))
         pipe.lut.copy_(torch.from_numpy(lut))
         pipe.obj_record.copy_(torch.from_numpy(obj_record))
         pipe.slot_class.copy_(torch.from_numpy(slot_class))
         pipe.records_in.copy_(torch.from_numpy(records))
         pipe.cam.copy_(torch.from_numpy(cam))
-        host = [(torch.empty(pipe.records.shape, dtype=torch.uint8, pin_memory=True),
-                 torch.empty((B,), dtype=torch.int32, pin_memory=True), torch.cuda.Event()) for _ in range(2)]
         torch.cuda.synchronize(device)
 
         label_dir = None
         if out_dir is not None and emit is not None:
             label_dir = os.path.join(out_dir, "labels")
             os.makedirs(label_dir, exist_ok=True)
-        coco_imgs: List[dict] = []
+        head, full, tail = split_range(lo, hi, B)
+        groups = [full[i:i + group] for i in range(0, len(full) - len(full) % group, group)] if use_graph else []
+        eager = head + full[len(groups) * group:] + tail
+        graphs = [_GroupGraph(pipe, group, want_records, want_yolo) for _ in range(min(2, len(groups)))]
+        eager_slot = _BatchOut(pipe, want_records, want_yolo, None) if eager else None
+        workers = max(1, min(8, (os.cpu_count() or 2) // max(1, world))) if io_threads is None else max(1, io_threads)
+        io_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="cspe-io") \
+            if (want_records or label_dir is not None) else None
+        slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
+
+        emitted = 0
+        text_bytes = 0
+        coco_imgs: List[bytes] = []
         coco_anns: List[bytes] = []
         coco_count = 0
-        slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
-        io_pool = None
-        if emit == "json":
-            from concurrent.futures import ThreadPoolExecutor
+        pending = []   # futures of worker jobs, in frame order
+        timers = {"launch_s": 0.0, "wait_s": 0.0, "consume_s": 0.0}
 
-            io_pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1), thread_name_prefix="cspe-io")
-        emitted = 0
-        hist_host = np.zeros(_lib.NUM_CLASSES, dtype=np.int64)
-        batches = sharding.batches(lo, hi, B)
+        def write_file(name: str, data) -> int:
+            with open(os.path.join(label_dir, name), "wb") as fh:
+                fh.write(data)
+            return len(data)
+
+        def consume(slot: _BatchOut, s: int, e: int, j0: int) -> None:
+            """Host side of one batch: frames [s, e) = pool frames j0 .. (outputs are rows 0 .. e - s)."""
+            nonlocal emitted, text_bytes, coco_count
+            nf = e - s
+            n_all = slot.n_out_h.numpy()[:nf]
+            count = int(n_all.sum())
+            emitted += count
+            if want_yolo:
+                nb = slot.n_bytes_h.numpy()[:nf]
+                if (nb < 0).any() or (nb > slot.stride).any():
+                    raise RuntimeError(f"YOLO text of frames {s}..{e}: sizes {nb.min()}..{nb.max()} outside [0, {slot.stride}]")
+                text_bytes += int(nb.sum())
+                if label_dir is not None:
+                    # the pinned buffer is reused by the next replay: take the bytes now, write them on the workers
+                    rows = [bytes(memoryview(slot.text_h.numpy()[j, : nb[j]])) for j in range(nf)]
+                    pending.append(io_pool.submit(lambda rows=rows, s=s: sum(
+                        write_file(f"label_{s + j:06d}.txt", r) for j, r in enumerate(rows))))
+                return
+            if not want_records:
+                return
+            recs = slot.records_h.numpy().view(_lib.RECORD_DTYPE).reshape(B, N)[:nf].copy()   # buffer is reused
+            n_copy = n_all.copy()
+            if emit == "coco":   # native formatter, one call per batch, on a worker (ctypes releases the GIL)
+                ids = list(range(s, e))
+                first_id = coco_count + 1
+                coco_count += count
+                coco_imgs.append(formats.coco_images_text(ids, W, H))
+                pending.append(io_pool.submit(
+                    lambda: formats.coco_annotations_text(recs, n_copy, ids, first_id)[0]))
+            elif emit == "json":   # label_%06d.json, gcd.py:2071
+                def one(j: int) -> int:
+                    pj = j0 + j
+                    text = formats.label_json_bytes(s + j, pool[pj]["camera_pose"], pool[pj]["camera_params"], H, W,
+                                                    recs[j, : n_copy[j]], objects[pj], slot_strings[pj])
+                    return write_file(f"label_{s + j:06d}.json", text) if label_dir is not None else len(text)
+
+                pending.extend(io_pool.submit(one, j) for j in range(nf))
+            elif emit == "records":   # raw records kept in memory (tests)
+                kept_records.extend(recs[j, : n_copy[j]] for j in range(nf))
+
+        def drain(limit: int) -> None:
+            """Collect finished worker jobs (keeps at most `limit` in flight); COCO chunks stay in order."""
+            nonlocal text_bytes
+            while len(pending) > limit:
+                r = pending.pop(0).result()
+                if emit == "coco":
+                    coco_anns.append(r)
+                    text_bytes += len(r)
+                elif isinstance(r, int) and emit == "json":
+                    text_bytes += r
+
+        kept_records: List[np.ndarray] = []
+        pipe.class_hist.zero_()
+        torch.cuda.synchronize(device)
         t0 = time.perf_counter()
 
-        def launch(k: int) -> None:
-            rec_h, n_h, ev = host[k % 2]
-            pipe.run()
-            rec_h.copy_(pipe.records, non_blocking=True)
-            n_h.copy_(pipe.n_out, non_blocking=True)
-            ev.record()
+        # ---- head of the range and whatever does not fill a graph group: eager, one batch at a time ----
+        def run_eager(s: int, e: int) -> None:
+            j0 = s % B
+            parity = pipe._parity
+            pipe._parity ^= 1
+            st = torch.cuda.current_stream(device).cuda_stream
+            pipe.enqueue(parity, records=eager_slot.records, n_out=eager_slot.n_out, frame_base=s, frames=e - s, first=j0)
+            if want_yolo:
+                eager_slot.enqueue_text(lib, e - s, st)
+            eager_slot.enqueue_readback(lib, e - s, st)
+            torch.cuda.current_stream(device).synchronize()
+            consume(eager_slot, s, e, j0)
 
-        def consume(k: int) -> None:
-            nonlocal emitted, hist_host, coco_count
-            rec_h, n_h, ev = host[k % 2]
-            ev.synchronize()
-            s, e = batches[k]
-            recs_all = rec_h.numpy().view(_lib.RECORD_DTYPE).reshape(B, N)
-            n_all = n_h.numpy()
-            nf = e - s
-            valid = np.arange(N)[None, :] < n_all[:nf, None]
-            emitted += int(n_all[:nf].sum())
-            hist_host += np.bincount(recs_all["class_id"][:nf][valid], minlength=_lib.NUM_CLASSES)[: _lib.NUM_CLASSES]
-            if emit == "yolo":
-                buf, off = formats.yolo_text_batch(recs_all, n_all, nf)   # native formatter (libcspe, f3)
-                if label_dir is not None:
-                    raw = buf.tobytes()
-                    for j in range(nf):
-                        with open(os.path.join(label_dir, f"label_{s + j:06d}.txt"), "wb") as fh:
-                            fh.write(raw[off[j]:off[j + 1]])
-                return
-            if emit == "json":   # native formatter (libcspe, f3) on the I/O threads: label_%06d.json, gcd.py:2071
-                def one(j: int) -> int:
-                    text = formats.label_json_bytes(s + j, pool[j]["camera_pose"], pool[j]["camera_params"], H, W,
-                                                    recs_all[j, : n_all[j]], objects[j], slot_strings[j])
-                    if label_dir is not None:
-                        with open(os.path.join(label_dir, f"label_{s + j:06d}.json"), "wb") as fh:
-                            fh.write(text)
-                    return len(text)
+        for s, e in head:
+            run_eager(s, e)
 
-                sum(io_pool.map(one, range(nf)))
-                return
-            if emit == "coco":   # native formatter, one call per batch
-                ids = list(range(s, e))               # global frame ids; pipeline frames are batch-relative
-                coco_imgs.extend(formats.coco_image(fid, W, H, f"rgb_{fid:06d}.png") for fid in ids)
-                text, count = formats.coco_annotations_text(recs_all, n_all, ids, coco_count + 1)
-                coco_anns.append(text)
-                coco_count += count
+        # ---- the bulk: graph groups, two instances alternating -----------------------------------------
+        for gi, grp in enumerate(groups):
+            g = graphs[gi % 2]
+            t1 = time.perf_counter()
+            g.launch(grp[0][0])
+            timers["launch_s"] += time.perf_counter() - t1
+            if gi > 0:   # consume the previous group while this one runs
+                prev, pgrp = graphs[(gi - 1) % 2], groups[gi - 1]
+                t1 = time.perf_counter()
+                prev.done.synchronize()
+                t2 = time.perf_counter()
+                for slot, (s, e) in zip(prev.slots, pgrp):
+                    consume(slot, s, e, 0)
+                drain(4 * workers)
+                timers["wait_s"] += t2 - t1
+                timers["consume_s"] += time.perf_counter() - t2
+        if groups:
+            prev, pgrp = graphs[(len(groups) - 1) % 2], groups[-1]
+            t1 = time.perf_counter()
+            prev.done.synchronize()
+            t2 = time.perf_counter()
+            for slot, (s, e) in zip(prev.slots, pgrp):
+                consume(slot, s, e, 0)
+            timers["wait_s"] += t2 - t1
+            timers["consume_s"] += time.perf_counter() - t2
 
-        # The device histogram (K4) counts every frame of every launched batch; a trailing partial
-        # batch still runs the whole pool, so the frames this rank OWNS are counted on the host from
-        # the consumed records and cross-checked against the device when all batches were full.
-        pipe.class_hist.zero_()
-        for k in range(len(batches)):
-            launch(k)
-            if k > 0:
-                consume(k - 1)
-        if batches:
-            consume(len(batches) - 1)
+        for s, e in full[len(groups) * group:] + tail:
+            run_eager(s, e)
+        drain(0)
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
         if io_pool is not None:
             io_pool.shutdown()
-        if batches and all(e - s == B for s, e in batches):
-            dev_hist = pipe.class_hist.cpu().numpy()
-            if not np.array_equal(dev_hist, hist_host):
-                raise RuntimeError(f"class histogram mismatch: device {dev_hist.tolist()} vs host {hist_host.tolist()}")
-        hist_dev = torch.from_numpy(hist_host).to(device)
+
+        # K4 accumulated exactly this rank's frames on the device (partial batches run with their own frame count)
+        hist_host = pipe.class_hist.cpu().numpy()
+        if int(hist_host.sum()) != emitted:
+            raise RuntimeError(f"class histogram holds {int(hist_host.sum())} labels, n_out sums to {emitted}")
 
         import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            gathered = sharding.all_gather_histogram(hist_dev)
+            gathered = sharding.all_gather_histogram(pipe.class_hist)
         else:
             gathered = hist_host.reshape(1, -1)
         if emit == "coco" and out_dir is not None:
             formats.write_coco_file(os.path.join(out_dir, f"coco_rank{rank:02d}.json"), coco_imgs, coco_anns)
-    return {"rank": rank, "world": world, "frames": hi - lo, "frame_range": [lo, hi], "records": emitted,
-            "seconds": dt, "frames_per_s": (hi - lo) / dt if dt > 0 else 0.0, "class_hist_rank": hist_host.tolist(),
-            "class_hist_total": gathered.sum(axis=0).tolist(), "class_hist_per_rank": gathered.tolist()}
+    out = {"rank": rank, "world": world, "frames": hi - lo, "frame_range": [lo, hi], "records": emitted,
+           "emit": emit, "text_bytes": text_bytes, "batch": B, "group": group, "graph_groups": len(groups),
+           "eager_batches": len(eager), "io_threads": workers if io_pool is not None else 0,
+           "seconds": dt, "frames_per_s": (hi - lo) / dt if dt > 0 else 0.0, "host_timers": timers,
+           "graph_edges": graphs[0].edges if graphs else None,
+           "class_hist_rank": hist_host.tolist(),
+           "class_hist_total": gathered.sum(axis=0).tolist(), "class_hist_per_rank": gathered.tolist()}
+    if emit == "records":
+        out["kept_records"] = kept_records
+    return out
 
 
 def main() -> int:
@@ -177,26 +351,45 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=100_000)
     ap.add_argument("--pool", type=int, default=64)
+    ap.add_argument("--group", type=int, default=8, help="batches per CUDA graph")
     ap.add_argument("--config", default="c2")
     ap.add_argument("--emit", default="yolo", choices=["yolo", "coco", "json", "none"])
     ap.add_argument("--out", default=None)
+    ap.add_argument("--eager", action="store_true", help="no graphs: one batch at a time")
+    ap.add_argument("--io-threads", type=int, default=None)
+    ap.add_argument("--repeat", type=int, default=1, help="run the sweep this many times and report the best (first run warms up)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    res = run_sweep(args.frames, rank, world, torch.device("cuda", local), args.pool, args.config,
-                    None if args.emit == "none" else args.emit, args.out)
-    if world > 1:
-        t = torch.tensor([res["seconds"]], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.init_process_group("nccl", device_id=dev)
+    best = None
+    runs = []
+    for _ in range(max(1, args.repeat)):
+        if world > 1:
+            dist.barrier()
+        res = run_sweep(args.frames, rank, world, dev, args.pool, args.config,
+                        None if args.emit == "none" else args.emit, args.out, not args.eager, args.group, args.io_threads)
+        t = torch.tensor([res["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
         res["seconds_max_over_ranks"] = float(t.item())
         res["frames_per_s_all_ranks"] = args.frames / float(t.item())
+        runs.append(res["frames_per_s_all_ranks"])
+        if best is None or res["seconds_max_over_ranks"] < best["seconds_max_over_ranks"]:
+            best = res
+    best["frames_per_s_all_ranks_runs"] = runs
+    if world > 1:
+        # every rank's own rate next to rank 0's line: a straggling rank shows up here
+        rates = [None] * world
+        dist.all_gather_object(rates, {"rank": rank, "frames_per_s": best["frames_per_s"], "host_timers": best["host_timers"]})
+        best["per_rank"] = rates
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(res), flush=True)
+        print(json.dumps(best), flush=True)
     return 0
 
 

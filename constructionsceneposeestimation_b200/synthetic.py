@@ -54,6 +54,15 @@ class SceneSpec:
     split_people: bool = True    # one object per person (False = the reference's single DHGen root)
     with_rgb: bool = False
     max_meshes: int = 3          # meshes (= instance ids) per object
+    # camera ring around the site centre: (r_min, r_max, z_min, z_max) in metres, scaled with the site.
+    # The default keeps the whole site in view from outside; SURVEY §8d's ring (4-12 m out, 1.6-3 m up,
+    # gcd.py:790,857) puts the camera among the objects, which then fill the frame ("dense" configs)
+    camera_ring: Tuple[float, float, float, float] = (30.0, 42.0, 7.0, 12.0)
+    # see-through textures: fence panels become a wire mesh (one object pixel line every 4 px in x and y)
+    # and tree crowns foliage (a hashed 60 % pixel pattern) — whatever lies behind shows through at pixel
+    # scale, the most fragmented masks the reference's scene produces (24 fence panels, 12 trees,
+    # gcd.py:128-141)
+    textured: bool = False
 
 
 def joint_template(num_joints: int) -> np.ndarray:
@@ -151,8 +160,9 @@ def make_frame(spec: SceneSpec, frame: int = 0) -> Dict[str, object]:
     # camera on a ring around the site, looking at its centre at roughly eye height
     ang = rng.uniform(0.0, 2.0 * np.pi)
     site = max(1.0, np.sqrt(spec.num_instances / 100.0))  # the site grows with the instance count
-    rad = rng.uniform(30.0, 42.0) * site
-    pos = np.array([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(7.0, 12.0) * site])
+    r_lo, r_hi, z_lo, z_hi = spec.camera_ring
+    rad = rng.uniform(r_lo, r_hi) * site
+    pos = np.array([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(z_lo, z_hi) * site])
     target = np.array([rng.uniform(-3.0, 3.0), rng.uniform(-3.0, 3.0), rng.uniform(0.8, 2.0)])
     pose7 = _look_at_pose(pos, target)
     rcw = quat_xyzw_to_matrix(pose7[3:])
@@ -259,6 +269,10 @@ def make_frame(spec: SceneSpec, frame: int = 0) -> Dict[str, object]:
         else:  # inset rectangle
             ix, iy = (x1 - x0) // 10, (y1 - y0) // 10
             blob = (xs >= x0 + ix) & (xs < x1 - ix) & (ys >= y0 + iy) & (ys < y1 - iy)
+        if spec.textured and kind == "fence":      # wire mesh
+            blob = blob & (((xs & 3) == 0) | ((ys & 3) == 0))
+        elif spec.textured and kind == "tree":     # foliage
+            blob = blob & ((((xs * 73856093) ^ (ys * 19349663) ^ (oi * 83492791)) % 5) < 3)
         if not blob.any():
             continue
         mids = mesh_ids[oi]
@@ -308,4 +322,8 @@ CONFIGS = {
     "c2": SceneSpec(1920, 1080, 100, 4, 17, config_id=2),
     "c3": SceneSpec(1920, 1080, 60, 50, 17, config_id=3),
     "c4": SceneSpec(3840, 2160, 500, 8, 17, config_id=4),
+    # stress variants of c2 for the mask scan (not BASELINE configs): the camera on SURVEY §8d's ring, inside
+    # the site, and the same with see-through fences / trees
+    "c2_dense": SceneSpec(1920, 1080, 100, 4, 17, config_id=12, camera_ring=(4.0, 12.0, 1.6, 3.0)),
+    "c2_textured": SceneSpec(1920, 1080, 100, 4, 17, config_id=13, camera_ring=(4.0, 12.0, 1.6, 3.0), textured=True),
 }

@@ -153,6 +153,11 @@ int cspe_mask_scan_accumulate_overlapped(const uint32_t* mask, int B, int H, int
                                          const int32_t* id2slot, int lut_len, int64_t lut_stride,
                                          int N, int32_t* out, void* stream);
 
+/* 1 when cspe_mask_scan* on a [B][H][W] batch launches its full persistent grid (two CTAs on every SM).
+ * A pipeline may chain the `*_overlapped` entry points across batches with double-buffered K2 / K3
+ * outputs only then (see DESIGN.md "Step pipeline"); smaller batches must use the plain entry points. */
+int cspe_mask_scan_fills_device(int B, int H, int W);
+
 /* K1 plus the depth-quality statistics of gcd.py:314-359 in one call (two HBM-bound launches on
  * `stream`; a fused kernel measured slower).
  * depth float32 [B][H][W]; stats cspe_depth_stats_t[B], fully overwritten. */
@@ -221,6 +226,35 @@ int cspe_emit_reset_scan(int32_t* scan, const double* uv, const double* z, const
                          const double* loose, const uint8_t* flags, const int32_t* slot_class,
                          int B, int N, int H, int W, int min_pixels, int frame_base,
                          cspe_record* records, int32_t* n_out, int64_t* class_hist, void* stream);
+
+/* K4 (reset form) whose frame numbering comes from device memory: record.frame = frame_base +
+ * *frame_base_dev + f.  A captured CUDA graph of several batches can then be replayed for any frame
+ * range by rewriting one int32 (the per-frame loop counter of gcd.py:1540 / frame_id of gcd.py:2057). */
+int cspe_emit_reset_scan_indirect(int32_t* scan, const double* uv, const double* z, const double* pose,
+                                  const double* loose, const uint8_t* flags, const int32_t* slot_class,
+                                  int B, int N, int H, int W, int min_pixels, int frame_base,
+                                  const int32_t* frame_base_dev, cspe_record* records, int32_t* n_out,
+                                  int64_t* class_hist, void* stream);
+
+/* S6 / f3: YOLO label text on the DEVICE (the label file written at gcd.py:2055-2072, YOLO flavour):
+ * for every frame f the lines "class cx cy w h\n" (six decimals, byte-identical to
+ * cspe_format_yolo_host and to Python's f"{c} {cx:.6f} ...") of its n_out[f] kept records, contiguous at
+ * text + f * frame_stride.  n_bytes int32 [B] = size of the frame's text (bytes past frame_stride are
+ * dropped but counted; -1 = a box value that is not finite or >= 2^20).  38 bytes per record for class
+ * ids 0..9, so frame_stride = 48 * N is always enough for valid boxes.  D2H then carries ~2 KB of text
+ * per 1080p frame instead of 26 KB of records. */
+int cspe_format_yolo(const cspe_record* records, const int32_t* n_out, int B, int N,
+                     char* text, int64_t frame_stride, int32_t* n_bytes, void* stream);
+
+/* ---- plumbing for captured step graphs ----------------------------------------------------- */
+
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) through the library's runtime, so a host
+ * driver can capture the D2H read-back of a batch into the same CUDA graph as the kernels. */
+int cspe_memcpy_async(void* dst, const void* src, size_t bytes, void* stream);
+
+/* Diagnostics: node count, edge count and number of PROGRAMMATIC dependency edges of a cudaGraph_t
+ * (passed as void*) — a captured step graph must keep one programmatic edge per overlapped launch. */
+int cspe_graph_edge_kinds(void* cuda_graph, int* num_nodes, int* num_edges, int* num_programmatic);
 
 /* ---- next rows ------------------------------------------------------------- */
 

@@ -187,6 +187,45 @@ def test_scan_synthetic_configs(T, ops, cfg, nframes):
     assert (got[..., 0] > 0).sum() >= N // 4
 
 
+@pytest.mark.parametrize("variant", [(1, 1), (0, 0), (1, 0), (0, 1)])
+@pytest.mark.parametrize("pattern", ["checker2", "stripes3", "mesh", "noise100", "noise2", "blocks16", "textured"])
+def test_scan_fragmented_masks(T, ops, pattern, variant, monkeypatch):
+    """Masks that live on the scan's slow path — see-through textures (two or three ids alternating at
+    pixel scale), per-pixel noise, 16x16 id blocks, the textured synthetic scene — through every flush /
+    slow-path variant of the kernel (CSPE_SCAN_FLUSH / CSPE_SCAN_SLOW are read per launch)."""
+    monkeypatch.setenv("CSPE_SCAN_FLUSH", str(variant[0]))
+    monkeypatch.setenv("CSPE_SCAN_SLOW", str(variant[1]))
+    rng = np.random.default_rng(abs(hash(pattern)) % 2**32)
+    B, H, W, N = 2, 150, 300, 40
+    ys, xs = np.mgrid[0:H, 0:W]
+    lut = _dense_lut(rng, 100, N, merge=True)
+    if pattern == "checker2":
+        mask = np.where((xs + ys) & 1, 5, 9).astype(np.uint32)[None].repeat(B, 0)
+    elif pattern == "stripes3":
+        mask = (2 + (xs + 2 * ys) % 3 * 7).astype(np.uint32)[None].repeat(B, 0)
+    elif pattern == "mesh":
+        base = _random_mask(rng, B, H, W, 30)
+        wire = ((xs & 3) == 0) | ((ys & 3) == 0)
+        mask = np.where(wire[None], np.uint32(77), base).astype(np.uint32)
+    elif pattern == "noise100":
+        mask = rng.integers(0, 102, size=(B, H, W), dtype=np.uint32)
+    elif pattern == "noise2":
+        mask = rng.integers(4, 6, size=(B, H, W), dtype=np.uint32)
+    elif pattern == "blocks16":
+        g = rng.integers(2, 102, size=(B, (H + 15) // 16, (W + 15) // 16), dtype=np.uint32)
+        mask = np.ascontiguousarray(g.repeat(16, 1).repeat(16, 2)[:, :H, :W])
+    else:
+        from constructionsceneposeestimation_b200 import synthetic
+        frames = synthetic.make_batch(synthetic.CONFIGS["c2_textured"], 2)
+        lut, obj_record, *_ = helpers.host_tables(frames)
+        mask = np.stack([f["instance_segmentation"]["data"] for f in frames])
+        N = obj_record.shape[1]
+    got = _scan_gpu(T, ops, mask, lut, N)
+    assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=True))
+    if pattern != "textured":
+        assert np.array_equal(got, O.mask_scan(mask, lut, N, fast=False))
+
+
 def test_scan_full_size_properties(T, ops):
     """BASELINE config 2 at full size (64 x 1080p): size-independent properties instead of the
     (slow) oracle — pixel conservation, idempotence, batch == per-frame, and box sanity."""
@@ -582,6 +621,53 @@ def test_depth_colormap_and_bgr(T, ops):
                           O.rgb_to_bgr(rgb))
 
 
+def test_yolo_text_on_device_matches_python(T, ops):
+    """cspe_format_yolo (device) == cspe_format_yolo_host == Python's f-string formatter, byte for byte: boxes from
+    the emitted records of a synthetic batch plus hand-made values (ties, carries, negatives, >= 1, class ids with
+    two digits / a sign), a frame cut by a short stride, and unprintable values flagged with -1."""
+    from constructionsceneposeestimation_b200 import _lib, formats
+    rng = np.random.default_rng(5)
+    B, N = 5, 300
+    recs = np.zeros((B, N), dtype=_lib.RECORD_DTYPE)
+    recs["class_id"] = rng.integers(0, 10, size=(B, N))
+    recs["yolo"] = rng.random((B, N, 4), dtype=np.float32)
+    nasty = np.array([0.0, -0.0, 1.0, 0.5, 0.0000005, 0.0000015, 0.0000025, 0.9999995, 0.99999994, 1e-7, 1e-30, 1e-45,
+                      0.1234565, 0.1234575, 2.5, 12.000001, 1048575.9, -3.25, 0.000001, 0.0000004999], dtype=np.float32)
+    recs["yolo"][1, : len(nasty), 0] = nasty
+    recs["yolo"][1, : len(nasty), 3] = nasty[::-1]
+    recs["yolo"][2] = (rng.integers(0, 2 ** 21, size=(N, 4)) / np.float32(2 ** 21)).astype(np.float32)   # k / 2^21: many ties
+    recs["class_id"][3, :4] = [10, 123, -1, -27]
+    n_out = np.array([N, 40, N, 7, 0], dtype=np.int32)
+    d_rec = T.from_numpy(recs.view(np.uint8).reshape(B, N, -1)).cuda()
+    d_n = T.from_numpy(n_out).cuda()
+    text, nb = ops.format_yolo(d_rec, d_n, frame_stride=96 * N)
+    T.cuda.synchronize()
+    text, nb = text.cpu().numpy(), nb.cpu().numpy()
+    buf, off = formats.yolo_text_batch(recs, n_out)
+    for f in range(B):
+        want = "".join(line + "\n" for line in formats.yolo_lines(recs[f, : n_out[f]])).encode()
+        assert bytes(buf[off[f]: off[f + 1]]) == want
+        assert nb[f] == len(want), (f, nb[f], len(want))
+        assert text[f, : nb[f]].tobytes() == want, f
+    # a stride that cuts the text: the size is still reported in full, what fits is identical
+    text2, nb2 = ops.format_yolo(d_rec, d_n, frame_stride=1000)
+    T.cuda.synchronize()
+    assert np.array_equal(nb2.cpu().numpy(), nb)
+    assert np.array_equal(text2.cpu().numpy()[0], text[0, :1000])
+    # default stride: 48 bytes per slot is enough for class ids 0..9 and boxes in [0, 1]
+    text3, nb3 = ops.format_yolo(d_rec[:1], d_n[:1])
+    T.cuda.synchronize()
+    assert int(nb3[0]) == 38 * N and text3.shape[1] == 48 * N
+    # not finite / >= 2^20 -> -1 for that frame only
+    bad = recs.copy()
+    bad["yolo"][0, 3, 1] = np.inf
+    bad["yolo"][2, 0, 0] = np.float32(2 ** 20)
+    bad["yolo"][3, 6, 2] = np.nan
+    _, nb4 = ops.format_yolo(T.from_numpy(bad.view(np.uint8).reshape(B, N, -1)).cuda(), d_n, frame_stride=96 * N)
+    T.cuda.synchronize()
+    assert nb4.cpu().numpy().tolist() == [-1, int(nb[1]), -1, -1, 0]
+
+
 def test_label_pipeline_graph_equals_eager_and_oracle(T, ops):
     """The CUDA-graph pipeline (K1 || K2 -> K4) reproduces the oracle and the eager launches."""
     from constructionsceneposeestimation_b200 import synthetic, _lib
@@ -610,6 +696,152 @@ def test_label_pipeline_graph_equals_eager_and_oracle(T, ops):
         outs.append(rec.copy())
     for f in range(4):
         assert np.array_equal(outs[0][f, : o["n_out"][f]], outs[1][f, : o["n_out"][f]])   # graph == eager, bit for bit
+
+
+def test_step_graph_keeps_programmatic_edges_and_matches_eager(T, ops):
+    """K steps captured as ONE CUDA graph: same records as K eager runs, one histogram accumulation per step, and the
+    kernel nodes keep their programmatic-dependent-launch edges (every node but the first follows a kernel)."""
+    from constructionsceneposeestimation_b200 import _lib, synthetic
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline, graph_edge_kinds
+    import dataclasses
+    spec = dataclasses.replace(synthetic.CONFIGS["c1"], width=512, height=270)
+    frames = synthetic.make_batch(spec, 16)
+    o = helpers.oracle_pipeline(frames)
+    lut = np.full((16, (o["lut"].shape[1] + 3) & ~3), -1, dtype=np.int32)
+    lut[:, : o["lut"].shape[1]] = o["lut"]
+    H, W = o["mask"].shape[1:]
+    N, R = o["obj_record"].shape[1], o["records"].shape[1]
+    pipe = LabelPipeline(16, H, W, N, R, lut.shape[1], T.device("cuda"), use_graph=False)
+    assert pipe.overlapped          # 16 x 512x270 = 320 scan passes >= 296 CTAs: the full persistent grid
+    pipe.mask.copy_(T.from_numpy(o["mask"].view(np.int32)))
+    pipe.lut.copy_(T.from_numpy(lut))
+    pipe.obj_record.copy_(T.from_numpy(o["obj_record"]))
+    pipe.slot_class.copy_(T.from_numpy(o["slot_class"]))
+    pipe.records_in.copy_(T.from_numpy(o["records"].view(np.uint8).reshape(16, R, -1)))
+    pipe.cam.copy_(T.from_numpy(o["cam"]))
+    for steps in (4, 3):
+        pipe.class_hist.zero_()
+        g = pipe.step_graph(steps)
+        kinds = graph_edge_kinds(g)
+        assert kinds["nodes"] == 3 * steps and kinds["edges"] == 3 * steps - 1, kinds
+        assert kinds["programmatic"] == 3 * steps - 1, kinds
+        for _ in range(2):
+            pipe.run_steps(steps)
+        T.cuda.synchronize()
+        rec = pipe.records.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(16, N)
+        n_out = pipe.n_out.cpu().numpy()
+        assert np.array_equal(n_out, o["n_out"])
+        for f in range(16):
+            helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
+        assert np.array_equal(pipe.class_hist.cpu().numpy(), 2 * steps * o["hist"])
+    # a batch that does not fill the device takes the plain (stream-ordered) entry points
+    small = LabelPipeline(2, H, W, N, R, lut.shape[1], T.device("cuda"), use_graph=False)
+    assert not small.overlapped
+
+
+def test_partial_batch_with_offset(T, ops):
+    """enqueue(frames=n, first=j): resident frames j .. j+n as a batch of their own (head / tail of a sweep range)."""
+    from constructionsceneposeestimation_b200 import _lib, synthetic
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
+    frames = synthetic.make_batch(synthetic.CONFIGS["c1"], 6)
+    o = helpers.oracle_pipeline(frames, frame_base=100)
+    lut = np.full((6, (o["lut"].shape[1] + 3) & ~3), -1, dtype=np.int32)
+    lut[:, : o["lut"].shape[1]] = o["lut"]
+    H, W = o["mask"].shape[1:]
+    N, R = o["obj_record"].shape[1], o["records"].shape[1]
+    pipe = LabelPipeline(6, H, W, N, R, lut.shape[1], T.device("cuda"), use_graph=False)
+    pipe.mask.copy_(T.from_numpy(o["mask"].view(np.int32)))
+    pipe.lut.copy_(T.from_numpy(lut))
+    pipe.obj_record.copy_(T.from_numpy(o["obj_record"]))
+    pipe.slot_class.copy_(T.from_numpy(o["slot_class"]))
+    pipe.records_in.copy_(T.from_numpy(o["records"].view(np.uint8).reshape(6, R, -1)))
+    pipe.cam.copy_(T.from_numpy(o["cam"]))
+    for first, n in ((0, 6), (2, 3), (5, 1), (0, 1), (1, 5)):
+        pipe.class_hist.zero_()
+        pipe.enqueue(0, frame_base=100 + first, frames=n, first=first)
+        T.cuda.synchronize()
+        rec = pipe.records.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(6, N)
+        n_out = pipe.n_out.cpu().numpy()
+        assert np.array_equal(n_out[:n], o["n_out"][first: first + n])
+        for f in range(n):
+            helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][first + f, : n_out[f]])
+        want_hist = sum(np.bincount(o["recs"][first + f, : o["n_out"][first + f]]["class_id"], minlength=10) for f in range(n))
+        assert np.array_equal(pipe.class_hist.cpu().numpy(), want_hist)
+
+
+def test_sweep_shards_union_equals_single_rank(T, ops, tmp_path):
+    """the union of the ranks' shards == the one-rank output (records, global frame ids, YOLO files, COCO
+    annotations) and the per-rank histograms add up to np.bincount over the one-rank class ids.  The ranks run one
+    after the other on this GPU (the 2-process NCCL form is test_multirank_sweep_nccl)."""
+    from constructionsceneposeestimation_b200 import synthetic, sweep
+    import dataclasses
+    import json
+    spec = dataclasses.replace(synthetic.CONFIGS["c1"], width=512, height=270)
+    synthetic.CONFIGS["_t"] = spec
+    dev = T.device("cuda")
+    try:
+        one = sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="records", group=2)
+        assert one["graph_groups"] == 4 and one["eager_batches"] == 2
+        # 2 batches x (3 kernels + the YOLO text kernel would be 4) -> here 3 kernels: every kernel but the first
+        # follows a kernel through a programmatic edge, whatever copies hang off the side branch
+        assert one["graph_edges"]["programmatic"] == 2 * 3 - 1, one["graph_edges"]
+        flat_one = np.concatenate(one["kept_records"])
+        assert np.array_equal(np.unique(flat_one["frame"]), np.arange(150))
+        sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="yolo", out_dir=str(tmp_path / "one"), group=2)
+        sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="coco", out_dir=str(tmp_path / "one"), group=2)
+        parts, hists, coco = [], [], []
+        for r in range(3):
+            res = sweep.run_sweep(150, r, 3, dev, pool_frames=16, config="_t", emit="records", group=2)
+            assert res["frame_range"] == [50 * r, 50 * (r + 1)]
+            parts.extend(res["kept_records"])
+            hists.append(res["class_hist_rank"])
+            y = sweep.run_sweep(150, r, 3, dev, pool_frames=16, config="_t", emit="yolo", out_dir=str(tmp_path / "three"), group=2)
+            assert y["graph_edges"] is None or y["graph_edges"]["programmatic"] == 2 * 4 - 1, y["graph_edges"]
+            sweep.run_sweep(150, r, 3, dev, pool_frames=16, config="_t", emit="coco", out_dir=str(tmp_path / "three"), group=2)
+            coco.append(json.loads((tmp_path / "three" / f"coco_rank{r:02d}.json").read_text()))
+    finally:
+        del synthetic.CONFIGS["_t"]
+    flat = np.concatenate(parts)
+    assert flat.tobytes() == flat_one.tobytes()
+    assert np.array_equal(np.sum(hists, axis=0), np.bincount(flat_one["class_id"], minlength=10))
+    assert one["class_hist_total"] == np.bincount(flat_one["class_id"], minlength=10).tolist()
+    for i in range(150):
+        a = (tmp_path / "one" / "labels" / f"label_{i:06d}.txt").read_bytes()
+        assert a == (tmp_path / "three" / "labels" / f"label_{i:06d}.txt").read_bytes()
+        assert len(a.splitlines()) == int((flat_one["frame"] == i).sum())
+    ref = json.loads((tmp_path / "one" / "coco_rank00.json").read_text())
+    assert [im["id"] for im in ref["images"]] == list(range(150))
+    assert sum((c["images"] for c in coco), []) == ref["images"]
+    strip = lambda anns: [{k: v for k, v in a.items() if k != "id"} for a in anns]   # annotation ids count per rank
+    assert strip(sum((c["annotations"] for c in coco), [])) == strip(ref["annotations"])
+    assert [a["id"] for a in ref["annotations"]] == list(range(1, len(flat_one) + 1))
+
+
+def test_multirank_sweep_nccl(T, ops, tmp_path):
+    """Two ranks on two GPUs (torchrun, NCCL): shard outputs == one-rank output, gathered histogram == np.bincount."""
+    import json
+    import subprocess
+    import sys
+    if T.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from constructionsceneposeestimation_b200 import sweep
+    root = str(__import__("pathlib").Path(__file__).resolve().parents[1])
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", "-m", "constructionsceneposeestimation_b200.sweep", "--frames", "300", "--pool", "16",
+           "--group", "2", "--config", "c1", "--emit", "yolo", "--out", str(tmp_path / "two")]
+    proc = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-3000:]
+    res = json.loads([ln for ln in proc.stdout.splitlines() if ln.startswith("{")][-1])
+    one = sweep.run_sweep(300, 0, 1, T.device("cuda"), pool_frames=16, config="c1", emit="records", group=2)
+    flat = np.concatenate(one["kept_records"])
+    want = np.bincount(flat["class_id"], minlength=10)
+    assert res["world"] == 2 and res["class_hist_total"] == want.tolist()
+    assert np.array_equal(np.sum(res["class_hist_per_rank"], axis=0), want)
+    assert res["class_hist_per_rank"][0] == np.bincount(flat["class_id"][flat["frame"] < 150], minlength=10).tolist()
+    sweep.run_sweep(300, 0, 1, T.device("cuda"), pool_frames=16, config="c1", emit="yolo", out_dir=str(tmp_path / "one"), group=2)
+    for i in range(300):
+        assert (tmp_path / "one" / "labels" / f"label_{i:06d}.txt").read_bytes() == \
+            (tmp_path / "two" / "labels" / f"label_{i:06d}.txt").read_bytes(), i
 
 
 def test_sweep_frame_range_and_histogram(T, ops, tmp_path):
