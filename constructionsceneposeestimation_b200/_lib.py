@@ -22,7 +22,8 @@ SCAN_FIELDS = 5
 NUM_CLASSES = 10
 BBOX3D_RECORD_BYTES = 96
 
-OBJ_HAS_RECORD, OBJ_ANY_FRONT, OBJ_ALL_FRONT, OBJ_POSE_VALID = 1, 2, 4, 8
+OBJ_HAS_RECORD, OBJ_ANY_FRONT, OBJ_ALL_FRONT, OBJ_POSE_VALID, OBJ_APPROX_RECORD = 1, 2, 4, 8, 16
+OBJ_RECORD_APPROX_BIT = 1 << 30   # OR into an obj_record entry: the record only approximates the object
 KP_OUT, KP_OCCLUDED, KP_VISIBLE = 0, 1, 2
 
 # host view of `cspe_record` (include/cspe.h); emit.cu static_asserts the 408-byte size
@@ -120,11 +121,14 @@ PROTOTYPES = {
     "cspe_graph_edge_kinds": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),
     "cspe_depth_to_pointcloud": (_I, [_P, _P, _I, _I, _I, _P, _P, _I64, _P, _P, _P]),
+    "cspe_pointcloud_batch_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "cspe_depth_to_pointcloud_batch": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I64, _P, _P, _P]),
     "cspe_depth_stats": (_I, [_P, _I, _I, _I, _P, _P]),
     "cspe_depth_colormap": (_I, [_P, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_rgb_to_bgr": (_I, [_P, _I, _I64, _P, _P]),
     "cspe_text_workspace_bytes": (C.c_size_t, [_I64, _I]),
     "cspe_format_fixed6": (_I, [_P, _I, _I64, _P, _I, C.c_char_p, _P, _I64, _P, _I64, _P, _P, _P]),
+    "cspe_write_files_host": (_I64, [C.c_char_p, C.c_char_p, _I, C.c_char_p, _I64, _I, _P, _I64, _P]),
     "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
     "cspe_format_coco_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P, _P, _P, _I, _I, _P, _I64]),
     "cspe_format_label_json_host": (_I64, [_P, _I, _I64, _P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _P, _P, _P, _I,

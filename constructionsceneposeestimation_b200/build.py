@@ -20,7 +20,7 @@ LIB_PATH = PKG_DIR / "libcspe.so"
 STAMP_PATH = PKG_DIR / ".libcspe.stamp"
 
 SOURCES = ["abi.cu", "mask_scan.cu", "project.cu", "keypoints.cu", "emit.cu", "pointcloud.cu", "depth_stats.cu", "depth_viz.cu", "format.cu", "yolo_text.cu", "text_format.cu",
-           "label_json.cpp"]
+           "label_json.cpp", "host_io.cpp"]
 
 # -fmad=false: every f32/f64 operation rounds on its own, exactly like the numpy oracle's
 # elementwise arithmetic, so projections and flags are reproducible bit for bit.

@@ -85,3 +85,62 @@ def pack_camera(pose7: Sequence[float], params: Mapping, near: float = DEFAULT_N
     blk[18], blk[19] = params["width"], params["height"]
     blk[20:24] = 0.0
     return blk
+
+
+def matrix_to_quat_xyzw(r: np.ndarray) -> np.ndarray:
+    """Scalar-last quaternion of a rotation matrix, the way scipy's ``Rotation.from_matrix(r).as_quat()``
+    produces it at gcd.py:602 (largest of the three diagonal entries and the trace picks the branch; the sign
+    is whatever that branch gives — not canonicalised, like the reference's)."""
+    m = np.asarray(r, dtype=np.float64).reshape(3, 3)
+    decision = np.array([m[0, 0], m[1, 1], m[2, 2], m[0, 0] + m[1, 1] + m[2, 2]])
+    choice = int(np.argmax(decision))
+    q = np.empty(4, dtype=np.float64)
+    if choice != 3:
+        i = choice
+        j = (i + 1) % 3
+        k = (j + 1) % 3
+        q[i] = 1.0 - decision[3] + 2.0 * m[i, i]
+        q[j] = m[j, i] + m[i, j]
+        q[k] = m[k, i] + m[i, k]
+        q[3] = m[k, j] - m[j, k]
+    else:
+        q[0] = m[2, 1] - m[1, 2]
+        q[1] = m[0, 2] - m[2, 0]
+        q[2] = m[1, 0] - m[0, 1]
+        q[3] = 1.0 + decision[3]
+    return q / np.sqrt(q @ q)
+
+
+def is_replicator_camera_params(params) -> bool:
+    """True for the dict Replicator's ``camera_params`` annotator delivers (``cameraViewTransform``,
+    ``cameraFocalLength``, ``cameraAperture``, ``renderProductResolution`` ...) as opposed to the reference's own
+    five-field dict (gcd.py:2039-2045)."""
+    return isinstance(params, Mapping) and "cameraViewTransform" in params
+
+
+def from_replicator_camera_params(params: Mapping, width: Optional[int] = None, height: Optional[int] = None):
+    """(pose7, reference-style params dict) from Replicator's native ``camera_params`` payload.
+
+    ``cameraViewTransform`` is the world -> camera matrix in USD's row-vector convention (16 values, row-major):
+    its inverse is the camera prim's local-to-world matrix, from which the pose follows exactly as ``get_obj_pose``
+    takes it (gcd.py:596-605): translation = last row, rotation = transposed upper 3x3, scipy quaternion.
+    Intrinsics follow gcd.py:2036-2045 / 646-649: ``focal_length`` = cameraFocalLength, ``horizontal_aperture`` =
+    cameraAperture[0], ``vertical_aperture`` = horizontal * H / W, W x H = renderProductResolution (units cancel
+    in fx = W * f / aperture)."""
+    view = np.asarray(params["cameraViewTransform"], dtype=np.float64).reshape(4, 4)
+    t, rcw = pose_from_usd_matrix(np.linalg.inv(view))
+    pose7 = np.concatenate([t, matrix_to_quat_xyzw(rcw)])
+    res = params.get("renderProductResolution")
+    if res is not None and len(res) >= 2:
+        width, height = int(res[0]), int(res[1])
+    if width is None or height is None:
+        raise ValueError("camera_params has no renderProductResolution and no image shape is known")
+    aperture = params.get("cameraAperture")
+    ha = float(np.asarray(aperture).reshape(-1)[0]) if aperture is not None else DEFAULT_HORIZONTAL_APERTURE
+    f = params.get("cameraFocalLength")
+    f = float(np.asarray(f).reshape(-1)[0]) if f is not None else DEFAULT_FOCAL_LENGTH
+    out = {"horizontal_aperture": ha, "vertical_aperture": ha * (height / width), "focal_length": f,
+           "width": width, "height": height}
+    near_far = params.get("cameraNearFar")
+    clip = (float(near_far[0]), float(near_far[1])) if near_far is not None and len(near_far) >= 2 else None
+    return [float(v) for v in pose7], out, clip

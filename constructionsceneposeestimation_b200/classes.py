@@ -185,14 +185,20 @@ def aggregate_objects(prim_paths: Iterable[str], resolver: ObjectRootResolver) -
     return list(by_root.values())
 
 
-def record_index_for(objects: Sequence[SceneObject], prim_paths: Sequence[str], fallback: str = "first_mesh") -> List[int]:
+RECORD_APPROX_BIT = 1 << 30   # = CSPE_OBJ_RECORD_APPROX_BIT (include/cspe.h)
+
+
+def record_index_for(objects: Sequence[SceneObject], prim_paths: Sequence[str], fallback: str = "first_mesh",
+                     mark_approx: bool = True) -> List[int]:
     """bbox3d record index per object, or -1.
 
     ``primPaths.index(root)`` first (gcd.py:1934); crane parts (virtual ``root#part``) then try
     their mesh paths in order (gcd.py:1953-1975).  ``fallback="first_mesh"`` extends that mesh
     rule to every object because the reference's other fallback — reading the live USD stage
     (gcd.py:1977-2023) — does not exist outside Isaac Sim; ``fallback="reference"`` keeps the
-    reference's rule and leaves such objects without a record.
+    reference's rule and leaves such objects without a record.  A first-mesh stand-in for anything but a
+    crane part describes ONE mesh of a multi-mesh object, not the object: its index carries
+    ``RECORD_APPROX_BIT`` so K2 sets ``OBJ_APPROX_RECORD`` in the record's flags and the label says so.
     """
     if fallback not in ("first_mesh", "reference"):
         raise ValueError(f"unknown record fallback {fallback!r}")
@@ -207,6 +213,10 @@ def record_index_for(objects: Sequence[SceneObject], prim_paths: Sequence[str], 
                 idx = first_index.get(mp, -1)
                 if idx >= 0:
                     break
+            # the reference's own rule for crane parts (gcd.py:1953-1975) is not an approximation of ours; a
+            # single-mesh object is described exactly by its only mesh
+            if idx >= 0 and mark_approx and "#" not in obj.prim_path and len(obj.mesh_paths) > 1:
+                idx |= RECORD_APPROX_BIT
         out.append(idx)
     return out
 
@@ -237,5 +247,8 @@ def id_to_slot(id_to_labels: Mapping, objects: Sequence[SceneObject], resolver: 
         root, _, _ = resolver.resolve(path)
         slot = slot_of_root.get(root) if root is not None else None
         if slot is not None:
-            out[int(key)] = slot
+            try:
+                out[int(key)] = slot
+            except (TypeError, ValueError):
+                continue   # a non-numeric id key: skip the entry, never fatal (gcd.py:2024-2027 convention)
     return out

@@ -147,55 +147,51 @@ __device__ __forceinline__ void red_global_max(int32_t* p, int v) {
 
 // Merge one evicted register entry into the CTA table (shared) or straight into `out`.
 //
-// kFlush = 1 (default): the id goes through the LUT first — an ignored id (background, unlabelled,
-// unmapped) costs one shared-memory load and nothing else — then the lanes that are here are
-// grouped by SLOT with match.any and every group is reduced with redux before its leader issues
-// the five reds.  Lanes run down the rows of one strip, so a warp usually evicts one id at the
-// same moment (one group); where an object edge or a texture crosses the 32 rows it evicts a
-// few (one group each) — never 32 lanes x 5 same-address reds, which is what saturated the
-// shared-memory atomic unit on fragmented masks (16x16-pixel id blocks ran at 0.71 of peak).
-// kFlush = 0 keeps round 1's form (match.all on the id, else every lane on its own) for A/B runs.
+// Lanes run down the rows of one strip, so a whole warp usually evicts the SAME id at the same moment:
+// match.all finds that case, redux reduces across the lanes and one lane merges.  Where an object edge crosses
+// the 32 rows the lanes evict two or three ids and every lane merges on its own: 32 lanes x 5 reds on a few
+// addresses, which the shared-memory pipe serialises (16x16-pixel id blocks: 21.7 M conflict wavefronts, the pipe
+// 61 % busy).  The reds are fire-and-forget, so the warp itself does not wait for them — which is why both
+// attempts to aggregate them first measured SLOWER on every mask content (profiles/r02_scan_variants.log):
+// match.any + one redux per group (divergent groups: 0.52 vs 0.70 of peak on the id blocks), and up to three
+// converged shfl / ballot / 5 x redux rounds (0.60).
+// kFlush = 1: before its four min / max reds a lane reads the entry and drops the ones that cannot change it
+// (extents only ever grow, so a value that does not improve the current entry never will): interior strips of a
+// large object then cost one red, the count.  kFlush = 0: always five reds.
 template <bool kSmemTable, int kFlush>
 __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx, int ymn, int ymx,
                                          const int32_t* lut, int lut_len, int N, int32_t* tab) {
-  int slot;
-  if (kFlush == 1) {
-    if (id >= static_cast<uint32_t>(lut_len)) return;
-    slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
-    if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
-    const unsigned active = __activemask();
-    const unsigned grp = __match_any_sync(active, slot);
-    if (grp & (grp - 1)) {  // more than one lane holds this slot: reduce inside the group
-      cnt = __reduce_add_sync(grp, cnt);
-      xmn = __reduce_min_sync(grp, xmn);
-      xmx = __reduce_max_sync(grp, xmx);
-      ymn = __reduce_min_sync(grp, ymn);
-      ymx = __reduce_max_sync(grp, ymx);
-      if ((threadIdx.x & 31) != __ffs(grp) - 1) return;
-    }
-  } else {
-    const unsigned active = __activemask();
-    int same;
-    __match_all_sync(active, id, &same);
-    if (same) {
-      cnt = __reduce_add_sync(active, cnt);
-      xmn = __reduce_min_sync(active, xmn);
-      xmx = __reduce_max_sync(active, xmx);
-      ymn = __reduce_min_sync(active, ymn);
-      ymx = __reduce_max_sync(active, ymx);
-      if ((threadIdx.x & 31) != __ffs(active) - 1) return;
-    }
-    if (id >= static_cast<uint32_t>(lut_len)) return;
-    slot = lut[id];
-    if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
+  const unsigned active = __activemask();
+  int same;
+  __match_all_sync(active, id, &same);
+  if (same) {
+    cnt = __reduce_add_sync(active, cnt);
+    xmn = __reduce_min_sync(active, xmn);
+    xmx = __reduce_max_sync(active, xmx);
+    ymn = __reduce_min_sync(active, ymn);
+    ymx = __reduce_max_sync(active, ymx);
+    if ((threadIdx.x & 31) != __ffs(active) - 1) return;
   }
+  if (id >= static_cast<uint32_t>(lut_len)) return;
+  const int slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
+  if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
   int32_t* e = tab + slot * CSPE_SCAN_FIELDS;
   if (kSmemTable) {
     red_shared_add(e + CSPE_SCAN_COUNT, cnt);
-    red_shared_min(e + CSPE_SCAN_XMIN, xmn);
-    red_shared_min(e + CSPE_SCAN_YMIN, ymn);
-    red_shared_max(e + CSPE_SCAN_XMAX, xmx);
-    red_shared_max(e + CSPE_SCAN_YMAX, ymx);
+    if (kFlush == 1 && !same) {
+      const volatile int32_t* ev = e;
+      const int c_xmn = ev[CSPE_SCAN_XMIN], c_ymn = ev[CSPE_SCAN_YMIN], c_xmx = ev[CSPE_SCAN_XMAX],
+                c_ymx = ev[CSPE_SCAN_YMAX];
+      if (xmn < c_xmn) red_shared_min(e + CSPE_SCAN_XMIN, xmn);
+      if (ymn < c_ymn) red_shared_min(e + CSPE_SCAN_YMIN, ymn);
+      if (xmx > c_xmx) red_shared_max(e + CSPE_SCAN_XMAX, xmx);
+      if (ymx > c_ymx) red_shared_max(e + CSPE_SCAN_YMAX, ymx);
+    } else {
+      red_shared_min(e + CSPE_SCAN_XMIN, xmn);
+      red_shared_min(e + CSPE_SCAN_YMIN, ymn);
+      red_shared_max(e + CSPE_SCAN_XMAX, xmx);
+      red_shared_max(e + CSPE_SCAN_YMAX, ymx);
+    }
   } else {
     red_global_add(e + CSPE_SCAN_COUNT, cnt);
     red_global_min(e + CSPE_SCAN_XMIN, xmn);
@@ -451,13 +447,12 @@ __global__ void __maxnreg__(80)
         for (int j = 1; j < kStripPx; ++j) bm |= (v[j] != v[j - 1]) ? (1u << j) : 0u;
         const uint32_t live = len < kStripPx ? (1u << len) - 1u : 0xffffffffu;
         bm &= live;
-        // pixels not yet accounted for
-        uint32_t rem = live;
         if (kSlow == 1 && __popc(bm) >= kRunWalkMax) {
           // Many runs (a see-through texture: wire mesh, foliage, or an edge that zig-zags): the row
           // usually still holds only two or three DISTINCT ids, so account for it per id instead of
           // per run — equality bit mask of the id over the 32 pixels, count = popc, extent = ffs / clz.
-          // After kMaxDistinct ids whatever is left goes through the run walk below.
+          // After kMaxDistinct ids whatever is left goes through a run walk over the remaining pixels.
+          uint32_t rem = live;   // pixels not yet accounted for
           uint32_t id = a;
 #pragma unroll 1
           for (int k = 0; k < kMaxDistinct; ++k) {
@@ -478,20 +473,31 @@ __global__ void __maxnreg__(80)
             const int s = __ffs(rem) - 1;
             id = *reinterpret_cast<const uint32_t*>(base + (((s >> 2) ^ sw) << 4) + ((s & 3) << 2));
           }
-        }
-        // run walk over the pixels still in `rem` (all of them when the row has few runs): one
-        // iteration per run, one shared-memory load per run
-        const uint32_t stops = bm | ~rem;   // a run ends before the next run start or accounted pixel
+          const uint32_t stops = bm | ~rem;   // a run ends before the next run start or accounted pixel
 #pragma unroll 1
-        while (rem) {
-          const int s0 = __ffs(rem) - 1;
-          const uint32_t t = stops & (0xfffffffeu << s0);
-          const int e = t ? __ffs(t) - 2 : len - 1;   // last pixel of the run starting at s0
-          const uint32_t id =
-              *reinterpret_cast<const uint32_t*>(base + (((s0 >> 2) ^ sw) << 4) + ((s0 & 3) << 2));
-          CSPE_SWITCH(id);
-          CSPE_ACCUM(e - s0 + 1, x0 + s0, x0 + e);
-          rem &= 0xfffffffeu << e;   // clears bits 0..e (everything below s0 is already clear)
+          while (rem) {
+            const int s0 = __ffs(rem) - 1;
+            const uint32_t t = stops & (0xfffffffeu << s0);
+            const int e = t ? __ffs(t) - 2 : len - 1;   // last pixel of the run starting at s0
+            const uint32_t rid =
+                *reinterpret_cast<const uint32_t*>(base + (((s0 >> 2) ^ sw) << 4) + ((s0 & 3) << 2));
+            CSPE_SWITCH(rid);
+            CSPE_ACCUM(e - s0 + 1, x0 + s0, x0 + e);
+            rem &= 0xfffffffeu << e;   // clears bits 0..e (everything below s0 is already clear)
+          }
+        } else {
+          // few runs (an object edge crossing the strip): walk them, one shared-memory load per run
+          int s0 = 0;
+#pragma unroll 1
+          while (s0 < len) {
+            const uint32_t t = bm & (0xfffffffeu << s0);
+            const int e = t ? __ffs(t) - 2 : len - 1;   // last pixel of the run starting at s0
+            const uint32_t id =
+                *reinterpret_cast<const uint32_t*>(base + (((s0 >> 2) ^ sw) << 4) + ((s0 & 3) << 2));
+            CSPE_SWITCH(id);
+            CSPE_ACCUM(e - s0 + 1, x0 + s0, x0 + e);
+            s0 = e + 1;
+          }
         }
       }
     }
@@ -559,11 +565,15 @@ int scan_tma_dims() {
   return v;
 }
 
-// CSPE_SCAN_FLUSH / CSPE_SCAN_SLOW = 0 select round 1's flush (match.all) / slow path (run walk only) for
-// same-box A/B runs; default 1 / 1
-int scan_variant(const char* name) {
+// A/B switches, read per launch: CSPE_SCAN_FLUSH = 0 always issues the five reds (default 1: lanes that merge on
+// their own skip min / max reds that cannot change the entry), CSPE_SCAN_SLOW = 0 the run walk only (default 1: rows
+// with many runs are accounted per distinct id).  Measured on B200 (profiles/r02_scan_variants.log): the defaults
+// cost ~1.5 % on config 2 and buy 2.5x on see-through textures and +5 % on 16x16-pixel id blocks.
+constexpr int kDefaultFlush = 1, kDefaultSlow = 1;
+int scan_variant(const char* name, int dflt) {
   const char* e = getenv(name);
-  return (e && atoi(e) == 0) ? 0 : 1;
+  if (!e || !*e) return dflt;
+  return atoi(e) != 0 ? 1 : 0;
 }
 
 template <int kBoxes>
@@ -650,15 +660,18 @@ int launch_scan_geo(const uint32_t* mask, int B, int H, int W, const int32_t* id
   p.smem_lut = lut_len > 0 && (smem_table ? table_bytes : 0) + lut_bytes <= static_cast<size_t>(G::kSmemFree);
   const size_t smem_bytes = G::kSmemFixed + (smem_table ? table_bytes : 0) + (p.smem_lut ? lut_bytes : 0);
 
-  const int flush_v = scan_variant("CSPE_SCAN_FLUSH"), slow_v = scan_variant("CSPE_SCAN_SLOW");  // read per launch
-  auto kern = smem_table ? mask_scan_kernel<true, kBoxes, 1, 1> : mask_scan_kernel<false, kBoxes, 1, 1>;
-  if constexpr (kBoxes == kDefaultBoxes) if (!(flush_v == 1 && slow_v == 1)) {   // A/B variants exist for the default geometry only
+  const int flush_v = scan_variant("CSPE_SCAN_FLUSH", kDefaultFlush), slow_v = scan_variant("CSPE_SCAN_SLOW", kDefaultSlow);
+  auto kern = smem_table ? mask_scan_kernel<true, kBoxes, kDefaultFlush, kDefaultSlow>
+                         : mask_scan_kernel<false, kBoxes, kDefaultFlush, kDefaultSlow>;
+  if constexpr (kBoxes == kDefaultBoxes) {   // A/B variants exist for the default geometry only
     if (flush_v == 0 && slow_v == 0)
       kern = smem_table ? mask_scan_kernel<true, kBoxes, 0, 0> : mask_scan_kernel<false, kBoxes, 0, 0>;
-    else if (flush_v == 0)
+    else if (flush_v == 0 && slow_v == 1)
       kern = smem_table ? mask_scan_kernel<true, kBoxes, 0, 1> : mask_scan_kernel<false, kBoxes, 0, 1>;
-    else
+    else if (flush_v == 1 && slow_v == 0)
       kern = smem_table ? mask_scan_kernel<true, kBoxes, 1, 0> : mask_scan_kernel<false, kBoxes, 1, 0>;
+    else
+      kern = smem_table ? mask_scan_kernel<true, kBoxes, 1, 1> : mask_scan_kernel<false, kBoxes, 1, 1>;
   }
   CSPE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
   CSPE_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(G::kThreads), smem_bytes, st, p, tmap));

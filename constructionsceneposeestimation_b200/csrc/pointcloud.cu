@@ -8,14 +8,17 @@
 // into (N, 6) float64.
 //
 // HBM-bound on the OUTPUT: 48 bytes written per valid pixel against 4 (depth) + C (rgb) bytes read,
-// both read twice.  Two launches chained by programmatic dependent launch (a single 1080p frame is
-// latency-bound, every launch costs):
-//   1. per tile (1024 px): valid count and the maximum colour over valid pixels; the LAST CTA to
-//      finish (atomic ticket) scans the tile counts into tile offsets and the total;
+// both read twice.  A whole BATCH of frames goes through two launches chained by programmatic dependent
+// launch (one frame at a time is latency-bound: 2 025 short-lived CTAs per pass never fill the machine, and its
+// 64 MB of points stay in L2); a CTA owns kPcGroup consecutive 1024-pixel tiles of one frame and keeps their
+// loads in flight together:
+//   1. per tile: valid count and the maximum colour over valid pixels; the LAST CTA of each frame (atomic
+//      ticket) scans that frame's tile counts into tile offsets, and the last of those scans the frame totals
+//      into offsets[0 .. B] — frames are compacted back to back, each in row-major order;
 //   2. per tile: recompute validity, in-tile ranks, build the tile's points in shared memory and
 //      stream them out as one contiguous run of 16-byte stores (a thread writing its own 48-byte
-//      points directly costs ~6x the sector traffic); colours are scaled by 255 when the maximum
-//      found by pass 1 is <= 1 (the reference's [0,1]-image rule, gcd.py:693).
+//      points directly costs ~6x the sector traffic); colours are scaled by 255 when the frame's maximum
+//      found by pass 1 is <= 1 (the reference's [0,1]-image rule, gcd.py:693, per frame as it is per call there).
 #include <math.h>
 
 #include "cspe_common.cuh"
@@ -26,14 +29,46 @@ namespace {
 constexpr int kPcThreads = 256;
 constexpr int kPcPerThread = 4;
 constexpr int kPcTile = kPcThreads * kPcPerThread;  // 1024 pixels
+constexpr int kPcGroup = 4;                         // consecutive tiles of one frame per CTA
 constexpr int kPcStageBytes = kPcTile * (3 * 8 + 4);  // a tile's points as x[], y[], z[] (f64) + packed colour: 28 KB
 
-struct PcWorkspace {  // layout of the caller-provided scratch
-  unsigned int rgb_max;  // maximum colour byte over valid pixels
-  unsigned int done;     // CTAs of pass 1 that have published their count (ticket for the last-CTA scan)
-  long long total;
-  // followed by: int64 tile_offset[tiles]; int32 tile_count[tiles]
+// Caller-provided scratch, one batch: per-frame headers, then per-(frame, tile) counts and offsets.
+struct PcFrameHeader {
+  unsigned int rgb_max;  // maximum colour byte over the frame's valid pixels
+  unsigned int done;     // CTAs of pass 1 that have published their counts (ticket for the frame's scan)
+  long long total;       // valid pixels of the frame
 };
+struct PcBatchHeader {
+  unsigned int frames_done;  // frames whose scan is complete (ticket for the scan over frames)
+  unsigned int pad;
+};
+
+__host__ __device__ inline size_t pc_align16(size_t v) { return (v + 15) & ~static_cast<size_t>(15); }
+
+struct PcLayout {
+  PcBatchHeader* batch;
+  PcFrameHeader* frame;     // [B]
+  int32_t* tile_count;      // [B][tiles]
+  int32_t* tile_offset;     // [B][tiles]  first point of the tile, relative to its frame
+  size_t header_bytes;      // what a call has to zero
+  size_t bytes;
+};
+
+__host__ __device__ inline PcLayout pc_layout(void* ws, int B, long long tiles) {
+  PcLayout l;
+  unsigned char* p = static_cast<unsigned char*>(ws);
+  l.batch = reinterpret_cast<PcBatchHeader*>(p);
+  size_t off = pc_align16(sizeof(PcBatchHeader));
+  l.frame = reinterpret_cast<PcFrameHeader*>(p + off);
+  off = pc_align16(off + static_cast<size_t>(B) * sizeof(PcFrameHeader));
+  l.header_bytes = off;
+  l.tile_count = reinterpret_cast<int32_t*>(p + off);
+  off = pc_align16(off + static_cast<size_t>(B) * tiles * 4);
+  l.tile_offset = reinterpret_cast<int32_t*>(p + off);
+  off = pc_align16(off + static_cast<size_t>(B) * tiles * 4);
+  l.bytes = off;
+  return l;
+}
 
 __device__ __forceinline__ bool pc_valid(float d) {
   return (d > 0.0f) && (d < 250.0f);  // finite follows from < 250; NaN fails both
@@ -70,89 +105,129 @@ __device__ __forceinline__ void load_rgb4(const uint8_t* __restrict__ rgb, int C
   }
 }
 
-__global__ void __launch_bounds__(kPcThreads)
-    pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw, int vec,
-                    int rgb_vec, int32_t* tile_count, long long* tile_offset, int tiles, PcWorkspace* ws,
-                    long long* n_points) {
-  pdl_launch_dependents();
-  __shared__ int s_cnt[kPcThreads / 32];
-  __shared__ unsigned s_max[kPcThreads / 32];
-  __shared__ long long s_scan[kPcThreads / 32];
-  __shared__ long long s_base;
-  __shared__ bool s_last;
+// exclusive scan of n int64 values by one CTA (values read through `get`, results through `put`); returns the total
+template <typename Get, typename Put>
+__device__ __forceinline__ long long cta_exclusive_scan(int n, long long* s_scan, long long* s_base, Get get, Put put) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
-  float d[kPcPerThread];
-  load4(depth, base, hw, vec, d);
-  int cnt = 0;
-  unsigned mx = 0;
-#pragma unroll
-  for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
-  if (rgb != nullptr && cnt) {
-    uint32_t px[kPcPerThread];
-    load_rgb4(rgb, C, base, hw, rgb_vec, px);
-#pragma unroll
-    for (int k = 0; k < kPcPerThread; ++k)
-      if (pc_valid(d[k])) mx = max(mx, max(px[k] & 255u, max((px[k] >> 8) & 255u, (px[k] >> 16) & 255u)));
-  }
-  cnt = __reduce_add_sync(0xffffffffu, cnt);
-  mx = __reduce_max_sync(0xffffffffu, mx);
-  if (lane == 0) {
-    s_cnt[wid] = cnt;
-    s_max[wid] = mx;
-  }
+  if (threadIdx.x == 0) *s_base = 0;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int t = 0;
-    unsigned m = 0;
-#pragma unroll
-    for (int w = 0; w < kPcThreads / 32; ++w) {
-      t += s_cnt[w];
-      m = max(m, s_max[w]);
-    }
-    tile_count[blockIdx.x] = t;
-    if (m) atomicMax(&ws->rgb_max, m);
-    __threadfence();  // publish the count before taking the ticket
-    s_last = atomicAdd(&ws->done, 1u) == gridDim.x - 1;
-    s_base = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  // ---- last CTA: exclusive scan of every tile's count (all of them are published) ----
-  __threadfence();
-  for (int t0 = 0; t0 < tiles; t0 += kPcThreads) {
+  for (int t0 = 0; t0 < n; t0 += kPcThreads) {
     const int t = t0 + threadIdx.x;
-    const long long v = t < tiles ? __ldcg(tile_count + t) : 0;
+    const long long v = t < n ? get(t) : 0;
     long long inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const long long n = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += n;
+      const long long m = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += m;
     }
     if (lane == 31) s_scan[wid] = inc;
     __syncthreads();
-    long long before = s_base + inc - v, chunk = 0;
+    long long before = *s_base + inc - v, chunk = 0;
 #pragma unroll
     for (int w = 0; w < kPcThreads / 32; ++w) {
       if (w < wid) before += s_scan[w];
       chunk += s_scan[w];
     }
-    if (t < tiles) tile_offset[t] = before;
+    if (t < n) put(t, before);
     __syncthreads();
-    if (threadIdx.x == 0) s_base += chunk;
+    if (threadIdx.x == 0) *s_base += chunk;
     __syncthreads();
   }
+  return *s_base;
+}
+
+// Pass 1.  Grid = B x groups; CTA (f, g) counts the valid pixels of tiles g*kPcGroup .. of frame f and folds the
+// frame's colour maximum.  The last CTA of a frame (atomic ticket) scans the frame's tile counts; the last of those
+// scans the frame totals into `offsets`.
+__global__ void __launch_bounds__(kPcThreads)
+    pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw, int vec,
+                    int rgb_vec, int B, int tiles, int groups, void* ws_raw, long long* offsets) {
+  pdl_launch_dependents();
+  __shared__ int s_cnt[kPcGroup][kPcThreads / 32];
+  __shared__ unsigned s_max[kPcThreads / 32];
+  __shared__ long long s_scan[kPcThreads / 32];
+  __shared__ long long s_base;
+  __shared__ bool s_last;
+  const PcLayout L = pc_layout(ws_raw, B, tiles);
+  const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float* dep = depth + static_cast<long long>(f) * hw;
+  const uint8_t* col = rgb ? rgb + static_cast<long long>(f) * hw * C : nullptr;
+  float d[kPcGroup][kPcPerThread];
+#pragma unroll
+  for (int i = 0; i < kPcGroup; ++i) {
+    const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+    if (g * kPcGroup + i < tiles) load4(dep, base, hw, vec, d[i]);
+    else d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.0f;
+  }
+  unsigned mx = 0;
+#pragma unroll
+  for (int i = 0; i < kPcGroup; ++i) {
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[i][k]);
+    if (col != nullptr && cnt) {
+      uint32_t px[kPcPerThread];
+      const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+      load_rgb4(col, C, base, hw, rgb_vec, px);
+#pragma unroll
+      for (int k = 0; k < kPcPerThread; ++k)
+        if (pc_valid(d[i][k])) mx = max(mx, max(px[k] & 255u, max((px[k] >> 8) & 255u, (px[k] >> 16) & 255u)));
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) s_cnt[i][wid] = cnt;
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  if (lane == 0) s_max[wid] = mx;
+  __syncthreads();
+  if (threadIdx.x < kPcGroup && g * kPcGroup + threadIdx.x < tiles) {
+    int t = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; ++w) t += s_cnt[threadIdx.x][w];
+    L.tile_count[static_cast<long long>(f) * tiles + g * kPcGroup + threadIdx.x] = t;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    ws->total = s_base;
-    *n_points = s_base;
-    ws->done = 0;  // ready for the next call on this workspace
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; ++w) m = max(m, s_max[w]);
+    if (m) atomicMax(&L.frame[f].rgb_max, m);
+    __threadfence();  // publish the counts before taking the ticket
+    s_last = atomicAdd(&L.frame[f].done, 1u) == static_cast<unsigned>(groups) - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA of frame f: exclusive scan of the frame's tile counts (all of them are published) ----
+  __threadfence();
+  const int32_t* tc = L.tile_count + static_cast<long long>(f) * tiles;
+  int32_t* to = L.tile_offset + static_cast<long long>(f) * tiles;
+  const long long total = cta_exclusive_scan(
+      tiles, s_scan, &s_base, [&](int t) { return static_cast<long long>(__ldcg(tc + t)); },
+      [&](int t, long long v) { to[t] = static_cast<int32_t>(v); });
+  if (threadIdx.x == 0) {
+    L.frame[f].total = total;
+    L.frame[f].done = 0;  // ready for the next call on this workspace
+    __threadfence();
+    s_last = atomicAdd(&L.batch->frames_done, 1u) == static_cast<unsigned>(B) - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last frame to finish: exclusive scan of the frame totals -> offsets[0 .. B] ----
+  __threadfence();
+  const long long all = cta_exclusive_scan(
+      B, s_scan, &s_base, [&](int t) { return *reinterpret_cast<volatile long long*>(&L.frame[t].total); },
+      [&](int t, long long v) { offsets[t] = v; });
+  if (threadIdx.x == 0) {
+    offsets[B] = all;
+    L.batch->frames_done = 0;
   }
 }
 
+// Pass 2.  Same grid; every tile's points are built in shared memory and streamed out as one contiguous run.
 __global__ void __launch_bounds__(kPcThreads)
     pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
-                    int rgb_vec, const double* __restrict__ cam, const PcWorkspace* __restrict__ ws,
-                    const long long* __restrict__ tile_offset, double* __restrict__ out, long long capacity) {
+                    int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, int groups, void* ws_raw,
+                    const long long* __restrict__ offsets, double* __restrict__ out, long long capacity) {
   pdl_launch_dependents();
   // structure of arrays: 28 bytes per point instead of 48 doubles the resident CTAs per SM, and
   // consecutive ranks hit consecutive banks
@@ -161,85 +236,119 @@ __global__ void __launch_bounds__(kPcThreads)
   double* sy = stage + kPcTile;
   double* sz = stage + 2 * kPcTile;
   uint32_t* sc = reinterpret_cast<uint32_t*>(stage + 3 * kPcTile);
-  __shared__ int s_warp[kPcThreads / 32];
-  const long long base = static_cast<long long>(blockIdx.x) * kPcTile + threadIdx.x * kPcPerThread;
-  float d[kPcPerThread];
-  load4(depth, base, hw, vec, d);   // depth / rgb are inputs of the chain: no need to wait for pass 1 yet
-  int cnt = 0;
-#pragma unroll
-  for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
-  uint32_t px[kPcPerThread] = {0, 0, 0, 0};
-  if (rgb != nullptr && cnt) load_rgb4(rgb, C, base, hw, rgb_vec, px);
+  __shared__ int s_warp[kPcGroup][kPcThreads / 32];
+  const PcLayout L = pc_layout(ws_raw, B, tiles);
+  const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = cnt;
+  const float* dep = depth + static_cast<long long>(f) * hw;
+  const uint8_t* col = rgb ? rgb + static_cast<long long>(f) * hw * C : nullptr;
+  const double* cam = cam_all + static_cast<long long>(f) * CSPE_CAM_STRIDE;
+  // depth / rgb are inputs of the chain: everything up to the first store runs before waiting for pass 1
+  float d[kPcGroup][kPcPerThread];
+  uint32_t px[kPcGroup][kPcPerThread];
+  int cnt[kPcGroup], inc[kPcGroup];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
+  for (int i = 0; i < kPcGroup; ++i) {
+    const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+    if (g * kPcGroup + i < tiles) load4(dep, base, hw, vec, d[i]);
+    else d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.0f;
   }
-  if (lane == 31) s_warp[wid] = inc;
+#pragma unroll
+  for (int i = 0; i < kPcGroup; ++i) {
+    cnt[i] = 0;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) cnt[i] += pc_valid(d[i][k]);
+    px[i][0] = px[i][1] = px[i][2] = px[i][3] = 0;
+    if (col != nullptr && cnt[i]) {
+      const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+      load_rgb4(col, C, base, hw, rgb_vec, px[i]);
+    }
+    int v = cnt[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    inc[i] = v;
+    if (lane == 31) s_warp[i][wid] = v;
+  }
   __syncthreads();
-  int before = inc - cnt, tile_total = 0;
-#pragma unroll
-  for (int w = 0; w < kPcThreads / 32; ++w) {
-    if (w < wid) before += s_warp[w];
-    tile_total += s_warp[w];
-  }
 
   const double t0 = cam[0], t1 = cam[1], t2 = cam[2];
   const double fx = cam[12], fy = cam[13], cx = cam[14], cy = cam[15];
-  int r = before;
+  bool waited = false;
+  bool scale = false;
+  long long frame_first = 0;
+#pragma unroll   // static indices keep d / px / cnt / inc in registers
+  for (int i = 0; i < kPcGroup; ++i) {
+    const int tile = g * kPcGroup + i;
+    if (tile >= tiles) break;
+    int before = inc[i] - cnt[i], tile_total = 0;
 #pragma unroll
-  for (int k = 0; k < kPcPerThread; ++k) {
-    if (!pc_valid(d[k])) continue;
-    const long long i = base + k;
-    const int v = static_cast<int>(i / W);
-    const int u = static_cast<int>(i - static_cast<long long>(v) * W);
-    const double zc = static_cast<double>(d[k]);
-    const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
-    const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
-    sx[r] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
-    sy[r] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
-    sz[r] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
-    sc[r] = rgb ? px[k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
-    ++r;
-  }
-  __syncthreads();  // stage complete
-
-  pdl_wait();       // tile offsets and the colour maximum come from pass 1
-  // gcd.py:693: rgb.max() <= 1.0 over the valid pixels -> the colours were a [0,1] image: x255
-  const bool scale = rgb != nullptr && ws->rgb_max <= 1u;
-  // stream the tile's points out: ranks are consecutive, so it is one contiguous run
-  const long long first = tile_offset[blockIdx.x];
-  long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
-  if (keep > tile_total) keep = tile_total;
-  if (keep <= 0) return;
-  const double cs = scale ? 255.0 : 1.0;
-  const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs: (x,y) (z,r) (g,b)
-  double* dst = out + first * 6;
-  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-    double2* d2 = reinterpret_cast<double2*>(dst);
-    for (int j = threadIdx.x; j < n2; j += kPcThreads) {
-      const int pt = j / 3, m = j - pt * 3;
-      const uint32_t c = sc[pt];
-      double2 vv;
-      if (m == 0) {
-        vv.x = sx[pt];
-        vv.y = sy[pt];
-      } else if (m == 1) {
-        vv.x = sz[pt];
-        vv.y = static_cast<double>(c & 255u) * cs;
+    for (int w = 0; w < kPcThreads / 32; ++w) {
+      const int s = s_warp[i][w];
+      if (w < wid) before += s;
+      tile_total += s;
+    }
+    const long long base = static_cast<long long>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    int r = before;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) {
+      if (!pc_valid(d[i][k])) continue;
+      const long long p = base + k;
+      const int v = static_cast<int>(p / W);
+      const int u = static_cast<int>(p - static_cast<long long>(v) * W);
+      const double zc = static_cast<double>(d[i][k]);
+      const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
+      const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
+      sx[r] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
+      sy[r] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
+      sz[r] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
+      sc[r] = col ? px[i][k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
+      ++r;
+    }
+    __syncthreads();  // stage complete
+    if (!waited) {
+      pdl_wait();  // tile offsets, frame offsets and the colour maximum come from pass 1
+      waited = true;
+      // gcd.py:693: rgb.max() <= 1.0 over the frame's valid pixels -> the colours were a [0,1] image: x255
+      scale = col != nullptr && L.frame[f].rgb_max <= 1u;
+      frame_first = offsets[f];
+    }
+    // stream the tile's points out: ranks are consecutive, so it is one contiguous run
+    const long long first = frame_first + L.tile_offset[static_cast<long long>(f) * tiles + tile];
+    long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
+    if (keep > tile_total) keep = tile_total;
+    if (keep > 0) {
+      const double cs = scale ? 255.0 : 1.0;
+      const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs: (x,y) (z,r) (g,b)
+      double* dst = out + first * 6;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        double2* d2 = reinterpret_cast<double2*>(dst);
+        for (int j = threadIdx.x; j < n2; j += kPcThreads) {
+          const int pt = j / 3, m = j - pt * 3;
+          const uint32_t c = sc[pt];
+          double2 vv;
+          if (m == 0) {
+            vv.x = sx[pt];
+            vv.y = sy[pt];
+          } else if (m == 1) {
+            vv.x = sz[pt];
+            vv.y = static_cast<double>(c & 255u) * cs;
+          } else {
+            vv.x = static_cast<double>((c >> 8) & 255u) * cs;
+            vv.y = static_cast<double>((c >> 16) & 255u) * cs;
+          }
+          asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
+        }
       } else {
-        vv.x = static_cast<double>((c >> 8) & 255u) * cs;
-        vv.y = static_cast<double>((c >> 16) & 255u) * cs;
+        for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) {
+          const int pt = j / 6, m = j - pt * 6;
+          dst[j] = m == 0 ? sx[pt] : m == 1 ? sy[pt] : m == 2 ? sz[pt] : static_cast<double>((sc[pt] >> (8 * (m - 3))) & 255u) * cs;
+        }
       }
-      asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
     }
-  } else {
-    for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) {
-      const int pt = j / 6, m = j - pt * 6;
-      dst[j] = m == 0 ? sx[pt] : m == 1 ? sy[pt] : m == 2 ? sz[pt] : static_cast<double>((sc[pt] >> (8 * (m - 3))) & 255u) * cs;
-    }
+    __syncthreads();  // the stage is rewritten by the next tile
   }
 }
 
@@ -250,50 +359,75 @@ using namespace cspe;
 
 static long long pc_tiles(long long hw) { return (hw + kPcTile - 1) / kPcTile; }
 
-extern "C" size_t cspe_pointcloud_workspace_bytes(int H, int W) {
-  if (H <= 0 || W <= 0) return sizeof(PcWorkspace);
-  const long long tiles = pc_tiles(static_cast<long long>(H) * W);
-  // header | int64 tile_offset[tiles] | int32 tile_count[tiles]
-  return sizeof(PcWorkspace) + static_cast<size_t>(tiles) * (8 + 4) + 16;
+extern "C" size_t cspe_pointcloud_batch_workspace_bytes(int B, int H, int W) {
+  if (B <= 0) B = 1;
+  const long long tiles = (H <= 0 || W <= 0) ? 0 : pc_tiles(static_cast<long long>(H) * W);
+  return pc_layout(nullptr, B, tiles).bytes + 16;
 }
 
-extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_channels, int H, int W,
-                                        const double* cam, double* out, int64_t capacity, int64_t* n_points,
-                                        void* workspace, void* stream) {
-  CSPE_REQUIRE(H >= 0 && W >= 0 && capacity >= 0, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: negative size");
-  CSPE_REQUIRE(n_points && workspace && cam, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: null pointer");
+extern "C" size_t cspe_pointcloud_workspace_bytes(int H, int W) { return cspe_pointcloud_batch_workspace_bytes(1, H, W); }
+
+extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t* rgb, int rgb_channels, int B, int H, int W,
+                                              const double* cam, double* out, int64_t capacity, int64_t* offsets,
+                                              void* workspace, void* stream) {
+  CSPE_REQUIRE(B >= 0 && H >= 0 && W >= 0 && capacity >= 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_depth_to_pointcloud: negative size");
+  if (B == 0) return CSPE_OK;
+  CSPE_REQUIRE(offsets && workspace && cam, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: null pointer");
   CSPE_REQUIRE(rgb == nullptr || rgb_channels >= 3, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_depth_to_pointcloud: rgb needs >= 3 channels (got %d)", rgb_channels);
-  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
-               CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: workspace/out must be 8-byte aligned");
+  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0 &&
+                   (reinterpret_cast<uintptr_t>(offsets) & 7) == 0,
+               CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: workspace must be 16-byte, out / offsets 8-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long hw = static_cast<long long>(H) * W;
-  PcWorkspace* ws = static_cast<PcWorkspace*>(workspace);
   if (hw == 0) {
-    CSPE_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(PcWorkspace), st));
-    CSPE_CUDA_OK(cudaMemsetAsync(n_points, 0, sizeof(int64_t), st));
+    CSPE_CUDA_OK(cudaMemsetAsync(offsets, 0, sizeof(int64_t) * (static_cast<size_t>(B) + 1), st));
     return CSPE_OK;
   }
   CSPE_REQUIRE(depth != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: depth is null");
   CSPE_REQUIRE(capacity == 0 || out != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: out is null");
+  CSPE_REQUIRE(hw < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: frame too large");
   const long long tiles = pc_tiles(hw);
-  CSPE_REQUIRE(tiles < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: frame too large");
-  long long* tile_offset = reinterpret_cast<long long*>(ws + 1);
-  int32_t* tile_count = reinterpret_cast<int32_t*>(tile_offset + tiles);
-  const int vec = (reinterpret_cast<uintptr_t>(depth) & 15) == 0;
+  const long long groups = (tiles + kPcGroup - 1) / kPcGroup;
+  CSPE_REQUIRE(groups * B < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: batch too large");
+  const PcLayout L = pc_layout(workspace, B, tiles);
+  // frames of a batch start at multiples of hw floats: vector loads need every frame base 16-byte aligned
+  const int vec = (reinterpret_cast<uintptr_t>(depth) & 15) == 0 && (B == 1 || hw % 4 == 0);
   static const cudaError_t smem_attr =
       cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
   (void)smem_attr;
-  const int rgb_vec = rgb != nullptr && rgb_channels == 4 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0;
-  CSPE_CUDA_OK(cudaMemsetAsync(ws, 0, sizeof(PcWorkspace), st));
+  const int rgb_vec = rgb != nullptr && rgb_channels == 4 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 &&
+                      (B == 1 || hw % 4 == 0);
+  CSPE_CUDA_OK(cudaMemsetAsync(workspace, 0, L.header_bytes, st));
+  const unsigned grid = static_cast<unsigned>(groups * B);
   // plain launch first (serialised behind whatever produced depth / rgb), then the PDL-chained writer
-  pc_count_kernel<<<static_cast<unsigned>(tiles), kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, tile_count,
-                                                                      tile_offset, static_cast<int>(tiles), ws,
-                                                                      reinterpret_cast<long long*>(n_points));
+  pc_count_kernel<<<grid, kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, B, static_cast<int>(tiles),
+                                              static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets));
   CSPE_LAUNCH_OK("pc_count_kernel");
   if (capacity > 0)
-    CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(static_cast<unsigned>(tiles)), dim3(kPcThreads), kPcStageBytes, st, depth,
-                            rgb, rgb_channels, W, hw, vec, rgb_vec, cam, static_cast<const PcWorkspace*>(ws),
-                            static_cast<const long long*>(tile_offset), out, static_cast<long long>(capacity)));
+    CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(grid), dim3(kPcThreads), kPcStageBytes, st, depth, rgb, rgb_channels, W, hw,
+                            vec, rgb_vec, cam, B, static_cast<int>(tiles), static_cast<int>(groups), workspace,
+                            static_cast<const long long*>(reinterpret_cast<long long*>(offsets)), out,
+                            static_cast<long long>(capacity)));
+  return CSPE_OK;
+}
+
+// one frame: offsets[1] doubles as the point count (n_points = &pair[1] of a caller-side int64[2] is not required —
+// the single-frame entry point keeps its one-value result by scanning into a two-element scratch in the workspace)
+extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_channels, int H, int W,
+                                        const double* cam, double* out, int64_t capacity, int64_t* n_points,
+                                        void* workspace, void* stream) {
+  CSPE_REQUIRE(n_points != nullptr && workspace != nullptr, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_depth_to_pointcloud: null pointer");
+  CSPE_REQUIRE(H >= 0 && W >= 0, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: negative size");
+  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_depth_to_pointcloud: workspace must be 16-byte aligned");
+  // offsets[0..1] live at the end of the workspace; the total is copied to n_points on the stream
+  const long long tiles = (H <= 0 || W <= 0) ? 0 : pc_tiles(static_cast<long long>(H) * W);
+  int64_t* pair = reinterpret_cast<int64_t*>(static_cast<unsigned char*>(workspace) + pc_layout(nullptr, 1, tiles).bytes);
+  const int rc = cspe_depth_to_pointcloud_batch(depth, rgb, rgb_channels, 1, H, W, cam, out, capacity, pair, workspace, stream);
+  if (rc != CSPE_OK) return rc;
+  CSPE_CUDA_OK(cudaMemcpyAsync(n_points, pair + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return CSPE_OK;
 }

@@ -176,7 +176,11 @@ __device__ __forceinline__ void project_one(const unsigned char* __restrict__ re
   const double kNaN = __longlong_as_double(0x7ff8000000000000ll);
   double* po = pose + obj * CSPE_POSE_STRIDE;
 
-  const int rec = obj_record[obj];
+  // bit 30 of the record index marks a record that only approximates the object (a mesh record standing in
+  // for an object whose root prim has none): passed through to the flags, stripped from the index
+  const int rec_raw = obj_record[obj];
+  const bool approx = rec_raw >= 0 && (rec_raw & CSPE_OBJ_RECORD_APPROX_BIT);
+  const int rec = rec_raw >= 0 ? (rec_raw & ~CSPE_OBJ_RECORD_APPROX_BIT) : rec_raw;
   if (rec < 0 || rec >= recs_per_frame) {
     // no record for this slot: defined outputs, flags 0
 #pragma unroll
@@ -306,6 +310,7 @@ __device__ __forceinline__ void project_one(const unsigned char* __restrict__ re
   if (fm) fl |= CSPE_OBJ_ANY_FRONT;
   if (fm == 0xffu) fl |= CSPE_OBJ_ALL_FRONT;
   if (pose_ok) fl |= CSPE_OBJ_POSE_VALID;
+  if (approx) fl |= CSPE_OBJ_APPROX_RECORD;
   flags[obj] = fl;
 }
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import json
 import math
+import os
 from typing import Union, Dict, Iterable, List, Mapping, Optional, Sequence
 
 import numpy as np
@@ -169,6 +170,26 @@ def yolo_text_batch(records: np.ndarray, n_out: np.ndarray, frames: Optional[int
                                    offsets.ctypes.data)
     _lib.check("cspe_format_yolo_host", rc)
     return buf[:rc], offsets
+
+
+def write_files(directory: str, prefix: str, suffix: str, first_id: int, data: np.ndarray, sizes: np.ndarray,
+                count: Optional[int] = None, digits: int = 6) -> int:
+    """Native batch file writer (libcspe ``cspe_write_files_host``, no GIL): file j =
+    ``<directory>/<prefix><first_id + j:0{digits}d><suffix>`` holds ``data[j, :sizes[j]]`` (data u8 [B, stride],
+    e.g. the D2H buffer of ``cspe_format_yolo``).  Returns the bytes written."""
+    from . import _lib
+
+    lib = _lib.load()
+    if data.ndim != 2 or data.dtype != np.uint8 or not data.flags.c_contiguous:
+        raise ValueError("data must be a C-contiguous uint8 [B, stride] array")
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    count = len(sizes) if count is None else int(count)
+    if count > data.shape[0] or count > len(sizes):
+        raise ValueError("count exceeds the rows of data / sizes")
+    rc = lib.cspe_write_files_host(os.fsencode(directory), prefix.encode(), int(digits), suffix.encode(), int(first_id),
+                                   count, data.ctypes.data, data.shape[1], sizes.ctypes.data)
+    _lib.check("cspe_write_files_host", rc)
+    return int(rc)
 
 
 def coco_categories() -> List[Dict[str, object]]:

@@ -242,6 +242,39 @@ def depth_to_pointcloud(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: t
     return out, n
 
 
+def depth_to_pointcloud_batch(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: torch.Tensor,
+                              capacity: Optional[int] = None):
+    """f1 for a batch: depth f32 [B,H,W], rgb u8 [B,H,W,C>=3] or None, cam f64 [B,24] -> (points f64 [cap,6],
+    offsets int64 [B+1]); frame f's cloud is ``points[offsets[f]:offsets[f+1]]`` (row-major pixel order), two
+    launches for the whole batch."""
+    lib = _lib.load()
+    _dev(depth, torch.float32, "depth")
+    _dev(cam, torch.float64, "cam")
+    if depth.dim() != 3:
+        raise ValueError(f"depth must be [B,H,W], got {tuple(depth.shape)}")
+    B, H, W = depth.shape
+    if tuple(cam.shape) != (B, CAM_STRIDE):
+        raise ValueError(f"cam must be [{B},{CAM_STRIDE}], got {tuple(cam.shape)}")
+    ch = 0
+    if rgb is not None:
+        _dev(rgb, torch.uint8, "rgb")
+        if rgb.dim() != 4 or tuple(rgb.shape[:3]) != (B, H, W):
+            raise ValueError(f"rgb must be [B,H,W,C], got {tuple(rgb.shape)}")
+        ch = rgb.shape[3]
+    if capacity is None:
+        capacity = B * H * W
+    dev = depth.device
+    out = torch.empty((capacity, 6), dtype=torch.float64, device=dev)
+    offsets = torch.empty((B + 1,), dtype=torch.int64, device=dev)
+    ws_bytes = lib.cspe_pointcloud_batch_workspace_bytes(B, H, W)
+    ws = torch.empty(((ws_bytes + 7) // 8,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.cspe_depth_to_pointcloud_batch(depth.data_ptr(), _ptr(rgb), ch, B, H, W, cam.data_ptr(), out.data_ptr(),
+                                                capacity, offsets.data_ptr(), ws.data_ptr(), _stream_ptr())
+    _lib.check("cspe_depth_to_pointcloud_batch", rc)
+    return out, offsets
+
+
 def format_fixed6(values: torch.Tensor, n_rows: Optional[torch.Tensor] = None, header: Optional[str] = None,
                   split_rows: int = 0, capacity: Optional[int] = None, out: Optional[torch.Tensor] = None):
     """f3: the bytes ``np.savetxt(f, values, fmt='%.6f', delimiter=' ', header=header, comments='')`` writes

@@ -131,7 +131,7 @@ class _GroupGraph:
         self.frame_base_h = torch.zeros((1,), dtype=torch.int32, pin_memory=True)
         self.frame_base_d = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.done = torch.cuda.Event()
-        self.busy = False
+        self.jobs: List = []     # worker jobs still reading this instance's pinned buffers
         side = torch.cuda.Stream(device=dev)
         p0 = pipe._parity
 
@@ -157,10 +157,12 @@ class _GroupGraph:
         self.edges = graph_edge_kinds(self.graph)
 
     def launch(self, first_frame: int) -> None:
+        for job in self.jobs:    # the replay overwrites the pinned buffers: their readers must be done
+            job.result()
+        self.jobs = []
         self.frame_base_h[0] = first_frame
         self.graph.replay()
         self.done.record()
-        self.busy = True
 
 
 def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[torch.device] = None,
@@ -214,45 +216,56 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 fh.write(data)
             return len(data)
 
-        def consume(slot: _BatchOut, s: int, e: int, j0: int) -> None:
-            """Host side of one batch: frames [s, e) = pool frames j0 .. (outputs are rows 0 .. e - s)."""
+        def consume(slot: _BatchOut, s: int, e: int, j0: int, jobs: Optional[List]) -> None:
+            """Host side of one batch: frames [s, e) = pool frames j0 .. (outputs are rows 0 .. e - s).  Worker jobs
+            read the slot's pinned buffers in place; ``jobs`` collects them for the owner of the buffers (None =
+            the caller reuses the slot right away, so the jobs work on copies)."""
             nonlocal emitted, text_bytes, coco_count
             nf = e - s
             n_all = slot.n_out_h.numpy()[:nf]
             count = int(n_all.sum())
             emitted += count
+            in_place = jobs is not None
+
+            def submit(fn):
+                fut = io_pool.submit(fn)
+                pending.append(fut)
+                if in_place:
+                    jobs.append(fut)
+
             if want_yolo:
                 nb = slot.n_bytes_h.numpy()[:nf]
                 if (nb < 0).any() or (nb > slot.stride).any():
                     raise RuntimeError(f"YOLO text of frames {s}..{e}: sizes {nb.min()}..{nb.max()} outside [0, {slot.stride}]")
                 text_bytes += int(nb.sum())
-                if label_dir is not None:
-                    # the pinned buffer is reused by the next replay: take the bytes now, write them on the workers
-                    rows = [bytes(memoryview(slot.text_h.numpy()[j, : nb[j]])) for j in range(nf)]
-                    pending.append(io_pool.submit(lambda rows=rows, s=s: sum(
-                        write_file(f"label_{s + j:06d}.txt", r) for j, r in enumerate(rows))))
+                if label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
+                    text = slot.text_h.numpy() if in_place else slot.text_h.numpy()[:nf].copy()
+                    sizes = nb if in_place else nb.copy()
+                    submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
             if not want_records:
                 return
-            recs = slot.records_h.numpy().view(_lib.RECORD_DTYPE).reshape(B, N)[:nf].copy()   # buffer is reused
-            n_copy = n_all.copy()
+            recs = slot.records_h.numpy().view(_lib.RECORD_DTYPE).reshape(B, N)[:nf]
+            n_use = n_all
+            if not in_place:
+                recs, n_use = recs.copy(), n_all.copy()
             if emit == "coco":   # native formatter, one call per batch, on a worker (ctypes releases the GIL)
-                ids = list(range(s, e))
+                ids = np.arange(s, e, dtype=np.int64)
                 first_id = coco_count + 1
                 coco_count += count
-                coco_imgs.append(formats.coco_images_text(ids, W, H))
-                pending.append(io_pool.submit(
-                    lambda: formats.coco_annotations_text(recs, n_copy, ids, first_id)[0]))
+                coco_imgs.append(formats.coco_images_text(range(s, e), W, H))
+                submit(lambda: formats.coco_annotations_text(recs, n_use, ids, first_id)[0])
             elif emit == "json":   # label_%06d.json, gcd.py:2071
                 def one(j: int) -> int:
                     pj = j0 + j
                     text = formats.label_json_bytes(s + j, pool[pj]["camera_pose"], pool[pj]["camera_params"], H, W,
-                                                    recs[j, : n_copy[j]], objects[pj], slot_strings[pj])
+                                                    recs[j, : n_use[j]], objects[pj], slot_strings[pj])
                     return write_file(f"label_{s + j:06d}.json", text) if label_dir is not None else len(text)
 
-                pending.extend(io_pool.submit(one, j) for j in range(nf))
+                for j in range(nf):
+                    submit(lambda j=j: one(j))
             elif emit == "records":   # raw records kept in memory (tests)
-                kept_records.extend(recs[j, : n_copy[j]] for j in range(nf))
+                kept_records.extend(recs[j, : n_use[j]].copy() for j in range(nf))
 
         def drain(limit: int) -> None:
             """Collect finished worker jobs (keeps at most `limit` in flight); COCO chunks stay in order."""
@@ -281,7 +294,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 eager_slot.enqueue_text(lib, e - s, st)
             eager_slot.enqueue_readback(lib, e - s, st)
             torch.cuda.current_stream(device).synchronize()
-            consume(eager_slot, s, e, j0)
+            consume(eager_slot, s, e, j0, None)
 
         for s, e in head:
             run_eager(s, e)
@@ -298,8 +311,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 prev.done.synchronize()
                 t2 = time.perf_counter()
                 for slot, (s, e) in zip(prev.slots, pgrp):
-                    consume(slot, s, e, 0)
-                drain(4 * workers)
+                    consume(slot, s, e, 0, prev.jobs)
+                drain(8 * group * (64 if emit == "json" else 1))
                 timers["wait_s"] += t2 - t1
                 timers["consume_s"] += time.perf_counter() - t2
         if groups:
@@ -308,7 +321,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             prev.done.synchronize()
             t2 = time.perf_counter()
             for slot, (s, e) in zip(prev.slots, pgrp):
-                consume(slot, s, e, 0)
+                consume(slot, s, e, 0, prev.jobs)
             timers["wait_s"] += t2 - t1
             timers["consume_s"] += time.perf_counter() - t2
 

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import json
 import os
+import warnings
+import weakref
 from dataclasses import dataclass, field
 from typing import Dict, List, Mapping, Optional, Sequence, Tuple, Union
 
@@ -25,7 +27,8 @@ import torch
 from . import _lib, formats, ops
 from .quality import FrameQualityLog, depth_quality_from_stats
 from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
-from .camera import DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, pack_camera
+from .camera import (DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, from_replicator_camera_params,
+                     is_replicator_camera_params, pack_camera)
 from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot, label_path,
                       record_index_for)
 
@@ -67,6 +70,17 @@ class BatchLabels:
     _synced: bool = False
     rgb_images: Optional[List[Optional[ArrayLike]]] = None   # per-frame RGB(A) for the point-cloud file
     _yolo: Optional[Tuple[np.ndarray, np.ndarray]] = None
+    # recorded on the writer's stream after the last kernel / copy that reads the caller's annotator buffers
+    inputs_consumed: Optional[torch.cuda.Event] = None
+    missing_masks: Optional[List[int]] = None   # batch indices whose instance_segmentation annotator was absent
+
+    def wait_inputs_consumed(self) -> "BatchLabels":
+        """Block the host until the GPU no longer reads the annotator buffers this batch was built from (pinned
+        host arrays being copied, device tensors used in place).  Producers that run on the CUDA stream that was
+        current when the batch was submitted need not call this: that stream already waits for the event."""
+        if self.inputs_consumed is not None:
+            self.inputs_consumed.synchronize()
+        return self
 
     def synchronize(self) -> "BatchLabels":
         if not self._synced:
@@ -233,6 +247,114 @@ def _payload(annot):
     return annot
 
 
+_ANNOTATOR_KEYS = ("instance_segmentation", "distance_to_image_plane", "bounding_box_3d", "camera_params",
+                   "skeleton_data", "rgb", "camera_pose", "pointcloud")
+
+
+def _annotator_name(key: str) -> Tuple[Optional[str], Optional[str]]:
+    """(canonical annotator name, render-product suffix) of a Replicator payload key: writers attached to a
+    render product receive ``"<annotator>-<render product>"`` keys, and the ``*_fast`` variants deliver the same
+    payload as their plain annotator.  (None, None) for keys that are not annotators of this path."""
+    base, _, suffix = key.partition("-")
+    if base.endswith("_fast"):
+        base = base[:-5]
+    if base == "LdrColor":
+        base = "rgb"
+    return (base, suffix or None) if base in _ANNOTATOR_KEYS else (None, None)
+
+
+def split_render_products(data: Mapping) -> List[Dict[str, object]]:
+    """One frame dict per render product of a Replicator ``write(data)`` payload, annotator keys canonicalised.
+    A multi-camera rig (BASELINE config 4) arrives as ONE payload with suffixed keys; its cameras are returned in
+    sorted render-product order (the order ``sharding.rig_frame_range`` flattens (rig frame, camera) pairs in)."""
+    shared: Dict[str, object] = {}
+    per: Dict[str, Dict[str, object]] = {}
+    for key, value in data.items():
+        name, suffix = _annotator_name(key) if isinstance(key, str) else (None, None)
+        if name is None:
+            shared[key] = value
+        elif suffix is None:
+            shared[name] = value
+        else:
+            per.setdefault(suffix, {})[name] = value
+    if not per:
+        return [shared]
+    frames = []
+    for suffix in sorted(per):
+        fr = dict(shared)
+        fr.update(per[suffix])
+        fr["render_product"] = suffix
+        frames.append(fr)
+    return frames
+
+
+def skeleton_joints(sk) -> Optional[np.ndarray]:
+    """World joint positions float32 [P,J,3] from a ``skeleton_data`` payload, or None.  Accepted shapes: an array
+    [P,J,3] (or [J,3] for one skeleton); ``{"globalTranslations": array}`` (also under ``"data"``); a list of
+    per-skeleton dicts each holding ``globalTranslations`` [J,3]; a dict of parallel per-skeleton lists
+    (``{"skeletonData" | "skeletons": [...]}``); or any of these as a JSON string.  (Replicator's exact payload
+    cannot be checked offline — see INTEGRATION.md; whatever does not parse is treated as "no skeletons".)"""
+    if sk is None:
+        return None
+    if isinstance(sk, (str, bytes)):
+        try:
+            sk = json.loads(sk)
+        except (ValueError, TypeError):
+            return None
+    if isinstance(sk, Mapping):
+        for key in ("globalTranslations", "global_translations"):
+            if sk.get(key) is not None:
+                return skeleton_joints(sk[key])
+        for key in ("data", "skeletonData", "skeletons", "skeleton_data"):
+            if sk.get(key) is not None:
+                return skeleton_joints(sk[key])
+        return None
+    if isinstance(sk, (list, tuple)) and sk and isinstance(sk[0], (Mapping, str, bytes)):
+        per = [skeleton_joints(item) for item in sk]
+        per = [p[0] if p is not None and p.ndim == 3 and p.shape[0] == 1 else p for p in per]
+        if any(p is None or p.ndim != 2 for p in per) or len({p.shape for p in per}) != 1:
+            return None
+        return np.stack(per).astype(np.float32, copy=False)
+    try:
+        j = np.asarray(sk, dtype=np.float32)
+    except (ValueError, TypeError):
+        return None
+    if j.ndim == 2 and j.shape[-1] == 3:
+        j = j[None]
+    return j if j.ndim == 3 and j.shape[-1] == 3 else None
+
+
+class _TableBlock:
+    """The small per-batch host tables laid out in ONE pinned block — [lut | obj_record | slot_class | cam | records]
+    — so that they reach the device in a single H2D copy into a matching device block."""
+
+    def __init__(self, writer: "ConstructionLabelWriter", lut_rows: int, L: int, B: int, N: int, R: int):
+        sizes = [lut_rows * L * 4, B * N * 4, B * N * 4, B * CAM_STRIDE * 8, B * R * BBOX3D_DTYPE.itemsize]
+        offs = [0]
+        for sz in sizes:
+            offs.append((offs[-1] + sz + 15) & ~15)
+        self.buffers: List[Tuple[Tuple, torch.Tensor]] = []
+        self.host = writer._take_pinned("tables", (offs[-1],), torch.uint8, self.buffers)
+        self.device = writer.device
+        h = self.host.numpy()
+        self.lut = h[offs[0]: offs[0] + sizes[0]].view(np.int32).reshape(lut_rows, L)
+        self.obj_record = h[offs[1]: offs[1] + sizes[1]].view(np.int32).reshape(B, N)
+        self.slot_class = h[offs[2]: offs[2] + sizes[2]].view(np.int32).reshape(B, N)
+        self.cam = h[offs[3]: offs[3] + sizes[3]].view(np.float64).reshape(B, CAM_STRIDE)
+        self.records = h[offs[4]: offs[4] + sizes[4]].reshape(B, R, BBOX3D_DTYPE.itemsize)
+        self._offs, self._sizes, self._shapes = offs, sizes, (lut_rows, L, B, N, R)
+
+    def upload(self):
+        lut_rows, L, B, N, R = self._shapes
+        d = self.host.to(self.device, non_blocking=True)
+        o, z = self._offs, self._sizes
+        return (d[o[0]: o[0] + z[0]].view(torch.int32).view(lut_rows, L),
+                d[o[1]: o[1] + z[1]].view(torch.int32).view(B, N),
+                d[o[2]: o[2] + z[2]].view(torch.int32).view(B, N),
+                d[o[4]: o[4] + z[4]].view(B, R, BBOX3D_DTYPE.itemsize),
+                d[o[3]: o[3] + z[3]].view(torch.float64).view(B, CAM_STRIDE))
+
+
 class ConstructionLabelWriter:
     """Drop-in writer for the reference's per-frame label path.
 
@@ -277,7 +399,10 @@ class ConstructionLabelWriter:
         self.io_threads = min(16, os.cpu_count() or 1) if io_threads is None else max(1, int(io_threads))
         self._io_pool = None
         self._tables_cache: Dict[Tuple, FrameTables] = {}
+        self._free_pinned: Dict[Tuple, List[torch.Tensor]] = {}
+        self._warned_empty_lut = False
         self._next_frame_id = 0
+        self._next_rig_frame = 0
         self._pending: List[Tuple[BatchLabels, Optional[List[np.ndarray]]]] = []
         self._coco_images: List[Dict] = []
         self._coco_annotation_text: List[bytes] = []   # natively formatted, one chunk per batch
@@ -317,8 +442,17 @@ class ConstructionLabelWriter:
 
     # ------------------------------------------------------------------ public surface
     def write(self, data: Mapping) -> None:
-        """One frame (Replicator ``Writer.write`` signature)."""
-        self.write_batch([data])
+        """One Replicator payload (``Writer.write`` signature): one frame, or — when the payload carries several
+        render products (``"<annotator>-<render product>"`` keys) — one frame per camera of the rig, numbered
+        ``frame_id * cameras + camera`` in sorted render-product order."""
+        frames = split_render_products(data)
+        if len(frames) > 1:
+            fid = data.get("frame_id")
+            base = (int(fid) if fid is not None else self._next_rig_frame) * len(frames)
+            self._next_rig_frame = (int(fid) if fid is not None else self._next_rig_frame) + 1
+            for c, fr in enumerate(frames):
+                fr["frame_id"] = base + c
+        self.write_batch(frames)
 
     def write_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
         """Annotate B frames in one set of launches and queue them for serialisation.  ``frames`` is a list of
@@ -327,15 +461,39 @@ class ConstructionLabelWriter:
         if isinstance(frames, Mapping):
             frames = _unstack(frames)
         labels = self.annotate_batch(frames)
-        masks = None
-        if "mask" in self.formats and self.output_dir is not None:
-            masks = [_payload(fr.get("instance_segmentation")) for fr in frames]
+        # Serialisation is deferred by up to max_pending batches, so whatever it needs besides the records is
+        # snapshotted NOW into the writer's own device memory (the mask batch inside annotate_batch, RGB here):
+        # the caller may reuse its annotator buffers as soon as inputs_consumed has fired.
         if {"pointcloud", "rgb_png"} & set(self.formats) and self.output_dir is not None:
-            labels.rgb_images = [_payload(fr.get("rgb")) for fr in frames]
-        self._pending.append((labels, masks))
+            labels.rgb_images = self._snapshot_rgb(frames, labels)
+        self._pending.append((labels, None))
         while len(self._pending) > self.max_pending:
             self._serialise(*self._pending.pop(0))
         return labels
+
+    def _snapshot_rgb(self, frames, labels: BatchLabels) -> List[Optional[torch.Tensor]]:
+        dev = self.device
+        caller_stream = torch.cuda.current_stream(dev)
+        out: List[Optional[torch.Tensor]] = []
+        with torch.cuda.device(dev), torch.cuda.stream(self.stream):
+            for fr in frames:
+                rgb = None
+                for key, value in fr.items():   # keys may still carry a render-product suffix here
+                    if isinstance(key, str) and _annotator_name(key)[0] == "rgb":
+                        rgb = _payload(value)
+                if rgb is None:
+                    out.append(None)
+                elif isinstance(rgb, torch.Tensor) and rgb.is_cuda:
+                    rgb.record_stream(self.stream)
+                    out.append(rgb.to(dev).clone())
+                else:
+                    src = rgb if isinstance(rgb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rgb))
+                    out.append(src.to(dev, non_blocking=True))
+            consumed = torch.cuda.Event()
+            consumed.record(self.stream)
+        caller_stream.wait_event(consumed)
+        labels.inputs_consumed = consumed
+        return out
 
     def flush(self) -> None:
         while self._pending:
@@ -389,32 +547,48 @@ class ConstructionLabelWriter:
     # ------------------------------------------------------------------ the hot path
     def annotate_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
         """Enqueue the whole path for B frames (list of frame dicts or one stacked dict, like ``write_batch``)
-        and return at once; the result is fenced by ``BatchLabels.synchronize()``."""
+        and return at once; the result is fenced by ``BatchLabels.synchronize()``.
+
+        Buffer contract (INTEGRATION.md "Input lifetime"): the annotator arrays are read by the GPU after this
+        call returns — pinned host arrays by asynchronous H2D copies, CUDA tensors in place.  The CUDA stream that
+        is current on entry is made to wait for ``BatchLabels.inputs_consumed``, so producers that write those
+        buffers from that stream are ordered automatically; anything else (a host thread refilling a pinned staging
+        buffer, another stream) must call ``BatchLabels.wait_inputs_consumed()`` first."""
+        stacked: Dict[str, ArrayLike] = {}
         if isinstance(frames, Mapping):
             frames = _unstack(frames)
+            stacked = frames.stacked
         if len(frames) == 0:
             raise ValueError("annotate_batch needs at least one frame")
+        frames = [self._normalise(fr) for fr in frames]
         B = len(frames)
         dev = self.device
 
         # ---- the big copy first: enqueue the H2D of the masks (PCIe-bound, ~10 ms for 64 x 1080p)
         # before building the host tables, so the table work hides under it -----------------
-        masks: List[ArrayLike] = []
-        for i, fr in enumerate(frames):
-            mask = _payload(fr.get("instance_segmentation"))
-            if mask is None:
-                raise ValueError(f"frame {i}: instance_segmentation annotator is missing")
-            masks.append(mask)
-        H, W = int(masks[0].shape[-2]), int(masks[0].shape[-1])
+        masks: List[Optional[ArrayLike]] = [_payload(fr.get("instance_segmentation")) for fr in frames]
+        missing = [i for i, m in enumerate(masks) if m is None or getattr(m, "ndim", 0) != 2]
+        shape = next(((int(m.shape[0]), int(m.shape[1])) for i, m in enumerate(masks) if i not in missing), None)
+        if shape is None:   # no mask at all: take the image size from depth, the camera, or the script default
+            shape = self._fallback_shape(frames[0])
+        H, W = shape
         for i, m in enumerate(masks):
-            if m.ndim != 2 or tuple(m.shape) != (H, W):
+            if i not in missing and tuple(m.shape) != (H, W):
                 raise ValueError(f"frame {i}: mask shape {tuple(m.shape)} differs from {(H, W)} (one [H,W] resolution per batch)")
+        caller_stream = torch.cuda.current_stream(dev)
         with torch.cuda.device(dev):
             # device-resident annotators (device="cuda" in Replicator) were produced on the caller's stream
-            self.stream.wait_stream(torch.cuda.current_stream(dev))
+            self.stream.wait_stream(caller_stream)
             with torch.cuda.stream(self.stream):
-                stacked = getattr(frames, "stacked", {})
-                d_mask = self._stack_to_device(masks, torch.int32, stacked.get("instance_segmentation"))
+                if missing:   # an absent annotator gives an empty-label frame, never an error (gcd.py:1682,1788,1919)
+                    d_mask = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
+                    present = [i for i in range(B) if i not in missing]
+                    if present:
+                        d_mask[present] = self._stack_to_device([masks[i] for i in present], torch.int32)
+                    mask_owned = True
+                else:
+                    d_mask, mask_owned = self._stack_to_device(masks, torch.int32, stacked.get("instance_segmentation"),
+                                                               return_owned=True)
 
         # ---- host: per-frame tables ----------------------------------------------------
         tables: List[FrameTables] = []
@@ -430,13 +604,21 @@ class ConstructionLabelWriter:
             if recs is not None and len(recs) != len(prim_paths):
                 n = min(len(recs), len(prim_paths))
                 recs, prim_paths = recs[:n], prim_paths[:n]
-            tables.append(self.frame_tables(prim_paths, _info(seg).get("idToLabels", {}) or {}))
+            id_to_labels = _info(seg).get("idToLabels", {}) or {}
+            tables.append(self.frame_tables(prim_paths, id_to_labels))
+            if prim_paths and not tables[-1].lut_ids.size and i not in missing and not self._warned_empty_lut:
+                self._warned_empty_lut = True
+                warnings.warn("bounding_box_3d lists prims but no idToLabels entry of instance_segmentation resolves to "
+                              "one of them: every object of such frames has 0 pixels and is dropped (min_pixels >= 1)")
             rec_arrays.append(recs if recs is not None and len(recs) else None)
             params = fr.get("camera_params") or default_camera_params(W, H)
+            if "width" not in params or "height" not in params:
+                params = {**params, "width": params.get("width", W), "height": params.get("height", H)}
             pose = fr.get("camera_pose")
             if pose is None:
                 pose = _IDENTITY_POSE
-            pack_camera(pose, params, self.near, self.far, out=cams[i])
+            near, far = fr.get("_clip") or (self.near, self.far)
+            pack_camera(pose, params, near, far, out=cams[i])
             poses.append(pose)
             params_list.append(params)
             fid = fr.get("frame_id")
@@ -456,10 +638,14 @@ class ConstructionLabelWriter:
             # are prim indices in Replicator, so this only trips on ids that are not instance ids
             raise ValueError(f"instance ids up to {L - 1} need a {L * lut_rows * 4 / 2**20:.0f} MiB id->slot table "
                              f"(limit {self.max_lut_entries * 4 / 2**20:.0f} MiB, max_lut_entries)")
-        lut = np.full((lut_rows, L), -1, dtype=np.int32)
-        obj_record = np.full((B, N), -1, dtype=np.int32)
-        slot_class = np.full((B, N), -1, dtype=np.int32)
-        rec_bytes = np.zeros((B, R, BBOX3D_DTYPE.itemsize), dtype=np.uint8)
+        # small tables go up as ONE pinned block: [lut | obj_record | slot_class | records | cam]
+        blk = _TableBlock(self, lut_rows, L, B, N, R)
+        lut, obj_record, slot_class, rec_bytes = blk.lut, blk.obj_record, blk.slot_class, blk.records
+        lut.fill(-1)
+        obj_record.fill(-1)
+        slot_class.fill(-1)
+        rec_bytes.fill(0)
+        blk.cam[:] = cams
         for i, t in enumerate(tables):
             n = len(t.objects)
             obj_record[i, :n] = t.obj_record
@@ -476,19 +662,18 @@ class ConstructionLabelWriter:
                 obj_record[i, :] = -1
 
         # ---- device: uploads + kernels on the writer's stream ----------------------------
+        owned: List[Tuple[Tuple, torch.Tensor]] = list(blk.buffers)
         with torch.cuda.device(dev), torch.cuda.stream(self.stream):
-            d_lut = torch.from_numpy(lut if not same_tables else lut[0]).to(dev, non_blocking=True)
-            d_obj_record = torch.from_numpy(obj_record).to(dev, non_blocking=True)
-            d_slot_class = torch.from_numpy(slot_class).to(dev, non_blocking=True)
-            d_rec = torch.from_numpy(rec_bytes).to(dev, non_blocking=True)
-            d_cam = torch.from_numpy(cams).to(dev, non_blocking=True)
+            d_lut, d_obj_record, d_slot_class, d_rec, d_cam = blk.upload()
+            if same_tables:
+                d_lut = d_lut[0]
 
             scan = ops.mask_scan(d_mask, d_lut, N)
             uv, z, pose, loose, flags = ops.project_objects(d_rec, d_obj_record, d_cam)
             kp_host = vis_host = None
             person_slots = None
             d_kp = d_vis = d_depth = None
-            joints_list = [self._joints_of(fr) for fr in frames]
+            joints_list = [skeleton_joints(fr.get("skeleton_data")) for fr in frames]
             depth_list = [_payload(fr.get("distance_to_image_plane")) for fr in frames]
             if all(j is not None and j.shape[0] > 0 for j in joints_list) and all(d is not None for d in depth_list) \
                     and len({tuple(j.shape) for j in joints_list}) == 1:
@@ -501,47 +686,135 @@ class ConstructionLabelWriter:
                 if d_depth is None:
                     d_depth = self._stack_to_device(depth_list, torch.float32, stacked.get("distance_to_image_plane"))
                 d_stats = ops.depth_stats(d_depth)                                  # f2, gcd.py:314-359
-                stats_host = torch.empty(d_stats.shape, dtype=torch.uint8, pin_memory=True)
+                stats_host = self._take_pinned("stats", tuple(d_stats.shape), torch.uint8, owned)
                 stats_host.copy_(d_stats, non_blocking=True)
                 if "depth_png" in self.formats:
                     d_viz = ops.depth_colormap(d_depth, self._jet_lut(), d_stats)   # f4, gcd.py:1691-1709
-                    viz_host = torch.empty(d_viz.shape, dtype=torch.uint8, pin_memory=True)
+                    viz_host = self._take_pinned("viz", tuple(d_viz.shape), torch.uint8, owned)
                     viz_host.copy_(d_viz, non_blocking=True)
-            if contiguous_ids:
-                rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels,
-                                             frame_base, class_hist=self.class_hist)
-            else:
-                rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels, 0,
-                                             class_hist=self.class_hist)
-            rec_host = torch.empty(rec_dev.shape, dtype=torch.uint8, pin_memory=True)
-            nout_host = torch.empty(n_out.shape, dtype=torch.int32, pin_memory=True)
+            rec_dev, n_out, _ = ops.emit(scan, uv, z, pose, loose, flags, d_slot_class, H, W, self.min_pixels,
+                                         frame_base if contiguous_ids else 0, class_hist=self.class_hist)
+            # everything that reads the caller's buffers has been enqueued: mark it, make the caller's stream wait
+            # for it, and keep the allocator from recycling caller tensors we read in place
+            keep_depth = d_depth is not None and bool({"depth_csv", "pointcloud"} & set(self.formats))
+            keep_mask = "mask" in self.formats and self.output_dir is not None
+            if keep_mask and not mask_owned:
+                d_mask = d_mask.clone()      # deferred serialisation must not depend on the caller's buffer
+            if keep_depth and self._is_caller_tensor(d_depth, depth_list, stacked.get("distance_to_image_plane")):
+                d_depth = d_depth.clone()
+            consumed = torch.cuda.Event()
+            consumed.record(self.stream)
+            for t in [stacked.get("instance_segmentation"), stacked.get("distance_to_image_plane"), *masks, *depth_list]:
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(self.stream)
+            rec_host = self._take_pinned("rec", tuple(rec_dev.shape), torch.uint8, owned)
+            nout_host = self._take_pinned("nout", tuple(n_out.shape), torch.int32, owned)
             rec_host.copy_(rec_dev, non_blocking=True)
             nout_host.copy_(n_out, non_blocking=True)
             if d_kp is not None:
-                kp_host = torch.empty(d_kp.shape, dtype=torch.float64, pin_memory=True)
-                vis_host = torch.empty(d_vis.shape, dtype=torch.uint8, pin_memory=True)
+                kp_host = self._take_pinned("kp", tuple(d_kp.shape), torch.float64, owned)
+                vis_host = self._take_pinned("vis", tuple(d_vis.shape), torch.uint8, owned)
                 kp_host.copy_(d_kp, non_blocking=True)
                 vis_host.copy_(d_vis, non_blocking=True)
             event = torch.cuda.Event()
             event.record(self.stream)
+        caller_stream.wait_event(consumed)
 
         labels = BatchLabels(frame_ids, tables, H, W, poses, params_list, rec_host, nout_host, event, kp_host,
                              vis_host, person_slots,
                              {"scan": scan, "uv": uv, "z": z, "pose": pose, "loose": loose, "flags": flags,
                               "records": rec_dev, "n_out": n_out, "cam": d_cam,
-                              **({"depth": d_depth} if d_depth is not None and
-                                 {"depth_csv", "pointcloud"} & set(self.formats) else {})}, stats_host, viz_host)
+                              **({"depth": d_depth} if keep_depth else {}),
+                              **({"mask": d_mask} if keep_mask else {})}, stats_host, viz_host)
+        labels.inputs_consumed = consumed
+        labels.missing_masks = missing
+        # pinned blocks go back to the writer's free lists when the result object dies
+        weakref.finalize(labels, self._give_back, owned, event)
         if not contiguous_ids:
             labels.synchronize()
             for f in range(B):  # frame field was written relative to 0
                 labels._rec_host[f].numpy().view(RECORD_DTYPE).reshape(-1)["frame"][: int(nout_host[f])] = frame_ids[f]
         return labels
 
+    # ------------------------------------------------------------------ input normalisation
+    def _normalise(self, fr: Mapping) -> Dict[str, object]:
+        """Canonical frame dict: annotator keys without render-product / ``_fast`` suffixes; Replicator's native
+        ``camera_params`` payload turned into the reference's five-field dict plus the pose it implies (a separate
+        ``camera_pose`` entry, as the reference passes it at gcd.py:1599, wins)."""
+        out: Dict[str, object] = {}
+        for key, value in fr.items():
+            name, _ = _annotator_name(key) if isinstance(key, str) else (None, None)
+            if name is None:
+                out[key] = value
+            elif name not in out or out[name] is None:
+                out[name] = value
+        cp = out.get("camera_params")
+        if isinstance(cp, Mapping) and "data" in cp and isinstance(cp["data"], Mapping):
+            cp = cp["data"]
+        if is_replicator_camera_params(cp):
+            seg = _payload(out.get("instance_segmentation"))
+            hw = (int(seg.shape[-1]), int(seg.shape[-2])) if seg is not None and getattr(seg, "ndim", 0) >= 2 else (None, None)
+            pose7, params, clip = from_replicator_camera_params(cp, *hw)
+            out["camera_params"] = params
+            if out.get("camera_pose") is None:
+                out["camera_pose"] = pose7
+            if clip is not None:
+                out["_clip"] = clip
+        elif cp is not None:
+            out["camera_params"] = cp
+        return out
+
+    @staticmethod
+    def _fallback_shape(fr: Mapping) -> Tuple[int, int]:
+        depth = _payload(fr.get("distance_to_image_plane"))
+        if depth is not None and getattr(depth, "ndim", 0) == 2:
+            return int(depth.shape[0]), int(depth.shape[1])
+        params = fr.get("camera_params") or {}
+        if params.get("width") and params.get("height"):
+            return int(params["height"]), int(params["width"])
+        return 720, 1280   # the script's capture resolution, gcd.py:46-47
+
+    @staticmethod
+    def _is_caller_tensor(t: torch.Tensor, parts: Sequence, stacked) -> bool:
+        """True when ``t`` aliases a CUDA tensor the caller handed in (used in place, not copied)."""
+        cands = [stacked] + list(parts)
+        return any(isinstance(c, torch.Tensor) and c.is_cuda and c.untyped_storage().data_ptr() == t.untyped_storage().data_ptr()
+                   for c in cands)
+
+    # ------------------------------------------------------------------ buffer reuse
+    def _take_pinned(self, kind: str, shape: Tuple[int, ...], dtype: torch.dtype, owned: List) -> torch.Tensor:
+        """A pinned host tensor from the writer's free lists (allocated on first use); registered in ``owned`` so it
+        returns to the list when the batch's result object is garbage collected."""
+        key = (kind, shape, dtype)
+        free = self._free_pinned.get(key) or []
+        t = None
+        for i, (cand, ev) in enumerate(free):
+            if ev is None or ev.query():   # the batch that used it last has run to its end on the GPU
+                t = cand
+                del free[i]
+                break
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+        owned.append((key, t))
+        return t
+
+    def _give_back(self, owned: List, event: Optional[torch.cuda.Event] = None) -> None:
+        for key, t in owned:
+            free = self._free_pinned.setdefault(key, [])
+            if len(free) < 4:
+                free.append((t, event))
+
     # ------------------------------------------------------------------ helpers
     def _stack_to_device(self, arrays: Sequence[ArrayLike], dtype: torch.dtype,
-                         stacked: Optional[ArrayLike] = None) -> torch.Tensor:
+                         stacked: Optional[ArrayLike] = None, return_owned: bool = False):
         """[B, ...] device tensor from per-frame host arrays / device tensors (async copies); ``stacked`` is the
-        same data as one [B, ...] array when the caller has it (one copy, or none if it is on the device)."""
+        same data as one [B, ...] array when the caller has it (one copy, or none if it is on the device).
+        ``return_owned=True`` also tells whether the result is the writer's own memory (False = the caller's CUDA
+        tensor used in place)."""
+        out, owned = self._stack_impl(arrays, dtype, stacked)
+        return (out, owned) if return_owned else out
+
+    def _stack_impl(self, arrays, dtype, stacked):
         if stacked is not None:
             if isinstance(stacked, torch.Tensor):
                 t = stacked.view(torch.int32) if dtype == torch.int32 and stacked.dtype == torch.uint32 else stacked
@@ -549,11 +822,15 @@ class ConstructionLabelWriter:
                 a = np.ascontiguousarray(stacked)
                 t = torch.from_numpy(a.view(np.int32) if dtype == torch.int32 and a.dtype == np.uint32 else a)
             if t.dtype == dtype:
-                return t.to(self.device, non_blocking=True).contiguous()
+                in_place = t.is_cuda and t.device == self.device and t.is_contiguous()
+                return t.to(self.device, non_blocking=True).contiguous(), not in_place
         first = arrays[0]
         if len(arrays) == 1 and isinstance(first, torch.Tensor) and first.is_cuda:
             t = first if first.dtype == dtype or (dtype == torch.int32 and first.dtype == torch.uint32) else first.to(dtype)
-            return t.contiguous().unsqueeze(0)
+            if t.dtype == torch.uint32:
+                t = t.view(torch.int32)
+            in_place = t.data_ptr() == first.data_ptr() and t.is_contiguous()
+            return t.contiguous().unsqueeze(0), not in_place
         shape = tuple(first.shape)
         out = torch.empty((len(arrays),) + shape, dtype=dtype, device=self.device)
         for i, a in enumerate(arrays):
@@ -571,7 +848,7 @@ class ConstructionLabelWriter:
                     a = a.astype(np.float32)
                 src = torch.from_numpy(np.ascontiguousarray(a))
             out[i].copy_(src, non_blocking=True)
-        return out
+        return out, True
 
     def _jet_lut(self) -> torch.Tensor:
         """cv2.COLORMAP_JET as a [256,3] BGR table on the device (the table the reference applies, gcd.py:1702)."""
@@ -583,17 +860,6 @@ class ConstructionLabelWriter:
             lut = torch.from_numpy(np.ascontiguousarray(table)).to(self.device)
             self._jet_lut_dev = lut
         return lut
-
-    @staticmethod
-    def _joints_of(fr: Mapping) -> Optional[np.ndarray]:
-        sk = fr.get("skeleton_data")
-        if sk is None:
-            return None
-        j = sk.get("globalTranslations") if isinstance(sk, Mapping) else sk
-        if j is None:
-            return None
-        j = np.asarray(j, dtype=np.float32)
-        return j if j.ndim == 3 and j.shape[-1] == 3 else None
 
     @staticmethod
     def _person_slots(t: FrameTables, num_people: int) -> List[int]:
@@ -647,30 +913,48 @@ class ConstructionLabelWriter:
                 with open(os.path.join(ddir, f"depth_{labels.frame_ids[f0 + k]:06d}.csv"), "wb") as fh:
                     fh.write(self._host_bytes(text, offs[k], offs[k + 1]))
 
-    def _write_pointcloud(self, labels: BatchLabels, f: int) -> Optional[int]:
-        """gcd.py:1729-1759: pointcloud/pointcloud_%06d.txt from the depth map and the RGB image; returns the
-        number of points (None when the frame has no depth)."""
+    def _write_pointclouds(self, labels: BatchLabels, chunk: int = 8) -> Optional[List[int]]:
+        """gcd.py:1729-1759: pointcloud/pointcloud_%06d.txt from the depth maps and the RGB images of the batch;
+        returns the number of points per frame (None when the batch has no depth).  The clouds of ``chunk`` frames
+        come out of one pair of launches (``cspe_depth_to_pointcloud_batch``), the text of each is formatted on the
+        device and only its bytes cross PCIe."""
         depth = labels.device_outputs.get("depth")
         if depth is None:
             return None
-        rgb = labels.rgb_images[f] if labels.rgb_images is not None else None
         pdir = os.path.join(self.output_dir, "pointcloud")
         os.makedirs(pdir, exist_ok=True)
-        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            d_rgb = None
-            if rgb is not None:
-                d_rgb = rgb if isinstance(rgb, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rgb))
-                d_rgb = d_rgb.to(self.device, non_blocking=True).contiguous()
-            pts, n = ops.depth_to_pointcloud(depth[f], d_rgb, labels.device_outputs["cam"][f])
-            text, n_bytes, _ = ops.format_fixed6(pts, n_rows=n, header="x y z r g b")
-            total, points = int(n_bytes.item()), int(n.item())
-            if total > text.numel():
-                text, n_bytes, _ = ops.format_fixed6(pts, n_rows=n, header="x y z r g b", capacity=total)
-        if points == 0:   # the reference saves nothing for an empty cloud (gcd.py:1749)
-            return 0
-        with open(os.path.join(pdir, f"pointcloud_{labels.frame_ids[f]:06d}.txt"), "wb") as fh:
-            fh.write(self._host_bytes(text, 0, total))
-        return points
+        B = depth.shape[0]
+        rgbs = labels.rgb_images if labels.rgb_images is not None else [None] * B
+        counts: List[int] = []
+        for f0 in range(0, B, chunk):
+            nb = min(chunk, B - f0)
+            part = rgbs[f0:f0 + nb]
+            with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                d_rgb = None
+                if all(r is not None for r in part) and len({tuple(r.shape) for r in part}) == 1:
+                    d_rgb = torch.stack([r.to(self.device) for r in part]).contiguous()
+                if d_rgb is not None or all(r is None for r in part):
+                    pts, offsets = ops.depth_to_pointcloud_batch(depth[f0:f0 + nb], d_rgb, labels.device_outputs["cam"][f0:f0 + nb])
+                    offs = offsets.cpu().tolist()
+                    clouds = [pts[offs[k]:offs[k + 1]] for k in range(nb)]
+                else:   # frames with and without colour in one chunk: one frame at a time
+                    clouds = []
+                    for k in range(nb):
+                        r = part[k].to(self.device).contiguous() if part[k] is not None else None
+                        p1, n1 = ops.depth_to_pointcloud(depth[f0 + k], r, labels.device_outputs["cam"][f0 + k])
+                        clouds.append(p1[: int(n1.item())])
+                for k, cloud in enumerate(clouds):
+                    points = int(cloud.shape[0])
+                    counts.append(points)
+                    if points == 0:   # the reference saves nothing for an empty cloud (gcd.py:1749)
+                        continue
+                    text, n_bytes, _ = ops.format_fixed6(cloud, header="x y z r g b")
+                    total = int(n_bytes.item())
+                    if total > text.numel():
+                        text, n_bytes, _ = ops.format_fixed6(cloud, header="x y z r g b", capacity=total)
+                    with open(os.path.join(pdir, f"pointcloud_{labels.frame_ids[f0 + k]:06d}.txt"), "wb") as fh:
+                        fh.write(self._host_bytes(text, 0, total))
+        return counts
 
     def _write_frame_files(self, labels: BatchLabels, f: int, masks: Optional[List[ArrayLike]]) -> None:
         """The per-frame label files; runs on a worker thread (the native formatters, cv2.imwrite, np.save and
@@ -695,9 +979,10 @@ class ConstructionLabelWriter:
             with torch.cuda.device(self.device), torch.cuda.stream(self._io_stream()):   # f4 kernel, gcd.py:1671
                 bgr = ops.rgb_to_bgr(src.to(self.device, non_blocking=True).contiguous()).cpu().numpy()
             cv2.imwrite(os.path.join(self.output_dir, "rgb", f"rgb_{fid:06d}.png"), bgr)   # gcd.py:1672-1673
-        if "mask" in self.formats and masks is not None:
-            m = masks[f]
-            m = m.detach().cpu().numpy() if isinstance(m, torch.Tensor) else np.asarray(m)
+        if "mask" in self.formats and labels.device_outputs.get("mask") is not None:
+            # the real mask where the reference saves a -1 placeholder (gcd.py:2066-2069), from the writer's own
+            # device copy of the batch
+            m = labels.device_outputs["mask"][f].cpu().numpy()
             np.save(os.path.join(ldir, f"instance_mask_{fid:06d}.npy"), m.astype(np.int32, copy=False))
 
     def _serialise(self, labels: BatchLabels, masks: Optional[List[ArrayLike]]) -> None:
@@ -728,12 +1013,13 @@ class ConstructionLabelWriter:
                 self._coco_annotation_text.append(text)
                 self._coco_annotation_count += count
         # bookkeeping stays on the caller's thread, in frame order
+        cloud_points = None
+        if "pointcloud" in self.formats and self.output_dir is not None:
+            cloud_points = self._write_pointclouds(labels)
         for f in range(B):
             fid = labels.frame_ids[f]
             recs = labels.records(f)
-            points = None
-            if "pointcloud" in self.formats and self.output_dir is not None:
-                points = self._write_pointcloud(labels, f)
+            points = cloud_points[f] if cloud_points is not None else None
             if "coco" in self.formats:
                 self._coco_images.append(formats.coco_image(fid, labels.width, labels.height, f"rgb_{fid:06d}.png"))
             dq = labels.depth_quality(f)

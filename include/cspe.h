@@ -78,8 +78,13 @@ enum {
   CSPE_OBJ_HAS_RECORD = 1,  /* a bbox3d record was resolved for the slot */
   CSPE_OBJ_ANY_FRONT = 2,   /* at least one 3D-box corner has z > near */
   CSPE_OBJ_ALL_FRONT = 4,   /* all eight corners have z > near */
-  CSPE_OBJ_POSE_VALID = 8   /* rotation part is finite with det > 0 (scipy would not raise) */
+  CSPE_OBJ_POSE_VALID = 8,  /* rotation part is finite with det > 0 (scipy would not raise) */
+  CSPE_OBJ_APPROX_RECORD = 16 /* the 3D box / pose come from a record that only approximates the object: a mesh
+                               * record standing in for an object whose root prim has none (the reference reads
+                               * the whole object's bound from the live USD stage there, gcd.py:1977-2023) */
 };
+/* obj_record entries (K2 input): OR this bit into a record index to mark it as such a stand-in */
+#define CSPE_OBJ_RECORD_APPROX_BIT (1 << 30)
 
 /* keypoint visibility, COCO convention */
 enum { CSPE_KP_OUT = 0, CSPE_KP_OCCLUDED = 1, CSPE_KP_VISIBLE = 2 };
@@ -169,7 +174,8 @@ int cspe_mask_scan_depth_stats(const uint32_t* mask, const float* depth, int B, 
  * gcd.py:1924-1950 -> bboxDict_to_transform gcd.py:553-584, and adds corner projection and
  * the object-in-camera pose the reference leaves out) --------------------------------------
  * records     bbox3d records, frame f record r at records + (f*recs_per_frame + r)*rec_stride
- * obj_record  int32 [B][N]: record index of slot n in frame f, or -1 (no record -> flags 0)
+ * obj_record  int32 [B][N]: record index of slot n in frame f, or -1 (no record -> flags 0); bit 30
+ *             (CSPE_OBJ_RECORD_APPROX_BIT) set = stand-in record -> CSPE_OBJ_APPROX_RECORD in flags
  * cam         double [B][CSPE_CAM_STRIDE]
  * uv          double [B][N][8][2]   z double [B][N][8]   pose double [B][N][CSPE_POSE_STRIDE]
  * loose       double [B][N][4] = u_min,v_min,u_max,v_max over in-front corners (NaN if none)
@@ -262,13 +268,25 @@ int cspe_graph_edge_kinds(void* cuda_graph, int* num_nodes, int* num_edges, int*
  * depth float32 [H][W]; rgb uint8 [H][W][C] (C = 3 or 4) or NULL (white);
  * cam double[CSPE_CAM_STRIDE] (uses t, Rcw, fx, fy, cx, cy exactly as gcd.py:664-685 does);
  * out double [capacity][6] x,y,z,r,g,b in row-major pixel order (stable compaction);
- * n_points int64[1]; scratch: cspe_pointcloud_workspace_bytes(H, W) bytes.
+ * n_points int64[1]; scratch: cspe_pointcloud_workspace_bytes(H, W) bytes, 16-byte aligned.
  * Valid pixel: isfinite & > 0 & < 250 (gcd.py:655).  Points beyond capacity are dropped
  * but still counted. */
 size_t cspe_pointcloud_workspace_bytes(int H, int W);
 int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_channels,
                              int H, int W, const double* cam, double* out, int64_t capacity,
                              int64_t* n_points, void* workspace, void* stream);
+
+/* f1 for a batch (the per-frame loop around gcd.py:1720-1759): depth float32 [B][H][W]; rgb uint8
+ * [B][H][W][C] or NULL; cam double [B][CSPE_CAM_STRIDE]; the frames' points are compacted back to back
+ * into out double [capacity][6], each frame in row-major pixel order; offsets int64 [B + 1] (device) =
+ * first point of every frame, offsets[B] = total (points beyond capacity are dropped but counted).  The
+ * "max <= 1 -> x255" colour rule (gcd.py:693) is applied per frame, as the reference applies it per call.
+ * Two launches for the whole batch; scratch: cspe_pointcloud_batch_workspace_bytes(B, H, W) bytes, 16-byte
+ * aligned. */
+size_t cspe_pointcloud_batch_workspace_bytes(int B, int H, int W);
+int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t* rgb, int rgb_channels,
+                                   int B, int H, int W, const double* cam, double* out,
+                                   int64_t capacity, int64_t* offsets, void* workspace, void* stream);
 
 /* f2: depth statistics alone (gcd.py:314-359); stats cspe_depth_stats_t[B]. */
 int cspe_depth_stats(const float* depth, int B, int H, int W, cspe_depth_stats_t* stats,
@@ -313,6 +331,15 @@ int cspe_format_fixed6(const void* values, int dtype, int64_t max_rows, const in
  * Returns the number of bytes written, or a negative CSPE_ERR_* (buffer too small, bad n_out). */
 int64_t cspe_format_yolo_host(const cspe_record* records_host, const int32_t* n_out_host, int B, int N,
                               int frames, char* out_host, int64_t capacity, int64_t* offsets_host);
+
+/* f3: the label files of a batch, written natively (no CUDA; HOST pointers): file j is
+ * "<dir>/<prefix><first_id + j, zero-padded to `digits`><suffix>" — the naming of gcd.py:2071
+ * (label_%06d.json) — and holds sizes_host[j] bytes from data_host + j * stride (the layout
+ * cspe_format_yolo leaves after D2H).  Existing files are truncated.  Returns the bytes written or a
+ * negative CSPE_ERR_* (cspe_last_error names the file and errno). */
+int64_t cspe_write_files_host(const char* dir, const char* prefix, int digits, const char* suffix,
+                              int64_t first_id, int count, const char* data_host, int64_t stride,
+                              const int32_t* sizes_host);
 
 /* f3: host-side label JSON of ONE frame (no CUDA; all pointers are HOST pointers) — the text
  * json.dump(label, f, indent=2, ensure_ascii=False) writes (gcd.py:608-613) for the frame dict of

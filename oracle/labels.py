@@ -18,7 +18,8 @@ from scipy.spatial.transform import Rotation
 CAM_STRIDE = 24
 POSE_STRIDE = 16
 NUM_CLASSES = 10
-OBJ_HAS_RECORD, OBJ_ANY_FRONT, OBJ_ALL_FRONT, OBJ_POSE_VALID = 1, 2, 4, 8
+OBJ_HAS_RECORD, OBJ_ANY_FRONT, OBJ_ALL_FRONT, OBJ_POSE_VALID, OBJ_APPROX_RECORD = 1, 2, 4, 8, 16
+OBJ_RECORD_APPROX_BIT = 1 << 30   # marks an obj_record entry whose record only approximates the object
 KP_OUT, KP_OCCLUDED, KP_VISIBLE = 0, 1, 2
 
 # Replicator bounding_box_3d record; field order is what gcd.py:562-564 indexes (1..6 extents,
@@ -197,6 +198,9 @@ def project_objects(records: np.ndarray, obj_record: np.ndarray, cam: np.ndarray
             t, rcw, fx, fy, cx, cy, near = _cam_parts(cam[f])
             for n in range(N):
                 ri = int(obj_record[f, n])
+                approx = ri >= 0 and bool(ri & OBJ_RECORD_APPROX_BIT)
+                if ri >= 0:
+                    ri &= ~OBJ_RECORD_APPROX_BIT
                 if ri < 0 or ri >= R:
                     continue
                 rec = records[f, ri]
@@ -238,6 +242,8 @@ def project_objects(records: np.ndarray, obj_record: np.ndarray, cam: np.ndarray
                     pose[f, n, 3:7] = quat_xyzw_canonical(rcw.T @ rwo)
                     pose[f, n, 13:16] = Rotation.from_matrix(rwo).as_euler("xyz", degrees=True)
                     fl |= OBJ_POSE_VALID
+                if approx:
+                    fl |= OBJ_APPROX_RECORD
                 flags[f, n] = fl
     return uv, z, pose, loose, flags
 

@@ -8,6 +8,12 @@ from oracle import labels as O
 
 PX_ATOL = 1e-4   # north_star: float projections within 1e-4 px
 REL_TOL = 1e-5   # north_star: poses within 1e-5 relative
+# Euler angles against the REFERENCE's own bboxDict_to_transform (gcd.py:553-584), whose SVD runs in float32: the
+# f64 polar factor of the kernel / oracle sits within 3.9e-6 degrees of it on the golden records, so the bar is
+# 1e-5 degrees absolute + 1e-5 relative
+EULER_REF_ATOL = 1e-5
+# kernel against oracle (both f64, different algorithms for the polar factor): 1e-5 relative + 1e-9 degrees
+EULER_ATOL = 1e-9
 
 
 def host_tables(frames, split_people=True, fallback="first_mesh"):
@@ -62,8 +68,8 @@ def oracle_pipeline(frames, min_pixels=1, tol=0.15, frame_base=0, **kw):
 
 
 def assert_pose_close(got: np.ndarray, want: np.ndarray, valid: np.ndarray):
-    """pose blocks [.., 16]: translation/centre/size to 1e-5 relative, quaternion and Euler to
-    1e-5 of their natural scale (unit norm / 180 degrees)."""
+    """pose blocks [.., 16]: translation/centre/size to 1e-5 relative, quaternion to 1e-5 of its unit norm, Euler
+    angles to 1e-5 RELATIVE (+ 1e-9 degrees) — north_star's bar, not a fraction of the 180-degree range."""
     g, w = got[valid], want[valid]
     for sl in (slice(0, 3), slice(7, 10), slice(10, 13)):
         scale = np.maximum(np.linalg.norm(w[:, sl], axis=1, keepdims=True), 1e-12)
@@ -71,7 +77,7 @@ def assert_pose_close(got: np.ndarray, want: np.ndarray, valid: np.ndarray):
     assert np.all(np.abs(g[:, 3:7] - w[:, 3:7]) <= REL_TOL), "quaternion"
     de = np.abs(g[:, 13:16] - w[:, 13:16])
     de = np.minimum(de, 360.0 - de)  # +-180 wrap
-    assert np.all(de <= 180.0 * REL_TOL), f"euler max diff {de.max()}"
+    assert np.all(de <= EULER_ATOL + REL_TOL * np.abs(w[:, 13:16])), f"euler max diff {de.max()}"
 
 
 def assert_records_equal(got: np.ndarray, want: np.ndarray, pose_tol=True):

@@ -357,14 +357,16 @@ def test_reference_transform_matches_kernel(T, ops):
     _, _, pose, _, flags = _project_gpu(T, ops, o["records"], o["obj_record"], o["cam"])
     for f in range(2):
         for n in range(o["obj_record"].shape[1]):
-            ri = o["obj_record"][f, n]
+            ri = int(o["obj_record"][f, n])
             if ri < 0:
                 continue
+            ri &= ~O.OBJ_RECORD_APPROX_BIT   # stand-in records carry a marker bit
             center, size, euler = O.bbox_to_transform(o["records"][f, ri])
             assert np.allclose(pose[f, n, 7:10], center, rtol=helpers.REL_TOL, atol=1e-9)
             assert np.allclose(pose[f, n, 10:13], size, rtol=helpers.REL_TOL, atol=1e-9)
             de = np.abs(pose[f, n, 13:16] - np.asarray(euler))
-            assert np.all(np.minimum(de, 360 - de) <= 1e-3)  # the reference's SVD runs in float32
+            # the reference's SVD runs in float32 (measured: <= 3.9e-6 deg against the f64 polar factor)
+            assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(euler))
 
 
 # ------------------------------------------------------------------------------ K3 keypoints
@@ -516,6 +518,147 @@ def test_writer_end_to_end(T, ops, tmp_path):
     assert summary["quality"] == q["statistics"]
 
 
+def _native_camera_params(frame):
+    """The payload Replicator's camera_params annotator delivers for the camera of a synthetic frame."""
+    from constructionsceneposeestimation_b200 import camera
+    pose, p = frame["camera_pose"], frame["camera_params"]
+    m = np.eye(4)
+    m[:3, :3] = camera.quat_xyzw_to_matrix(pose[3:]).T      # USD local-to-world, row-vector convention
+    m[3, :3] = pose[:3]
+    return {"cameraViewTransform": np.linalg.inv(m).reshape(-1), "cameraProjection": np.eye(4).reshape(-1),
+            "cameraFocalLength": np.float32(p["focal_length"]), "cameraFocusDistance": 0.0, "cameraFStop": 0.0,
+            "cameraAperture": np.array([p["horizontal_aperture"], p["vertical_aperture"]], dtype=np.float32),
+            "cameraApertureOffset": np.zeros(2, dtype=np.float32), "cameraModel": "pinhole",
+            "cameraNearFar": np.array([0.5, 250.0], dtype=np.float32), "metersPerSceneUnit": 1.0,
+            "renderProductResolution": np.array([p["width"], p["height"]], dtype=np.int32)}
+
+
+def test_writer_replicator_native_payloads(T, ops, tmp_path):
+    """What Replicator hands a Writer — suffixed annotator keys, the native camera_params dict (view matrix,
+    focal length, aperture, resolution), skeleton_data as a list of per-skeleton dicts — gives the same labels as the
+    reference's own dict (gcd.py:587-605, 2035-2045); a rig payload with two render products becomes two frames."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(640, 360, 20, 4, 17, config_id=21), 2)
+    want = ConstructionLabelWriter(None, split_people=True).annotate_batch(frames)
+    native = []
+    for fr in frames:
+        j = fr["skeleton_data"]["globalTranslations"]
+        native.append({
+            "instance_segmentation-RenderProduct_Replicator": fr["instance_segmentation"],
+            "distance_to_image_plane-RenderProduct_Replicator": fr["distance_to_image_plane"],
+            "bounding_box_3d_fast-RenderProduct_Replicator": fr["bounding_box_3d"],
+            "camera_params-RenderProduct_Replicator": _native_camera_params(fr),
+            "skeleton_data-RenderProduct_Replicator": [{"skelPath": f"/World/p{p}", "globalTranslations": j[p]} for p in range(len(j))],
+            "trigger_outputs": {"on_time": 0}, "frame_id": fr["frame_id"]})
+    got = ConstructionLabelWriter(None, split_people=True).annotate_batch(native)
+    assert np.array_equal(got.n_out, want.n_out)
+    for f in range(2):
+        a, b = got.records(f), want.records(f)
+        for name in ("frame", "inst_idx", "class_id", "count", "x_min", "y_min", "x_max", "y_max", "flags", "loose"):
+            assert np.array_equal(a[name], b[name]), name
+        assert np.allclose(a["uv"], b["uv"], rtol=0, atol=1e-8) and np.allclose(a["pose"], b["pose"], rtol=1e-10, atol=1e-9, equal_nan=True)
+        assert np.array_equal(got.keypoints(f)[1], want.keypoints(f)[1])
+        assert np.allclose(got.keypoints(f)[0], want.keypoints(f)[0], rtol=0, atol=1e-8)
+        assert np.allclose(got.camera_poses[f], frames[f]["camera_pose"], atol=1e-12) or \
+            np.allclose(got.camera_poses[f][3:], -np.asarray(frames[f]["camera_pose"][3:]), atol=1e-12)
+        assert got.camera_params[f] == pytest.approx(frames[f]["camera_params"])
+    # a two-camera rig in ONE payload: frames 2*fid + camera, cameras in sorted render-product order
+    rig = {"frame_id": 7}
+    for c, fr in enumerate(frames):
+        for name in ("instance_segmentation", "distance_to_image_plane", "bounding_box_3d"):
+            rig[f"{name}-RenderProduct_cam{c}"] = fr[name]
+        rig[f"camera_params-RenderProduct_cam{c}"] = _native_camera_params(fr)
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "yolo"), split_people=True)
+    w.write(rig)
+    w.on_final_frame()
+    import json
+    for c in range(2):
+        lab = json.loads((tmp_path / "labels" / f"label_{14 + c:06d}.json").read_text())
+        assert lab["frame_id"] == 14 + c and lab["num_objects"] == int(want.n_out[c])
+        assert lab["camera_params"]["width"] == 640 and lab["camera_params"]["focal_length"] == 12.0
+
+
+def test_writer_missing_mask_gives_empty_labels(T, ops, tmp_path):
+    """An absent instance_segmentation annotator is not an error (gcd.py:1682, 1788, 1919): that frame gets an empty
+    label file, the other frames of the batch are unaffected."""
+    import json
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(640, 360, 20, 4, 17, config_id=22), 3)
+    o = helpers.oracle_pipeline(frames)
+    broken = [dict(fr) for fr in frames]
+    broken[1]["instance_segmentation"] = None
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json",), split_people=True)
+    labels = w.write_batch(broken)
+    w.on_final_frame()
+    assert labels.missing_masks == [1]
+    assert labels.n_out.tolist() == [int(o["n_out"][0]), 0, int(o["n_out"][2])]
+    helpers.assert_records_equal(labels.records(2), o["recs"][2, : o["n_out"][2]])
+    assert json.loads((tmp_path / "labels" / "label_000001.json").read_text())["num_objects"] == 0
+    # no mask anywhere and nothing else to take the size from: still no exception
+    w2 = ConstructionLabelWriter(None)
+    lab = w2.annotate_batch([{"bounding_box_3d": frames[0]["bounding_box_3d"]}])
+    assert lab.n_out.tolist() == [0] and (lab.height, lab.width) == (720, 1280)
+
+
+def test_writer_input_lifetime_contract(T, ops, tmp_path):
+    """The writer reads annotator buffers after write() returns; it must (a) order the caller's stream behind its
+    reads, (b) expose inputs_consumed, (c) serialise deferred files from its OWN snapshot, and (d) recycle pinned
+    blocks only after the batch that used them has run."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    spec = synthetic.SceneSpec(640, 360, 20, 4, 17, config_id=23, with_rgb=True)
+    frames = synthetic.make_batch(spec, 2)
+    o = helpers.oracle_pipeline(frames)
+    masks = [fr["instance_segmentation"]["data"].copy() for fr in frames]
+    # (a) + (c): device-resident annotators, overwritten on the caller's stream right after write_batch()
+    dev_frames = []
+    for fr in frames:
+        d = dict(fr)
+        d["instance_segmentation"] = {"data": T.from_numpy(fr["instance_segmentation"]["data"].view(np.int32)).cuda(),
+                                      "info": fr["instance_segmentation"]["info"]}
+        d["distance_to_image_plane"] = T.from_numpy(fr["distance_to_image_plane"]).cuda()
+        d["rgb"] = T.from_numpy(fr["rgb"]).cuda()
+        dev_frames.append(d)
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json", "mask", "rgb_png"), split_people=True, max_pending=2)
+    labels = w.write_batch(dev_frames)
+    assert labels.inputs_consumed is not None
+    for d in dev_frames:                      # the "renderer" reuses its buffers for the next frame at once
+        d["instance_segmentation"]["data"].zero_()
+        d["distance_to_image_plane"].zero_()
+        d["rgb"].zero_()
+    w.on_final_frame()
+    assert np.array_equal(labels.n_out, o["n_out"])
+    import cv2
+    for f in range(2):
+        helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
+        assert np.array_equal(np.load(tmp_path / "labels" / f"instance_mask_{f:06d}.npy").view(np.uint32), masks[f])
+        assert np.array_equal(cv2.imread(str(tmp_path / "rgb" / f"rgb_{f:06d}.png")), frames[f]["rgb"][..., 2::-1])
+    # (b): a pinned staging buffer refilled by the host after wait_inputs_consumed()
+    stage = T.empty((2, 360, 640), dtype=T.int32, pin_memory=True)
+    stage.copy_(T.from_numpy(np.stack(masks).view(np.int32)))
+    batch = {"instance_segmentation": {"data": stage, "info": [fr["instance_segmentation"]["info"] for fr in frames]},
+             "bounding_box_3d": {"data": [fr["bounding_box_3d"]["data"] for fr in frames],
+                                 "info": [fr["bounding_box_3d"]["info"] for fr in frames]},
+             "camera_pose": np.asarray([fr["camera_pose"] for fr in frames]),
+             "camera_params": [fr["camera_params"] for fr in frames], "frame_id": 0}
+    w2 = ConstructionLabelWriter(None, split_people=True)
+    lab = w2.annotate_batch(batch)
+    lab.wait_inputs_consumed()
+    stage.zero_()
+    assert np.array_equal(lab.n_out, o["n_out"])
+    # (d): results dropped at once -> their pinned blocks are reused, but never before their batch has run
+    for _ in range(6):
+        stage.copy_(T.from_numpy(np.stack(masks).view(np.int32)))
+        w2.annotate_batch(batch)
+    last = w2.annotate_batch(batch)
+    assert np.array_equal(last.n_out, o["n_out"])
+    for f in range(2):
+        helpers.assert_records_equal(last.records(f), o["recs"][f, : o["n_out"][f]])
+    assert sum(len(v) for v in w2._free_pinned.values()) <= 4 * len(w2._free_pinned)
+
+
 def test_writer_accepts_device_resident_annotators(T, ops):
     """Annotators created with device="cuda" arrive as CUDA tensors: same labels, no host copy of the pixels."""
     from constructionsceneposeestimation_b200 import synthetic
@@ -585,6 +728,48 @@ def test_pointcloud(T, ops):
     assert int(n3.item()) == n and bool((pts3[:n, 3:] == 255.0).all())
     _, n4 = ops.depth_to_pointcloud(T.full((180, 320), float("inf"), device="cuda"), None, cam)
     assert int(n4.item()) == 0
+
+
+def test_pointcloud_batch(T, ops):
+    """f1 batched: B frames through one pair of launches == the per-frame oracle (gcd.py:616-711), frames back to back,
+    each in row-major order; per-frame "max <= 1 -> x255" colour rule; capacity cut; odd sizes; no colour."""
+    from constructionsceneposeestimation_b200 import camera
+    rng = np.random.default_rng(11)
+    for (B, H, W, C) in ((5, 37, 53, 4), (3, 64, 128, 3), (2, 1, 1, 4), (4, 45, 100, 0)):
+        depth = rng.uniform(-1.0, 300.0, size=(B, H, W)).astype(np.float32)
+        depth[rng.random((B, H, W)) < 0.2] = np.inf
+        depth[rng.random((B, H, W)) < 0.05] = np.nan
+        depth[0, 0, 0] = 5.0
+        if B > 1:
+            depth[1] = np.inf                 # a frame without a single valid pixel
+        rgb = rng.integers(0, 256, size=(B, H, W, C), dtype=np.uint8) if C else None
+        if rgb is not None and B > 2:
+            rgb[2] = rng.integers(0, 2, size=(H, W, C), dtype=np.uint8)   # a [0,1] image: the reference scales it by 255
+        poses = [[rng.normal(), rng.normal(), rng.normal(), *rng.normal(size=4)] for _ in range(B)]
+        params = camera.camera_params(W, H)
+        cam = np.stack([camera.pack_camera(p, params) for p in poses])
+        want = [O.depth_to_pointcloud(depth[f], rgb[f] if rgb is not None else None, params, poses[f]) for f in range(B)]
+        want = [w if w is not None else np.zeros((0, 6)) for w in want]
+        d_rgb = T.from_numpy(rgb).cuda() if rgb is not None else None
+        pts, offsets = ops.depth_to_pointcloud_batch(T.from_numpy(depth).cuda(), d_rgb, T.from_numpy(cam).cuda())
+        T.cuda.synchronize()
+        pts, offsets = pts.cpu().numpy(), offsets.cpu().numpy()
+        assert offsets[0] == 0 and np.array_equal(np.diff(offsets), [len(w) for w in want])
+        for f in range(B):
+            got = pts[offsets[f]: offsets[f + 1]]
+            assert np.allclose(got[:, :3], want[f][:, :3], rtol=1e-12, atol=1e-9)
+            assert np.array_equal(got[:, 3:], want[f][:, 3:])
+        # capacity smaller than the total: the counts stay, the prefix that fits is identical
+        cap = int(offsets[-1]) // 2 + 1
+        pts2, off2 = ops.depth_to_pointcloud_batch(T.from_numpy(depth).cuda(), d_rgb, T.from_numpy(cam).cuda(), capacity=cap)
+        T.cuda.synchronize()
+        assert np.array_equal(off2.cpu().numpy(), offsets)
+        assert np.array_equal(pts2.cpu().numpy()[:cap], pts[:cap])
+        # the one-frame entry point is the batch of one
+        p1, n1 = ops.depth_to_pointcloud(T.from_numpy(depth[0]).cuda(), d_rgb[0].contiguous() if d_rgb is not None else None,
+                                         T.from_numpy(cam[0]).cuda())
+        T.cuda.synchronize()
+        assert int(n1) == offsets[1] and np.array_equal(p1.cpu().numpy()[: int(n1)], pts[: offsets[1]])
 
 
 def test_depth_colormap_and_bgr(T, ops):
@@ -1178,7 +1363,7 @@ def test_kernels_against_reference_goldens(T, ops):
     assert np.allclose(pose[0, :, 7:10], g["center"], rtol=1e-6, atol=1e-9)
     assert np.allclose(pose[0, :, 10:13], g["size"], rtol=1e-6, atol=1e-9)
     de = np.abs(pose[0, :, 13:16] - g["euler"])
-    assert np.all(np.minimum(de, 360 - de) <= 1e-3)          # the reference's SVD runs in float32
+    assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(g["euler"]))   # f32 SVD in the reference
     # f1
     g = np.load(GOLD / "pointcloud.npz")
     params, pose7 = json.loads(str(g["params"])), list(g["pose"])

@@ -396,3 +396,104 @@ def test_tables_cache_key_accepts_replicator_label_shapes():
     assert hash(key) == hash(tables_cache_key(["/World/a/mesh", "/World/b"], dict(labels)))
     assert key != tables_cache_key(["/World/a/mesh", "/World/b"], {**labels, "2": "/World/c/mesh"})
     assert key[1][3] == ("3", None) and key[1][4] == ("4", "/World/b")
+
+
+# ------------------------------------------------------------------ Replicator-native payloads (boundary)
+def test_replicator_camera_params_and_pose_convention():
+    """cameraViewTransform -> (t, Rcw, quaternion) exactly as get_obj_pose takes them from the camera prim
+    (gcd.py:596-605): the inverse view matrix is the prim's local-to-world matrix; scipy's from_matrix().as_quat()
+    is restated in camera.matrix_to_quat_xyzw and checked against scipy here."""
+    from scipy.spatial.transform import Rotation
+    from constructionsceneposeestimation_b200 import camera, synthetic
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        m = Rotation.random(random_state=rng).as_matrix()
+        assert np.allclose(camera.matrix_to_quat_xyzw(m), Rotation.from_matrix(m).as_quat(), atol=1e-15)
+    fr = synthetic.make_frame(synthetic.CONFIGS["c1"], 3)
+    pose, p = np.asarray(fr["camera_pose"]), fr["camera_params"]
+    rcw = camera.quat_xyzw_to_matrix(pose[3:])
+    m = np.eye(4)
+    m[:3, :3], m[3, :3] = rcw.T, pose[:3]
+    native = {"cameraViewTransform": np.linalg.inv(m).reshape(-1), "cameraFocalLength": p["focal_length"],
+              "cameraAperture": [p["horizontal_aperture"], p["vertical_aperture"]],
+              "renderProductResolution": [p["width"], p["height"]], "cameraNearFar": [0.1, 1000.0]}
+    assert camera.is_replicator_camera_params(native) and not camera.is_replicator_camera_params(p)
+    pose7, params, clip = camera.from_replicator_camera_params(native)
+    assert params == pytest.approx(p) and clip == (0.1, 1000.0)
+    want = camera.pack_camera(pose, p)
+    got = camera.pack_camera(pose7, params)
+    assert np.allclose(got, want, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        camera.from_replicator_camera_params({"cameraViewTransform": np.eye(4).reshape(-1)})
+    # image size from the mask when the payload has no resolution
+    _, params2, _ = camera.from_replicator_camera_params({"cameraViewTransform": np.eye(4).reshape(-1)}, 1920, 1080)
+    assert (params2["width"], params2["height"]) == (1920, 1080)
+    assert params2["horizontal_aperture"] == camera.DEFAULT_HORIZONTAL_APERTURE
+
+
+def test_render_product_keys_and_skeleton_shapes():
+    import json
+    from constructionsceneposeestimation_b200.writer import _annotator_name, skeleton_joints, split_render_products
+    assert _annotator_name("instance_segmentation-RenderProduct_Replicator") == ("instance_segmentation", "RenderProduct_Replicator")
+    assert _annotator_name("bounding_box_3d_fast") == ("bounding_box_3d", None)
+    assert _annotator_name("LdrColor-rp") == ("rgb", "rp")
+    assert _annotator_name("trigger_outputs") == (None, None)
+    one = split_render_products({"instance_segmentation": 1, "frame_id": 4})
+    assert one == [{"instance_segmentation": 1, "frame_id": 4}]
+    rig = split_render_products({"instance_segmentation-b": "mb", "instance_segmentation-a": "ma", "camera_params-a": "ca",
+                                 "camera_params-b": "cb", "frame_id": 2, "trigger_outputs": {}})
+    assert [fr["render_product"] for fr in rig] == ["a", "b"]
+    assert rig[0]["instance_segmentation"] == "ma" and rig[1]["camera_params"] == "cb" and rig[1]["frame_id"] == 2
+    j = np.arange(2 * 5 * 3, dtype=np.float32).reshape(2, 5, 3)
+    for payload in (j, {"globalTranslations": j}, {"data": {"globalTranslations": j.tolist()}},
+                    [{"skelPath": "/a", "globalTranslations": j[0]}, {"skelPath": "/b", "globalTranslations": j[1].tolist()}],
+                    json.dumps([{"globalTranslations": j[0].tolist()}, {"globalTranslations": j[1].tolist()}]),
+                    {"skeletonData": [{"globalTranslations": j[0]}, {"globalTranslations": j[1]}]}):
+        got = skeleton_joints(payload)
+        assert got is not None and got.dtype == np.float32 and np.array_equal(got, j)
+    assert np.array_equal(skeleton_joints(j[0]), j[:1])
+    for bad in (None, "not json", {"skelPath": "/a"}, [{"globalTranslations": j[0]}, {"globalTranslations": j[1, :3]}],
+                np.zeros((4, 2))):
+        assert skeleton_joints(bad) is None
+
+
+def test_record_index_marks_stand_in_records():
+    """first_mesh fallback: a mesh record standing in for a multi-mesh object carries RECORD_APPROX_BIT (K2 turns it into
+    OBJ_APPROX_RECORD); crane parts (the reference's own rule, gcd.py:1953-1975), single-mesh objects and objects with a
+    record of their own do not; a non-numeric idToLabels key is skipped, not fatal."""
+    from constructionsceneposeestimation_b200 import classes, synthetic
+    res = classes.ObjectRootResolver()
+    fence = synthetic.FENCE_PREFIX + "03"
+    paths = [fence + "/Mesh_0", fence + "/Mesh_1", "/World/Tree/Tree", "/World/Tree/Tree/trunk",
+             "/World/GroundPlane/Cone001/Cone001", synthetic.CRANE_ROOT + "/S104GG03A_SW/part_0",
+             synthetic.CRANE_ROOT + "/S104GG03A_SW/part_1"]
+    objs = classes.aggregate_objects(paths, res)
+    idx = classes.record_index_for(objs, paths, "first_mesh")
+    by_name = {o.class_name: i for o, i in zip(objs, idx)}
+    assert by_name["fence"] == (0 | classes.RECORD_APPROX_BIT)
+    assert by_name["tree"] == 2 and by_name["trafficcone"] == 4
+    crane = [i for o, i in zip(objs, idx) if "#" in o.prim_path]
+    assert crane and all(i >= 0 and not (i & classes.RECORD_APPROX_BIT) for i in crane)
+    assert classes.record_index_for(objs, paths, "first_mesh", mark_approx=False)[0] == 0
+    assert classes.record_index_for(objs, paths, "reference")[0] == -1
+    m = classes.id_to_slot({"7": paths[0], "x9": paths[1], 8: paths[2]}, objs, res)
+    assert m == {7: 0, 8: objs[[o.class_name for o in objs].index("tree")].inst_idx}
+
+
+def test_native_batch_file_writer(tmp_path):
+    """cspe_write_files_host: label_%06d naming of gcd.py:2071, one file per row of a strided text buffer."""
+    from constructionsceneposeestimation_b200 import _lib, formats
+    data = np.zeros((4, 32), dtype=np.uint8)
+    texts = [b"0 0.5 0.5 0.1 0.1\n", b"", b"3 0.25 0.75 0.5 0.5\n1 0 0 1 1\n"[:32], b"x" * 32]
+    for j, t in enumerate(texts):
+        data[j, : len(t)] = np.frombuffer(t, dtype=np.uint8)
+    sizes = np.array([len(t) for t in texts], dtype=np.int32)
+    assert formats.write_files(str(tmp_path), "label_", ".txt", 41, data, sizes) == int(sizes.sum())
+    for j, t in enumerate(texts):
+        assert (tmp_path / f"label_{41 + j:06d}.txt").read_bytes() == t
+    formats.write_files(str(tmp_path), "label_", ".txt", 41, data, np.array([3, 0, 0, 0], dtype=np.int32), count=1)
+    assert (tmp_path / "label_000041.txt").read_bytes() == texts[0][:3]          # truncated, not appended
+    with pytest.raises(_lib.CspeError):
+        formats.write_files(str(tmp_path / "missing_dir"), "label_", ".txt", 0, data, sizes)
+    with pytest.raises(_lib.CspeError):
+        formats.write_files(str(tmp_path), "label_", ".txt", 0, data, np.array([33, 0, 0, 0], dtype=np.int32))

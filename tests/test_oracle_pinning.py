@@ -14,6 +14,7 @@ import numpy as np
 import pytest
 
 from oracle import labels as O
+from tests import helpers
 from oracle import reference_extract
 
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -91,7 +92,9 @@ def test_aggregation_matches_reference_loop():
         elif "#" in o.prim_path:
             assert a == b and paths[a] in o.mesh_paths
         else:
-            assert a == -1 and paths[b] == o.mesh_paths[0]
+            # a mesh record standing in for a multi-mesh object is marked as approximate (bit 30)
+            assert a == -1 and paths[b & ~classes.RECORD_APPROX_BIT] == o.mesh_paths[0]
+            assert bool(b & classes.RECORD_APPROX_BIT) == (len(o.mesh_paths) > 1)
 
 
 # ------------------------------------------------------------------ R3: bbox record -> centre / size / euler
@@ -102,7 +105,8 @@ def test_bbox_to_transform_golden():
         assert np.allclose(c, g["center"][i], rtol=1e-12, atol=1e-12)
         assert np.allclose(s, g["size"][i], rtol=1e-12, atol=1e-12)
         de = np.abs(np.asarray(e) - g["euler"][i])
-        assert np.all(np.minimum(de, 360 - de) <= 1e-3)  # f32 LAPACK may differ across numpy builds
+        # f32 LAPACK may differ across numpy builds, but only in the last bits of a float32 rotation
+        assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(g["euler"][i]))
     meta = json.loads((GOLD / "META.json").read_text())
     if meta["numpy"] == np.__version__:  # same numpy build as the fixture: bit-identical
         for i, rec in enumerate(g["records"]):
@@ -138,7 +142,7 @@ def test_project_objects_pose_consistent_with_r3():
     assert np.allclose(pose[0, :, 7:10], g["center"], rtol=1e-6, atol=1e-9)
     assert np.allclose(pose[0, :, 10:13], g["size"], rtol=1e-6, atol=1e-9)
     de = np.abs(pose[0, :, 13:16] - g["euler"])
-    assert np.all(np.minimum(de, 360 - de) <= 1e-3)
+    assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(g["euler"]))
     q = pose[0, :, 3:7]
     assert np.allclose(np.linalg.norm(q, axis=1), 1.0, atol=1e-12) and np.all(q[:, 3] >= 0)
 

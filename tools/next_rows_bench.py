@@ -44,6 +44,24 @@ ms = timed(lambda: lib.cspe_depth_to_pointcloud(d0.data_ptr(), rgb0.data_ptr(), 
 npts = int(n.item()); byts = H * W * 4 + H * W * 4 + npts * 48   # depth + rgba read once, points written
 print(json.dumps({"case": "f1 depth_to_pointcloud one 1080p frame", "ms": round(ms, 4), "points": npts,
                   "algorithmic_GB/s": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / PEAK, 3)}))
+# ---- f1 batched: all 64 frames in one pair of launches (5 GB of points: nothing stays in L2) ----------
+try:
+    PEAK = float(json.loads((Path(__file__).resolve().parents[1] / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+except (OSError, ValueError, KeyError):
+    pass
+camB = torch.from_numpy(np.stack([camera.pack_camera(frames[i % 8]["camera_pose"], frames[i % 8]["camera_params"])
+                                  for i in range(B)])).to(dev)
+outB = torch.empty((B * H * W, 6), dtype=torch.float64, device=dev)
+offB = torch.empty(B + 1, dtype=torch.int64, device=dev)
+wsB = torch.empty((lib.cspe_pointcloud_batch_workspace_bytes(B, H, W) + 7) // 8, dtype=torch.int64, device=dev)
+for label, rgb_ptr, ch in (("RGBA", rgb.data_ptr(), 4), ("no colour", None, 0)):
+    ms = timed(lambda: lib.cspe_depth_to_pointcloud_batch(depth.data_ptr(), rgb_ptr, ch, B, H, W, camB.data_ptr(), outB.data_ptr(),
+                                                          B * H * W, offB.data_ptr(), wsB.data_ptr(), s), n=10)
+    nptsB = int(offB[-1].item())
+    bytsB = B * H * W * (4 + ch) * 2 + nptsB * 48      # depth (+ colour) read by both passes, 48 B per point written
+    print(json.dumps({"case": f"f1 depth_to_pointcloud_batch 64 x 1080p, {label}", "ms": round(ms, 4), "ms_per_frame": round(ms / B, 5),
+                      "points": nptsB, "algorithmic_GB/s": round(bytsB / ms / 1e6, 1), "frac": round(bytsB / ms / 1e6 / PEAK, 3)}))
+del outB
 # ---- f3: "%.6f" text of the point cloud and of the depth map (gcd.py:1752, 1688) --------------------
 import time
 tws = torch.empty((lib.cspe_text_workspace_bytes(H * W, 6) + 7) // 8, dtype=torch.int64, device=dev)
