@@ -7,8 +7,9 @@ frame) and its output becomes the device tables the kernels consume: ``id -> slo
 ``slot -> record`` for K2 and ``slot -> class`` for K4.
 
 The implementation is a rule table, memoised per path, rather than the reference's
-if-chain; ``tests/test_classes.py`` pins it against golden vectors produced by the
-reference function itself.
+if-chain; ``tests/test_oracle_pinning.py`` pins it against golden vectors produced by the
+reference function itself (``tests/golden/object_roots.json``, ``frame_label.json``) and fuzzes it
+against the live function where ``/root/reference`` exists.
 """
 from __future__ import annotations
 

@@ -65,6 +65,12 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+// RULE (measured on B200, round 2): whatever such a kernel reads BEFORE griddepcontrol.wait must bypass L1 — use
+// __ldcg() / ld.global.cg or TMA, never __ldg() / plain loads / const __restrict__ dereferences.  A kernel that starts
+// early as a programmatic dependent does not get the L1 invalidation an ordinary kernel boundary gives: lines an
+// EARLIER kernel left in that SM's L1 survive, so an L1-cached load can return what the address held before the
+// last host write (H2D copy) to it.  Seen as cspe_format_fixed6 formatting the PREVIOUS call's row count about once
+// in 100 calls (tools/text_race_probe.py); loads issued after the wait were never seen stale.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif

@@ -42,7 +42,9 @@ __device__ __forceinline__ void acc_four(Acc& a, const float4 v) {
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  // .cg = L2 only: the kernel streams before its PDL wait, and a line another kernel left in L1 must not be hit
+  // (cspe_common.cuh, PDL rule)
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
   return r;
@@ -96,8 +98,8 @@ __global__ void __launch_bounds__(kStatThreads) depth_stats_kernel(const float* 
   for (; i < n4; i += gthreads) acc_four(a, ldg_stream(d4 + i));
   const long long tail0 = head + n4 * 4;
   float part = 0.0f;
-  for (long long j = gtid; j < head; j += gthreads) acc_one(a, d[j], part);
-  for (long long j = tail0 + gtid; j < hw; j += gthreads) acc_one(a, d[j], part);
+  for (long long j = gtid; j < head; j += gthreads) acc_one(a, __ldcg(d + j), part);
+  for (long long j = tail0 + gtid; j < hw; j += gthreads) acc_one(a, __ldcg(d + j), part);
   a.sum += static_cast<double>(part);
 
   // warp, then block reduction; one set of atomics per block

@@ -56,7 +56,10 @@ __global__ void __launch_bounds__(kThreads)
   pdl_wait();
 
   // graph-replayable frame numbering: the id of the batch's first frame may come from device memory
-  if (frame_base_dev) frame_base += __ldg(frame_base_dev);
+  // Everything below was written by the kernels this one depends on WHILE it was already resident (programmatic
+  // dependent launch), so none of it is read-only for this kernel's lifetime: no ld.global.nc (__ldg / const
+  // __restrict__), every such load is an explicit L2 load (__ldcg) — cspe_common.cuh, PDL rule.
+  if (frame_base_dev) frame_base += __ldcg(frame_base_dev);
   const int32_t* uv32 = reinterpret_cast<const int32_t*>(uv);
   const int32_t* z32 = reinterpret_cast<const int32_t*>(z);
   const int32_t* pose32 = reinterpret_cast<const int32_t*>(pose);
@@ -68,13 +71,13 @@ __global__ void __launch_bounds__(kThreads)
     int cls = -1, cnt = 0, x0 = 0, y0 = 0, x1 = -1, y1 = -1;
     uint8_t fl = 0;
     if (n < N) {
-      cls = slot_class[o];
+      cls = __ldcg(slot_class + o);
       const int32_t* sc = scan + o * CSPE_SCAN_FIELDS;
-      cnt = sc[CSPE_SCAN_COUNT];
-      x0 = sc[CSPE_SCAN_XMIN];
-      y0 = sc[CSPE_SCAN_YMIN];
-      x1 = sc[CSPE_SCAN_XMAX];
-      y1 = sc[CSPE_SCAN_YMAX];
+      cnt = __ldcg(sc + CSPE_SCAN_COUNT);
+      x0 = __ldcg(sc + CSPE_SCAN_XMIN);
+      y0 = __ldcg(sc + CSPE_SCAN_YMIN);
+      x1 = __ldcg(sc + CSPE_SCAN_XMAX);
+      y1 = __ldcg(sc + CSPE_SCAN_YMAX);
       if (scan_reset) {  // leave the entry as cspe_mask_scan's init would: the next batch can accumulate
         int32_t* sr = scan_reset + o * CSPE_SCAN_FIELDS;
         sr[CSPE_SCAN_COUNT] = 0;
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kThreads)
         sr[CSPE_SCAN_XMAX] = -1;
         sr[CSPE_SCAN_YMAX] = -1;
       }
-      fl = flags[o];
+      fl = __ldcg(flags + o);
       keep = (cls >= 0) && (cnt >= min_pixels) && (fl & CSPE_OBJ_ANY_FRONT);
     }
     // stable rank = exclusive prefix sum of keep flags
@@ -106,7 +109,8 @@ __global__ void __launch_bounds__(kThreads)
       const int tw = x1 - x0 + 1, th = y1 - y0 + 1;
       const long long tight_area = static_cast<long long>(tw) * th;
       // loose box: projected 3D box clipped to the image and integerised
-      const double umin = loose[o * 4 + 0], vmin = loose[o * 4 + 1], umax = loose[o * 4 + 2], vmax = loose[o * 4 + 3];
+      const double umin = __ldcg(loose + o * 4 + 0), vmin = __ldcg(loose + o * 4 + 1), umax = __ldcg(loose + o * 4 + 2),
+                   vmax = __ldcg(loose + o * 4 + 3);
       const double dW = static_cast<double>(W), dH = static_cast<double>(H);
       const int lx0 = static_cast<int>(fmin(fmax(floor(umin), 0.0), dW));
       const int ly0 = static_cast<int>(fmin(fmax(floor(vmin), 0.0), dH));
@@ -190,9 +194,9 @@ __global__ void __launch_bounds__(kThreads)
         const long long so = static_cast<long long>(f) * N + n0 + t;
         int32_t v;
         if (k < kHdrWords) v = hdr_s[t][k];
-        else if (k < kHdrWords + 32) v = __ldg(uv32 + so * 32 + (k - kHdrWords));
-        else if (k < kHdrWords + 48) v = __ldg(z32 + so * 16 + (k - kHdrWords - 32));
-        else v = __ldg(pose32 + so * 32 + (k - kHdrWords - 48));
+        else if (k < kHdrWords + 32) v = __ldcg(uv32 + so * 32 + (k - kHdrWords));
+        else if (k < kHdrWords + 48) v = __ldcg(z32 + so * 16 + (k - kHdrWords - 32));
+        else v = __ldcg(pose32 + so * 32 + (k - kHdrWords - 48));
         dst[w] = v;
       }
     }

@@ -39,10 +39,13 @@ __device__ __forceinline__ void keypoint_one(const float* __restrict__ joints, l
                                              const double* __restrict__ cam, double tol, double* __restrict__ kp,
                                              double* __restrict__ kz, uint8_t* __restrict__ vis) {
   const int frame = static_cast<int>(i / per_frame);
-  const double* cm = cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE;
-  const double d0 = static_cast<double>(__ldg(joints + i * 3 + 0)) - cm[0];
-  const double d1 = static_cast<double>(__ldg(joints + i * 3 + 1)) - cm[1];
-  const double d2 = static_cast<double>(__ldg(joints + i * 3 + 2)) - cm[2];
+  // in overlapped mode everything here is read before the PDL wait: L1 bypass (cspe_common.cuh, PDL rule)
+  double cm[17];
+#pragma unroll
+  for (int j = 0; j < 17; ++j) cm[j] = __ldcg(cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE + j);
+  const double d0 = static_cast<double>(__ldcg(joints + i * 3 + 0)) - cm[0];
+  const double d1 = static_cast<double>(__ldcg(joints + i * 3 + 1)) - cm[1];
+  const double d2 = static_cast<double>(__ldcg(joints + i * 3 + 2)) - cm[2];
   // p_c = Rcw^T d  (column i of Rcw)
   const double pc0 = (cm[3] * d0 + cm[6] * d1) + cm[9] * d2;
   const double pc1 = (cm[4] * d0 + cm[7] * d1) + cm[10] * d2;
@@ -59,7 +62,7 @@ __device__ __forceinline__ void keypoint_one(const float* __restrict__ joints, l
   if (in_view) {
     const int ui = static_cast<int>(floor(u));
     const int vi = static_cast<int>(floor(v));
-    const float dz = __ldg(depth + (static_cast<long long>(frame) * H + vi) * W + ui);
+    const float dz = __ldcg(depth + (static_cast<long long>(frame) * H + vi) * W + ui);
     const bool visible = isfinite(dz) && (z <= static_cast<double>(dz) + tol);
     flag = visible ? CSPE_KP_VISIBLE : CSPE_KP_OCCLUDED;
   }

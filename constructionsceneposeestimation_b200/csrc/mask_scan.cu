@@ -160,7 +160,7 @@ __device__ __forceinline__ void red_global_max(int32_t* p, int v) {
 // large object then cost one red, the count.  kFlush = 0: always five reds.
 template <bool kSmemTable, int kFlush>
 __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx, int ymn, int ymx,
-                                         const int32_t* lut, int lut_len, int N, int32_t* tab) {
+                                         const int32_t* lut, int lut_len, int N, int32_t* tab, bool lut_in_smem) {
   const unsigned active = __activemask();
   int same;
   __match_all_sync(active, id, &same);
@@ -173,7 +173,8 @@ __device__ __noinline__ void flush_entry(uint32_t id, int cnt, int xmn, int xmx,
     if ((threadIdx.x & 31) != __ffs(active) - 1) return;
   }
   if (id >= static_cast<uint32_t>(lut_len)) return;
-  const int slot = lut[id];  // shared-memory copy of the frame's LUT when it fits, else global
+  // shared-memory copy of the frame's LUT when it fits, else global memory (L1 bypassed: may run before the PDL wait)
+  const int slot = lut_in_smem ? lut[id] : __ldcg(lut + id);
   if (static_cast<uint32_t>(slot) >= static_cast<uint32_t>(N)) return;
   int32_t* e = tab + slot * CSPE_SCAN_FIELDS;
   if (kSmemTable) {
@@ -217,7 +218,7 @@ __device__ __forceinline__ int table_identity(int field) {
       } else {                                                                          \
         if (e1.cnt)                                                                     \
           flush_entry<kSmemTable, kFlush>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut,   \
-                                  p.lut_len, p.N, tab);                                 \
+                                  p.lut_len, p.N, tab, p.smem_lut != 0);                \
         e1 = e0;                                                                        \
         entry_reset(e0, v__);                                                           \
       }                                                                                 \
@@ -319,7 +320,8 @@ __global__ void __maxnreg__(80)
         for (int r = 0; r < rows; ++r)
           for (int c = lane; c < cols; c += 32) {
             const int off = (c >> 5) * kBoxBytes + r * 128 + ((((c & 31) >> 2) ^ (r & 7)) << 4) + ((c & 3) << 2);
-            *reinterpret_cast<uint32_t*>(dst + off) = __ldg(src + static_cast<long long>(r) * p.W + c);
+            // (L1 bypass: in overlapped mode the mask is read before the PDL wait, cspe_common.cuh)
+            *reinterpret_cast<uint32_t*>(dst + off) = __ldcg(src + static_cast<long long>(r) * p.W + c);
           }
         __syncwarp();
         if (lane == 0) mbar_arrive(&full_bar[stage]);  // release: orders the warp's stores (after __syncwarp)
@@ -354,7 +356,7 @@ __global__ void __maxnreg__(80)
   auto open_frame = [&]() {
     const int32_t* glut = p.lut + static_cast<long long>(cur_frame) * p.lut_stride;
     if (p.smem_lut) {
-      for (int i = tid; i < p.lut_len; i += kConsumers) lut_s[i] = __ldg(glut + i);
+      for (int i = tid; i < p.lut_len; i += kConsumers) lut_s[i] = __ldcg(glut + i);   // L1 bypass (PDL rule)
       named_bar_sync(1, kConsumers);
       lut = lut_s;
     } else {
@@ -364,8 +366,10 @@ __global__ void __maxnreg__(80)
   };
 
   auto close_frame = [&]() {
-    if (e0.cnt) flush_entry<kSmemTable, kFlush>(e0.id, e0.cnt, e0.xmn, e0.xmx, e0.ymn, e0.ymx, lut, p.lut_len, p.N, tab);
-    if (e1.cnt) flush_entry<kSmemTable, kFlush>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut, p.lut_len, p.N, tab);
+    if (e0.cnt)
+      flush_entry<kSmemTable, kFlush>(e0.id, e0.cnt, e0.xmn, e0.xmx, e0.ymn, e0.ymx, lut, p.lut_len, p.N, tab, p.smem_lut != 0);
+    if (e1.cnt)
+      flush_entry<kSmemTable, kFlush>(e1.id, e1.cnt, e1.xmn, e1.xmx, e1.ymn, e1.ymx, lut, p.lut_len, p.N, tab, p.smem_lut != 0);
     entry_reset(e0, 0u);
     entry_reset(e1, 0u);
     if (kSmemTable || p.smem_lut) named_bar_sync(1, kConsumers);  // all flushes landed / LUT no longer read

@@ -76,14 +76,14 @@ __device__ __forceinline__ bool pc_valid(float d) {
 
 __device__ __forceinline__ void load4(const float* __restrict__ depth, long long base, long long hw, bool vec, float* d) {
   if (vec && base + 3 < hw) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(depth + base));
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(depth + base));   // L1 bypass: pass 2 reads before its PDL wait
     d[0] = v.x;
     d[1] = v.y;
     d[2] = v.z;
     d[3] = v.w;
   } else {
 #pragma unroll
-    for (int k = 0; k < kPcPerThread; ++k) d[k] = base + k < hw ? __ldg(depth + base + k) : 0.0f;
+    for (int k = 0; k < kPcPerThread; ++k) d[k] = base + k < hw ? __ldcg(depth + base + k) : 0.0f;
   }
 }
 
@@ -91,7 +91,7 @@ __device__ __forceinline__ void load4(const float* __restrict__ depth, long long
 __device__ __forceinline__ void load_rgb4(const uint8_t* __restrict__ rgb, int C, long long base, long long hw, bool vec,
                                           uint32_t* px) {
   if (vec && base + 3 < hw) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(rgb + base * 4));
+    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(rgb + base * 4));
     px[0] = v.x, px[1] = v.y, px[2] = v.z, px[3] = v.w;
   } else {
 #pragma unroll
@@ -99,7 +99,8 @@ __device__ __forceinline__ void load_rgb4(const uint8_t* __restrict__ rgb, int C
       px[k] = 0;
       if (base + k < hw) {
         const uint8_t* c = rgb + (base + k) * C;
-        px[k] = static_cast<uint32_t>(c[0]) | (static_cast<uint32_t>(c[1]) << 8) | (static_cast<uint32_t>(c[2]) << 16);
+        px[k] = static_cast<uint32_t>(__ldcg(c)) | (static_cast<uint32_t>(__ldcg(c + 1)) << 8) |
+                (static_cast<uint32_t>(__ldcg(c + 2)) << 16);
       }
     }
   }
@@ -223,9 +224,146 @@ __global__ void __launch_bounds__(kPcThreads)
   }
 }
 
-// Pass 2.  Same grid; every tile's points are built in shared memory and streamed out as one contiguous run.
+// ---- bulk (TMA) stores -------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {   // at most kPending groups still READING shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kPcBulkBufBytes = kPcTile * 48;          // a tile's points as the (N, 6) float64 rows they become: 48 KB
+constexpr int kPcBulkSmemBytes = 2 * kPcBulkBufBytes;  // double-buffered: the bulk store of tile i drains under tile i+1
+
+// Pass 2.  Same grid; every tile's points are built in shared memory exactly as they lie in `out` — rows of six
+// doubles, written as three conflict-free 16-byte stores per point — and leave with ONE bulk copy
+// (cp.async.bulk shared -> global, SASS UBLKCP) per tile: no thread spends instructions on the copy, and the store of
+// tile i drains while the CTA projects tile i+1 into the other buffer.
 __global__ void __launch_bounds__(kPcThreads)
     pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
+                    int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, int groups, void* ws_raw,
+                    const long long* __restrict__ offsets, double* __restrict__ out, long long capacity) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char pc_smem[];
+  __shared__ int s_warp[kPcGroup][kPcThreads / 32];
+  const PcLayout L = pc_layout(ws_raw, B, tiles);
+  const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const float* dep = depth + static_cast<long long>(f) * hw;
+  const uint8_t* col = rgb ? rgb + static_cast<long long>(f) * hw * C : nullptr;
+  const double* cam = cam_all + static_cast<long long>(f) * CSPE_CAM_STRIDE;
+  // depth / rgb are inputs of the chain: everything up to the first store runs before waiting for pass 1
+  float d[kPcGroup][kPcPerThread];
+  uint32_t px[kPcGroup][kPcPerThread];
+  int cnt[kPcGroup], inc[kPcGroup];
+#pragma unroll
+  for (int i = 0; i < kPcGroup; ++i) {
+    const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+    if (g * kPcGroup + i < tiles) load4(dep, base, hw, vec, d[i]);
+    else d[i][0] = d[i][1] = d[i][2] = d[i][3] = 0.0f;
+  }
+#pragma unroll
+  for (int i = 0; i < kPcGroup; ++i) {
+    cnt[i] = 0;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) cnt[i] += pc_valid(d[i][k]);
+    px[i][0] = px[i][1] = px[i][2] = px[i][3] = 0;
+    if (col != nullptr && cnt[i]) {
+      const long long base = (static_cast<long long>(g) * kPcGroup + i) * kPcTile + threadIdx.x * kPcPerThread;
+      load_rgb4(col, C, base, hw, rgb_vec, px[i]);
+    }
+    int v = cnt[i];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    inc[i] = v;
+    if (lane == 31) s_warp[i][wid] = v;
+  }
+  __syncthreads();
+
+  // the camera block is read before the PDL wait as well: L1 bypass
+  double cm[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cm[j] = __ldcg(cam + j);
+  const double t0 = cm[0], t1 = cm[1], t2 = cm[2];
+  const double fx = cm[12], fy = cm[13], cx = cm[14], cy = cm[15];
+  // pass 1's results (tile offsets, frame offsets, the frame's colour maximum) are needed from the first point on:
+  // the colour scale goes into the staged rows.  Loads, counts and prefix sums above ran before this wait.
+  pdl_wait();
+  // gcd.py:693: rgb.max() <= 1.0 over the frame's valid pixels -> the colours were a [0,1] image: x255
+  // (written while this kernel was resident: explicit L2 loads, cspe_common.cuh PDL rule)
+  const unsigned cmul = (col != nullptr && __ldcg(&L.frame[f].rgb_max) <= 1u) ? 255u : 1u;
+  const long long frame_first = __ldcg(offsets + f);
+#pragma unroll   // static indices keep d / px / cnt / inc in registers
+  for (int i = 0; i < kPcGroup; ++i) {
+    const int tile = g * kPcGroup + i;
+    if (tile >= tiles) break;
+    double2* buf = reinterpret_cast<double2*>(pc_smem + (i & 1) * kPcBulkBufBytes);
+    if (i >= 2) {  // the bulk store issued two tiles ago has to be done READING this buffer
+      if (threadIdx.x == 0) bulk_wait_read<1>();
+      __syncthreads();
+    }
+    int before = inc[i] - cnt[i], tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; ++w) {
+      const int s = s_warp[i][w];
+      if (w < wid) before += s;
+      tile_total += s;
+    }
+    // pixel index of the thread's first pixel (a frame has < 2^31 pixels): one 32-bit division per tile, the
+    // other three pixels follow by stepping (u, v)
+    const unsigned p0 = static_cast<unsigned>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    int v = static_cast<int>(p0 / static_cast<unsigned>(W));
+    int u = static_cast<int>(p0 - static_cast<unsigned>(v) * static_cast<unsigned>(W));
+    int r = before;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) {
+      if (pc_valid(d[i][k])) {
+        const double zc = static_cast<double>(d[i][k]);
+        const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
+        const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
+        const uint32_t c = col ? px[i][k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
+        double2 a, b2, c2;
+        a.x = ((cm[3] * xc + cm[4] * yc) + cm[5] * zc) + t0;
+        a.y = ((cm[6] * xc + cm[7] * yc) + cm[8] * zc) + t1;
+        b2.x = ((cm[9] * xc + cm[10] * yc) + cm[11] * zc) + t2;
+        b2.y = static_cast<double>((c & 255u) * cmul);
+        c2.x = static_cast<double>(((c >> 8) & 255u) * cmul);
+        c2.y = static_cast<double>(((c >> 16) & 255u) * cmul);
+        // 48-byte rows: the eight lanes of a quarter-warp cover all 32 banks exactly once per 16-byte store
+        buf[r * 3 + 0] = a;
+        buf[r * 3 + 1] = b2;
+        buf[r * 3 + 2] = c2;
+        ++r;
+      }
+      if (++u == W) {
+        u = 0;
+        ++v;
+      }
+    }
+    fence_async_smem();  // the rows were written through the generic proxy, the bulk copy reads through the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long first = frame_first + __ldcg(L.tile_offset + static_cast<long long>(f) * tiles + tile);
+      long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
+      if (keep > tile_total) keep = tile_total;
+      if (keep > 0) bulk_store_s2g(out + first * 6, buf, static_cast<uint32_t>(keep) * 48u);
+      bulk_commit();   // an empty group keeps the wait_group arithmetic uniform
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the copies that read it
+}
+
+// Pass 2, fallback for an `out` that is not 16-byte aligned: the tile's points are staged as x[] y[] z[] + packed colour
+// and copied out by the threads themselves.
+__global__ void __launch_bounds__(kPcThreads)
+    pc_write_loop_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
                     int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, int groups, void* ws_raw,
                     const long long* __restrict__ offsets, double* __restrict__ out, long long capacity) {
   pdl_launch_dependents();
@@ -274,8 +412,12 @@ __global__ void __launch_bounds__(kPcThreads)
   }
   __syncthreads();
 
-  const double t0 = cam[0], t1 = cam[1], t2 = cam[2];
-  const double fx = cam[12], fy = cam[13], cx = cam[14], cy = cam[15];
+  // the camera block is read before the PDL wait as well: L1 bypass
+  double cm[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cm[j] = __ldcg(cam + j);
+  const double t0 = cm[0], t1 = cm[1], t2 = cm[2];
+  const double fx = cm[12], fy = cm[13], cx = cm[14], cy = cm[15];
   bool waited = false;
   bool scale = false;
   long long frame_first = 0;
@@ -290,39 +432,46 @@ __global__ void __launch_bounds__(kPcThreads)
       if (w < wid) before += s;
       tile_total += s;
     }
-    const long long base = static_cast<long long>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    // pixel index of the thread's first pixel (a frame has < 2^31 pixels): one 32-bit division per tile, the
+    // other three pixels follow by stepping (u, v)
+    const unsigned p0 = static_cast<unsigned>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    int v = static_cast<int>(p0 / static_cast<unsigned>(W));
+    int u = static_cast<int>(p0 - static_cast<unsigned>(v) * static_cast<unsigned>(W));
     int r = before;
 #pragma unroll
     for (int k = 0; k < kPcPerThread; ++k) {
-      if (!pc_valid(d[i][k])) continue;
-      const long long p = base + k;
-      const int v = static_cast<int>(p / W);
-      const int u = static_cast<int>(p - static_cast<long long>(v) * W);
-      const double zc = static_cast<double>(d[i][k]);
-      const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
-      const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
-      sx[r] = ((cam[3] * xc + cam[4] * yc) + cam[5] * zc) + t0;
-      sy[r] = ((cam[6] * xc + cam[7] * yc) + cam[8] * zc) + t1;
-      sz[r] = ((cam[9] * xc + cam[10] * yc) + cam[11] * zc) + t2;
-      sc[r] = col ? px[i][k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
-      ++r;
+      if (pc_valid(d[i][k])) {
+        const double zc = static_cast<double>(d[i][k]);
+        const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
+        const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
+        sx[r] = ((cm[3] * xc + cm[4] * yc) + cm[5] * zc) + t0;
+        sy[r] = ((cm[6] * xc + cm[7] * yc) + cm[8] * zc) + t1;
+        sz[r] = ((cm[9] * xc + cm[10] * yc) + cm[11] * zc) + t2;
+        sc[r] = col ? px[i][k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
+        ++r;
+      }
+      if (++u == W) {
+        u = 0;
+        ++v;
+      }
     }
     __syncthreads();  // stage complete
     if (!waited) {
       pdl_wait();  // tile offsets, frame offsets and the colour maximum come from pass 1
       waited = true;
       // gcd.py:693: rgb.max() <= 1.0 over the frame's valid pixels -> the colours were a [0,1] image: x255
-      scale = col != nullptr && L.frame[f].rgb_max <= 1u;
-      frame_first = offsets[f];
+      // (written while this kernel was resident: explicit L2 loads, cspe_common.cuh PDL rule)
+      scale = col != nullptr && __ldcg(&L.frame[f].rgb_max) <= 1u;
+      frame_first = __ldcg(offsets + f);
     }
     // stream the tile's points out: ranks are consecutive, so it is one contiguous run
-    const long long first = frame_first + L.tile_offset[static_cast<long long>(f) * tiles + tile];
+    const long long first = frame_first + __ldcg(L.tile_offset + static_cast<long long>(f) * tiles + tile);
     long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
     if (keep > tile_total) keep = tile_total;
     if (keep > 0) {
-      const double cs = scale ? 255.0 : 1.0;
       const int n2 = static_cast<int>(keep) * 3;  // 16-byte pairs: (x,y) (z,r) (g,b)
       double* dst = out + first * 6;
+      const unsigned cm = scale ? 255u : 1u;   // [0,1] image: 0 / 1 -> 0 / 255, exact in integers
       if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         double2* d2 = reinterpret_cast<double2*>(dst);
         for (int j = threadIdx.x; j < n2; j += kPcThreads) {
@@ -334,17 +483,18 @@ __global__ void __launch_bounds__(kPcThreads)
             vv.y = sy[pt];
           } else if (m == 1) {
             vv.x = sz[pt];
-            vv.y = static_cast<double>(c & 255u) * cs;
+            vv.y = static_cast<double>((c & 255u) * cm);
           } else {
-            vv.x = static_cast<double>((c >> 8) & 255u) * cs;
-            vv.y = static_cast<double>((c >> 16) & 255u) * cs;
+            vv.x = static_cast<double>(((c >> 8) & 255u) * cm);
+            vv.y = static_cast<double>(((c >> 16) & 255u) * cm);
           }
           asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(d2 + j), "d"(vv.x), "d"(vv.y) : "memory");
         }
       } else {
         for (int j = threadIdx.x; j < n2 * 2; j += kPcThreads) {
           const int pt = j / 6, m = j - pt * 6;
-          dst[j] = m == 0 ? sx[pt] : m == 1 ? sy[pt] : m == 2 ? sz[pt] : static_cast<double>((sc[pt] >> (8 * (m - 3))) & 255u) * cs;
+          dst[j] = m == 0 ? sx[pt] : m == 1 ? sy[pt] : m == 2 ? sz[pt]
+                                                              : static_cast<double>(((sc[pt] >> (8 * (m - 3))) & 255u) * cm);
         }
       }
     }
@@ -395,8 +545,11 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   // frames of a batch start at multiples of hw floats: vector loads need every frame base 16-byte aligned
   const int vec = (reinterpret_cast<uintptr_t>(depth) & 15) == 0 && (B == 1 || hw % 4 == 0);
   static const cudaError_t smem_attr =
-      cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
+      cudaFuncSetAttribute(pc_write_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
+  static const cudaError_t smem_attr2 =
+      cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcBulkSmemBytes);
   (void)smem_attr;
+  (void)smem_attr2;
   const int rgb_vec = rgb != nullptr && rgb_channels == 4 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 &&
                       (B == 1 || hw % 4 == 0);
   CSPE_CUDA_OK(cudaMemsetAsync(workspace, 0, L.header_bytes, st));
@@ -405,11 +558,15 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   pc_count_kernel<<<grid, kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, B, static_cast<int>(tiles),
                                               static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets));
   CSPE_LAUNCH_OK("pc_count_kernel");
-  if (capacity > 0)
-    CSPE_CUDA_OK(launch_pdl(pc_write_kernel, dim3(grid), dim3(kPcThreads), kPcStageBytes, st, depth, rgb, rgb_channels, W, hw,
+  if (capacity > 0) {
+    // bulk (TMA) stores need a 16-byte aligned destination; every tile starts at a multiple of 48 bytes from `out`
+    const bool bulk = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    CSPE_CUDA_OK(launch_pdl(bulk ? pc_write_kernel : pc_write_loop_kernel, dim3(grid), dim3(kPcThreads),
+                            static_cast<size_t>(bulk ? kPcBulkSmemBytes : kPcStageBytes), st, depth, rgb, rgb_channels, W, hw,
                             vec, rgb_vec, cam, B, static_cast<int>(tiles), static_cast<int>(groups), workspace,
                             static_cast<const long long*>(reinterpret_cast<long long*>(offsets)), out,
                             static_cast<long long>(capacity)));
+  }
   return CSPE_OK;
 }
 

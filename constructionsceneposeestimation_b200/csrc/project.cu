@@ -178,7 +178,8 @@ __device__ __forceinline__ void project_one(const unsigned char* __restrict__ re
 
   // bit 30 of the record index marks a record that only approximates the object (a mesh record standing in
   // for an object whose root prim has none): passed through to the flags, stripped from the index
-  const int rec_raw = obj_record[obj];
+  // in overlapped mode every input is read before the PDL wait: L1 bypass (cspe_common.cuh, PDL rule)
+  const int rec_raw = __ldcg(obj_record + obj);
   const bool approx = rec_raw >= 0 && (rec_raw & CSPE_OBJ_RECORD_APPROX_BIT);
   const int rec = rec_raw >= 0 ? (rec_raw & ~CSPE_OBJ_RECORD_APPROX_BIT) : rec_raw;
   if (rec < 0 || rec >= recs_per_frame) {
@@ -198,19 +199,21 @@ __device__ __forceinline__ void project_one(const unsigned char* __restrict__ re
   const float* rp = reinterpret_cast<const float*>(records + (static_cast<long long>(frame) * recs_per_frame + rec) *
                                                                  static_cast<long long>(rec_stride));
   // [0] semanticId, [1..6] extents, [7..22] transform (row-vector convention), [23] occlusionRatio
-  const float ext_min[3] = {__ldg(rp + 1), __ldg(rp + 2), __ldg(rp + 3)};
-  const float ext_max[3] = {__ldg(rp + 4), __ldg(rp + 5), __ldg(rp + 6)};
+  const float ext_min[3] = {__ldcg(rp + 1), __ldcg(rp + 2), __ldcg(rp + 3)};
+  const float ext_max[3] = {__ldcg(rp + 4), __ldcg(rp + 5), __ldcg(rp + 6)};
   float T32[4][3];
   double T[4][3];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      T32[i][j] = __ldg(rp + 7 + i * 4 + j);
+      T32[i][j] = __ldcg(rp + 7 + i * 4 + j);
       T[i][j] = static_cast<double>(T32[i][j]);
     }
 
-  const double* cm = cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE;
+  double cm[17];
+#pragma unroll
+  for (int j = 0; j < 17; ++j) cm[j] = __ldcg(cam + static_cast<long long>(frame) * CSPE_CAM_STRIDE + j);
   const double t[3] = {cm[0], cm[1], cm[2]};
   double Rcw[3][3];
 #pragma unroll

@@ -297,14 +297,15 @@ __device__ __forceinline__ void fixed6_put(char* p, const Fixed6& r, double x, i
 
 template <bool kF64>
 __device__ __forceinline__ double load_value(const void* __restrict__ values, long long i) {
-  if (kF64) return __ldg(static_cast<const double*>(values) + i);
-  return static_cast<double>(__ldg(static_cast<const float*>(values) + i));  // exact widening
+  // read before griddepcontrol.wait in tx_write_kernel: L1 must be bypassed (cspe_common.cuh, PDL rule)
+  if (kF64) return __ldcg(static_cast<const double*>(values) + i);
+  return static_cast<double>(__ldcg(static_cast<const float*>(values) + i));  // exact widening
 }
 
 __device__ __forceinline__ long long live_values(long long max_rows, const long long* n_rows, int cols) {
   long long rows = max_rows;
   if (n_rows) {
-    const long long n = *n_rows;
+    const long long n = __ldcg(n_rows);   // L1 bypass: read before the PDL wait (cspe_common.cuh)
     rows = n < 0 ? 0 : (n < max_rows ? n : max_rows);
   }
   return rows * cols;
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(1024) tx_scan_kernel(const int32_t* __restrict
   __syncthreads();
   for (int t0 = 0; t0 < tiles; t0 += 1024) {
     const int t = t0 + tid;
-    const long long v = t < tiles ? tile_count[t] : 0;
+    const long long v = t < tiles ? __ldcg(tile_count + t) : 0;   // written by the kernel this one waited for: L2 load
     long long inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(1024) tx_scan_kernel(const int32_t* __restrict
   }
   if (tid == 0) {
     ws->total = s_base;
-    *n_bytes = (ws->flags & 1u) ? -1 : s_base;
+    *n_bytes = (__ldcg(&ws->flags) & 1u) ? -1 : s_base;
   }
 }
 
@@ -422,7 +423,7 @@ __global__ void __launch_bounds__(kTxThreads)
   }
 
   pdl_wait();  // tile offsets come from the scan kernel
-  const long long first = tile_offset[blockIdx.x];
+  const long long first = __ldcg(tile_offset + blockIdx.x);   // written while this kernel was resident: L2 load
   // shared-memory text starts at the same offset modulo 16 as its place in `text`, so that the
   // copy below moves whole aligned 16-byte words
   const int skew = static_cast<int>(reinterpret_cast<uintptr_t>(text + first) & 15);

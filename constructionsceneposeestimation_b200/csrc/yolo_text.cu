@@ -74,7 +74,9 @@ __global__ void __launch_bounds__(kYoloThreads)
   }
   __syncthreads();
   pdl_wait();  // K4's records and n_out are complete after this
-  int n = n_out[f];
+  // ... but they were written while this kernel was already resident: explicit L2 loads, never ld.global.nc
+  // (cspe_common.cuh, PDL rule)
+  int n = __ldcg(n_out + f);
   n = n < 0 ? 0 : (n > N ? N : n);
   const cspe_record* rec = records + static_cast<long long>(f) * N;
   char* out = text + static_cast<long long>(f) * frame_stride;
@@ -85,11 +87,11 @@ __global__ void __launch_bounds__(kYoloThreads)
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     unsigned long long q[4] = {0, 0, 0, 0};
     if (r < n) {
-      cls = rec[r].class_id;
+      cls = __ldcg(&rec[r].class_id);
       len = (cls < 0 ? 1 : 0) + dec_digits(static_cast<unsigned long long>(cls < 0 ? -static_cast<long long>(cls) : cls)) + 1;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        v[k] = rec[r].yolo[k];
+        v[k] = __ldcg(&rec[r].yolo[k]);
         if (!fixed6_units(v[k], &q[k])) bad_s = 1;
         len += 1 + fixed6_len(v[k], q[k]);
       }

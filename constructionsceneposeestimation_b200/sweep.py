@@ -35,6 +35,7 @@ from .camera import pack_camera
 from .pipeline import LabelPipeline, graph_edge_kinds
 
 YOLO_BYTES_PER_SLOT = 48   # 38 bytes per line for class ids 0..9 and boxes inside the image
+_POOL_CACHE: Dict[Tuple, Tuple] = {}   # synthetic pool + host tables of the last (config, pool size): --repeat reuses them
 
 
 def build_host_tables(frames, split_people=True):
@@ -172,8 +173,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     lo, hi = sharding.frame_range(rank, world, num_frames)
     spec = synthetic.CONFIGS[config]
-    pool = synthetic.make_batch(spec, pool_frames, first_frame=0)   # the same pool on every rank: frame g = pool[g % B]
-    lut, obj_record, slot_class, records, cam, objects = build_host_tables(pool)
+    key = (config, pool_frames, id(spec))
+    if key not in _POOL_CACHE:   # the same pool on every rank: frame g = pool[g % B]
+        _POOL_CACHE.clear()
+        pool = synthetic.make_batch(spec, pool_frames, first_frame=0)
+        _POOL_CACHE[key] = (pool, build_host_tables(pool))
+    pool, (lut, obj_record, slot_class, records, cam, objects) = _POOL_CACHE[key]
     H, W = pool[0]["instance_segmentation"]["data"].shape
     B, N = pool_frames, obj_record.shape[1]
     want_yolo = emit == "yolo"

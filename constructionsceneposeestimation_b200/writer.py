@@ -28,7 +28,7 @@ from . import _lib, formats, ops
 from .quality import FrameQualityLog, depth_quality_from_stats
 from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
 from .camera import (DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, from_replicator_camera_params,
-                     is_replicator_camera_params, pack_camera)
+                     is_replicator_camera_params, pack_camera, pack_cameras)
 from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot, label_path,
                       record_index_for)
 
@@ -230,8 +230,15 @@ def _unstack(data: Mapping) -> _FrameList:
 
 def tables_cache_key(prim_paths: Sequence[str], id_to_labels: Mapping) -> Tuple:
     """Hashable signature of a scene: the prim paths and (id, labelled path) pairs.  Replicator's idToLabels
-    values are strings or ``{"class": ...}`` dicts and its keys may be strings (gcd.py:1826-1837)."""
-    return tuple(prim_paths), tuple((str(k), label_path(v)) for k, v in id_to_labels.items())
+    values are strings or ``{"class": ...}`` dicts and its keys may be strings (gcd.py:1826-1837).  The common case
+    (every value a string) is keyed on the raw key / value tuples — no per-entry Python work; dict values are not
+    hashable and take the normalising path."""
+    try:
+        key = (tuple(prim_paths), tuple(id_to_labels.keys()), tuple(id_to_labels.values()))
+        hash(key)
+        return key
+    except TypeError:
+        return tuple(prim_paths), tuple((str(k), label_path(v)) for k, v in id_to_labels.items())
 
 
 def _info(annot) -> Mapping:
@@ -595,7 +602,7 @@ class ConstructionLabelWriter:
         rec_arrays: List[Optional[np.ndarray]] = []
         cams = np.zeros((B, CAM_STRIDE), dtype=np.float64)
         frame_ids: List[int] = []
-        poses, params_list = [], []
+        poses, params_list, clips = [], [], []
         for i, fr in enumerate(frames):
             seg = fr.get("instance_segmentation")
             bbox = fr.get("bounding_box_3d")
@@ -617,12 +624,12 @@ class ConstructionLabelWriter:
             pose = fr.get("camera_pose")
             if pose is None:
                 pose = _IDENTITY_POSE
-            near, far = fr.get("_clip") or (self.near, self.far)
-            pack_camera(pose, params, near, far, out=cams[i])
+            clips.append(fr.get("_clip") or (self.near, self.far))
             poses.append(pose)
             params_list.append(params)
             fid = fr.get("frame_id")
             frame_ids.append(int(fid) if fid is not None else self._next_frame_id + i)
+        pack_cameras(poses, params_list, clips, out=cams)
         frame_base = frame_ids[0]
         contiguous_ids = all(frame_ids[i] == frame_base + i for i in range(B))
         self._next_frame_id = max(self._next_frame_id, max(frame_ids) + 1)

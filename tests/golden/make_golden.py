@@ -225,6 +225,75 @@ def make_label_json(ref):
     return len(text)
 
 
+def make_frame_golden(ref):
+    """R2 + the per-object loop + the label file of ONE frame, produced by the reference's own functions.
+
+    The loops at gcd.py:1858-1886 (aggregation, inst_idx order) and gcd.py:1924-1975 (record lookup: primPaths.index(root),
+    crane parts through their mesh paths) live inside generate_data() and cannot be extracted, so they are driven from
+    here exactly as written there, calling the reference's get_object_root / bboxDict_to_transform / save_label_json for
+    every value.  The USD-stage fallback (gcd.py:1977-2023) does not exist offline: objects it would serve are absent
+    from pose_list, as they are when the stage lookup fails."""
+    from constructionsceneposeestimation_b200 import synthetic
+
+    reference_extract.set_crane_part_map({})
+    spec = synthetic.SceneSpec(64, 48, 40, 3, 17, config_id=31, split_people=False)
+    frame = synthetic.make_frame(spec, 0)
+    prim_paths = list(frame["bounding_box_3d"]["info"]["primPaths"])
+    records = frame["bounding_box_3d"]["data"]
+    # a camera far outside the site looking at it: every box is in front of it
+    cam_pose = [0.0, -220.0, 6.0, 0.7071067811865476, 0.0, 0.0, 0.7071067811865476]
+    object_roots = {}
+    for prim_path in prim_paths:                                           # gcd.py:1864-1875
+        object_root, class_name, class_id = ref.get_object_root(prim_path)
+        if object_root is not None:
+            if object_root not in object_roots:
+                object_roots[object_root] = {"class_id": class_id, "class_name": class_name, "mesh_paths": []}
+            object_roots[object_root]["mesh_paths"].append(prim_path)
+    object_list = []
+    inst_idx = 0
+    for object_root, obj_info in object_roots.items():                     # gcd.py:1877-1886
+        object_list.append({"inst_idx": inst_idx, "class_id": obj_info["class_id"], "class_name": obj_info["class_name"],
+                            "prim_path": object_root, "mesh_count": len(obj_info["mesh_paths"]),
+                            "mesh_paths": obj_info["mesh_paths"]})
+        inst_idx += 1
+    pose_list, record_index = [], []
+    for obj in object_list:                                                # gcd.py:1924-1975
+        prim_path = obj["prim_path"]
+        actual_prim_path = prim_path.split("#")[0] if "#" in prim_path else prim_path
+        idx = -1
+        try:
+            idx = prim_paths.index(actual_prim_path)
+        except ValueError:
+            if "#" in prim_path:
+                for mesh_path in obj.get("mesh_paths", []):
+                    try:
+                        idx = prim_paths.index(mesh_path)
+                        break
+                    except ValueError:
+                        continue
+        record_index.append(idx)
+        if idx < 0:
+            continue
+        center, size, euler = ref.bboxDict_to_transform(records[idx])
+        pose_list.append({"inst_idx": obj["inst_idx"], "class_id": obj["class_id"], "class_name": obj["class_name"],
+                          "center": center, "size": size, "rotation": euler, "prim_path": prim_path})
+    cam_params = {"horizontal_aperture": 25.0, "vertical_aperture": 25.0 * (48 / 64), "focal_length": 12.0,
+                  "width": 64, "height": 48}                               # gcd.py:2036-2045
+    label_data = {"frame_id": 5, "camera_pose": cam_pose, "camera_params": cam_params, "objects": pose_list,
+                  "instance_mask_shape": [48, 64], "num_objects": len(pose_list),
+                  "class_mapping": ref.construction_class}                 # gcd.py:2056-2064
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "label_000005.json"
+        ref.save_label_json(label_data, str(path))
+        text = path.read_text(encoding="utf-8")
+    np.savez(HERE / "frame_records.npz", records=records)
+    (HERE / "frame_label.json").write_text(json.dumps({
+        "prim_paths": prim_paths, "id_to_labels": frame["instance_segmentation"]["info"]["idToLabels"],
+        "camera_pose": cam_pose, "camera_params": cam_params, "frame_id": 5,
+        "object_list": object_list, "record_index": record_index, "label_text": text}, ensure_ascii=False, indent=1))
+    return len(object_list), len(pose_list)
+
+
 def main():
     ref = reference_extract.load()
     import contextlib
@@ -237,9 +306,11 @@ def main():
         stats = make_depth_stats(ref)
         n_text = make_label_json(ref)
         n_quality = make_quality_log(ref)
+        n_objects, n_posed = make_frame_golden(ref)
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "paths": n_paths, "records": n_recs,
             "mirrored_transform_raises": raised, "pointcloud_shape": list(pc_shape), "depth_cases": stats,
-            "label_text_bytes": n_text, "quality_frames": n_quality, "source": str(reference_extract.REFERENCE_SCRIPT)}
+            "label_text_bytes": n_text, "quality_frames": n_quality, "frame_objects": n_objects,
+            "frame_objects_with_record": n_posed, "source": str(reference_extract.REFERENCE_SCRIPT)}
     (HERE / "META.json").write_text(json.dumps(meta, indent=1))
     print(json.dumps(meta, indent=1))
 

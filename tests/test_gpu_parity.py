@@ -579,6 +579,39 @@ def test_writer_replicator_native_payloads(T, ops, tmp_path):
         assert lab["camera_params"]["width"] == 640 and lab["camera_params"]["focal_length"] == 12.0
 
 
+def test_writer_reference_frame_golden(T, ops, tmp_path):
+    """Full-frame [REF] golden: with min_pixels=0 and record_fallback="reference" the reference keys of every objects[]
+    entry — and which objects are listed at all — equal what the reference's own get_object_root + bboxDict_to_transform
+    + save_label_json wrote for the same annotator dict (gcd.py:1858-1947, 2056-2064; tests/golden/frame_label.json)."""
+    import json
+    from pathlib import Path
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    gold = Path(__file__).parent / "golden"
+    g = json.loads((gold / "frame_label.json").read_text(encoding="utf-8"))
+    recs = np.load(gold / "frame_records.npz")["records"]
+    want = json.loads(g["label_text"])
+    frame = {"frame_id": g["frame_id"],
+             "instance_segmentation": {"data": np.zeros((48, 64), dtype=np.uint32), "info": {"idToLabels": g["id_to_labels"]}},
+             "bounding_box_3d": {"data": recs, "info": {"primPaths": g["prim_paths"]}},
+             "camera_pose": g["camera_pose"], "camera_params": g["camera_params"]}
+    w = ConstructionLabelWriter(str(tmp_path), formats=("json",), min_pixels=0, record_fallback="reference")
+    w.write(frame)
+    w.on_final_frame()
+    got = json.loads((tmp_path / "labels" / "label_000005.json").read_text(encoding="utf-8"))
+    for key in ("frame_id", "camera_pose", "camera_params", "instance_mask_shape", "num_objects", "class_mapping"):
+        assert got[key] == want[key], key
+    assert list(got)[:7] == list(want)
+    assert len(got["objects"]) == len(want["objects"]) == 25
+    for a, b in zip(got["objects"], want["objects"]):
+        assert list(a)[:7] == list(b)
+        for key in ("inst_idx", "class_id", "class_name", "prim_path"):
+            assert a[key] == b[key], key
+        assert np.allclose(a["center"], b["center"], rtol=1e-6, atol=1e-9) and np.allclose(a["size"], b["size"], rtol=1e-6, atol=1e-9)
+        de = np.abs(np.asarray(a["rotation"]) - np.asarray(b["rotation"]))
+        assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(b["rotation"]))
+        assert a["pixel_count"] == 0 and not (a["flags"] & 16)        # nothing approximated under the reference's rule
+
+
 def test_writer_missing_mask_gives_empty_labels(T, ops, tmp_path):
     """An absent instance_segmentation annotator is not an error (gcd.py:1682, 1788, 1919): that frame gets an empty
     label file, the other frames of the batch are unaffected."""
@@ -657,6 +690,28 @@ def test_writer_input_lifetime_contract(T, ops, tmp_path):
     for f in range(2):
         helpers.assert_records_equal(last.records(f), o["recs"][f, : o["n_out"][f]])
     assert sum(len(v) for v in w2._free_pinned.values()) <= 4 * len(w2._free_pinned)
+
+
+def test_writer_config4_rig_frames(T, ops, tmp_path):
+    """Config 4 through the writer: two 3840x2160 camera frames of the rig, ~500 objects each — the > 256-slot path of
+    K4 (emit_kernel<1024>, several decide passes per frame) and the global scan table (500 x 20 B no longer fits the CTA's
+    shared memory next to the LUT) checked end to end against the oracle, plus the YOLO files of both frames."""
+    from constructionsceneposeestimation_b200 import formats, synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.CONFIGS["c4"], 2)
+    for fr in frames:
+        fr.pop("skeleton_data", None)
+        fr.pop("distance_to_image_plane", None)
+    o = helpers.oracle_pipeline(frames)
+    assert o["obj_record"].shape[1] > 256
+    w = ConstructionLabelWriter(str(tmp_path), formats=("yolo",), split_people=True)
+    labels = w.write_batch(frames)
+    w.on_final_frame()
+    assert np.array_equal(labels.n_out, o["n_out"]) and int(o["n_out"].min()) > 100
+    for f in range(2):
+        helpers.assert_records_equal(labels.records(f), o["recs"][f, : o["n_out"][f]])
+        assert (tmp_path / "labels" / f"label_{f:06d}.txt").read_text().splitlines() == formats.yolo_lines(labels.records(f))
+    assert np.array_equal(w.gather_class_histogram()["total"], o["hist"])
 
 
 def test_writer_accepts_device_resident_annotators(T, ops):
@@ -1118,6 +1173,67 @@ def test_pipeline_overlap_stress(T, ops):
     # the table is back to "nothing seen" after the last K4
     scan = pipe.scan.cpu().numpy()
     assert np.array_equal(scan, np.tile(np.array([0, 1280, 720, -1, -1], dtype=np.int32), (6, N, 1)))
+
+
+@pytest.mark.parametrize("mode", ["eager", "graph", "steps"])
+def test_pipeline_inputs_rewritten_in_place(T, ops, mode):
+    """The SAME device buffers hold scene A, then scene B, then A ... (H2D copies between runs, as a capture loop
+    refills its annotator buffers): every run must label what the buffers hold NOW.  Kernels that start early as
+    programmatic dependents read their inputs before griddepcontrol.wait; those loads bypass L1 (cspe_common.cuh, PDL
+    rule) — an L1-cached load there returned the previous scene's values once in ~100 calls."""
+    from constructionsceneposeestimation_b200 import synthetic, _lib
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
+    import dataclasses
+    spec = dataclasses.replace(synthetic.CONFIGS["c1"], width=512, height=270, num_people=3)
+    sets = []
+    for first in (0, 16):
+        frames = synthetic.make_batch(spec, 16, first)
+        sets.append(helpers.oracle_pipeline(frames))
+    N = max(o["obj_record"].shape[1] for o in sets)
+    R = max(o["records"].shape[1] for o in sets)
+    L = (max(o["lut"].shape[1] for o in sets) + 3) & ~3
+    P, J = sets[0]["joints"].shape[1:3]
+    pipe = LabelPipeline(16, 270, 512, N, R, L, T.device("cuda"), use_graph=(mode == "graph"), num_people=P, num_joints=J)
+    assert pipe.overlapped
+
+    def upload(o):
+        n, r, l = o["obj_record"].shape[1], o["records"].shape[1], o["lut"].shape[1]
+        lut = np.full((16, L), -1, dtype=np.int32)
+        lut[:, :l] = o["lut"]
+        obj = np.full((16, N), -1, dtype=np.int32)
+        obj[:, :n] = o["obj_record"]
+        cls = np.full((16, N), -1, dtype=np.int32)
+        cls[:, :n] = o["slot_class"]
+        rec = np.zeros((16, R, _lib.BBOX3D_RECORD_BYTES), dtype=np.uint8)
+        rec[:, :r] = o["records"].view(np.uint8).reshape(16, r, -1)
+        pipe.mask.copy_(T.from_numpy(o["mask"].view(np.int32)))
+        pipe.lut.copy_(T.from_numpy(lut))
+        pipe.obj_record.copy_(T.from_numpy(obj))
+        pipe.slot_class.copy_(T.from_numpy(cls))
+        pipe.records_in.copy_(T.from_numpy(rec))
+        pipe.cam.copy_(T.from_numpy(o["cam"]))
+        pipe.joints.copy_(T.from_numpy(o["joints"]))
+        pipe.depth.copy_(T.from_numpy(o["depth"]))
+
+    for it in range(40):
+        o = sets[it & 1]
+        upload(o)
+        pipe.class_hist.zero_()
+        if mode == "steps":
+            pipe.run_steps(2)
+        else:
+            pipe.run()
+            pipe.run()
+        T.cuda.synchronize()
+        n_out = pipe.n_out.cpu().numpy()
+        assert np.array_equal(n_out, o["n_out"]), it
+        rec = pipe.records.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(16, N)
+        for f in range(16):
+            helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
+        kp, kz, vis = pipe.keypoints
+        assert np.array_equal(vis.cpu().numpy(), o["vis"]), it
+        assert np.array_equal(kp.cpu().numpy(), o["kp"]), it
+        assert np.array_equal(pipe.class_hist.cpu().numpy(), 2 * o["hist"]), it
 
 
 @pytest.mark.parametrize("use_graph", [False, True])

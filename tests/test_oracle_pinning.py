@@ -97,6 +97,40 @@ def test_aggregation_matches_reference_loop():
             assert bool(b & classes.RECORD_APPROX_BIT) == (len(o.mesh_paths) > 1)
 
 
+def test_frame_golden_aggregation_and_record_lookup():
+    """R2 frozen (runs without /root/reference): grouping, inst_idx order, mesh lists and the record lookup of
+    gcd.py:1858-1886 / 1924-1975, as the reference's own functions produced them for one frame
+    (tests/golden/make_golden.py::make_frame_golden)."""
+    from constructionsceneposeestimation_b200 import classes
+    g = json.loads((GOLD / "frame_label.json").read_text(encoding="utf-8"))
+    paths = g["prim_paths"]
+    objs = classes.aggregate_objects(paths, classes.ObjectRootResolver())
+    assert len(objs) == len(g["object_list"])
+    for o, want in zip(objs, g["object_list"]):
+        assert (o.inst_idx, o.class_id, o.class_name, o.prim_path, o.mesh_count, o.mesh_paths) == \
+            (want["inst_idx"], want["class_id"], want["class_name"], want["prim_path"], want["mesh_count"], want["mesh_paths"])
+    assert classes.record_index_for(objs, paths, "reference") == g["record_index"]
+    ext = classes.record_index_for(objs, paths, "first_mesh")
+    for o, a, b in zip(objs, g["record_index"], ext):
+        if a >= 0:
+            assert b == a                                   # the reference's own rule wins wherever it finds a record
+        else:
+            assert paths[b & ~classes.RECORD_APPROX_BIT] == o.mesh_paths[0]
+            assert bool(b & classes.RECORD_APPROX_BIT) == (o.mesh_count > 1)
+    # the objects[] of the label file are the oracle's bbox_to_transform of those records
+    recs = np.load(GOLD / "frame_records.npz")["records"]
+    label = json.loads(g["label_text"])
+    posed = [(o, i) for o, i in zip(objs, g["record_index"]) if i >= 0]
+    assert label["num_objects"] == len(posed) == len(label["objects"])
+    for (o, i), entry in zip(posed, label["objects"]):
+        c, s, e = O.bbox_to_transform(recs[i])
+        assert (entry["inst_idx"], entry["class_id"], entry["class_name"], entry["prim_path"]) == \
+            (o.inst_idx, o.class_id, o.class_name, o.prim_path)
+        assert np.allclose(c, entry["center"], rtol=1e-12, atol=1e-12) and np.allclose(s, entry["size"], rtol=1e-12, atol=1e-12)
+        de = np.abs(np.asarray(e) - np.asarray(entry["rotation"]))
+        assert np.all(np.minimum(de, 360 - de) <= helpers.EULER_REF_ATOL + helpers.REL_TOL * np.abs(entry["rotation"]))
+
+
 # ------------------------------------------------------------------ R3: bbox record -> centre / size / euler
 def test_bbox_to_transform_golden():
     g = np.load(GOLD / "bbox_to_transform.npz")
