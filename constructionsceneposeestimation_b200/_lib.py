@@ -117,6 +117,7 @@ PROTOTYPES = {
     "cspe_emit_reset_scan": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "cspe_emit_reset_scan_indirect": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cspe_format_yolo": (_I, [_P, _P, _I, _I, _P, _I64, _P, _P]),
+    "cspe_format_coco": (_I, [_P, _P, _I, _I, _P, _P, _I64, _P, _P]),
     "cspe_memcpy_async": (_I, [_P, _P, C.c_size_t, _P]),
     "cspe_graph_edge_kinds": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),
@@ -129,6 +130,7 @@ PROTOTYPES = {
     "cspe_text_workspace_bytes": (C.c_size_t, [_I64, _I]),
     "cspe_format_fixed6": (_I, [_P, _I, _I64, _P, _I, C.c_char_p, _P, _I64, _P, _I64, _P, _P, _P]),
     "cspe_write_files_host": (_I64, [C.c_char_p, C.c_char_p, _I, C.c_char_p, _I64, _I, _P, _I64, _P]),
+    "cspe_concat_rows_host": (_I64, [_P, _I64, _P, _I, _P, _I64]),
     "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
     "cspe_format_coco_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P, _P, _P, _I, _I, _P, _I64]),
     "cspe_format_label_json_host": (_I64, [_P, _I, _I64, _P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _P, _P, _P, _I,

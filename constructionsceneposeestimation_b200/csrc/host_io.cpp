@@ -69,3 +69,26 @@ extern "C" int64_t cspe_write_files_host(const char* dir, const char* prefix, in
   }
   return total;
 }
+
+extern "C" int64_t cspe_concat_rows_host(const char* data_host, int64_t stride, const int32_t* sizes_host, int count,
+                                         char* out_host, int64_t capacity) {
+  if (count < 0 || stride < 0 || capacity < 0 || (count > 0 && (!data_host || !sizes_host)) || (capacity > 0 && !out_host)) {
+    cspe::set_error("cspe_concat_rows_host: invalid argument");
+    return CSPE_ERR_INVALID_ARGUMENT;
+  }
+  int64_t pos = 0;
+  for (int j = 0; j < count; ++j) {
+    const int32_t n = sizes_host[j];
+    if (n < 0 || n > stride) {
+      cspe::set_error("cspe_concat_rows_host: size %d of row %d outside [0, %lld]", n, j, static_cast<long long>(stride));
+      return CSPE_ERR_INVALID_ARGUMENT;
+    }
+    if (pos + n > capacity) {
+      cspe::set_error("cspe_concat_rows_host: output buffer of %lld bytes is too small", static_cast<long long>(capacity));
+      return CSPE_ERR_INVALID_ARGUMENT;
+    }
+    memcpy(out_host + pos, data_host + static_cast<int64_t>(j) * stride, static_cast<size_t>(n));
+    pos += n;
+  }
+  return pos;
+}

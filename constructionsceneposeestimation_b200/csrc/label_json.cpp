@@ -17,6 +17,7 @@
 #include <cstring>
 
 #include "cspe.h"
+#include "repr6.h"
 
 namespace cspe {
 void set_error(const char* fmt, ...);
@@ -51,6 +52,12 @@ struct Out {
     char b[24];
     auto r = std::to_chars(b, b + sizeof(b), v);
     raw(b, static_cast<size_t>(r.ptr - b));
+  }
+  // repr(round(float(v), 6)) of a float32 — the COCO ratio fields (repr6.h)
+  void repr6(float v) {
+    if (!(std::fabs(v) < 1048576.0f)) return repr(static_cast<double>(v));  // NaN / inf / >= 2^20: rounding changes nothing
+    const unsigned long long q = static_cast<unsigned long long>(std::nearbyint(std::fabs(static_cast<double>(v)) * 1e6));
+    p += cspe::repr_units6(std::signbit(v), q, p);
   }
   // Python float.__repr__
   void repr(double v) {
@@ -355,9 +362,9 @@ extern "C" int64_t cspe_format_coco_host(const cspe_record* records_host, const 
       o.lit("], \"area\": ");
       o.integer(r->count);
       o.lit(", \"iscrowd\": 0, \"occlusion\": ");
-      o.repr(static_cast<double>(r->occlusion));
+      o.repr6(r->occlusion);
       o.lit(", \"truncation\": ");
-      o.repr(static_cast<double>(r->truncation));
+      o.repr6(r->truncation);
       int person = -1;
       if (person_of_slot && r->inst_idx >= 0 && r->inst_idx < N)
         person = person_of_slot[static_cast<int64_t>(f) * N + r->inst_idx];

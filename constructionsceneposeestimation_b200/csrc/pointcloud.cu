@@ -20,6 +20,7 @@
 //      points directly costs ~6x the sector traffic); colours are scaled by 255 when the frame's maximum
 //      found by pass 1 is <= 1 (the reference's [0,1]-image rule, gcd.py:693, per frame as it is per call there).
 #include <math.h>
+#include <stdlib.h>
 
 #include "cspe_common.cuh"
 
@@ -29,7 +30,8 @@ namespace {
 constexpr int kPcThreads = 256;
 constexpr int kPcPerThread = 4;
 constexpr int kPcTile = kPcThreads * kPcPerThread;  // 1024 pixels
-constexpr int kPcGroup = 4;                         // consecutive tiles of one frame per CTA
+constexpr int kPcGroupBatch = 4;   // consecutive tiles of one frame per CTA when the batch fills the machine ...
+constexpr int kPcGroupSmall = 1;   // ... and one tile per CTA (more, shorter CTAs) when it does not: a single frame
 constexpr int kPcStageBytes = kPcTile * (3 * 8 + 4);  // a tile's points as x[], y[], z[] (f64) + packed colour: 28 KB
 
 // Caller-provided scratch, one batch: per-frame headers, then per-(frame, tile) counts and offsets.
@@ -140,6 +142,7 @@ __device__ __forceinline__ long long cta_exclusive_scan(int n, long long* s_scan
 // Pass 1.  Grid = B x groups; CTA (f, g) counts the valid pixels of tiles g*kPcGroup .. of frame f and folds the
 // frame's colour maximum.  The last CTA of a frame (atomic ticket) scans the frame's tile counts; the last of those
 // scans the frame totals into `offsets`.
+template <int kPcGroup>
 __global__ void __launch_bounds__(kPcThreads)
     pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw, int vec,
                     int rgb_vec, int B, int tiles, int groups, void* ws_raw, long long* offsets) {
@@ -237,25 +240,32 @@ __device__ __forceinline__ void bulk_wait_read() {   // at most kPending groups 
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 constexpr int kPcBulkBufBytes = kPcTile * 48;          // a tile's points as the (N, 6) float64 rows they become: 48 KB
-constexpr int kPcBulkSmemBytes = 2 * kPcBulkBufBytes;  // double-buffered: the bulk store of tile i drains under tile i+1
+// kBufs = 2: the bulk store of tile i drains under tile i+1 of the same CTA (2 CTAs per SM);
+// kBufs = 1: one buffer, more CTAs per SM overlap each other instead
 
 // Pass 2.  Same grid; every tile's points are built in shared memory exactly as they lie in `out` — rows of six
 // doubles, written as three conflict-free 16-byte stores per point — and leave with ONE bulk copy
 // (cp.async.bulk shared -> global, SASS UBLKCP) per tile: no thread spends instructions on the copy, and the store of
 // tile i drains while the CTA projects tile i+1 into the other buffer.
-__global__ void __launch_bounds__(kPcThreads)
+template <int kPcGroup, int kBufs>
+__global__ void __launch_bounds__(kPcThreads, kBufs == 1 ? 4 : 2)
     pc_write_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
                     int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, int groups, void* ws_raw,
                     const long long* __restrict__ offsets, double* __restrict__ out, long long capacity) {
   pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char pc_smem[];
   __shared__ int s_warp[kPcGroup][kPcThreads / 32];
+  __shared__ long long s_first[kPcGroup];
   const PcLayout L = pc_layout(ws_raw, B, tiles);
   const int f = blockIdx.x / groups, g = blockIdx.x - f * groups;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float* dep = depth + static_cast<long long>(f) * hw;
   const uint8_t* col = rgb ? rgb + static_cast<long long>(f) * hw * C : nullptr;
   const double* cam = cam_all + static_cast<long long>(f) * CSPE_CAM_STRIDE;
+  // the camera block is read before the PDL wait: L1 bypass; issued first so it travels with the pixel loads
+  double cm[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cm[j] = __ldcg(cam + j);
   // depth / rgb are inputs of the chain: everything up to the first store runs before waiting for pass 1
   float d[kPcGroup][kPcPerThread];
   uint32_t px[kPcGroup][kPcPerThread];
@@ -287,10 +297,6 @@ __global__ void __launch_bounds__(kPcThreads)
   }
   __syncthreads();
 
-  // the camera block is read before the PDL wait as well: L1 bypass
-  double cm[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) cm[j] = __ldcg(cam + j);
   const double t0 = cm[0], t1 = cm[1], t2 = cm[2];
   const double fx = cm[12], fy = cm[13], cx = cm[14], cy = cm[15];
   // pass 1's results (tile offsets, frame offsets, the frame's colour maximum) are needed from the first point on:
@@ -300,13 +306,16 @@ __global__ void __launch_bounds__(kPcThreads)
   // (written while this kernel was resident: explicit L2 loads, cspe_common.cuh PDL rule)
   const unsigned cmul = (col != nullptr && __ldcg(&L.frame[f].rgb_max) <= 1u) ? 255u : 1u;
   const long long frame_first = __ldcg(offsets + f);
+  // the group's tile offsets in one round trip (thread 0 needs them one by one at every bulk store)
+  if (threadIdx.x < kPcGroup && g * kPcGroup + threadIdx.x < tiles)
+    s_first[threadIdx.x] = frame_first + __ldcg(L.tile_offset + static_cast<long long>(f) * tiles + g * kPcGroup + threadIdx.x);
 #pragma unroll   // static indices keep d / px / cnt / inc in registers
   for (int i = 0; i < kPcGroup; ++i) {
     const int tile = g * kPcGroup + i;
     if (tile >= tiles) break;
-    double2* buf = reinterpret_cast<double2*>(pc_smem + (i & 1) * kPcBulkBufBytes);
-    if (i >= 2) {  // the bulk store issued two tiles ago has to be done READING this buffer
-      if (threadIdx.x == 0) bulk_wait_read<1>();
+    double2* buf = reinterpret_cast<double2*>(pc_smem + (i % kBufs) * kPcBulkBufBytes);
+    if (i >= kBufs) {  // the bulk store that used this buffer last has to be done READING it
+      if (threadIdx.x == 0) bulk_wait_read<kBufs - 1>();
       __syncthreads();
     }
     int before = inc[i] - cnt[i], tile_total = 0;
@@ -350,7 +359,7 @@ __global__ void __launch_bounds__(kPcThreads)
     fence_async_smem();  // the rows were written through the generic proxy, the bulk copy reads through the async proxy
     __syncthreads();
     if (threadIdx.x == 0) {
-      const long long first = frame_first + __ldcg(L.tile_offset + static_cast<long long>(f) * tiles + tile);
+      const long long first = s_first[i];   // written before the __syncthreads above
       long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
       if (keep > tile_total) keep = tile_total;
       if (keep > 0) bulk_store_s2g(out + first * 6, buf, static_cast<uint32_t>(keep) * 48u);
@@ -360,8 +369,126 @@ __global__ void __launch_bounds__(kPcThreads)
   if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the copies that read it
 }
 
+constexpr int kPcPersistentCtasPerSm = 3;   // 85 registers: the camera block alone is 32 (4 CTAs at 64 registers spill)
+
+// Pass 2, persistent form (the default for batches): 3 CTAs per SM, each walking a contiguous range of (frame, tile)
+// pairs.  The loads of tile t+1 are issued BEFORE tile t is projected, so their round trip hides under the
+// math (the per-CTA form above spends 41 % of its warp time waiting for its one burst of loads:
+// profiles/r02_pc_write_ncu_summary.txt), and the bulk store of tile t drains while tile t+1 is counted.
+__global__ void __launch_bounds__(kPcThreads, kPcPersistentCtasPerSm)
+    pc_write_persistent_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw,
+                               int vec, int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, void* ws_raw,
+                               const long long* __restrict__ offsets, double* __restrict__ out, long long capacity) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char pc_smem[];
+  __shared__ int s_warp[2][kPcThreads / 32];   // per-warp counts, double-buffered by tile parity
+  const PcLayout L = pc_layout(ws_raw, B, tiles);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const long long total = static_cast<long long>(B) * tiles;
+  const long long t_begin = total * blockIdx.x / gridDim.x, t_end = total * (blockIdx.x + 1) / gridDim.x;
+  if (t_begin >= t_end) return;
+  double2* buf = reinterpret_cast<double2*>(pc_smem);
+
+  auto load_tile = [&](long long t, float* d, uint32_t* px) {
+    const int f = static_cast<int>(t / tiles), tile = static_cast<int>(t - static_cast<long long>(f) * tiles);
+    const long long base = static_cast<long long>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    load4(depth + static_cast<long long>(f) * hw, base, hw, vec, d);
+    px[0] = px[1] = px[2] = px[3] = 0;
+    if (rgb != nullptr) load_rgb4(rgb + static_cast<long long>(f) * hw * C, C, base, hw, rgb_vec, px);
+  };
+
+  float d[kPcPerThread], dn[kPcPerThread];
+  uint32_t px[kPcPerThread], pxn[kPcPerThread];
+  load_tile(t_begin, dn, pxn);   // inputs of the chain: in flight before the PDL wait
+
+  int cur_f = -1;
+  double cm[16];
+  double t0 = 0, t1 = 0, t2 = 0, fx = 1, fy = 1, cx = 0, cy = 0;
+  unsigned cmul = 1u;
+  long long frame_first = 0;
+  pdl_wait();   // pass 1's tile offsets, frame offsets and colour maxima (read below through L2)
+  int it = 0;
+  for (long long t = t_begin; t < t_end; ++t, ++it) {
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) {
+      d[k] = dn[k];
+      px[k] = pxn[k];
+    }
+    if (t + 1 < t_end) load_tile(t + 1, dn, pxn);   // next tile's round trip hides under this tile's math
+    const int f = static_cast<int>(t / tiles), tile = static_cast<int>(t - static_cast<long long>(f) * tiles);
+    if (f != cur_f) {   // a CTA's range crosses at most a few frame boundaries
+      cur_f = f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) cm[j] = __ldcg(cam_all + static_cast<long long>(f) * CSPE_CAM_STRIDE + j);
+      t0 = cm[0], t1 = cm[1], t2 = cm[2];
+      fx = cm[12], fy = cm[13], cx = cm[14], cy = cm[15];
+      cmul = (rgb != nullptr && __ldcg(&L.frame[f].rgb_max) <= 1u) ? 255u : 1u;   // gcd.py:693, per frame
+      frame_first = __ldcg(offsets + f);
+    }
+    long long first = 0;
+    if (threadIdx.x == 0) first = frame_first + __ldcg(L.tile_offset + static_cast<long long>(f) * tiles + tile);
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) cnt += pc_valid(d[k]);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += n;
+    }
+    if (lane == 31) s_warp[it & 1][wid] = inc;
+    if (threadIdx.x == 0 && it > 0) bulk_wait_read<0>();   // the previous tile's bulk store is done reading `buf`
+    __syncthreads();
+    int before = inc - cnt, tile_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPcThreads / 32; ++w) {
+      const int sw = s_warp[it & 1][w];
+      if (w < wid) before += sw;
+      tile_total += sw;
+    }
+    const unsigned p0 = static_cast<unsigned>(tile) * kPcTile + threadIdx.x * kPcPerThread;
+    int v = static_cast<int>(p0 / static_cast<unsigned>(W));
+    int u = static_cast<int>(p0 - static_cast<unsigned>(v) * static_cast<unsigned>(W));
+    int r = before;
+#pragma unroll
+    for (int k = 0; k < kPcPerThread; ++k) {
+      if (pc_valid(d[k])) {
+        const double zc = static_cast<double>(d[k]);
+        const double xc = ((static_cast<double>(u) - cx) * zc) / fx;
+        const double yc = ((static_cast<double>(v) - cy) * zc) / fy;
+        const uint32_t c = rgb ? px[k] : 0x00ffffffu;  // no image: white, gcd.py:698-700
+        double2 a, b2, c2;
+        a.x = ((cm[3] * xc + cm[4] * yc) + cm[5] * zc) + t0;
+        a.y = ((cm[6] * xc + cm[7] * yc) + cm[8] * zc) + t1;
+        b2.x = ((cm[9] * xc + cm[10] * yc) + cm[11] * zc) + t2;
+        b2.y = static_cast<double>((c & 255u) * cmul);
+        c2.x = static_cast<double>(((c >> 8) & 255u) * cmul);
+        c2.y = static_cast<double>(((c >> 16) & 255u) * cmul);
+        buf[r * 3 + 0] = a;
+        buf[r * 3 + 1] = b2;
+        buf[r * 3 + 2] = c2;
+        ++r;
+      }
+      if (++u == W) {
+        u = 0;
+        ++v;
+      }
+    }
+    fence_async_smem();  // rows written through the generic proxy, read by the bulk copy through the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long keep = capacity - first;  // points beyond `capacity` are dropped but were counted
+      if (keep > tile_total) keep = tile_total;
+      if (keep > 0) bulk_store_s2g(out + first * 6, buf, static_cast<uint32_t>(keep) * 48u);
+      bulk_commit();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the copies that read it
+}
+
 // Pass 2, fallback for an `out` that is not 16-byte aligned: the tile's points are staged as x[] y[] z[] + packed colour
 // and copied out by the threads themselves.
+template <int kPcGroup>
 __global__ void __launch_bounds__(kPcThreads)
     pc_write_loop_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, int W, long long hw, int vec,
                     int rgb_vec, const double* __restrict__ cam_all, int B, int tiles, int groups, void* ws_raw,
@@ -539,31 +666,56 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   CSPE_REQUIRE(capacity == 0 || out != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: out is null");
   CSPE_REQUIRE(hw < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: frame too large");
   const long long tiles = pc_tiles(hw);
-  const long long groups = (tiles + kPcGroup - 1) / kPcGroup;
+  const bool small = tiles * B < 8192;   // not enough 4-tile CTAs to fill 148 SMs several times over
+  const int group0 = small ? kPcGroupSmall : ((getenv("CSPE_PC_VARIANT") && atoi(getenv("CSPE_PC_VARIANT")) == 2) ? 2 : kPcGroupBatch);
+  const long long groups = (tiles + group0 - 1) / group0;
   CSPE_REQUIRE(groups * B < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_depth_to_pointcloud: batch too large");
   const PcLayout L = pc_layout(workspace, B, tiles);
   // frames of a batch start at multiples of hw floats: vector loads need every frame base 16-byte aligned
   const int vec = (reinterpret_cast<uintptr_t>(depth) & 15) == 0 && (B == 1 || hw % 4 == 0);
-  static const cudaError_t smem_attr =
-      cudaFuncSetAttribute(pc_write_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcStageBytes);
-  static const cudaError_t smem_attr2 =
-      cudaFuncSetAttribute(pc_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPcBulkSmemBytes);
-  (void)smem_attr;
-  (void)smem_attr2;
   const int rgb_vec = rgb != nullptr && rgb_channels == 4 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0 &&
                       (B == 1 || hw % 4 == 0);
+  // bulk (TMA) stores need a 16-byte aligned destination; every tile starts at a multiple of 48 bytes from `out`
+  const bool bulk = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  auto count_k = small ? pc_count_kernel<kPcGroupSmall> : (group0 == 2 ? pc_count_kernel<2> : pc_count_kernel<kPcGroupBatch>);
+  // CSPE_PC_VARIANT (A/B runs): 0 = 4 tiles per CTA, 2 shared-memory buffers (2 CTAs per SM: 1.50 ms for 64 x 1080p RGBA),
+  // 1 (default) = 4 tiles, 1 buffer, 64 registers (4 CTAs per SM: 1.33 ms), 2 = 2 tiles, 1 buffer (2.27 ms: the fixed
+  // cost of a CTA — launch, load round trip, tickets — is what a CTA has to amortise)
+  static const int variant = []() {
+    const char* e = getenv("CSPE_PC_VARIANT");
+    return e ? atoi(e) : 3;   // 3 = the persistent, software-pipelined form
+  }();
+  const int group = small ? kPcGroupSmall : (variant == 2 ? 2 : kPcGroupBatch);
+  const int bufs = (small || variant >= 1) ? 1 : 2;
+  void (*write_k)(const float*, const uint8_t*, int, int, long long, int, int, const double*, int, int, int, void*,
+                  const long long*, double*, long long);
+  if (!bulk) write_k = small ? pc_write_loop_kernel<kPcGroupSmall> : (variant == 2 ? pc_write_loop_kernel<2> : pc_write_loop_kernel<kPcGroupBatch>);
+  else if (small) write_k = pc_write_kernel<kPcGroupSmall, 1>;
+  else if (variant == 2) write_k = pc_write_kernel<2, 1>;
+  else if (variant == 1) write_k = pc_write_kernel<kPcGroupBatch, 1>;
+  else write_k = pc_write_kernel<kPcGroupBatch, 2>;
+  const size_t smem = static_cast<size_t>(bulk ? bufs * kPcBulkBufBytes : kPcStageBytes);
+  CSPE_CUDA_OK(cudaFuncSetAttribute(write_k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   CSPE_CUDA_OK(cudaMemsetAsync(workspace, 0, L.header_bytes, st));
   const unsigned grid = static_cast<unsigned>(groups * B);
   // plain launch first (serialised behind whatever produced depth / rgb), then the PDL-chained writer
-  pc_count_kernel<<<grid, kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, B, static_cast<int>(tiles),
-                                              static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets));
+  count_k<<<grid, kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, B, static_cast<int>(tiles),
+                                      static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets));
   CSPE_LAUNCH_OK("pc_count_kernel");
-  if (capacity > 0) {
-    // bulk (TMA) stores need a 16-byte aligned destination; every tile starts at a multiple of 48 bytes from `out`
-    const bool bulk = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
-    CSPE_CUDA_OK(launch_pdl(bulk ? pc_write_kernel : pc_write_loop_kernel, dim3(grid), dim3(kPcThreads),
-                            static_cast<size_t>(bulk ? kPcBulkSmemBytes : kPcStageBytes), st, depth, rgb, rgb_channels, W, hw,
-                            vec, rgb_vec, cam, B, static_cast<int>(tiles), static_cast<int>(groups), workspace,
+  if (capacity > 0 && bulk && !small && variant == 3) {
+    static const cudaError_t attr3 = cudaFuncSetAttribute(pc_write_persistent_kernel,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kPcBulkBufBytes);
+    (void)attr3;
+    const long long all_tiles = tiles * B;
+    const long long ctas = static_cast<long long>(sm_count()) * kPcPersistentCtasPerSm;
+    CSPE_CUDA_OK(launch_pdl(pc_write_persistent_kernel, dim3(static_cast<unsigned>(all_tiles < ctas ? all_tiles : ctas)),
+                            dim3(kPcThreads), static_cast<size_t>(kPcBulkBufBytes), st, depth, rgb, rgb_channels, W, hw, vec,
+                            rgb_vec, cam, B, static_cast<int>(tiles), workspace,
+                            static_cast<const long long*>(reinterpret_cast<long long*>(offsets)), out,
+                            static_cast<long long>(capacity)));
+  } else if (capacity > 0) {
+    CSPE_CUDA_OK(launch_pdl(write_k, dim3(grid), dim3(kPcThreads), smem, st, depth, rgb, rgb_channels, W, hw, vec, rgb_vec,
+                            cam, B, static_cast<int>(tiles), static_cast<int>(groups), workspace,
                             static_cast<const long long*>(reinterpret_cast<long long*>(offsets)), out,
                             static_cast<long long>(capacity)));
   }

@@ -15,6 +15,7 @@
 #include <math.h>
 
 #include "cspe_common.cuh"
+#include "repr6.h"
 
 namespace cspe {
 namespace {
@@ -141,6 +142,165 @@ __global__ void __launch_bounds__(kYoloThreads)
   if (tid == 0) n_bytes[f] = bad_s ? -1 : static_cast<int32_t>(base_s);
 }
 
+// ---- COCO annotations on the device -----------------------------------------------------------------------------
+// One CTA per frame prints, for every kept record,
+//   {"id": i, "image_id": frame, "category_id": c, "bbox": [x, y, w, h], "area": a, "iscrowd": 0,
+//    "occlusion": o, "truncation": t}
+// each preceded by ", " unless it is annotation 1 — so the frames' texts, concatenated in order, are byte for byte
+// what cspe_format_coco_host / json.dump(formats.coco_annotations(...)) write for records without keypoints.  Annotation ids count up across frames and batches: ann_state[0] holds the number of
+// annotations printed so far (the caller zeroes it at sweep start), every CTA adds the counts of the frames before it
+// in the batch, and the LAST CTA to finish (ticket in ann_state[1]) adds the batch total.
+constexpr int kCocoMaxRecord = 224;   // longest record: 10-digit ids / coordinates, two 13-character ratios
+
+__device__ __forceinline__ int put_lit(char* p, const char* s) {
+  int n = 0;
+  while (s[n]) {
+    p[n] = s[n];
+    ++n;
+  }
+  return n;
+}
+
+__device__ __forceinline__ int put_int(char* p, long long v) {
+  int n = 0;
+  if (v < 0) {
+    p[n++] = '-';
+    v = -v;
+  }
+  return n + put_decimal(static_cast<unsigned long long>(v), p + n);
+}
+
+// text of one annotation into `p` (kCocoMaxRecord bytes); returns the length, or -1 for an unprintable ratio
+__device__ int coco_record(char* p, long long ann_id, int frame, int cls, int cnt, int x0, int y0, int x1, int y1,
+                           float occ, float trunc) {
+  if (!(fabsf(occ) < 1048576.0f) || !(fabsf(trunc) < 1048576.0f)) return -1;
+  int n = 0;
+  n += put_lit(p + n, "{\"id\": ");
+  n += put_int(p + n, ann_id);
+  n += put_lit(p + n, ", \"image_id\": ");
+  n += put_int(p + n, frame);
+  n += put_lit(p + n, ", \"category_id\": ");
+  n += put_int(p + n, cls);
+  n += put_lit(p + n, ", \"bbox\": [");
+  if (cnt > 0) {
+    n += put_int(p + n, x0);
+    n += put_lit(p + n, ", ");
+    n += put_int(p + n, y0);
+    n += put_lit(p + n, ", ");
+    n += put_int(p + n, static_cast<long long>(x1) - x0 + 1);
+    n += put_lit(p + n, ", ");
+    n += put_int(p + n, static_cast<long long>(y1) - y0 + 1);
+  } else {
+    n += put_lit(p + n, "0, 0, 0, 0");
+  }
+  n += put_lit(p + n, "], \"area\": ");
+  n += put_int(p + n, cnt);
+  n += put_lit(p + n, ", \"iscrowd\": 0, \"occlusion\": ");
+  n += repr_units6(signbit(occ), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(occ)) * 1e6)), p + n);
+  n += put_lit(p + n, ", \"truncation\": ");
+  n += repr_units6(signbit(trunc), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(trunc)) * 1e6)), p + n);
+  p[n++] = '}';
+  return n;
+}
+
+__global__ void __launch_bounds__(kYoloThreads)
+    coco_text_kernel(const cspe_record* records, const int32_t* n_out, int B, int N, unsigned long long* ann_state,
+                     char* text, long long frame_stride, int32_t* n_bytes) {
+  __shared__ int warp_sums[kYoloThreads / 32];
+  __shared__ long long base_s, first_id_s;
+  __shared__ int bad_s;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    base_s = 0;
+    bad_s = 0;
+  }
+  __syncthreads();
+  pdl_wait();  // K4's records and n_out are complete after this; read through L2 (cspe_common.cuh, PDL rule)
+  int n = __ldcg(n_out + f);
+  n = n < 0 ? 0 : (n > N ? N : n);
+  // annotation id of this frame's first record: everything printed before this batch + the frames before this one
+  long long before_frames = 0;
+  for (int g = tid; g < f; g += kYoloThreads) {
+    const int m = __ldcg(n_out + g);
+    before_frames += m < 0 ? 0 : (m > N ? N : m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before_frames += __shfl_xor_sync(0xffffffffu, before_frames, o);
+  __shared__ long long part_s[kYoloThreads / 32];
+  if (lane == 0) part_s[wid] = before_frames;
+  __syncthreads();
+  if (tid == 0) {
+    long long s = 0;
+#pragma unroll
+    for (int w = 0; w < kYoloThreads / 32; ++w) s += part_s[w];
+    first_id_s = static_cast<long long>(__ldcg(ann_state)) + s + 1;
+  }
+  __syncthreads();
+  const cspe_record* rec = records + static_cast<long long>(f) * N;
+  char* out = text + static_cast<long long>(f) * frame_stride;
+  for (int r0 = 0; r0 < n; r0 += kYoloThreads) {
+    const int r = r0 + tid;
+    char line[kCocoMaxRecord];
+    int len = 0;
+    if (r < n) {
+      const cspe_record* q = rec + r;
+      len = coco_record(line, first_id_s + r, __ldcg(&q->frame), __ldcg(&q->class_id), __ldcg(&q->count), __ldcg(&q->x_min),
+                        __ldcg(&q->y_min), __ldcg(&q->x_max), __ldcg(&q->y_max), __ldcg(&q->occlusion), __ldcg(&q->truncation));
+      if (len < 0) {
+        bad_s = 1;
+        len = 0;
+      } else if (first_id_s + r > 1) {
+        len += 2;   // ", " in front of every annotation but the sweep's first: frame texts simply concatenate
+      }
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kYoloThreads / 32; ++w) {
+      const int sw = warp_sums[w];
+      if (w < wid) before += sw;
+      total += sw;
+    }
+    if (r < n && len > 0) {
+      long long pos = base_s + before + incl - len;
+      const bool sep = first_id_s + r > 1;
+      const int body = sep ? len - 2 : len;
+      if (sep) {
+        if (pos < frame_stride) out[pos] = ',';
+        if (pos + 1 < frame_stride) out[pos + 1] = ' ';
+        pos += 2;
+      }
+      for (int i = 0; i < body; ++i)
+        if (pos + i < frame_stride) out[pos + i] = line[i];
+    }
+    __syncthreads();
+    if (tid == 0) base_s += total;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    n_bytes[f] = bad_s ? -1 : static_cast<int32_t>(base_s);
+    // last CTA of the batch: every CTA has read ann_state[0] by now -> add the batch total, reset the ticket
+    __threadfence();
+    if (atomicAdd(ann_state + 1, 1ull) == static_cast<unsigned long long>(B) - 1) {
+      long long total = 0;
+      for (int g = 0; g < B; ++g) {
+        const int m = __ldcg(n_out + g);
+        total += m < 0 ? 0 : (m > N ? N : m);
+      }
+      ann_state[0] = __ldcg(ann_state) + static_cast<unsigned long long>(total);
+      ann_state[1] = 0ull;
+    }
+  }
+}
+
 }  // namespace
 }  // namespace cspe
 
@@ -158,5 +318,23 @@ extern "C" int cspe_format_yolo(const cspe_record* records, const int32_t* n_out
   CSPE_CUDA_OK(launch_pdl(yolo_text_kernel, dim3(static_cast<unsigned>(B)), dim3(kYoloThreads), 0,
                           static_cast<cudaStream_t>(stream), records, n_out, N, text,
                           static_cast<long long>(frame_stride), n_bytes));
+  return CSPE_OK;
+}
+
+extern "C" int cspe_format_coco(const cspe_record* records, const int32_t* n_out, int B, int N, int64_t* ann_state,
+                                char* text, int64_t frame_stride, int32_t* n_bytes, void* stream) {
+  CSPE_REQUIRE(B >= 0 && N >= 0 && frame_stride >= 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_format_coco: negative size (B=%d N=%d frame_stride=%lld)", B, N, static_cast<long long>(frame_stride));
+  if (B == 0) return CSPE_OK;
+  CSPE_REQUIRE(n_out && n_bytes && ann_state && (N == 0 || records) && (frame_stride == 0 || text), CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_format_coco: null pointer");
+  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(ann_state) & 7) == 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_format_coco: ann_state must be 8-byte aligned");
+  CSPE_REQUIRE(static_cast<long long>(N) * (kCocoMaxRecord + 2) < (1ll << 31), CSPE_ERR_UNSUPPORTED,
+               "cspe_format_coco: %d slots per frame overflow the int32 byte count", N);
+  CSPE_CUDA_OK(launch_pdl(coco_text_kernel, dim3(static_cast<unsigned>(B)), dim3(kYoloThreads), 0,
+                          static_cast<cudaStream_t>(stream), records, n_out, B, N,
+                          reinterpret_cast<unsigned long long*>(ann_state), text, static_cast<long long>(frame_stride),
+                          n_bytes));
   return CSPE_OK;
 }

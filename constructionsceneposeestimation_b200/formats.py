@@ -192,6 +192,25 @@ def write_files(directory: str, prefix: str, suffix: str, first_id: int, data: n
     return int(rc)
 
 
+def concat_rows(data: np.ndarray, sizes: np.ndarray, count: Optional[int] = None) -> bytes:
+    """``data[j, :sizes[j]]`` for j < count, back to back (libcspe ``cspe_concat_rows_host``): the per-frame label text
+    of a D2H buffer (``cspe_format_yolo`` / ``cspe_format_coco``) as one chunk."""
+    from . import _lib
+
+    lib = _lib.load()
+    if data.ndim != 2 or data.dtype != np.uint8 or not data.flags.c_contiguous:
+        raise ValueError("data must be a C-contiguous uint8 [B, stride] array")
+    sizes = np.ascontiguousarray(sizes, dtype=np.int32)
+    count = len(sizes) if count is None else int(count)
+    if count > data.shape[0] or count > len(sizes):
+        raise ValueError("count exceeds the rows of data / sizes")
+    cap = int(np.clip(sizes[:count], 0, None).sum())
+    out = np.empty(cap, dtype=np.uint8)
+    rc = lib.cspe_concat_rows_host(data.ctypes.data, data.shape[1], sizes.ctypes.data, count, out.ctypes.data, cap)
+    _lib.check("cspe_concat_rows_host", rc)
+    return out[:rc].tobytes()
+
+
 def coco_categories() -> List[Dict[str, object]]:
     return [{"id": i, "name": n, "supercategory": "construction"} for i, n in enumerate(CLASS_NAMES)]
 
@@ -211,8 +230,9 @@ def coco_annotations(records: np.ndarray, image_id: int, first_ann_id: int,
             "bbox": [x0, y0, x1 - x0 + 1, y1 - y0 + 1] if int(r["count"]) > 0 else [0, 0, 0, 0],
             "area": int(r["count"]),
             "iscrowd": 0,
-            "occlusion": float(r["occlusion"]),
-            "truncation": float(r["truncation"]),
+            # ratios to six decimals: what a label consumer needs, and printable on the device (csrc/repr6.h)
+            "occlusion": round(float(r["occlusion"]), 6),
+            "truncation": round(float(r["truncation"]), 6),
         }
         kp = kps.get(int(r["inst_idx"]))
         if kp is not None:
@@ -266,7 +286,8 @@ def coco_images_text(image_ids: Sequence[int], width: int, height: int) -> bytes
                      for i in image_ids).encode("ascii")
 
 
-def write_coco_file(path, images: Sequence[Union[Mapping, bytes]], annotation_chunks: Sequence[bytes]) -> None:
+def write_coco_file(path, images: Sequence[Union[Mapping, bytes]], annotation_chunks: Sequence[bytes],
+                    joined: bool = False) -> None:
     """The bytes json.dump({"images": [...], "annotations": [...], "categories": [...]}, f) writes, with the
     annotations given as natively formatted chunks (``coco_annotations_text``) and the images either as dicts
     (``coco_image``) or as pre-formatted chunks (``coco_images_text``)."""
@@ -275,7 +296,8 @@ def write_coco_file(path, images: Sequence[Union[Mapping, bytes]], annotation_ch
             f.write(b'{"images": [' + b", ".join(c for c in images if c) + b'], "annotations": [')
         else:
             f.write(b'{"images": ' + json.dumps(list(images)).encode("ascii") + b', "annotations": [')
-        f.write(b", ".join(c for c in annotation_chunks if c))
+        # joined=True: the chunks already carry their ", " separators (device formatter)
+        f.write((b"" if joined else b", ").join(c for c in annotation_chunks if c))
         f.write(b'], "categories": ' + json.dumps(coco_categories()).encode("ascii") + b"}")
 
 

@@ -215,6 +215,29 @@ def format_yolo(records: torch.Tensor, n_out: torch.Tensor, frame_stride: Option
     return text, n_bytes
 
 
+def format_coco(records: torch.Tensor, n_out: torch.Tensor, ann_state: torch.Tensor, frame_stride: Optional[int] = None):
+    """S6 / f3 on the device: records u8 [B,N,408] + n_out int32 [B] -> (text u8 [B, frame_stride], n_bytes int32 [B]);
+    frame f's COCO annotation objects, ", "-joined, are ``text[f, :n_bytes[f]]`` (join the frames with ", " as well).
+    ``ann_state`` int64 [2] on the device carries the running annotation count across calls (zero it at sweep start)."""
+    lib = _lib.load()
+    _dev(records, torch.uint8, "records")
+    _dev(n_out, torch.int32, "n_out")
+    _dev(ann_state, torch.int64, "ann_state")
+    if records.dim() != 3 or records.shape[2] != _lib.RECORD_DTYPE.itemsize or records.shape[0] != n_out.shape[0]:
+        raise ValueError(f"records must be u8 [B,N,{_lib.RECORD_DTYPE.itemsize}] with B = len(n_out), got {tuple(records.shape)}")
+    if ann_state.numel() != 2:
+        raise ValueError("ann_state must be int64 [2]")
+    B, N = records.shape[0], records.shape[1]
+    stride = 224 * N if frame_stride is None else int(frame_stride)
+    text = torch.empty((B, stride), dtype=torch.uint8, device=records.device)
+    n_bytes = torch.empty((B,), dtype=torch.int32, device=records.device)
+    with torch.cuda.device(records.device):
+        rc = lib.cspe_format_coco(records.data_ptr(), n_out.data_ptr(), B, N, ann_state.data_ptr(), text.data_ptr(), stride,
+                                  n_bytes.data_ptr(), _stream_ptr())
+    _lib.check("cspe_format_coco", rc)
+    return text, n_bytes
+
+
 def depth_to_pointcloud(depth: torch.Tensor, rgb: Optional[torch.Tensor], cam: torch.Tensor,
                         capacity: Optional[int] = None):
     """f1: depth f32 [H,W], rgb u8 [H,W,C>=3] or None, cam f64 [24] -> (points f64 [cap,6], n int64 [1])."""

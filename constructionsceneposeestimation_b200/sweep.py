@@ -35,6 +35,7 @@ from .camera import pack_camera
 from .pipeline import LabelPipeline, graph_edge_kinds
 
 YOLO_BYTES_PER_SLOT = 48   # 38 bytes per line for class ids 0..9 and boxes inside the image
+COCO_BYTES_PER_SLOT = 192  # ~165 bytes per annotation for ids < 10^8 and 4-digit coordinates (224 is the hard maximum)
 _POOL_CACHE: Dict[Tuple, Tuple] = {}   # synthetic pool + host tables of the last (config, pool size): --repeat reuses them
 
 
@@ -83,7 +84,8 @@ def split_range(lo: int, hi: int, batch: int) -> Tuple[List[Tuple[int, int]], Li
 class _BatchOut:
     """Device outputs of one batch slot and their pinned host mirrors."""
 
-    def __init__(self, pipe: LabelPipeline, want_records: bool, want_yolo: bool, records_dev: Optional[torch.Tensor]):
+    def __init__(self, pipe: LabelPipeline, want_records: bool, want_yolo: bool, records_dev: Optional[torch.Tensor],
+                 text_kind: Optional[str] = None, ann_state: Optional[torch.Tensor] = None):
         B, N, dev = pipe.B, pipe.N, pipe.device
         self.n_out = torch.empty((B,), dtype=torch.int32, device=dev)
         self.n_out_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
@@ -93,17 +95,24 @@ class _BatchOut:
             torch.empty((B, N, _lib.RECORD_DTYPE.itemsize), dtype=torch.uint8, device=dev)
         self.records_h = torch.empty(self.records.shape, dtype=torch.uint8, pin_memory=True) if want_records else None
         self.text = self.text_h = self.n_bytes = self.n_bytes_h = None
-        if want_yolo:
-            self.stride = YOLO_BYTES_PER_SLOT * N
+        self.text_kind = text_kind if text_kind is not None else ("yolo" if want_yolo else None)
+        self.ann_state = ann_state
+        if self.text_kind is not None:
+            self.stride = (YOLO_BYTES_PER_SLOT if self.text_kind == "yolo" else COCO_BYTES_PER_SLOT) * N
             self.text = torch.empty((B, self.stride), dtype=torch.uint8, device=dev)
             self.text_h = torch.empty((B, self.stride), dtype=torch.uint8, pin_memory=True)
             self.n_bytes = torch.empty((B,), dtype=torch.int32, device=dev)
             self.n_bytes_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
 
     def enqueue_text(self, lib, nf: int, stream: int) -> None:
-        _lib.check("cspe_format_yolo", lib.cspe_format_yolo(
-            self.records.data_ptr(), self.n_out.data_ptr(), nf, self.records.shape[1], self.text.data_ptr(),
-            self.stride, self.n_bytes.data_ptr(), stream))
+        if self.text_kind == "yolo":
+            _lib.check("cspe_format_yolo", lib.cspe_format_yolo(
+                self.records.data_ptr(), self.n_out.data_ptr(), nf, self.records.shape[1], self.text.data_ptr(),
+                self.stride, self.n_bytes.data_ptr(), stream))
+        else:
+            _lib.check("cspe_format_coco", lib.cspe_format_coco(
+                self.records.data_ptr(), self.n_out.data_ptr(), nf, self.records.shape[1], self.ann_state.data_ptr(),
+                self.text.data_ptr(), self.stride, self.n_bytes.data_ptr(), stream))
 
     def enqueue_readback(self, lib, nf: int, stream: int) -> None:
         def cp(dst, src, n):
@@ -122,13 +131,15 @@ class _GroupGraph:
     capture stream, the read-back of every batch on a side branch.  Replayed for any frame range by rewriting
     ``frame_base_h`` (a pinned int32 the upload node reads at execution time)."""
 
-    def __init__(self, pipe: LabelPipeline, group: int, want_records: bool, want_yolo: bool):
+    def __init__(self, pipe: LabelPipeline, group: int, want_records: bool, text_kind: Optional[str] = None,
+                 ann_state: Optional[torch.Tensor] = None):
         lib = pipe.lib
         dev = pipe.device
         self.pipe, self.group = pipe, group
         shared = torch.empty((pipe.B, pipe.N, _lib.RECORD_DTYPE.itemsize), dtype=torch.uint8, device=dev) \
             if not want_records else None
-        self.slots = [_BatchOut(pipe, want_records, want_yolo, shared) for _ in range(group)]
+        want_yolo = text_kind is not None
+        self.slots = [_BatchOut(pipe, want_records, want_yolo, shared, text_kind, ann_state) for _ in range(group)]
         self.frame_base_h = torch.zeros((1,), dtype=torch.int32, pin_memory=True)
         self.frame_base_d = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.done = torch.cuda.Event()
@@ -181,8 +192,11 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
     pool, (lut, obj_record, slot_class, records, cam, objects) = _POOL_CACHE[key]
     H, W = pool[0]["instance_segmentation"]["data"].shape
     B, N = pool_frames, obj_record.shape[1]
-    want_yolo = emit == "yolo"
-    want_records = emit in ("coco", "json", "records")
+    # "coco" prints the annotations on the device like "yolo" (no keypoint stage in a sweep); "coco_host" keeps the
+    # records + native host formatter path
+    text_kind = {"yolo": "yolo", "coco": "coco"}.get(emit)
+    want_yolo = text_kind is not None          # device-formatted text comes back instead of records
+    want_records = emit in ("coco_host", "json", "records")
     lib = _lib.load()
     with torch.cuda.device(device):
         pipe = LabelPipeline(B, H, W, N, records.shape[1], lut.shape[1], device, use_graph=False)
@@ -201,11 +215,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         head, full, tail = split_range(lo, hi, B)
         groups = [full[i:i + group] for i in range(0, len(full) - len(full) % group, group)] if use_graph else []
         eager = head + full[len(groups) * group:] + tail
-        graphs = [_GroupGraph(pipe, group, want_records, want_yolo) for _ in range(min(2, len(groups)))]
-        eager_slot = _BatchOut(pipe, want_records, want_yolo, None) if eager else None
+        ann_state = torch.zeros((2,), dtype=torch.int64, device=device) if text_kind == "coco" else None
+        graphs = [_GroupGraph(pipe, group, want_records, text_kind, ann_state) for _ in range(min(2, len(groups)))]
+        eager_slot = _BatchOut(pipe, want_records, want_yolo, None, text_kind, ann_state) if eager else None
         workers = max(1, min(8, (os.cpu_count() or 2) // max(1, world))) if io_threads is None else max(1, io_threads)
         io_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="cspe-io") \
-            if (want_records or label_dir is not None) else None
+            if (want_records or label_dir is not None or text_kind == "coco") else None
         slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
 
         emitted = 0
@@ -243,9 +258,13 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 if (nb < 0).any() or (nb > slot.stride).any():
                     raise RuntimeError(f"YOLO text of frames {s}..{e}: sizes {nb.min()}..{nb.max()} outside [0, {slot.stride}]")
                 text_bytes += int(nb.sum())
-                if label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
-                    text = slot.text_h.numpy() if in_place else slot.text_h.numpy()[:nf].copy()
-                    sizes = nb if in_place else nb.copy()
+                text = slot.text_h.numpy() if in_place else slot.text_h.numpy()[:nf].copy()
+                sizes = nb if in_place else nb.copy()
+                if text_kind == "coco":   # the frames' annotation text as one chunk (native memcpy loop on a worker)
+                    coco_count += count
+                    coco_imgs.append(formats.coco_images_text(range(s, e), W, H))
+                    submit(lambda: formats.concat_rows(text, sizes, nf))
+                elif label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
                     submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
             if not want_records:
@@ -254,7 +273,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             n_use = n_all
             if not in_place:
                 recs, n_use = recs.copy(), n_all.copy()
-            if emit == "coco":   # native formatter, one call per batch, on a worker (ctypes releases the GIL)
+            if emit == "coco_host":   # native formatter, one call per batch, on a worker (ctypes releases the GIL)
                 ids = np.arange(s, e, dtype=np.int64)
                 first_id = coco_count + 1
                 coco_count += count
@@ -278,6 +297,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             while len(pending) > limit:
                 r = pending.pop(0).result()
                 if emit == "coco":
+                    coco_anns.append(r)
+                elif emit == "coco_host":
                     coco_anns.append(r)
                     text_bytes += len(r)
                 elif isinstance(r, int) and emit == "json":
@@ -349,8 +370,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             gathered = sharding.all_gather_histogram(pipe.class_hist)
         else:
             gathered = hist_host.reshape(1, -1)
-        if emit == "coco" and out_dir is not None:
-            formats.write_coco_file(os.path.join(out_dir, f"coco_rank{rank:02d}.json"), coco_imgs, coco_anns)
+        if emit == "coco" and ann_state is not None and int(ann_state[0].item()) != emitted:
+            raise RuntimeError(f"device annotation counter {int(ann_state[0].item())} != {emitted} emitted records")
+        if emit in ("coco", "coco_host") and out_dir is not None:
+            # device chunks carry their own ", " separators (every annotation but the first); host chunks are joined
+            formats.write_coco_file(os.path.join(out_dir, f"coco_rank{rank:02d}.json"), coco_imgs, coco_anns,
+                                    joined=(emit == "coco"))
     out = {"rank": rank, "world": world, "frames": hi - lo, "frame_range": [lo, hi], "records": emitted,
            "emit": emit, "text_bytes": text_bytes, "batch": B, "group": group, "graph_groups": len(groups),
            "eager_batches": len(eager), "io_threads": workers if io_pool is not None else 0,
@@ -371,7 +396,8 @@ def main() -> int:
     ap.add_argument("--pool", type=int, default=64)
     ap.add_argument("--group", type=int, default=8, help="batches per CUDA graph")
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--emit", default="yolo", choices=["yolo", "coco", "json", "none"])
+    ap.add_argument("--emit", default="yolo", choices=["yolo", "coco", "coco_host", "json", "none"],
+                    help="yolo / coco: label text formatted on the device; coco_host / json: records come back, native host formatters")
     ap.add_argument("--out", default=None)
     ap.add_argument("--eager", action="store_true", help="no graphs: one batch at a time")
     ap.add_argument("--io-threads", type=int, default=None)

@@ -252,6 +252,19 @@ int cspe_emit_reset_scan_indirect(int32_t* scan, const double* uv, const double*
 int cspe_format_yolo(const cspe_record* records, const int32_t* n_out, int B, int N,
                      char* text, int64_t frame_stride, int32_t* n_bytes, void* stream);
 
+/* S6 / f3: COCO annotations on the DEVICE.  For every frame f the objects
+ *   {"id": i, "image_id": record.frame, "category_id": c, "bbox": [x_min, y_min, w, h], "area": count,
+ *    "iscrowd": 0, "occlusion": o, "truncation": t}
+ * of its n_out[f] kept records, each preceded by ", " unless it is annotation 1, contiguous at
+ * text + f * frame_stride: the frames' texts concatenated in order are the bytes cspe_format_coco_host writes
+ * for records without keypoints (the ratios are printed as Python prints round(x, 6)); cspe_concat_rows_host
+ * does that concatenation.  Annotation ids count up across frames and calls:
+ * ann_state int64[2] (device) = {annotations printed so far, internal ticket}; zero both at sweep start, the
+ * kernel advances [0] by the batch total.  n_bytes int32 [B] as for cspe_format_yolo (-1 = a ratio that is not
+ * finite or >= 2^20; bytes past frame_stride are dropped but counted); 224 bytes per record always suffice. */
+int cspe_format_coco(const cspe_record* records, const int32_t* n_out, int B, int N, int64_t* ann_state,
+                     char* text, int64_t frame_stride, int32_t* n_bytes, void* stream);
+
 /* ---- plumbing for captured step graphs ----------------------------------------------------- */
 
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) through the library's runtime, so a host
@@ -341,6 +354,12 @@ int64_t cspe_write_files_host(const char* dir, const char* prefix, int digits, c
                               int64_t first_id, int count, const char* data_host, int64_t stride,
                               const int32_t* sizes_host);
 
+/* f3: rows of a strided host buffer back to back (no CUDA; HOST pointers): out_host receives
+ * data_host[j * stride .. + sizes_host[j]) for j in [0, count) — the frames' label text of a D2H buffer as one
+ * chunk.  Returns the bytes written or a negative CSPE_ERR_* (a size outside [0, stride], capacity too small). */
+int64_t cspe_concat_rows_host(const char* data_host, int64_t stride, const int32_t* sizes_host, int count,
+                              char* out_host, int64_t capacity);
+
 /* f3: host-side label JSON of ONE frame (no CUDA; all pointers are HOST pointers) — the text
  * json.dump(label, f, indent=2, ensure_ascii=False) writes (gcd.py:608-613) for the frame dict of
  * gcd.py:2056-2064 with the object dicts of gcd.py:1938-1946 plus the added fields
@@ -365,7 +384,7 @@ int64_t cspe_format_label_json_host(const cspe_record* records_host, int n, int6
 /* f3 / S6: host-side COCO annotations of a batch (no CUDA; HOST pointers).  For every kept record of
  * frames [0, frames) of records_host [B][N] / n_out_host [B] one object
  *   {"id", "image_id", "category_id", "bbox": [x_min, y_min, w, h], "area": count, "iscrowd": 0,
- *    "occlusion", "truncation"[, "keypoints": [x, y, v]*J, "num_keypoints"]}
+ *    "occlusion", "truncation" (both as Python prints round(x, 6))[, "keypoints": [x, y, v]*J, "num_keypoints"]}
  * joined by ", " — what json.dump(list) writes between its brackets.  image_ids int64 [frames];
  * annotation ids count up from first_annotation_id; keypoints double [B][P][J][2], visibility uint8
  * [B][P][J], person_of_slot int32 [B][N] (-1 = none), all three NULL without skeletons.

@@ -908,6 +908,66 @@ def test_yolo_text_on_device_matches_python(T, ops):
     assert nb4.cpu().numpy().tolist() == [-1, int(nb[1]), -1, -1, 0]
 
 
+def test_coco_text_on_device_matches_host_and_python(T, ops):
+    """cspe_format_coco (device) == cspe_format_coco_host == json.dumps(formats.coco_annotations(...)), byte for byte:
+    running annotation ids across frames and across calls, empty frames, zero-pixel records, ratios that print in
+    exponent form (< 1e-4), ties, exact 0 / 1, a cut frame, unprintable ratios flagged with -1."""
+    import json
+    from constructionsceneposeestimation_b200 import _lib, formats
+    rng = np.random.default_rng(9)
+    B, N = 6, 140
+    recs = np.zeros((B, N), dtype=_lib.RECORD_DTYPE)
+    recs["class_id"] = rng.integers(0, 10, size=(B, N))
+    recs["frame"] = (1000 + np.arange(B))[:, None]
+    recs["count"] = rng.integers(1, 2_000_000, size=(B, N))
+    recs["x_min"] = rng.integers(0, 3000, size=(B, N))
+    recs["y_min"] = rng.integers(0, 2000, size=(B, N))
+    recs["x_max"] = recs["x_min"] + rng.integers(0, 800, size=(B, N))
+    recs["y_max"] = recs["y_min"] + rng.integers(0, 150, size=(B, N))
+    recs["occlusion"] = rng.random((B, N), dtype=np.float32)
+    recs["truncation"] = (rng.integers(0, 2 ** 21, size=(B, N)) / np.float32(2 ** 21)).astype(np.float32)   # many ties
+    nasty = np.array([0.0, 1.0, 0.5, 5e-7, 4.9e-7, 1.2e-5, 9.95e-5, 9.96e-5, 1e-4, 1e-6, 0.9999995, 0.99999994, 1e-30,
+                      0.1234565, 0.000123, 0.25, 3.3e-5, 5.05e-5], dtype=np.float32)
+    recs["occlusion"][1, : len(nasty)] = nasty
+    recs["truncation"][1, : len(nasty)] = nasty[::-1]
+    recs["count"][2, :5] = 0                                  # unseen objects kept by min_pixels = 0: bbox [0, 0, 0, 0]
+    n_out = np.array([N, 30, N, 0, 1, 77], dtype=np.int32)
+    d_rec = T.from_numpy(recs.view(np.uint8).reshape(B, N, -1)).cuda()
+    d_n = T.from_numpy(n_out).cuda()
+    state = T.zeros(2, dtype=T.int64, device="cuda")
+    chunks = []
+    for call in range(2):                                      # the running id continues across calls
+        text, nb = ops.format_coco(d_rec, d_n, state)
+        T.cuda.synchronize()
+        text, nb = text.cpu().numpy(), nb.cpu().numpy()
+        assert state.cpu().tolist() == [(call + 1) * int(n_out.sum()), 0]
+        chunks.append(formats.concat_rows(text, nb))           # frame texts simply concatenate
+    first = 1
+    for call in range(2):
+        ids = [int(recs["frame"][f, 0]) for f in range(B)]
+        host, count = formats.coco_annotations_text(recs, n_out, ids, first)
+        py = []
+        for f in range(B):
+            py += formats.coco_annotations(recs[f, : n_out[f]], ids[f], first + len(py))
+        assert host == json.dumps(py)[1:-1].encode() and count == int(n_out.sum())
+        assert chunks[call] == (host if call == 0 else b", " + host), call
+        first += count
+    # a stride that cuts a frame: full size still reported, what fits is identical
+    text_f, nb_f = ops.format_coco(d_rec, d_n, T.zeros(2, dtype=T.int64, device="cuda"))
+    text2, nb2 = ops.format_coco(d_rec, d_n, T.zeros(2, dtype=T.int64, device="cuda"), frame_stride=500)
+    T.cuda.synchronize()
+    assert np.array_equal(nb2.cpu().numpy(), nb_f.cpu().numpy()) and int(nb2[0]) > 500
+    assert np.array_equal(text2.cpu().numpy()[0], text_f.cpu().numpy()[0, :500])
+    # unprintable ratios -> -1 for that frame only
+    bad = recs.copy()
+    bad["occlusion"][0, 3] = np.nan
+    bad["truncation"][5, 0] = np.inf
+    _, nb3 = ops.format_coco(T.from_numpy(bad.view(np.uint8).reshape(B, N, -1)).cuda(), d_n, T.zeros(2, dtype=T.int64, device="cuda"))
+    T.cuda.synchronize()
+    nb3 = nb3.cpu().numpy()
+    assert nb3[0] == -1 and nb3[5] == -1 and nb3[3] == 0 and nb3[1] > 0
+
+
 def test_label_pipeline_graph_equals_eager_and_oracle(T, ops):
     """The CUDA-graph pipeline (K1 || K2 -> K4) reproduces the oracle and the eager launches."""
     from constructionsceneposeestimation_b200 import synthetic, _lib
@@ -1029,6 +1089,9 @@ def test_sweep_shards_union_equals_single_rank(T, ops, tmp_path):
         assert np.array_equal(np.unique(flat_one["frame"]), np.arange(150))
         sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="yolo", out_dir=str(tmp_path / "one"), group=2)
         sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="coco", out_dir=str(tmp_path / "one"), group=2)
+        # annotations printed on the device == the native host formatter == json.dump of the Python statement
+        sweep.run_sweep(150, 0, 1, dev, pool_frames=16, config="_t", emit="coco_host", out_dir=str(tmp_path / "host"), group=2)
+        assert (tmp_path / "one" / "coco_rank00.json").read_bytes() == (tmp_path / "host" / "coco_rank00.json").read_bytes()
         parts, hists, coco = [], [], []
         for r in range(3):
             res = sweep.run_sweep(150, r, 3, dev, pool_frames=16, config="_t", emit="records", group=2)

@@ -35,3 +35,13 @@ for label, cap in (("both passes", B * H * W), ("pass 1 only (capacity 0)", 0)):
     byts = B * H * W * 8 * (2 if cap else 1) + (npts * 48 if cap else 0)
     print(json.dumps({"case": f"f1 batch 64 x 1080p RGBA, {label}", "ms": round(ms, 4), "points": npts,
                       "algorithmic_GB/s": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / PEAK, 3)}), flush=True)
+# ---- what the HBM does on a pure WRITE stream and on a pure READ stream (the copy peak mixes both 50 / 50) --------
+buf = torch.empty(1 << 32, dtype=torch.uint8, device=dev)            # 4 GiB
+ms_w = timed(lambda: buf.fill_(7), 10)
+src = buf.view(torch.int64)
+ms_r = timed(lambda: src.sum(), 10)
+half = buf[: 1 << 31]
+ms_c = timed(lambda: buf[1 << 31:].copy_(half), 10)
+print(json.dumps({"case": "HBM probes (torch kernels, 4 GiB)", "fill_GB/s": round((1 << 32) / ms_w / 1e6, 1),
+                  "sum_read_GB/s": round((1 << 32) / ms_r / 1e6, 1), "copy_read+write_GB/s": round((1 << 32) / ms_c / 1e6, 1),
+                  "measured_copy_peak": PEAK}), flush=True)
