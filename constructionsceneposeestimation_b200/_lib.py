@@ -118,6 +118,7 @@ PROTOTYPES = {
     "cspe_emit_reset_scan_indirect": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "cspe_format_yolo": (_I, [_P, _P, _I, _I, _P, _I64, _P, _P]),
     "cspe_format_coco": (_I, [_P, _P, _I, _I, _P, _P, _I64, _P, _P]),
+    "cspe_pack_rows": (_I, [_P, _I64, _P, _I, _P, _I64, _P, _P]),
     "cspe_memcpy_async": (_I, [_P, _P, C.c_size_t, _P]),
     "cspe_graph_edge_kinds": (_I, [_P, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "cspe_pointcloud_workspace_bytes": (C.c_size_t, [_I, _I]),

@@ -145,7 +145,7 @@ __device__ __forceinline__ long long cta_exclusive_scan(int n, long long* s_scan
 template <int kPcGroup>
 __global__ void __launch_bounds__(kPcThreads)
     pc_count_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ rgb, int C, long long hw, int vec,
-                    int rgb_vec, int B, int tiles, int groups, void* ws_raw, long long* offsets) {
+                    int rgb_vec, int B, int tiles, int groups, void* ws_raw, long long* offsets, long long* total_out) {
   pdl_launch_dependents();
   __shared__ int s_cnt[kPcGroup][kPcThreads / 32];
   __shared__ unsigned s_max[kPcThreads / 32];
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(kPcThreads)
       [&](int t, long long v) { offsets[t] = v; });
   if (threadIdx.x == 0) {
     offsets[B] = all;
+    if (total_out) *total_out = all;   // the one-frame entry point's n_points
     L.batch->frames_done = 0;
   }
 }
@@ -644,9 +645,9 @@ extern "C" size_t cspe_pointcloud_batch_workspace_bytes(int B, int H, int W) {
 
 extern "C" size_t cspe_pointcloud_workspace_bytes(int H, int W) { return cspe_pointcloud_batch_workspace_bytes(1, H, W); }
 
-extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t* rgb, int rgb_channels, int B, int H, int W,
-                                              const double* cam, double* out, int64_t capacity, int64_t* offsets,
-                                              void* workspace, void* stream) {
+static int pointcloud_batch_impl(const float* depth, const uint8_t* rgb, int rgb_channels, int B, int H, int W,
+                                 const double* cam, double* out, int64_t capacity, int64_t* offsets, void* workspace,
+                                 void* stream, int64_t* total_out) {
   CSPE_REQUIRE(B >= 0 && H >= 0 && W >= 0 && capacity >= 0, CSPE_ERR_INVALID_ARGUMENT,
                "cspe_depth_to_pointcloud: negative size");
   if (B == 0) return CSPE_OK;
@@ -660,6 +661,7 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   const long long hw = static_cast<long long>(H) * W;
   if (hw == 0) {
     CSPE_CUDA_OK(cudaMemsetAsync(offsets, 0, sizeof(int64_t) * (static_cast<size_t>(B) + 1), st));
+    if (total_out) CSPE_CUDA_OK(cudaMemsetAsync(total_out, 0, sizeof(int64_t), st));
     return CSPE_OK;
   }
   CSPE_REQUIRE(depth != nullptr, CSPE_ERR_INVALID_ARGUMENT, "cspe_depth_to_pointcloud: depth is null");
@@ -695,17 +697,32 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   else if (variant == 1) write_k = pc_write_kernel<kPcGroupBatch, 1>;
   else write_k = pc_write_kernel<kPcGroupBatch, 2>;
   const size_t smem = static_cast<size_t>(bulk ? bufs * kPcBulkBufBytes : kPcStageBytes);
-  CSPE_CUDA_OK(cudaFuncSetAttribute(write_k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // dynamic shared-memory limits, once per process (the call costs tens of microseconds of host time)
+  static const cudaError_t attrs = []() {
+    cudaError_t e = cudaSuccess;
+    auto set = [&](auto k, int bytes) {
+      const cudaError_t r = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e == cudaSuccess) e = r;
+    };
+    set(pc_write_kernel<kPcGroupSmall, 1>, kPcBulkBufBytes);
+    set(pc_write_kernel<2, 1>, kPcBulkBufBytes);
+    set(pc_write_kernel<kPcGroupBatch, 1>, kPcBulkBufBytes);
+    set(pc_write_kernel<kPcGroupBatch, 2>, 2 * kPcBulkBufBytes);
+    set(pc_write_loop_kernel<kPcGroupSmall>, kPcStageBytes);
+    set(pc_write_loop_kernel<2>, kPcStageBytes);
+    set(pc_write_loop_kernel<kPcGroupBatch>, kPcStageBytes);
+    set(pc_write_persistent_kernel, kPcBulkBufBytes);
+    return e;
+  }();
+  CSPE_CUDA_OK(attrs);
   CSPE_CUDA_OK(cudaMemsetAsync(workspace, 0, L.header_bytes, st));
   const unsigned grid = static_cast<unsigned>(groups * B);
   // plain launch first (serialised behind whatever produced depth / rgb), then the PDL-chained writer
   count_k<<<grid, kPcThreads, 0, st>>>(depth, rgb, rgb_channels, hw, vec, rgb_vec, B, static_cast<int>(tiles),
-                                      static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets));
+                                      static_cast<int>(groups), workspace, reinterpret_cast<long long*>(offsets),
+                                      reinterpret_cast<long long*>(total_out));
   CSPE_LAUNCH_OK("pc_count_kernel");
   if (capacity > 0 && bulk && !small && variant == 3) {
-    static const cudaError_t attr3 = cudaFuncSetAttribute(pc_write_persistent_kernel,
-                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kPcBulkBufBytes);
-    (void)attr3;
     const long long all_tiles = tiles * B;
     const long long ctas = static_cast<long long>(sm_count()) * kPcPersistentCtasPerSm;
     CSPE_CUDA_OK(launch_pdl(pc_write_persistent_kernel, dim3(static_cast<unsigned>(all_tiles < ctas ? all_tiles : ctas)),
@@ -722,6 +739,12 @@ extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t*
   return CSPE_OK;
 }
 
+extern "C" int cspe_depth_to_pointcloud_batch(const float* depth, const uint8_t* rgb, int rgb_channels, int B, int H, int W,
+                                              const double* cam, double* out, int64_t capacity, int64_t* offsets,
+                                              void* workspace, void* stream) {
+  return pointcloud_batch_impl(depth, rgb, rgb_channels, B, H, W, cam, out, capacity, offsets, workspace, stream, nullptr);
+}
+
 // one frame: offsets[1] doubles as the point count (n_points = &pair[1] of a caller-side int64[2] is not required —
 // the single-frame entry point keeps its one-value result by scanning into a two-element scratch in the workspace)
 extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, int rgb_channels, int H, int W,
@@ -735,8 +758,6 @@ extern "C" int cspe_depth_to_pointcloud(const float* depth, const uint8_t* rgb, 
   // offsets[0..1] live at the end of the workspace; the total is copied to n_points on the stream
   const long long tiles = (H <= 0 || W <= 0) ? 0 : pc_tiles(static_cast<long long>(H) * W);
   int64_t* pair = reinterpret_cast<int64_t*>(static_cast<unsigned char*>(workspace) + pc_layout(nullptr, 1, tiles).bytes);
-  const int rc = cspe_depth_to_pointcloud_batch(depth, rgb, rgb_channels, 1, H, W, cam, out, capacity, pair, workspace, stream);
-  if (rc != CSPE_OK) return rc;
-  CSPE_CUDA_OK(cudaMemcpyAsync(n_points, pair + 1, sizeof(int64_t), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
-  return CSPE_OK;
+  // offsets[0..1] live in the workspace; the count kernel writes the total to n_points as well
+  return pointcloud_batch_impl(depth, rgb, rgb_channels, 1, H, W, cam, out, capacity, pair, workspace, stream, n_points);
 }

@@ -301,6 +301,43 @@ __global__ void __launch_bounds__(kYoloThreads)
   }
 }
 
+// ---- frames' text back to back ------------------------------------------------------------------------------------
+// The formatters above leave every frame's text at a fixed stride (no cross-frame dependency while printing).  A
+// sweep that keeps the text of a whole batch wants ONE chunk: CTA f copies row f behind the rows before it; the host
+// then takes packed[0 .. total) with a single memcpy instead of B slices.
+__global__ void __launch_bounds__(kYoloThreads)
+    pack_rows_kernel(const char* text, long long stride, const int32_t* n_bytes, int B, char* packed, long long capacity,
+                     long long* total) {
+  __shared__ long long part_s[kYoloThreads / 32];
+  __shared__ long long off_s;
+  const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();   // the formatter's text and sizes, read through L2 (cspe_common.cuh, PDL rule)
+  long long before = 0;
+  for (int g = tid; g < f; g += kYoloThreads) {
+    const long long m = __ldcg(n_bytes + g);
+    before += m < 0 ? 0 : (m > stride ? stride : m);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+  if (lane == 0) part_s[wid] = before;
+  __syncthreads();
+  if (tid == 0) {
+    long long s = 0;
+#pragma unroll
+    for (int w = 0; w < kYoloThreads / 32; ++w) s += part_s[w];
+    off_s = s;
+  }
+  __syncthreads();
+  long long n = __ldcg(n_bytes + f);
+  n = n < 0 ? 0 : (n > stride ? stride : n);
+  const long long off = off_s;
+  const char* src = text + static_cast<long long>(f) * stride;
+  for (long long i = tid; i < n; i += kYoloThreads)
+    if (off + i < capacity) packed[off + i] = __ldcg(src + i);
+  if (f == B - 1 && tid == 0) *total = off + n;
+}
+
 }  // namespace
 }  // namespace cspe
 
@@ -336,5 +373,17 @@ extern "C" int cspe_format_coco(const cspe_record* records, const int32_t* n_out
                           static_cast<cudaStream_t>(stream), records, n_out, B, N,
                           reinterpret_cast<unsigned long long*>(ann_state), text, static_cast<long long>(frame_stride),
                           n_bytes));
+  return CSPE_OK;
+}
+
+extern "C" int cspe_pack_rows(const char* text, int64_t frame_stride, const int32_t* n_bytes, int B, char* packed,
+                              int64_t capacity, int64_t* total_bytes, void* stream) {
+  CSPE_REQUIRE(B >= 0 && frame_stride >= 0 && capacity >= 0, CSPE_ERR_INVALID_ARGUMENT, "cspe_pack_rows: negative size");
+  if (B == 0) return CSPE_OK;
+  CSPE_REQUIRE(n_bytes && total_bytes && (frame_stride == 0 || text) && (capacity == 0 || packed), CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_pack_rows: null pointer");
+  CSPE_CUDA_OK(launch_pdl(pack_rows_kernel, dim3(static_cast<unsigned>(B)), dim3(kYoloThreads), 0,
+                          static_cast<cudaStream_t>(stream), text, static_cast<long long>(frame_stride), n_bytes, B, packed,
+                          static_cast<long long>(capacity), reinterpret_cast<long long*>(total_bytes)));
   return CSPE_OK;
 }

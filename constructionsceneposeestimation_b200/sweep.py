@@ -103,6 +103,12 @@ class _BatchOut:
             self.text_h = torch.empty((B, self.stride), dtype=torch.uint8, pin_memory=True)
             self.n_bytes = torch.empty((B,), dtype=torch.int32, device=dev)
             self.n_bytes_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
+            self.packed = self.packed_h = self.total = self.total_h = None
+            if self.text_kind == "coco":   # the batch's annotation text as ONE chunk (cspe_pack_rows)
+                self.packed = torch.empty((B * self.stride,), dtype=torch.uint8, device=dev)
+                self.packed_h = torch.empty((B * self.stride,), dtype=torch.uint8, pin_memory=True)
+                self.total = torch.zeros((1,), dtype=torch.int64, device=dev)
+                self.total_h = torch.zeros((1,), dtype=torch.int64, pin_memory=True)
 
     def enqueue_text(self, lib, nf: int, stream: int) -> None:
         if self.text_kind == "yolo":
@@ -113,6 +119,9 @@ class _BatchOut:
             _lib.check("cspe_format_coco", lib.cspe_format_coco(
                 self.records.data_ptr(), self.n_out.data_ptr(), nf, self.records.shape[1], self.ann_state.data_ptr(),
                 self.text.data_ptr(), self.stride, self.n_bytes.data_ptr(), stream))
+            _lib.check("cspe_pack_rows", lib.cspe_pack_rows(
+                self.text.data_ptr(), self.stride, self.n_bytes.data_ptr(), nf, self.packed.data_ptr(), self.packed.numel(),
+                self.total.data_ptr(), stream))
 
     def enqueue_readback(self, lib, nf: int, stream: int) -> None:
         def cp(dst, src, n):
@@ -121,7 +130,11 @@ class _BatchOut:
         cp(self.n_out_h, self.n_out, nf * 4)
         if self.text is not None:
             cp(self.n_bytes_h, self.n_bytes, nf * 4)
-            cp(self.text_h, self.text, nf * self.stride)
+            if self.packed is not None:   # the chunk sits at the front; its size is only known on the device
+                cp(self.total_h, self.total, 8)
+                cp(self.packed_h, self.packed, nf * self.stride)
+            else:
+                cp(self.text_h, self.text, nf * self.stride)
         if self.records_h is not None:
             cp(self.records_h, self.records, nf * self.records.shape[1] * self.records.shape[2])
 
@@ -220,7 +233,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         eager_slot = _BatchOut(pipe, want_records, want_yolo, None, text_kind, ann_state) if eager else None
         workers = max(1, min(8, (os.cpu_count() or 2) // max(1, world))) if io_threads is None else max(1, io_threads)
         io_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="cspe-io") \
-            if (want_records or label_dir is not None or text_kind == "coco") else None
+            if (want_records or label_dir is not None) else None
         slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
 
         emitted = 0
@@ -258,12 +271,16 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 if (nb < 0).any() or (nb > slot.stride).any():
                     raise RuntimeError(f"YOLO text of frames {s}..{e}: sizes {nb.min()}..{nb.max()} outside [0, {slot.stride}]")
                 text_bytes += int(nb.sum())
-                text = slot.text_h.numpy() if in_place else slot.text_h.numpy()[:nf].copy()
-                sizes = nb if in_place else nb.copy()
-                if text_kind == "coco":   # the frames' annotation text as one chunk (native memcpy loop on a worker)
+                if text_kind != "coco":
+                    text = slot.text_h.numpy() if in_place else slot.text_h.numpy()[:nf].copy()
+                    sizes = nb if in_place else nb.copy()
+                if text_kind == "coco":   # the batch's annotation text is one chunk at the front of the packed buffer
                     coco_count += count
                     coco_imgs.append(formats.coco_images_text(range(s, e), W, H))
-                    submit(lambda: formats.concat_rows(text, sizes, nf))
+                    total = int(slot.total_h[0])
+                    if total != int(nb.sum()):
+                        raise RuntimeError(f"COCO text of frames {s}..{e}: packed {total} bytes, sizes sum to {int(nb.sum())}")
+                    coco_anns.append(bytes(memoryview(slot.packed_h.numpy())[:total]))
                 elif label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
                     submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
@@ -296,9 +313,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             nonlocal text_bytes
             while len(pending) > limit:
                 r = pending.pop(0).result()
-                if emit == "coco":
-                    coco_anns.append(r)
-                elif emit == "coco_host":
+                if emit == "coco_host":
                     coco_anns.append(r)
                     text_bytes += len(r)
                 elif isinstance(r, int) and emit == "json":
@@ -306,6 +321,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
 
         kept_records: List[np.ndarray] = []
         pipe.class_hist.zero_()
+        if ann_state is not None:
+            ann_state.zero_()   # the capture warm-ups advanced the annotation counter
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
 

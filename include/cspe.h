@@ -265,6 +265,12 @@ int cspe_format_yolo(const cspe_record* records, const int32_t* n_out, int B, in
 int cspe_format_coco(const cspe_record* records, const int32_t* n_out, int B, int N, int64_t* ann_state,
                      char* text, int64_t frame_stride, int32_t* n_bytes, void* stream);
 
+/* The strided text of cspe_format_yolo / cspe_format_coco back to back (device): packed receives row f's
+ * min(max(n_bytes[f], 0), frame_stride) bytes behind the rows before it (bytes past capacity are dropped);
+ * total_bytes int64[1] = the size of the whole chunk.  A host that keeps a batch's text then takes ONE slice. */
+int cspe_pack_rows(const char* text, int64_t frame_stride, const int32_t* n_bytes, int B, char* packed,
+                   int64_t capacity, int64_t* total_bytes, void* stream);
+
 /* ---- plumbing for captured step graphs ----------------------------------------------------- */
 
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) through the library's runtime, so a host

@@ -952,6 +952,15 @@ def test_coco_text_on_device_matches_host_and_python(T, ops):
         assert host == json.dumps(py)[1:-1].encode() and count == int(n_out.sum())
         assert chunks[call] == (host if call == 0 else b", " + host), call
         first += count
+    # cspe_pack_rows: the same frames' text back to back on the device
+    from constructionsceneposeestimation_b200 import _lib as L
+    t_dev, nb_dev = ops.format_coco(d_rec, d_n, T.zeros(2, dtype=T.int64, device="cuda"))
+    packed = T.zeros((t_dev.numel(),), dtype=T.uint8, device="cuda")
+    total = T.zeros(1, dtype=T.int64, device="cuda")
+    L.check("cspe_pack_rows", L.load().cspe_pack_rows(t_dev.data_ptr(), t_dev.shape[1], nb_dev.data_ptr(), B, packed.data_ptr(),
+                                                      packed.numel(), total.data_ptr(), T.cuda.current_stream().cuda_stream))
+    T.cuda.synchronize()
+    assert packed[: int(total)].cpu().numpy().tobytes() == chunks[0] and int(total) == len(chunks[0])
     # a stride that cuts a frame: full size still reported, what fits is identical
     text_f, nb_f = ops.format_coco(d_rec, d_n, T.zeros(2, dtype=T.int64, device="cuda"))
     text2, nb2 = ops.format_coco(d_rec, d_n, T.zeros(2, dtype=T.int64, device="cuda"), frame_stride=500)
