@@ -131,6 +131,7 @@ PROTOTYPES = {
     "cspe_text_workspace_bytes": (C.c_size_t, [_I64, _I]),
     "cspe_format_fixed6": (_I, [_P, _I, _I64, _P, _I, C.c_char_p, _P, _I64, _P, _I64, _P, _P, _P]),
     "cspe_write_files_host": (_I64, [C.c_char_p, C.c_char_p, _I, C.c_char_p, _I64, _I, _P, _I64, _P]),
+    "cspe_format_coco_images_host": (_I64, [_I64, _I, _I, _I, _P, _I64]),
     "cspe_concat_rows_host": (_I64, [_P, _I64, _P, _I, _P, _I64]),
     "cspe_format_yolo_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P]),
     "cspe_format_coco_host": (_I64, [_P, _P, _I, _I, _I, _P, _I64, _P, _P, _P, _I, _I, _P, _I64]),

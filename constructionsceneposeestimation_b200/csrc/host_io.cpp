@@ -92,3 +92,26 @@ extern "C" int64_t cspe_concat_rows_host(const char* data_host, int64_t stride, 
   }
   return pos;
 }
+
+// The "images" entries of a COCO file for a run of frames (json.dumps default separators):
+//   {"id": i, "width": W, "height": H, "file_name": "rgb_%06d.png"}  joined by ", "
+// — rgb_%06d.png is the name the capture loop gives its colour images (gcd.py:1672).
+extern "C" int64_t cspe_format_coco_images_host(int64_t first_id, int count, int width, int height, char* out_host,
+                                                int64_t capacity) {
+  if (count < 0 || capacity < 0 || (capacity > 0 && !out_host)) {
+    cspe::set_error("cspe_format_coco_images_host: invalid argument");
+    return CSPE_ERR_INVALID_ARGUMENT;
+  }
+  int64_t pos = 0;
+  for (int j = 0; j < count; ++j) {
+    if (capacity - pos < 160) {
+      cspe::set_error("cspe_format_coco_images_host: output buffer of %lld bytes is too small (160 per image)",
+                      static_cast<long long>(capacity));
+      return CSPE_ERR_INVALID_ARGUMENT;
+    }
+    const long long id = static_cast<long long>(first_id + j);
+    pos += snprintf(out_host + pos, 160, "%s{\"id\": %lld, \"width\": %d, \"height\": %d, \"file_name\": \"rgb_%06lld.png\"}",
+                    j ? ", " : "", id, width, height, id);
+  }
+  return pos;
+}

@@ -691,12 +691,13 @@ static int pointcloud_batch_impl(const float* depth, const uint8_t* rgb, int rgb
   const int bufs = (small || variant >= 1) ? 1 : 2;
   void (*write_k)(const float*, const uint8_t*, int, int, long long, int, int, const double*, int, int, int, void*,
                   const long long*, double*, long long);
-  if (!bulk) write_k = small ? pc_write_loop_kernel<kPcGroupSmall> : (variant == 2 ? pc_write_loop_kernel<2> : pc_write_loop_kernel<kPcGroupBatch>);
-  else if (small) write_k = pc_write_kernel<kPcGroupSmall, 1>;
+  // a single frame is latency-bound: the loop form projects its tile BEFORE it waits for pass 1 and keeps 28 KB of
+  // shared memory per CTA (the bulk forms need the frame's colour scale first: 0.086 ms against 0.04 ms for one 1080p frame)
+  if (!bulk || small) write_k = small ? pc_write_loop_kernel<kPcGroupSmall> : (variant == 2 ? pc_write_loop_kernel<2> : pc_write_loop_kernel<kPcGroupBatch>);
   else if (variant == 2) write_k = pc_write_kernel<2, 1>;
   else if (variant == 1) write_k = pc_write_kernel<kPcGroupBatch, 1>;
   else write_k = pc_write_kernel<kPcGroupBatch, 2>;
-  const size_t smem = static_cast<size_t>(bulk ? bufs * kPcBulkBufBytes : kPcStageBytes);
+  const size_t smem = static_cast<size_t>((bulk && !small) ? bufs * kPcBulkBufBytes : kPcStageBytes);
   // dynamic shared-memory limits, once per process (the call costs tens of microseconds of host time)
   static const cudaError_t attrs = []() {
     cudaError_t e = cudaSuccess;

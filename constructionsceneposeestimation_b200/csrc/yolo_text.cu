@@ -152,55 +152,79 @@ __global__ void __launch_bounds__(kYoloThreads)
 // in the batch, and the LAST CTA to finish (ticket in ann_state[1]) adds the batch total.
 constexpr int kCocoMaxRecord = 224;   // longest record: 10-digit ids / coordinates, two 13-character ratios
 
-__device__ __forceinline__ int put_lit(char* p, const char* s) {
+// Two writers with one interface: the first pass only counts, the second stores at the final position (bounded by the
+// frame's stride), so a record is never staged in local memory.
+struct CountWriter {
   int n = 0;
-  while (s[n]) {
-    p[n] = s[n];
-    ++n;
+  __device__ __forceinline__ void put(char) { ++n; }
+};
+struct TextWriter {
+  char* p;
+  long long pos, cap;
+  __device__ __forceinline__ void put(char c) {
+    if (pos < cap) p[pos] = c;
+    ++pos;
   }
-  return n;
+};
+
+template <class W>
+__device__ __forceinline__ void w_lit(W& w, const char* s) {
+  for (int i = 0; s[i]; ++i) w.put(s[i]);
 }
 
-__device__ __forceinline__ int put_int(char* p, long long v) {
-  int n = 0;
+template <class W>
+__device__ __forceinline__ void w_int(W& w, long long v) {
   if (v < 0) {
-    p[n++] = '-';
+    w.put('-');
     v = -v;
   }
-  return n + put_decimal(static_cast<unsigned long long>(v), p + n);
+  char tmp[20];
+  const int n = put_decimal(static_cast<unsigned long long>(v), tmp);
+  for (int i = 0; i < n; ++i) w.put(tmp[i]);
 }
 
-// text of one annotation into `p` (kCocoMaxRecord bytes); returns the length, or -1 for an unprintable ratio
-__device__ int coco_record(char* p, long long ann_id, int frame, int cls, int cnt, int x0, int y0, int x1, int y1,
-                           float occ, float trunc) {
-  if (!(fabsf(occ) < 1048576.0f) || !(fabsf(trunc) < 1048576.0f)) return -1;
-  int n = 0;
-  n += put_lit(p + n, "{\"id\": ");
-  n += put_int(p + n, ann_id);
-  n += put_lit(p + n, ", \"image_id\": ");
-  n += put_int(p + n, frame);
-  n += put_lit(p + n, ", \"category_id\": ");
-  n += put_int(p + n, cls);
-  n += put_lit(p + n, ", \"bbox\": [");
-  if (cnt > 0) {
-    n += put_int(p + n, x0);
-    n += put_lit(p + n, ", ");
-    n += put_int(p + n, y0);
-    n += put_lit(p + n, ", ");
-    n += put_int(p + n, static_cast<long long>(x1) - x0 + 1);
-    n += put_lit(p + n, ", ");
-    n += put_int(p + n, static_cast<long long>(y1) - y0 + 1);
+template <class W>
+__device__ __forceinline__ void w_ratio(W& w, float v) {
+  char tmp[28];
+  const int n = repr_units6(signbit(v), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(v)) * 1e6)), tmp);
+  for (int i = 0; i < n; ++i) w.put(tmp[i]);
+}
+
+struct CocoFields {
+  long long ann_id;
+  int frame, cls, cnt, x0, y0, x1, y1;
+  float occ, trunc;
+  bool sep;   // ", " in front (every annotation but the sweep's first)
+};
+
+template <class W>
+__device__ __forceinline__ void coco_record(W& w, const CocoFields& r) {
+  if (r.sep) w_lit(w, ", ");
+  w_lit(w, "{\"id\": ");
+  w_int(w, r.ann_id);
+  w_lit(w, ", \"image_id\": ");
+  w_int(w, r.frame);
+  w_lit(w, ", \"category_id\": ");
+  w_int(w, r.cls);
+  w_lit(w, ", \"bbox\": [");
+  if (r.cnt > 0) {
+    w_int(w, r.x0);
+    w_lit(w, ", ");
+    w_int(w, r.y0);
+    w_lit(w, ", ");
+    w_int(w, static_cast<long long>(r.x1) - r.x0 + 1);
+    w_lit(w, ", ");
+    w_int(w, static_cast<long long>(r.y1) - r.y0 + 1);
   } else {
-    n += put_lit(p + n, "0, 0, 0, 0");
+    w_lit(w, "0, 0, 0, 0");
   }
-  n += put_lit(p + n, "], \"area\": ");
-  n += put_int(p + n, cnt);
-  n += put_lit(p + n, ", \"iscrowd\": 0, \"occlusion\": ");
-  n += repr_units6(signbit(occ), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(occ)) * 1e6)), p + n);
-  n += put_lit(p + n, ", \"truncation\": ");
-  n += repr_units6(signbit(trunc), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(trunc)) * 1e6)), p + n);
-  p[n++] = '}';
-  return n;
+  w_lit(w, "], \"area\": ");
+  w_int(w, r.cnt);
+  w_lit(w, ", \"iscrowd\": 0, \"occlusion\": ");
+  w_ratio(w, r.occ);
+  w_lit(w, ", \"truncation\": ");
+  w_ratio(w, r.trunc);
+  w.put('}');
 }
 
 __global__ void __launch_bounds__(kYoloThreads)
@@ -208,6 +232,7 @@ __global__ void __launch_bounds__(kYoloThreads)
                      char* text, long long frame_stride, int32_t* n_bytes) {
   __shared__ int warp_sums[kYoloThreads / 32];
   __shared__ long long base_s, first_id_s;
+  __shared__ long long part_s[kYoloThreads / 32];
   __shared__ int bad_s;
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   pdl_launch_dependents();
@@ -227,7 +252,6 @@ __global__ void __launch_bounds__(kYoloThreads)
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) before_frames += __shfl_xor_sync(0xffffffffu, before_frames, o);
-  __shared__ long long part_s[kYoloThreads / 32];
   if (lane == 0) part_s[wid] = before_frames;
   __syncthreads();
   if (tid == 0) {
@@ -241,17 +265,27 @@ __global__ void __launch_bounds__(kYoloThreads)
   char* out = text + static_cast<long long>(f) * frame_stride;
   for (int r0 = 0; r0 < n; r0 += kYoloThreads) {
     const int r = r0 + tid;
-    char line[kCocoMaxRecord];
+    CocoFields fld{};
     int len = 0;
     if (r < n) {
       const cspe_record* q = rec + r;
-      len = coco_record(line, first_id_s + r, __ldcg(&q->frame), __ldcg(&q->class_id), __ldcg(&q->count), __ldcg(&q->x_min),
-                        __ldcg(&q->y_min), __ldcg(&q->x_max), __ldcg(&q->y_max), __ldcg(&q->occlusion), __ldcg(&q->truncation));
-      if (len < 0) {
-        bad_s = 1;
-        len = 0;
-      } else if (first_id_s + r > 1) {
-        len += 2;   // ", " in front of every annotation but the sweep's first: frame texts simply concatenate
+      fld.ann_id = first_id_s + r;
+      fld.frame = __ldcg(&q->frame);
+      fld.cls = __ldcg(&q->class_id);
+      fld.cnt = __ldcg(&q->count);
+      fld.x0 = __ldcg(&q->x_min);
+      fld.y0 = __ldcg(&q->y_min);
+      fld.x1 = __ldcg(&q->x_max);
+      fld.y1 = __ldcg(&q->y_max);
+      fld.occ = __ldcg(&q->occlusion);
+      fld.trunc = __ldcg(&q->truncation);
+      fld.sep = fld.ann_id > 1;
+      if (!(fabsf(fld.occ) < 1048576.0f) || !(fabsf(fld.trunc) < 1048576.0f)) {
+        bad_s = 1;   // an unprintable ratio: the frame is flagged, nothing is written for the record
+      } else {
+        CountWriter cw;
+        coco_record(cw, fld);
+        len = cw.n;
       }
     }
     int incl = len;
@@ -269,17 +303,9 @@ __global__ void __launch_bounds__(kYoloThreads)
       if (w < wid) before += sw;
       total += sw;
     }
-    if (r < n && len > 0) {
-      long long pos = base_s + before + incl - len;
-      const bool sep = first_id_s + r > 1;
-      const int body = sep ? len - 2 : len;
-      if (sep) {
-        if (pos < frame_stride) out[pos] = ',';
-        if (pos + 1 < frame_stride) out[pos + 1] = ' ';
-        pos += 2;
-      }
-      for (int i = 0; i < body; ++i)
-        if (pos + i < frame_stride) out[pos + i] = line[i];
+    if (len > 0) {
+      TextWriter tw{out, base_s + before + incl - len, frame_stride};
+      coco_record(tw, fld);
     }
     __syncthreads();
     if (tid == 0) base_s += total;
@@ -333,8 +359,18 @@ __global__ void __launch_bounds__(kYoloThreads)
   n = n < 0 ? 0 : (n > stride ? stride : n);
   const long long off = off_s;
   const char* src = text + static_cast<long long>(f) * stride;
-  for (long long i = tid; i < n; i += kYoloThreads)
-    if (off + i < capacity) packed[off + i] = __ldcg(src + i);
+  if (((reinterpret_cast<uintptr_t>(src)) & 15) == 0) {   // rows at a 16-byte stride: one 16-byte load per 16 bytes
+    for (long long i = static_cast<long long>(tid) * 16; i < n; i += kYoloThreads * 16) {
+      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
+      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        if (i + k < n && off + i + k < capacity) packed[off + i + k] = static_cast<char>((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+    }
+  } else {
+    for (long long i = tid; i < n; i += kYoloThreads)
+      if (off + i < capacity) packed[off + i] = __ldcg(src + i);
+  }
   if (f == B - 1 && tid == 0) *total = off + n;
 }
 

@@ -192,7 +192,7 @@ def write_files(directory: str, prefix: str, suffix: str, first_id: int, data: n
     return int(rc)
 
 
-def concat_rows(data: np.ndarray, sizes: np.ndarray, count: Optional[int] = None) -> bytes:
+def concat_rows(data: np.ndarray, sizes: np.ndarray, count: Optional[int] = None, as_array: bool = False):
     """``data[j, :sizes[j]]`` for j < count, back to back (libcspe ``cspe_concat_rows_host``): the per-frame label text
     of a D2H buffer (``cspe_format_yolo`` / ``cspe_format_coco``) as one chunk."""
     from . import _lib
@@ -208,7 +208,7 @@ def concat_rows(data: np.ndarray, sizes: np.ndarray, count: Optional[int] = None
     out = np.empty(cap, dtype=np.uint8)
     rc = lib.cspe_concat_rows_host(data.ctypes.data, data.shape[1], sizes.ctypes.data, count, out.ctypes.data, cap)
     _lib.check("cspe_concat_rows_host", rc)
-    return out[:rc].tobytes()
+    return out[:rc] if as_array else out[:rc].tobytes()   # as_array: no second copy (a uint8 array is bytes-like)
 
 
 def coco_categories() -> List[Dict[str, object]]:
@@ -280,8 +280,19 @@ def coco_annotations_text(records: np.ndarray, n_out: np.ndarray, image_ids: Seq
 
 def coco_images_text(image_ids: Sequence[int], width: int, height: int) -> bytes:
     """The ``images`` entries of a run of frames as the text ``json.dumps([coco_image(...), ...])`` puts between
-    its brackets (a 100 k-frame sweep would otherwise build and dump 100 k dicts)."""
+    its brackets (a 100 k-frame sweep would otherwise build and dump 100 k dicts).  A contiguous ``range`` goes
+    through the native formatter (libcspe ``cspe_format_coco_images_host``), anything else through the Python
+    statement of the same text."""
     w, h = int(width), int(height)
+    if isinstance(image_ids, range) and image_ids.step == 1 and len(image_ids) > 0:
+        from . import _lib
+
+        lib = _lib.load()
+        cap = 160 * len(image_ids)
+        buf = np.empty(cap, dtype=np.uint8)
+        rc = lib.cspe_format_coco_images_host(int(image_ids.start), len(image_ids), w, h, buf.ctypes.data, cap)
+        _lib.check("cspe_format_coco_images_host", rc)
+        return buf[:rc].tobytes()
     return ", ".join(f'{{"id": {int(i)}, "width": {w}, "height": {h}, "file_name": "rgb_{int(i):06d}.png"}}'
                      for i in image_ids).encode("ascii")
 
@@ -293,11 +304,20 @@ def write_coco_file(path, images: Sequence[Union[Mapping, bytes]], annotation_ch
     (``coco_image``) or as pre-formatted chunks (``coco_images_text``)."""
     with open(path, "wb") as f:
         if images and isinstance(images[0], (bytes, bytearray)):
-            f.write(b'{"images": [' + b", ".join(c for c in images if c) + b'], "annotations": [')
+            f.write(b'{"images": [' + b", ".join(c for c in images if len(c)) + b'], "annotations": [')
         else:
             f.write(b'{"images": ' + json.dumps(list(images)).encode("ascii") + b', "annotations": [')
         # joined=True: the chunks already carry their ", " separators (device formatter)
-        f.write((b"" if joined else b", ").join(c for c in annotation_chunks if c))
+        # (chunks are bytes-like: bytes or uint8 arrays straight from the D2H buffer — len(), not truthiness)
+        sep = b"" if joined else b", "
+        first = True
+        for c in annotation_chunks:
+            if len(c) == 0:
+                continue
+            if not first and sep:
+                f.write(sep)
+            f.write(c)
+            first = False
         f.write(b'], "categories": ' + json.dumps(coco_categories()).encode("ascii") + b"}")
 
 

@@ -229,11 +229,16 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         groups = [full[i:i + group] for i in range(0, len(full) - len(full) % group, group)] if use_graph else []
         eager = head + full[len(groups) * group:] + tail
         ann_state = torch.zeros((2,), dtype=torch.int64, device=device) if text_kind == "coco" else None
-        graphs = [_GroupGraph(pipe, group, want_records, text_kind, ann_state) for _ in range(min(2, len(groups)))]
+        # three instances with their own output buffers take turns: one is running, one is being consumed, and the worker
+        # jobs that still read the third one's pinned buffers have a whole group time to finish before it is relaunched
+        n_inst = 3 if (want_records or text_kind == "coco" or label_dir is not None) else 2
+        graphs = [_GroupGraph(pipe, group, want_records, text_kind, ann_state) for _ in range(min(n_inst, len(groups)))]
         eager_slot = _BatchOut(pipe, want_records, want_yolo, None, text_kind, ann_state) if eager else None
         workers = max(1, min(8, (os.cpu_count() or 2) // max(1, world))) if io_threads is None else max(1, io_threads)
+        if text_kind == "coco" and io_threads is None:
+            workers = min(workers, 3)
         io_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="cspe-io") \
-            if (want_records or label_dir is not None) else None
+            if (want_records or label_dir is not None or text_kind == "coco") else None
         slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
 
         emitted = 0
@@ -276,11 +281,17 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                     sizes = nb if in_place else nb.copy()
                 if text_kind == "coco":   # the batch's annotation text is one chunk at the front of the packed buffer
                     coco_count += count
-                    coco_imgs.append(formats.coco_images_text(range(s, e), W, H))
                     total = int(slot.total_h[0])
                     if total != int(nb.sum()):
                         raise RuntimeError(f"COCO text of frames {s}..{e}: packed {total} bytes, sizes sum to {int(nb.sum())}")
-                    coco_anns.append(bytes(memoryview(slot.packed_h.numpy())[:total]))
+                    packed = slot.packed_h.numpy().reshape(1, -1)
+                    if not in_place:
+                        packed = packed[:, :total].copy()
+                    # off the launch thread, on ONE consumer thread: the images entries and the memcpy of the chunk are
+                    # native calls (no GIL); several Python workers only fought the launch thread for the interpreter
+                    # (8 workers: 199 k frames/s, the launch thread itself: 386 k)
+                    submit(lambda: (formats.coco_images_text(range(s, e), W, H),
+                                    formats.concat_rows(packed, np.array([total], dtype=np.int32), as_array=True)))
                 elif label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
                     submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
@@ -313,7 +324,10 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             nonlocal text_bytes
             while len(pending) > limit:
                 r = pending.pop(0).result()
-                if emit == "coco_host":
+                if emit == "coco":
+                    coco_imgs.append(r[0])
+                    coco_anns.append(r[1])
+                elif emit == "coco_host":
                     coco_anns.append(r)
                     text_bytes += len(r)
                 elif isinstance(r, int) and emit == "json":
@@ -344,12 +358,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
 
         # ---- the bulk: graph groups, two instances alternating -----------------------------------------
         for gi, grp in enumerate(groups):
-            g = graphs[gi % 2]
+            g = graphs[gi % len(graphs)]
             t1 = time.perf_counter()
             g.launch(grp[0][0])
             timers["launch_s"] += time.perf_counter() - t1
             if gi > 0:   # consume the previous group while this one runs
-                prev, pgrp = graphs[(gi - 1) % 2], groups[gi - 1]
+                prev, pgrp = graphs[(gi - 1) % len(graphs)], groups[gi - 1]
                 t1 = time.perf_counter()
                 prev.done.synchronize()
                 t2 = time.perf_counter()
@@ -359,7 +373,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 timers["wait_s"] += t2 - t1
                 timers["consume_s"] += time.perf_counter() - t2
         if groups:
-            prev, pgrp = graphs[(len(groups) - 1) % 2], groups[-1]
+            prev, pgrp = graphs[(len(groups) - 1) % len(graphs)], groups[-1]
             t1 = time.perf_counter()
             prev.done.synchronize()
             t2 = time.perf_counter()

@@ -366,6 +366,13 @@ int64_t cspe_write_files_host(const char* dir, const char* prefix, int digits, c
 int64_t cspe_concat_rows_host(const char* data_host, int64_t stride, const int32_t* sizes_host, int count,
                               char* out_host, int64_t capacity);
 
+/* f3: the "images" entries of a COCO file for frames first_id .. first_id + count (no CUDA; HOST pointers):
+ *   {"id": i, "width": W, "height": H, "file_name": "rgb_%06d.png"}   joined by ", "
+ * (rgb_%06d.png is the capture loop's image name, gcd.py:1672).  Returns the bytes written or a negative
+ * CSPE_ERR_* (160 bytes per image always suffice). */
+int64_t cspe_format_coco_images_host(int64_t first_id, int count, int width, int height, char* out_host,
+                                     int64_t capacity);
+
 /* f3: host-side label JSON of ONE frame (no CUDA; all pointers are HOST pointers) — the text
  * json.dump(label, f, indent=2, ensure_ascii=False) writes (gcd.py:608-613) for the frame dict of
  * gcd.py:2056-2064 with the object dicts of gcd.py:1938-1946 plus the added fields

@@ -497,3 +497,31 @@ def test_native_batch_file_writer(tmp_path):
         formats.write_files(str(tmp_path / "missing_dir"), "label_", ".txt", 0, data, sizes)
     with pytest.raises(_lib.CspeError):
         formats.write_files(str(tmp_path), "label_", ".txt", 0, data, np.array([33, 0, 0, 0], dtype=np.int32))
+
+
+def test_concat_rows_and_coco_ratio_rule():
+    """cspe_concat_rows_host (strided rows back to back) and the 6-decimal rule of the COCO ratio fields: the native host
+    formatter prints them exactly as Python prints round(x, 6) — fixed notation from 1e-4 up, exponent form below,
+    trailing zeros dropped (csrc/repr6.h is shared with the device formatter)."""
+    import json
+    from constructionsceneposeestimation_b200 import _lib, formats
+    data = np.frombuffer(b"abcdefgh" + b"ij------" + b"--------" + b"klmnopqr", dtype=np.uint8).reshape(4, 8).copy()
+    assert formats.concat_rows(data, np.array([8, 2, 0, 5], dtype=np.int32)) == b"abcdefghijklmno"
+    assert formats.concat_rows(data, np.array([8, 2, 0, 5], dtype=np.int32), count=2) == b"abcdefghij"
+    with pytest.raises(_lib.CspeError):
+        formats.concat_rows(data, np.array([9, 0, 0, 0], dtype=np.int32))
+    vals = np.array([0.0, 1.0, 0.5, 5e-7, 4.9e-7, 1.2e-5, 9.95e-5, 9.96e-5, 1e-4, 1e-6, 0.9999995, 0.99999994, 1e-30, 0.1234565,
+                     0.000123, 0.25, 3.3e-5, 5.05e-5, 0.1, 0.7, 2.5e-6], dtype=np.float32)
+    rng = np.random.default_rng(4)
+    vals = np.concatenate([vals, rng.random(500, dtype=np.float32), (rng.integers(0, 2 ** 21, 500) / np.float32(2 ** 21)).astype(np.float32),
+                           rng.random(200, dtype=np.float32) * np.float32(2e-4)])
+    recs = np.zeros((1, len(vals)), dtype=_lib.RECORD_DTYPE)
+    recs["count"], recs["x_max"], recs["y_max"] = 7, 3, 4
+    recs["occlusion"][0] = vals
+    recs["truncation"][0] = vals[::-1]
+    n = np.array([len(vals)], dtype=np.int32)
+    text, count = formats.coco_annotations_text(recs, n, [12], 1)
+    py = formats.coco_annotations(recs[0], 12, 1)
+    assert count == len(vals) and text == json.dumps(py)[1:-1].encode()
+    assert all(a["occlusion"] == round(float(v), 6) for a, v in zip(py, vals))
+    assert b'e-06, ' in text and b'"occlusion": 1.2e-05' in text and b'"occlusion": 0.0001,' in text

@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q > gpurun_out/p_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/p_pytest.log; tail -8 gpurun_out/p_pytest.log | cut -c1-300
+timeout 300 python -m constructionsceneposeestimation_b200.sweep --frames 100000 --emit coco --repeat 4 > gpurun_out/p_sweep_coco.json 2> gpurun_out/p_sweep_coco.err
+python -c "
+import json; d=json.load(open('gpurun_out/p_sweep_coco.json')); print('coco', [round(x) for x in d['frames_per_s_all_ranks_runs']], d['host_timers'], d['io_threads'])"
