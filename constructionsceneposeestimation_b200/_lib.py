@@ -111,6 +111,7 @@ PROTOTYPES = {
     "cspe_mask_scan_depth_stats": (_I, [_P, _P, _I, _I, _I, _P, _I, _I64, _I, _P, _P, _P]),
     "cspe_project_objects": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
     "cspe_project_objects_overlapped": (_I, [_P, _I, _I, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "cspe_union_records": (_I, [_P, _I, _I, _I, _P, _I64, _P, _I64, _I, _I, _P]),
     "cspe_keypoints": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, C.c_double, _P, _P, _P, _P]),
     "cspe_keypoints_overlapped": (_I, [_P, _I, _I, _I, _P, _I, _I, _P, C.c_double, _P, _P, _P, _P]),
     "cspe_emit": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

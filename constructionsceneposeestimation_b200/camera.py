@@ -7,7 +7,8 @@ SURVEY §8a rows R4 and R5:
 """
 from __future__ import annotations
 
-from typing import Mapping, Optional, Sequence
+from collections.abc import Mapping
+from typing import Optional, Sequence
 
 import numpy as np
 

@@ -14,7 +14,8 @@ against the live function where ``/root/reference`` exists.
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
+from collections.abc import Mapping
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 # substring (lower case) -> class id; insertion order matters for the generic fallback
 # (first key that occurs in the path wins), so it mirrors gcd.py:69-106 key for key.
@@ -200,26 +201,77 @@ def record_index_for(objects: Sequence[SceneObject], prim_paths: Sequence[str], 
     reference's rule and leaves such objects without a record.  A first-mesh stand-in for anything but a
     crane part describes ONE mesh of a multi-mesh object, not the object: its index carries
     ``RECORD_APPROX_BIT`` so K2 sets ``OBJ_APPROX_RECORD`` in the record's flags and the label says so.
+
+    ``fallback="union"`` gives those multi-mesh objects an object-level record instead: the u-th entry of
+    ``union_members(objects, prim_paths)`` gets index ``len(prim_paths) + u`` (still with ``RECORD_APPROX_BIT``: the
+    box is built from the mesh records, not read from the object's own prim) — the place where
+    ``cspe_union_records`` writes the world-axis-aligned range of all its mesh records, which is the bound the
+    reference's USD fallback computes (gcd.py:2000-2009).  A caller whose record array is padded to R > len(prim_paths)
+    records re-bases those entries to ``R + u``.
     """
-    if fallback not in ("first_mesh", "reference"):
+    if fallback not in ("first_mesh", "reference", "union"):
         raise ValueError(f"unknown record fallback {fallback!r}")
     first_index: Dict[str, int] = {}
     for i, p in enumerate(prim_paths):
         first_index.setdefault(p, i)
     out: List[int] = []
+    n_union = 0
     for obj in objects:
         idx = first_index.get(obj.actual_prim_path, -1)
-        if idx < 0 and ("#" in obj.prim_path or fallback == "first_mesh"):
-            for mp in obj.mesh_paths:
-                idx = first_index.get(mp, -1)
-                if idx >= 0:
-                    break
-            # the reference's own rule for crane parts (gcd.py:1953-1975) is not an approximation of ours; a
-            # single-mesh object is described exactly by its only mesh
-            if idx >= 0 and mark_approx and "#" not in obj.prim_path and len(obj.mesh_paths) > 1:
-                idx |= RECORD_APPROX_BIT
+        if idx < 0 and ("#" in obj.prim_path or fallback != "reference"):
+            multi = "#" not in obj.prim_path and len(obj.mesh_paths) > 1
+            if fallback == "union" and multi:
+                if any(mp in first_index for mp in obj.mesh_paths):
+                    idx = (len(prim_paths) + n_union) | RECORD_APPROX_BIT
+                    n_union += 1
+            else:
+                for mp in obj.mesh_paths:
+                    idx = first_index.get(mp, -1)
+                    if idx >= 0:
+                        break
+                # the reference's own rule for crane parts (gcd.py:1953-1975) is not an approximation of ours; a
+                # single-mesh object is described exactly by its only mesh
+                if idx >= 0 and mark_approx and multi:
+                    idx |= RECORD_APPROX_BIT
         out.append(idx)
     return out
+
+
+def union_members(objects: Sequence[SceneObject], prim_paths: Sequence[str]) -> List[Tuple[int, List[int]]]:
+    """``[(slot, [record index of every mesh path that has a record])]`` for the objects ``fallback="union"`` builds
+    an object-level record for, in slot order: no record under the object's own prim path, not a crane part (those
+    keep the reference's first-mesh rule, gcd.py:1953-1975), several mesh paths, at least one of them with a record."""
+    first_index: Dict[str, int] = {}
+    for i, p in enumerate(prim_paths):
+        first_index.setdefault(p, i)
+    out: List[Tuple[int, List[int]]] = []
+    for slot, obj in enumerate(objects):
+        if obj.actual_prim_path in first_index or "#" in obj.prim_path or len(obj.mesh_paths) <= 1:
+            continue
+        mem = [first_index[mp] for mp in obj.mesh_paths if mp in first_index]
+        if mem:
+            out.append((slot, mem))
+    return out
+
+
+def pack_union(per_frame: Sequence[Sequence[Tuple[int, Sequence[int]]]]):
+    """CSR tables of a batch for ``cspe_union_records``: (offsets int32 [B, U+1], members int32 [B, M], U) with U / M
+    the largest count of the batch (frames with fewer union objects get empty ranges; M >= 1)."""
+    import numpy as np
+
+    B = len(per_frame)
+    U = max((len(p) for p in per_frame), default=0)
+    M = max(1, max((sum(len(m) for _, m in p) for p in per_frame), default=0))
+    offsets = np.zeros((B, U + 1), dtype=np.int32)
+    members = np.full((B, M), -1, dtype=np.int32)
+    for f, plan in enumerate(per_frame):
+        pos = 0
+        for u, (_, mem) in enumerate(plan):
+            members[f, pos: pos + len(mem)] = mem
+            pos += len(mem)
+            offsets[f, u + 1] = pos
+        offsets[f, len(plan) + 1:] = pos
+    return offsets, members, U
 
 
 def label_path(label) -> Optional[str]:

@@ -317,6 +317,74 @@ __device__ __forceinline__ void project_one(const unsigned char* __restrict__ re
   flags[obj] = fl;
 }
 
+
+// ---- object-level records for multi-mesh objects (record_fallback = "union") ------------------------------------
+// The reference reads the bound of an object whose root prim has no bbox3d record from the live USD stage
+// (UsdGeom.BBoxCache.ComputeWorldBound(...).ComputeAlignedRange(), gcd.py:2000-2009): the world-axis-aligned range of
+// everything under the prim.  Outside Isaac Sim the same range is the min / max of the eight world-space corners of every
+// mesh record of the object.  One thread per (frame, union object): corners exactly as K2 computes them
+// (p_w = ((c0*T0j + c1*T1j) + c2*T2j) + T3j in double, -fmad=false), fmin / fmax over them (NaN corners drop out), the
+// range rounded to float32 and written as a record with an identity transform at records[frame][base + u] — K2 then
+// treats it like any other record (centre = middle of the range, size = its extent, rotation 0).
+__global__ void union_records_kernel(unsigned char* __restrict__ records, int rec_stride, int recs_per_frame, int base,
+                                     const int32_t* __restrict__ offsets, long long off_stride,
+                                     const int32_t* __restrict__ members, long long mem_stride, int B, int U) {
+  // launched as an ordinary kernel (no programmatic attribute, no early release of dependents): whatever follows in
+  // the stream — also a kernel that starts early behind the mask scan — sees these records complete
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long long>(B) * U) return;
+  const int frame = static_cast<int>(i / U), u = static_cast<int>(i % U);
+  const int32_t* off = offsets + frame * off_stride;
+  const int32_t* mem = members + frame * mem_stride;
+  const int lo = off[u], hi = off[u + 1];
+  unsigned char* frame_recs = records + static_cast<long long>(frame) * recs_per_frame * static_cast<long long>(rec_stride);
+  float* out = reinterpret_cast<float*>(frame_recs + static_cast<long long>(base + u) * rec_stride);
+  const double kInf = __longlong_as_double(0x7ff0000000000000ll);
+  double mn[3] = {kInf, kInf, kInf}, mx[3] = {-kInf, -kInf, -kInf};
+  float sem = 0.0f, occ = 0.0f;
+  bool first = true;
+  for (int m = lo; m < hi; ++m) {
+    const int rec = mem[m];
+    if (rec < 0 || rec >= base) continue;
+    const float* rp = reinterpret_cast<const float*>(frame_recs + static_cast<long long>(rec) * rec_stride);
+    if (first) {
+      sem = rp[0];   // semanticId bits / occlusionRatio of the first mesh record travel with the object
+      occ = rp[23];
+      first = false;
+    }
+    const float e0[3] = {rp[1], rp[2], rp[3]}, e1[3] = {rp[4], rp[5], rp[6]};
+    double T[4][3];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) T[a][j] = static_cast<double>(rp[7 + a * 4 + j]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const double c0 = static_cast<double>((k & 1) ? e1[0] : e0[0]), c1 = static_cast<double>((k & 2) ? e1[1] : e0[1]),
+                   c2 = static_cast<double>((k & 4) ? e1[2] : e0[2]);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double pw = ((c0 * T[0][j] + c1 * T[1][j]) + c2 * T[2][j]) + T[3][j];
+        mn[j] = fmin(mn[j], pw);
+        mx[j] = fmax(mx[j], pw);
+      }
+    }
+  }
+  const float kNaNf = __int_as_float(0x7fc00000);
+  const bool any = mn[0] <= mx[0] && mn[1] <= mx[1] && mn[2] <= mx[2];   // false when no finite corner was seen
+  out[0] = sem;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    out[1 + j] = any ? __double2float_rn(mn[j]) : kNaNf;
+    out[4 + j] = any ? __double2float_rn(mx[j]) : kNaNf;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[7 + a * 4 + j] = (a == j) ? 1.0f : 0.0f;
+  out[23] = occ;
+}
+
 }  // namespace
 }  // namespace cspe
 
@@ -368,4 +436,29 @@ extern "C" int cspe_project_objects_overlapped(const void* records, int rec_stri
                                                double* z, double* pose, double* loose, uint8_t* flags, void* stream) {
   return project_objects_impl(records, rec_stride, recs_per_frame, obj_record, cam, B, N, uv, z, pose, loose, flags,
                               stream, 1);
+}
+
+extern "C" int cspe_union_records(void* records, int rec_stride, int recs_per_frame, int base, const int32_t* offsets,
+                                  int64_t offsets_stride, const int32_t* members, int64_t members_stride, int B, int U,
+                                  void* stream) {
+  CSPE_REQUIRE(B >= 0 && U >= 0 && base >= 0 && recs_per_frame >= 0 && offsets_stride >= 0 && members_stride >= 0,
+               CSPE_ERR_INVALID_ARGUMENT, "cspe_union_records: negative size (B=%d U=%d base=%d recs_per_frame=%d)", B, U,
+               base, recs_per_frame);
+  if (B == 0 || U == 0) return CSPE_OK;
+  CSPE_REQUIRE(rec_stride >= CSPE_BBOX3D_RECORD_BYTES && rec_stride % 4 == 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_union_records: rec_stride %d (need >= %d and a multiple of 4)", rec_stride, CSPE_BBOX3D_RECORD_BYTES);
+  CSPE_REQUIRE(static_cast<long long>(base) + U <= recs_per_frame, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_union_records: base %d + U %d exceeds recs_per_frame %d", base, U, recs_per_frame);
+  CSPE_REQUIRE(records && offsets && members, CSPE_ERR_INVALID_ARGUMENT, "cspe_union_records: null pointer");
+  CSPE_REQUIRE((reinterpret_cast<uintptr_t>(records) & 3) == 0, CSPE_ERR_INVALID_ARGUMENT,
+               "cspe_union_records: misaligned records");
+  const long long total = static_cast<long long>(B) * U;
+  const int threads = 64;
+  const long long blocks = (total + threads - 1) / threads;
+  CSPE_REQUIRE(blocks < (1ll << 31), CSPE_ERR_UNSUPPORTED, "cspe_union_records: too many objects");
+  union_records_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<unsigned char*>(records), rec_stride, recs_per_frame, base, offsets, offsets_stride, members,
+      members_stride, B, U);
+  CSPE_LAUNCH_OK("union_records_kernel");
+  return CSPE_OK;
 }

@@ -113,6 +113,33 @@ def depth_stats(depth: torch.Tensor) -> torch.Tensor:
     return stats
 
 
+def union_records(records: torch.Tensor, base: int, offsets: torch.Tensor, members: torch.Tensor) -> torch.Tensor:
+    """Object-level records for multi-mesh objects (``record_fallback="union"``): records uint8 [B,R,stride] with
+    ``R >= base + U``; offsets int32 [U+1] or [B,U+1], members int32 [M] or [B,M] (record indices < base).  Writes
+    records[:, base + u] in place (world-axis-aligned range of the members' corners, identity transform) and returns
+    ``records``."""
+    lib = _lib.load()
+    _dev(records, torch.uint8, "records")
+    _dev(offsets, torch.int32, "offsets")
+    _dev(members, torch.int32, "members")
+    if records.dim() != 3:
+        raise ValueError(f"records must be uint8 [B,R,stride], got {tuple(records.shape)}")
+    B, R, stride = records.shape
+    if offsets.dim() != members.dim() or offsets.dim() not in (1, 2) or (offsets.dim() == 2 and
+                                                                         (offsets.shape[0] != B or members.shape[0] != B)):
+        raise ValueError(f"offsets {tuple(offsets.shape)} / members {tuple(members.shape)}: need [U+1] / [M] or [B,U+1] / [B,M]")
+    U = offsets.shape[-1] - 1
+    if U < 0 or base < 0 or base + U > R:
+        raise ValueError(f"base {base} + {U} union objects exceed the {R} records per frame")
+    off_stride = offsets.shape[1] if offsets.dim() == 2 else 0
+    mem_stride = members.shape[1] if members.dim() == 2 else 0
+    with torch.cuda.device(records.device):
+        rc = lib.cspe_union_records(records.data_ptr(), stride, R, base, offsets.data_ptr(), off_stride,
+                                    members.data_ptr(), mem_stride, B, U, _stream_ptr())
+    _lib.check("cspe_union_records", rc)
+    return records
+
+
 def project_objects(records: torch.Tensor, obj_record: torch.Tensor, cam: torch.Tensor):
     """K2: records uint8 [B,R,stride], obj_record int32 [B,N], cam f64 [B,24]
     -> uv f64 [B,N,8,2], z f64 [B,N,8], pose f64 [B,N,16], loose f64 [B,N,4], flags u8 [B,N]."""

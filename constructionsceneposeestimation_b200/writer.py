@@ -18,8 +18,9 @@ import json
 import os
 import warnings
 import weakref
+from collections.abc import Mapping   # isinstance() against typing.Mapping goes through a pure-Python __instancecheck__
 from dataclasses import dataclass, field
-from typing import Dict, List, Mapping, Optional, Sequence, Tuple, Union
+from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -29,8 +30,8 @@ from .quality import FrameQualityLog, depth_quality_from_stats
 from ._lib import BBOX3D_DTYPE, CAM_STRIDE, NUM_CLASSES, RECORD_DTYPE
 from .camera import (DEFAULT_FAR, DEFAULT_NEAR, camera_params as default_camera_params, from_replicator_camera_params,
                      is_replicator_camera_params, pack_camera, pack_cameras)
-from .classes import (CLASS_NAMES, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot, label_path,
-                      record_index_for)
+from .classes import (CLASS_NAMES, RECORD_APPROX_BIT, ObjectRootResolver, SceneObject, aggregate_objects, id_to_slot,
+                      label_path, pack_union, record_index_for, union_members)
 
 ArrayLike = Union[np.ndarray, torch.Tensor]
 
@@ -47,6 +48,9 @@ class FrameTables:
     lut_slots: np.ndarray       # int32 [K]
     max_id: int
     slot_strings: Optional[Tuple[bytes, np.ndarray]] = None   # JSON literals of class_name / prim_path per slot (lazy)
+    # record_fallback="union": [(slot, [mesh record indices])] of the objects that get an object-level record
+    union: Sequence[Tuple[int, Sequence[int]]] = ()
+    n_paths: int = 0            # len(primPaths) the table was built from (union indices are relative to it)
 
 
 @dataclass
@@ -173,6 +177,7 @@ class _FrameList(list):
     """Per-frame dicts cut from a stacked batch dict; remembers the stacked pixel arrays so that they reach the
     device in one copy (or none, when they already live there)."""
     stacked: Dict[str, ArrayLike]
+    canonical: bool = False
 
 
 def _unstack(data: Mapping) -> _FrameList:
@@ -190,20 +195,35 @@ def _unstack(data: Mapping) -> _FrameList:
             return value[i]
         return value
 
+    rows_of: Dict[int, Sequence] = {}
+
+    def rows(payload):
+        """payload[i] for every i: one unbind for a torch tensor (B Python-level indexing calls on a CUDA tensor cost
+        more than everything else in this function together)."""
+        r = rows_of.get(id(payload))
+        if r is None:
+            r = payload.unbind(0) if isinstance(payload, torch.Tensor) and payload.shape[0] == B else payload
+            rows_of[id(payload)] = r
+        return r
+
     def cut(annot, i):
         if annot is None:
             return None
-        if isinstance(annot, Mapping):
+        if type(annot) is dict or isinstance(annot, Mapping):
             payload = annot.get("data")
-            out = {"data": None if payload is None else payload[i]}
+            out = {"data": None if payload is None else rows(payload)[i]}
             if "info" in annot:
                 out["info"] = per_frame(annot["info"], i)
             return out
-        return annot[i]
+        return rows(annot)[i]
 
     frames = _FrameList()
     fid = data.get("frame_id")
     pose = data.get("camera_pose")
+    if pose is not None:
+        pose = np.asarray(pose, dtype=np.float64)
+        pose_rows = pose.tolist() if pose.ndim == 2 else None
+    fid_is_seq = fid is not None and np.ndim(fid) > 0
     for i in range(B):
         fr: Dict[str, object] = {}
         for name in ("instance_segmentation", "distance_to_image_plane", "bounding_box_3d", "rgb"):
@@ -214,14 +234,14 @@ def _unstack(data: Mapping) -> _FrameList:
             j = sk.get("globalTranslations") if isinstance(sk, Mapping) else sk
             fr["skeleton_data"] = {"globalTranslations": j[i]}
         if pose is not None:
-            p = np.asarray(pose, dtype=np.float64)
-            fr["camera_pose"] = list(p[i] if p.ndim == 2 else p)
+            fr["camera_pose"] = pose_rows[i] if pose_rows is not None else list(pose)
         if data.get("camera_params") is not None:
             fr["camera_params"] = per_frame(data["camera_params"], i)
         if fid is not None:
-            fr["frame_id"] = int(fid[i]) if np.ndim(fid) else int(fid) + i
+            fr["frame_id"] = int(fid[i]) if fid_is_seq else int(fid) + i
         frames.append(fr)
     frames.stacked = {"instance_segmentation": masks}
+    frames.canonical = True   # keys are plain annotator names already
     depth = _payload(data.get("distance_to_image_plane"))
     if depth is not None and getattr(depth, "ndim", 0) == 3:
         frames.stacked["distance_to_image_plane"] = depth
@@ -242,14 +262,14 @@ def tables_cache_key(prim_paths: Sequence[str], id_to_labels: Mapping) -> Tuple:
 
 
 def _info(annot) -> Mapping:
-    if isinstance(annot, Mapping):
+    if type(annot) is dict or isinstance(annot, Mapping):
         info = annot.get("info")
-        return info if isinstance(info, Mapping) else {}
+        return info if (type(info) is dict or isinstance(info, Mapping)) else {}
     return {}
 
 
 def _payload(annot):
-    if isinstance(annot, Mapping):
+    if type(annot) is dict or isinstance(annot, Mapping):
         return annot.get("data")
     return annot
 
@@ -258,16 +278,25 @@ _ANNOTATOR_KEYS = ("instance_segmentation", "distance_to_image_plane", "bounding
                    "skeleton_data", "rgb", "camera_pose", "pointcloud")
 
 
+_NAME_CACHE: Dict[str, Tuple[Optional[str], Optional[str]]] = {}
+
+
 def _annotator_name(key: str) -> Tuple[Optional[str], Optional[str]]:
     """(canonical annotator name, render-product suffix) of a Replicator payload key: writers attached to a
     render product receive ``"<annotator>-<render product>"`` keys, and the ``*_fast`` variants deliver the same
     payload as their plain annotator.  (None, None) for keys that are not annotators of this path."""
+    hit = _NAME_CACHE.get(key)
+    if hit is not None:
+        return hit
     base, _, suffix = key.partition("-")
     if base.endswith("_fast"):
         base = base[:-5]
     if base == "LdrColor":
         base = "rgb"
-    return (base, suffix or None) if base in _ANNOTATOR_KEYS else (None, None)
+    out = (base, suffix or None) if base in _ANNOTATOR_KEYS else (None, None)
+    if len(_NAME_CACHE) < 4096:
+        _NAME_CACHE[key] = out
+    return out
 
 
 def split_render_products(data: Mapping) -> List[Dict[str, object]]:
@@ -335,8 +364,11 @@ class _TableBlock:
     """The small per-batch host tables laid out in ONE pinned block — [lut | obj_record | slot_class | cam | records]
     — so that they reach the device in a single H2D copy into a matching device block."""
 
-    def __init__(self, writer: "ConstructionLabelWriter", lut_rows: int, L: int, B: int, N: int, R: int):
-        sizes = [lut_rows * L * 4, B * N * 4, B * N * 4, B * CAM_STRIDE * 8, B * R * BBOX3D_DTYPE.itemsize]
+    def __init__(self, writer: "ConstructionLabelWriter", lut_rows: int, L: int, B: int, N: int, R: int,
+                 union_shape: Tuple[int, int, int] = (0, 0, 0)):
+        u_rows, U1, M = union_shape   # record_fallback="union": offsets int32 [u_rows][U1], members int32 [u_rows][M]
+        sizes = [lut_rows * L * 4, B * N * 4, B * N * 4, B * CAM_STRIDE * 8, B * R * BBOX3D_DTYPE.itemsize,
+                 u_rows * U1 * 4, u_rows * M * 4]
         offs = [0]
         for sz in sizes:
             offs.append((offs[-1] + sz + 15) & ~15)
@@ -349,17 +381,27 @@ class _TableBlock:
         self.slot_class = h[offs[2]: offs[2] + sizes[2]].view(np.int32).reshape(B, N)
         self.cam = h[offs[3]: offs[3] + sizes[3]].view(np.float64).reshape(B, CAM_STRIDE)
         self.records = h[offs[4]: offs[4] + sizes[4]].reshape(B, R, BBOX3D_DTYPE.itemsize)
-        self._offs, self._sizes, self._shapes = offs, sizes, (lut_rows, L, B, N, R)
+        self.union_offsets = h[offs[5]: offs[5] + sizes[5]].view(np.int32).reshape(u_rows, U1)
+        self.union_members = h[offs[6]: offs[6] + sizes[6]].view(np.int32).reshape(u_rows, M)
+        self._offs, self._sizes, self._shapes, self._union_shape = offs, sizes, (lut_rows, L, B, N, R), union_shape
 
     def upload(self):
         lut_rows, L, B, N, R = self._shapes
         d = self.host.to(self.device, non_blocking=True)
+        self.device_block = d
         o, z = self._offs, self._sizes
         return (d[o[0]: o[0] + z[0]].view(torch.int32).view(lut_rows, L),
                 d[o[1]: o[1] + z[1]].view(torch.int32).view(B, N),
                 d[o[2]: o[2] + z[2]].view(torch.int32).view(B, N),
                 d[o[4]: o[4] + z[4]].view(B, R, BBOX3D_DTYPE.itemsize),
                 d[o[3]: o[3] + z[3]].view(torch.float64).view(B, CAM_STRIDE))
+
+    def union_on_device(self, d: torch.Tensor):
+        """(offsets, members) views of the device block ``d`` (the storage ``upload`` returned views of)."""
+        u_rows, U1, M = self._union_shape
+        o, z = self._offs, self._sizes
+        return (d[o[5]: o[5] + z[5]].view(torch.int32).view(u_rows, U1),
+                d[o[6]: o[6] + z[6]].view(torch.int32).view(u_rows, M))
 
 
 class ConstructionLabelWriter:
@@ -397,6 +439,8 @@ class ConstructionLabelWriter:
         self.min_pixels = int(min_pixels)
         self.keypoint_tolerance = float(keypoint_tolerance)
         self.near, self.far = float(near), float(far)
+        if record_fallback not in ("first_mesh", "reference", "union"):
+            raise ValueError(f"unknown record fallback {record_fallback!r}")
         self.record_fallback = record_fallback
         self.resolver = ObjectRootResolver(crane_part_map, split_people=split_people)
         self.rank, self.world_size = rank, world_size
@@ -442,6 +486,9 @@ class ConstructionLabelWriter:
         ok = (ids >= 0) & (ids < (1 << 32))
         ids, slots = ids[ok], slots[ok]
         tables = FrameTables(objects, rec_idx, slot_class, ids, slots, int(ids.max()) if ids.size else -1)
+        tables.n_paths = len(prim_paths)
+        if self.record_fallback == "union":
+            tables.union = union_members(objects, prim_paths)
         if len(self._tables_cache) > 4096:
             self._tables_cache.clear()
         self._tables_cache[key] = tables
@@ -567,7 +614,10 @@ class ConstructionLabelWriter:
             stacked = frames.stacked
         if len(frames) == 0:
             raise ValueError("annotate_batch needs at least one frame")
-        frames = [self._normalise(fr) for fr in frames]
+        if getattr(frames, "canonical", False):   # cut from a stacked dict: only the camera payload may need work
+            frames = [self._normalise_camera(fr) for fr in frames]
+        else:
+            frames = [self._normalise(fr) for fr in frames]
         B = len(frames)
         dev = self.device
 
@@ -603,17 +653,34 @@ class ConstructionLabelWriter:
         cams = np.zeros((B, CAM_STRIDE), dtype=np.float64)
         frame_ids: List[int] = []
         poses, params_list, clips = [], [], []
+        # info dicts that are the SAME OBJECT for several frames of this call (one info shared by a stacked batch,
+        # or a pool of frames repeated) are resolved once: {(id(primPaths), id(idToLabels), records): tables}
+        seen: Dict[Tuple[int, int, int], FrameTables] = {}
         for i, fr in enumerate(frames):
             seg = fr.get("instance_segmentation")
             bbox = fr.get("bounding_box_3d")
-            prim_paths = list(_info(bbox).get("primPaths", []) or [])  # tolerated empty, gcd.py:1788
+            raw_paths = _info(bbox).get("primPaths", None) or ()   # tolerated empty, gcd.py:1788
             recs = _payload(bbox)
-            if recs is not None and len(recs) != len(prim_paths):
-                n = min(len(recs), len(prim_paths))
-                recs, prim_paths = recs[:n], prim_paths[:n]
-            id_to_labels = _info(seg).get("idToLabels", {}) or {}
-            tables.append(self.frame_tables(prim_paths, id_to_labels))
-            if prim_paths and not tables[-1].lut_ids.size and i not in missing and not self._warned_empty_lut:
+            id_to_labels = _info(seg).get("idToLabels", None) or {}
+            n_paths = len(raw_paths)
+            n_recs = n_paths if recs is None else len(recs)
+            ident = (id(raw_paths), id(id_to_labels), min(n_recs, n_paths))
+            hit = seen.get(ident) if n_paths else None
+            if hit is not None:
+                tables.append(hit)
+                if n_recs > n_paths:
+                    recs = recs[:n_paths]
+            else:
+                prim_paths = list(raw_paths)
+                if recs is not None and n_recs != n_paths:
+                    n = min(n_recs, n_paths)
+                    recs, prim_paths = recs[:n], prim_paths[:n]
+                tables.append(self.frame_tables(prim_paths, id_to_labels))
+                if n_paths:
+                    seen[ident] = tables[-1]
+                prim_paths_nonempty = bool(prim_paths)
+            if hit is None and prim_paths_nonempty and not tables[-1].lut_ids.size and i not in missing \
+                    and not self._warned_empty_lut:
                 self._warned_empty_lut = True
                 warnings.warn("bounding_box_3d lists prims but no idToLabels entry of instance_segmentation resolves to "
                               "one of them: every object of such frames has 0 pixels and is dropped (min_pixels >= 1)")
@@ -645,28 +712,53 @@ class ConstructionLabelWriter:
             # are prim indices in Replicator, so this only trips on ids that are not instance ids
             raise ValueError(f"instance ids up to {L - 1} need a {L * lut_rows * 4 / 2**20:.0f} MiB id->slot table "
                              f"(limit {self.max_lut_entries * 4 / 2**20:.0f} MiB, max_lut_entries)")
-        # small tables go up as ONE pinned block: [lut | obj_record | slot_class | records | cam]
-        blk = _TableBlock(self, lut_rows, L, B, N, R)
+        # record_fallback="union": U object-level records per frame are built on the device behind the frame's own R
+        U = max(len(t.union) for t in tables)
+        R0 = R
+        if U:
+            u_off, u_mem, _ = pack_union([tables[0].union] if same_tables else [t.union for t in tables])
+            R = R0 + U
+        # small tables go up as ONE pinned block: [lut | obj_record | slot_class | records | cam | union tables]
+        blk = _TableBlock(self, lut_rows, L, B, N, R, (u_off.shape[0], u_off.shape[1], u_mem.shape[1]) if U else (0, 0, 0))
         lut, obj_record, slot_class, rec_bytes = blk.lut, blk.obj_record, blk.slot_class, blk.records
         lut.fill(-1)
         obj_record.fill(-1)
         slot_class.fill(-1)
         rec_bytes.fill(0)
         blk.cam[:] = cams
-        for i, t in enumerate(tables):
+        if same_tables:   # one scene for the whole batch: broadcast its rows
+            t = tables[0]
             n = len(t.objects)
-            obj_record[i, :n] = t.obj_record
-            slot_class[i, :n] = t.slot_class
-            if i == 0 or not same_tables:
-                lut[i if not same_tables else 0, t.lut_ids] = t.lut_slots
-            r = rec_arrays[i]
-            if r is not None:
-                r = np.ascontiguousarray(r)
-                if r.dtype.itemsize != BBOX3D_DTYPE.itemsize:
-                    raise ValueError(f"frame {i}: bounding_box_3d record itemsize {r.dtype.itemsize} != 96")
-                rec_bytes[i, : len(r)] = r.view(np.uint8).reshape(len(r), -1)
-            else:
-                obj_record[i, :] = -1
+            obj_record[:, :n] = t.obj_record
+            slot_class[:, :n] = t.slot_class
+            lut[0, t.lut_ids] = t.lut_slots
+        else:
+            for i, t in enumerate(tables):
+                n = len(t.objects)
+                obj_record[i, :n] = t.obj_record
+                slot_class[i, :n] = t.slot_class
+                lut[i, t.lut_ids] = t.lut_slots
+        if U:   # union objects point behind the frame's own records (their table entry is relative to len(primPaths))
+            blk.union_offsets[:] = u_off
+            blk.union_members[:] = u_mem
+            for i, t in ([(slice(None), tables[0])] if same_tables else enumerate(tables)):
+                for u, (slot, _) in enumerate(t.union):
+                    obj_record[i, slot] = (R0 + u) | RECORD_APPROX_BIT
+        item = BBOX3D_DTYPE.itemsize
+        dt0 = rec_arrays[0].dtype if type(rec_arrays[0]) is np.ndarray else None
+        if dt0 is not None and dt0.itemsize == item and \
+                all(type(r) is np.ndarray and r.ndim == 1 and len(r) == R and r.dtype == dt0 for r in rec_arrays):
+            # every frame brings R records: one C-level gather straight into the pinned block
+            np.concatenate(rec_arrays, out=rec_bytes.reshape(-1).view(rec_arrays[0].dtype))
+        else:
+            for i, r in enumerate(rec_arrays):
+                if r is not None:
+                    r = np.ascontiguousarray(r)
+                    if r.dtype.itemsize != item:
+                        raise ValueError(f"frame {i}: bounding_box_3d record itemsize {r.dtype.itemsize} != 96")
+                    rec_bytes[i, : len(r)] = r.view(np.uint8).reshape(len(r), -1)
+                else:
+                    obj_record[i, :] = -1
 
         # ---- device: uploads + kernels on the writer's stream ----------------------------
         owned: List[Tuple[Tuple, torch.Tensor]] = list(blk.buffers)
@@ -675,6 +767,9 @@ class ConstructionLabelWriter:
             if same_tables:
                 d_lut = d_lut[0]
 
+            if U:
+                d_uoff, d_umem = blk.union_on_device(blk.device_block)
+                ops.union_records(d_rec, R0, d_uoff[0] if same_tables else d_uoff, d_umem[0] if same_tables else d_umem)
             scan = ops.mask_scan(d_mask, d_lut, N)
             uv, z, pose, loose, flags = ops.project_objects(d_rec, d_obj_record, d_cam)
             kp_host = vis_host = None
@@ -711,7 +806,9 @@ class ConstructionLabelWriter:
                 d_depth = d_depth.clone()
             consumed = torch.cuda.Event()
             consumed.record(self.stream)
-            for t in [stacked.get("instance_segmentation"), stacked.get("distance_to_image_plane"), *masks, *depth_list]:
+            # (per-frame views cut from a stacked CUDA tensor share its storage: recording the stacked tensor covers them)
+            st_mask, st_depth = stacked.get("instance_segmentation"), stacked.get("distance_to_image_plane")
+            for t in [st_mask, st_depth, *(masks if st_mask is None else ()), *(depth_list if st_depth is None else ())]:
                 if isinstance(t, torch.Tensor) and t.is_cuda:
                     t.record_stream(self.stream)
             rec_host = self._take_pinned("rec", tuple(rec_dev.shape), torch.uint8, owned)
@@ -755,7 +852,13 @@ class ConstructionLabelWriter:
                 out[key] = value
             elif name not in out or out[name] is None:
                 out[name] = value
+        return self._normalise_camera(out)
+
+    @staticmethod
+    def _normalise_camera(out: Dict[str, object]) -> Dict[str, object]:
         cp = out.get("camera_params")
+        if cp is None:
+            return out
         if isinstance(cp, Mapping) and "data" in cp and isinstance(cp["data"], Mapping):
             cp = cp["data"]
         if is_replicator_camera_params(cp):

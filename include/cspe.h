@@ -195,6 +195,21 @@ int cspe_project_objects_overlapped(const void* records, int rec_stride, int rec
                                     double* uv, double* z, double* pose, double* loose, uint8_t* flags,
                                     void* stream);
 
+/* Object-level records for multi-mesh objects whose root prim has no bbox3d record of its own.  The reference
+ * reads that object's bound from the live USD stage — BBoxCache.ComputeWorldBound(prim).ComputeAlignedRange(),
+ * gcd.py:2000-2009 — which is the world-axis-aligned range of everything under the prim; here the same range is the
+ * min / max over the eight world-space corners of every mesh record of the object.
+ * records   the frame's record array as cspe_project_objects takes it, with room for U more records per frame:
+ *           frame f, union object u is WRITTEN at records + (f*recs_per_frame + base + u)*rec_stride as a record with
+ *           an identity transform whose extents are the range (float32); members are read from indices < base
+ * offsets   int32 [rows][U+1], members int32 [rows][M]: object u unites records members[offsets[u] .. offsets[u+1]);
+ *           rows = B with strides U+1 / M, or 1 with stride 0 (one scene for the whole batch)
+ * An object none of whose members has a finite corner gets NaN extents (K2 then clears CSPE_OBJ_POSE_VALID).
+ * Ordinary stream-ordered launch: queue it before the mask scan of a PDL chain, or anywhere before K2 otherwise. */
+int cspe_union_records(void* records, int rec_stride, int recs_per_frame, int base, const int32_t* offsets,
+                       int64_t offsets_stride, const int32_t* members, int64_t members_stride, int B, int U,
+                       void* stream);
+
 /* ---- K3: skeleton keypoint projection + depth-buffer visibility ([SPEC]; "skelroot" is
  * only a class keyword in the reference, gcd.py:105) ----------------------------------------
  * joints  float32 [B][P][J][3] world positions (Replicator skeleton_data globalTranslations)

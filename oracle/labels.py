@@ -177,6 +177,56 @@ def polar_rotation(rot: np.ndarray) -> np.ndarray:
     return u @ vt
 
 
+def union_records(records: np.ndarray, base: int, offsets: np.ndarray, members: np.ndarray) -> np.ndarray:
+    """Object-level records for multi-mesh objects without a record of their own: the world-axis-aligned range
+    the reference reads from the USD stage (BBoxCache.ComputeWorldBound(prim).ComputeAlignedRange(), gcd.py:2000-2009),
+    restated as the min / max over the eight world-space corners (p_w = M @ [c,1], gcd.py:568) of every mesh record.
+    records BBOX3D_DTYPE [B,R]; object u of frame f unites records members[f, offsets[f,u]:offsets[f,u+1]] (indices
+    < base) and is written to records[f, base + u]: extents = the range (float32), transform = identity, semanticId /
+    occlusionRatio of its first member.  offsets / members may be 1-D (shared by the batch).  Returns a copy."""
+    out = np.array(records, copy=True)
+    B = out.shape[0]
+    offsets, members = np.asarray(offsets), np.asarray(members)
+    U = offsets.shape[-1] - 1
+    with np.errstate(all="ignore"):
+        for f in range(B):
+            off = offsets[f] if offsets.ndim == 2 else offsets
+            mem = members[f] if members.ndim == 2 else members
+            for u in range(U):
+                mn = np.full(3, np.inf)
+                mx = np.full(3, -np.inf)
+                sem, occ, first = 0, np.float32(0), True
+                for ri in mem[int(off[u]):int(off[u + 1])]:
+                    ri = int(ri)
+                    if ri < 0 or ri >= base:
+                        continue
+                    rec = out[f, ri]
+                    if first:
+                        sem, occ, first = rec["semanticId"], rec["occlusionRatio"], False
+                    lo = np.array([rec["x_min"], rec["y_min"], rec["z_min"]], dtype=np.float32)
+                    hi = np.array([rec["x_max"], rec["y_max"], rec["z_max"]], dtype=np.float32)
+                    T = np.asarray(rec["transform"], dtype=np.float32).reshape(4, 4).astype(np.float64)
+                    k = np.arange(8)
+                    c0 = np.where(k & 1, hi[0], lo[0]).astype(np.float64)
+                    c1 = np.where(k & 2, hi[1], lo[1]).astype(np.float64)
+                    c2 = np.where(k & 4, hi[2], lo[2]).astype(np.float64)
+                    for j in range(3):
+                        pw = ((c0 * T[0, j] + c1 * T[1, j]) + c2 * T[2, j]) + T[3, j]
+                        mn[j] = np.fmin(mn[j], np.fmin.reduce(pw))
+                        mx[j] = np.fmax(mx[j], np.fmax.reduce(pw))
+                new = np.zeros((), dtype=out.dtype)
+                new["semanticId"] = sem
+                new["occlusionRatio"] = occ
+                ok = bool((mn <= mx).all())
+                lo32 = mn.astype(np.float32) if ok else np.full(3, np.nan, dtype=np.float32)
+                hi32 = mx.astype(np.float32) if ok else np.full(3, np.nan, dtype=np.float32)
+                new["x_min"], new["y_min"], new["z_min"] = lo32
+                new["x_max"], new["y_max"], new["z_max"] = hi32
+                new["transform"] = np.eye(4, dtype=np.float32).reshape(new["transform"].shape)
+                out[f, base + u] = new
+    return out
+
+
 def project_objects(records: np.ndarray, obj_record: np.ndarray, cam: np.ndarray):
     """records: BBOX3D_DTYPE [B,R]; obj_record int32 [B,N] (-1 = no record); cam f64 [B,24].
     Returns uv [B,N,8,2], z [B,N,8], pose [B,N,16], loose [B,N,4] (f64) and flags u8 [B,N].

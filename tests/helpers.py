@@ -18,7 +18,9 @@ EULER_ATOL = 1e-9
 
 def host_tables(frames, split_people=True, fallback="first_mesh"):
     """(lut [B,L], obj_record [B,N], slot_class [B,N], records [B,R], cam [B,24], objects) as numpy,
-    built with the PRODUCT's host logic (classes.py) and the ORACLE's camera packing."""
+    built with the PRODUCT's host logic (classes.py) and the ORACLE's camera packing.  ``fallback="union"``: the U
+    object-level records of a frame sit behind the batch's own R records (records is [B, R+U], filled by the
+    oracle's union_records; ``host_tables.union`` keeps (base, offsets, members) of the last call for kernel tests)."""
     res = classes.ObjectRootResolver(split_people=split_people)
     per = []
     for fr in frames:
@@ -26,24 +28,32 @@ def host_tables(frames, split_people=True, fallback="first_mesh"):
         objs = classes.aggregate_objects(paths, res)
         rec_idx = classes.record_index_for(objs, paths, fallback)
         mapping = classes.id_to_slot(fr["instance_segmentation"]["info"]["idToLabels"], objs, res)
-        per.append((objs, rec_idx, mapping))
+        plan = classes.union_members(objs, paths) if fallback == "union" else []
+        per.append((objs, rec_idx, mapping, plan))
     B = len(frames)
     N = max(1, max(len(p[0]) for p in per))
-    R = max(1, max(len(fr["bounding_box_3d"]["data"]) for fr in frames))
+    R0 = max(1, max(len(fr["bounding_box_3d"]["data"]) for fr in frames))
+    u_off, u_mem, U = classes.pack_union([p[3] for p in per])
+    R = R0 + U
     L = max(1, max((max(p[2].keys()) if p[2] else 0) for p in per) + 1)
     lut = np.full((B, L), -1, dtype=np.int32)
     obj_record = np.full((B, N), -1, dtype=np.int32)
     slot_class = np.full((B, N), -1, dtype=np.int32)
     records = np.zeros((B, R), dtype=O.BBOX3D_DTYPE)
     cam = np.zeros((B, O.CAM_STRIDE))
-    for i, (fr, (objs, rec_idx, mapping)) in enumerate(zip(frames, per)):
+    for i, (fr, (objs, rec_idx, mapping, plan)) in enumerate(zip(frames, per)):
         for k, v in mapping.items():
             lut[i, k] = v
         obj_record[i, : len(objs)] = rec_idx
+        for u, (slot, _) in enumerate(plan):   # re-base: union records follow the batch's R0 own records
+            obj_record[i, slot] = (R0 + u) | classes.RECORD_APPROX_BIT
         slot_class[i, : len(objs)] = [o.class_id for o in objs]
         r = fr["bounding_box_3d"]["data"]
         records[i, : len(r)] = r
         cam[i] = O.pack_camera(fr["camera_pose"], fr["camera_params"])
+    host_tables.union = (R0, u_off, u_mem, records.copy())   # records BEFORE the union pass
+    if U:
+        records = O.union_records(records, R0, u_off, u_mem)
     return lut, obj_record, slot_class, records, cam, [p[0] for p in per]
 
 

@@ -349,6 +349,102 @@ def test_project_objects_edge_cases(T, ops):
     assert abs(pose[0, 5, 15]) < 1e-9 and abs(abs(pose[0, 5, 14]) - 90.0) < 1e-6  # third angle 0 in gimbal lock
 
 
+def test_union_records(T, ops):
+    """cspe_union_records == oracle.union_records, bit for bit: the world-axis-aligned range of all mesh records of an
+    object (the bound the reference's USD fallback reads, gcd.py:2000-2009) written as an identity-transform record;
+    per-frame and shared CSR tables, empty ranges, out-of-range / negative members, NaN / inf corners."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(11)
+    B, R0, U = 3, 20, 6
+    recs = np.zeros((B, R0 + U), dtype=O.BBOX3D_DTYPE)
+    for f in range(B):
+        for r in range(R0):
+            lo = rng.uniform(-3, 0, 3).astype(np.float32)
+            hi = (lo + rng.uniform(0.1, 4, 3)).astype(np.float32)
+            recs[f, r]["semanticId"] = rng.integers(0, 2 ** 32, dtype=np.uint64)
+            recs[f, r]["x_min"], recs[f, r]["y_min"], recs[f, r]["z_min"] = lo
+            recs[f, r]["x_max"], recs[f, r]["y_max"], recs[f, r]["z_max"] = hi
+            m = np.eye(4)
+            m[:3, :3] = (Rotation.random(random_state=int(rng.integers(1 << 30))).as_matrix() * rng.uniform(0.5, 2, 3)).T
+            m[3, :3] = rng.uniform(-25, 25, 3)
+            recs[f, r]["transform"] = m.astype(np.float32)
+            recs[f, r]["occlusionRatio"] = rng.random()
+    recs[1, 3]["x_max"] = np.nan                   # a NaN corner drops out of fmin / fmax
+    recs[1, 4]["transform"][3, 0] = np.inf         # an infinite one does not
+    recs[2, 5]["x_min"] = np.nan
+    recs[2, 5]["x_max"] = np.nan                   # object 2 of frame 2 = this record only: no finite x -> NaN extents
+    plans = [[(0, [0, 1, 2]), (1, [3]), (2, [4, 5, 6, 7, 8]), (3, []), (4, [19, 18]), (5, [9, -1, 25, 10])],
+             [(0, [3, 2]), (1, [4, 0]), (2, [1]), (3, [5, 6]), (4, [7]), (5, [8, 9, 10, 11, 12, 13, 14])],
+             [(0, [0]), (1, [1, 2]), (2, [5]), (3, [19])]]          # fewer objects: the rest are empty ranges
+    from constructionsceneposeestimation_b200 import classes
+    off, mem, u = classes.pack_union(plans)
+    assert u == U and off.shape == (B, U + 1)
+    want = O.union_records(recs, R0, off, mem)
+    rb = T.from_numpy(recs.view(np.uint8).reshape(B, R0 + U, -1).copy()).cuda()
+    got = ops.union_records(rb, R0, T.from_numpy(off).cuda(), T.from_numpy(mem).cuda())
+    T.cuda.synchronize()
+    got = got.cpu().numpy().reshape(B, -1).view(O.BBOX3D_DTYPE).reshape(B, R0 + U)
+    assert got.tobytes() == want.tobytes()          # bit-exact, NaN payloads included
+    assert np.isnan(want[2, R0 + 2]["x_min"]) and np.isnan(want[0, R0 + 3]["x_min"])     # no finite corner / no member
+    assert np.isinf(want[1, R0 + 1]["x_max"]) and np.isfinite(want[1, R0 + 0]["x_max"])
+    assert want[0, R0]["semanticId"] == recs[0, 0]["semanticId"] and np.array_equal(want[0, R0]["transform"], np.eye(4))
+    # the range really contains every member corner
+    for j, (lo_k, hi_k) in enumerate((("x_min", "x_max"), ("y_min", "y_max"), ("z_min", "z_max"))):
+        for r in (0, 1, 2):
+            rec = recs[0, r]
+            c = np.array([[rec["x_max"] if k & 1 else rec["x_min"], rec["y_max"] if k & 2 else rec["y_min"],
+                           rec["z_max"] if k & 4 else rec["z_min"], 1.0] for k in range(8)], dtype=np.float64)
+            pw = c @ rec["transform"].astype(np.float64)
+            assert pw[:, j].min() >= want[0, R0][lo_k] - 1e-5 and pw[:, j].max() <= want[0, R0][hi_k] + 1e-5
+    # shared tables (stride 0): one plan for every frame
+    off1, mem1, _ = classes.pack_union([plans[0]])
+    want1 = O.union_records(recs, R0, off1[0], mem1[0])
+    rb = T.from_numpy(recs.view(np.uint8).reshape(B, R0 + U, -1).copy()).cuda()
+    got1 = ops.union_records(rb, R0, T.from_numpy(off1[0].copy()).cuda(), T.from_numpy(mem1[0].copy()).cuda())
+    T.cuda.synchronize()
+    assert got1.cpu().numpy().tobytes() == want1.tobytes()
+    with pytest.raises(ValueError):
+        ops.union_records(rb, R0 + 1, T.from_numpy(off).cuda(), T.from_numpy(mem).cuda())
+
+
+def test_writer_union_fallback(T, ops):
+    """record_fallback="union": a multi-mesh object without a record of its own gets the object-level box (union of
+    its mesh records) — records equal the oracle pipeline run on the same tables, the flag says APPROX, and the box
+    differs from the first-mesh stand-in exactly where the meshes differ."""
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    frames = synthetic.make_batch(synthetic.SceneSpec(1280, 720, 20, 4, 17, config_id=1), 3)
+    # pull the meshes of every multi-mesh object apart so that the union is not just the first mesh again
+    for fr in frames:
+        recs = fr["bounding_box_3d"]["data"]
+        paths = fr["bounding_box_3d"]["info"]["primPaths"]
+        for i, p in enumerate(paths):
+            if p.rsplit("/", 1)[-1].startswith("Mesh_"):
+                recs[i]["transform"][3, 0] += 0.4 * int(p.rsplit("_", 1)[-1])
+    o = helpers.oracle_pipeline(frames, fallback="union")
+    o_first = helpers.oracle_pipeline(frames)
+    w = ConstructionLabelWriter(None, split_people=True, record_fallback="union")
+    labels = w.annotate_batch(frames)
+    assert np.array_equal(labels.n_out, o["n_out"])
+    changed = 0
+    for f in range(3):
+        got = labels.records(f)
+        helpers.assert_records_equal(got, o["recs"][f, : o["n_out"][f]])
+        approx = (got["flags"] & O.OBJ_APPROX_RECORD) != 0
+        assert approx.any()
+        first = {int(r["inst_idx"]): r for r in o_first["recs"][f, : o_first["n_out"][f]]}
+        for r in got[approx]:
+            assert np.array_equal(r["pose"][13:16], np.zeros(3))          # a world-axis-aligned box: rotation 0
+            q = first.get(int(r["inst_idx"]))
+            changed += q is not None and not np.array_equal(q["pose"][10:13], r["pose"][10:13])
+    assert changed > 0
+    # the same call on the stacked form, one shared scene: the CSR tables go up once (stride 0)
+    one = [frames[0]] * 2
+    l2 = ConstructionLabelWriter(None, split_people=True, record_fallback="union").annotate_batch(one)
+    assert np.array_equal(l2.records(0)["pose"], l2.records(1)["pose"], equal_nan=True)
+    assert np.array_equal(l2.records(0)["pose"], labels.records(0)["pose"], equal_nan=True)
+
+
 def test_reference_transform_matches_kernel(T, ops):
     """R3: centre / size / Euler against the restated bboxDict_to_transform (gcd.py:553-584)."""
     from constructionsceneposeestimation_b200 import synthetic

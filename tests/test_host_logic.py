@@ -525,3 +525,62 @@ def test_concat_rows_and_coco_ratio_rule():
     assert count == len(vals) and text == json.dumps(py)[1:-1].encode()
     assert all(a["occlusion"] == round(float(v), 6) for a, v in zip(py, vals))
     assert b'e-06, ' in text and b'"occlusion": 1.2e-05' in text and b'"occlusion": 0.0001,' in text
+
+
+def test_union_record_fallback_rules():
+    """record_fallback="union": a multi-mesh object whose root has no record points behind the frame's own records
+    (index len(primPaths) + u, APPROX bit set) and union_members lists the records of all its meshes; crane parts keep
+    the reference's first-mesh rule (gcd.py:1953-1975), single-mesh objects their only mesh, objects with a record of
+    their own that record; pack_union pads the batch's CSR tables."""
+    from constructionsceneposeestimation_b200 import classes
+    res = classes.ObjectRootResolver()
+    fa, fb_root = synthetic.FENCE_PREFIX + "03", synthetic.FENCE_PREFIX + "04"
+    paths = [fa + "/Mesh_0", fa + "/Mesh_1", fa + "/Mesh_2",                                  # no root record: union
+             fb_root, fb_root + "/Mesh_0", fb_root + "/Mesh_1",                               # root record wins
+             "/World/GroundPlane/Cone001_01/Cone001",                                         # single mesh: exact
+             "/World/Tree/Tree_02/leaves", "/World/Tree/Tree_02/trunk"]                       # union
+    objs = classes.aggregate_objects(paths, res)
+    by_path = {o.prim_path: i for i, o in enumerate(objs)}
+    idx = classes.record_index_for(objs, paths, "union")
+    plan = classes.union_members(objs, paths)
+    assert len(objs) == 4
+    assert [s for s, _ in plan] == sorted(by_path[p] for p in by_path if p == fa or p.endswith("Tree_02"))
+    for u, (slot, mem) in enumerate(plan):
+        assert idx[slot] == (len(paths) + u) | classes.RECORD_APPROX_BIT
+        assert [paths[m].startswith(objs[slot].prim_path + "/") for m in mem] == [True] * len(mem)
+    fb = by_path[fb_root]
+    cone = next(i for p, i in by_path.items() if "Cone" in p)
+    assert idx[fb] == 3 and idx[cone] == 6
+    # the other fallbacks on the same scene
+    first = classes.record_index_for(objs, paths, "first_mesh")
+    assert first[plan[0][0]] == 0 | classes.RECORD_APPROX_BIT and classes.record_index_for(objs, paths, "reference")[plan[0][0]] == -1
+    off, mem, U = classes.pack_union([plan, [], plan[:1]])
+    assert U == 2 and off.shape == (3, 3) and mem.shape == (3, 5)
+    assert off.tolist() == [[0, 3, 5], [0, 0, 0], [0, 3, 3]] and mem[0].tolist() == [0, 1, 2, 7, 8] and mem[1].tolist() == [-1] * 5
+    off0, mem0, U0 = classes.pack_union([[], []])
+    assert U0 == 0 and off0.shape == (2, 1) and mem0.shape == (2, 1)
+
+
+def test_union_records_oracle_is_the_aligned_range():
+    """oracle.union_records against a direct statement: every corner of every member, transformed, min / max."""
+    rng = np.random.default_rng(3)
+    recs = np.zeros((1, 5), dtype=O.BBOX3D_DTYPE)
+    pts = []
+    for r in range(3):
+        lo, hi = rng.uniform(-2, 0, 3).astype(np.float32), rng.uniform(0.5, 2, 3).astype(np.float32)
+        recs[0, r]["x_min"], recs[0, r]["y_min"], recs[0, r]["z_min"] = lo
+        recs[0, r]["x_max"], recs[0, r]["y_max"], recs[0, r]["z_max"] = hi
+        m = np.eye(4, dtype=np.float32)
+        m[3, :3] = rng.uniform(-5, 5, 3)
+        m[:3, :3] = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        recs[0, r]["transform"] = m
+        for k in range(8):
+            c = np.array([hi[0] if k & 1 else lo[0], hi[1] if k & 2 else lo[1], hi[2] if k & 4 else lo[2], 1.0])
+            pts.append(c @ m.astype(np.float64))
+    out = O.union_records(recs, 3, np.array([0, 3, 3], dtype=np.int32), np.array([0, 1, 2], dtype=np.int32))
+    pts = np.array(pts)[:, :3]
+    got = out[0, 3]
+    assert np.allclose([got["x_min"], got["y_min"], got["z_min"]], pts.min(0), rtol=1e-6, atol=1e-6)
+    assert np.allclose([got["x_max"], got["y_max"], got["z_max"]], pts.max(0), rtol=1e-6, atol=1e-6)
+    assert np.array_equal(got["transform"], np.eye(4)) and np.isnan(out[0, 4]["x_min"])   # object 1 has no member
+    assert out[0, :3].tobytes() == recs[0, :3].tobytes()
