@@ -140,25 +140,46 @@ class LabelPipeline:
         n_out = self.n_out if n_out is None else n_out
         frame_base = self.frame_base if frame_base is None else int(frame_base)
         main = torch.cuda.current_stream(self.device).cuda_stream
-        scan_fn = lib.cspe_mask_scan_accumulate_overlapped if ovl else lib.cspe_mask_scan_accumulate
         j = int(first)   # input rows of the partial batch start at resident frame j
-        chk("cspe_mask_scan_accumulate", scan_fn(
-            self.mask.data_ptr() + j * self.H * self.W * 4, B, self.H, self.W,
-            self.lut.data_ptr() + j * self.lut_stride * 4, self.L, self.lut_stride, self.N,
-            self.scan.data_ptr(), main))
-        proj_fn = lib.cspe_project_objects_overlapped if ovl else lib.cspe_project_objects
-        chk("cspe_project_objects", proj_fn(
-            self.records_in.data_ptr() + j * self.R * _lib.BBOX3D_RECORD_BYTES, _lib.BBOX3D_RECORD_BYTES, self.R,
-            self.obj_record.data_ptr() + j * self.N * 4, self.cam.data_ptr() + j * CAM_STRIDE * 8, B, self.N, k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
-            k2["loose"].data_ptr(), k2["flags"].data_ptr(), main))
-        if self._k3 is not None:  # K3 rides the same chain: beside the scan, done before K4
+
+        def scan(fn):
+            chk("cspe_mask_scan_accumulate", fn(
+                self.mask.data_ptr() + j * self.H * self.W * 4, B, self.H, self.W,
+                self.lut.data_ptr() + j * self.lut_stride * 4, self.L, self.lut_stride, self.N,
+                self.scan.data_ptr(), main))
+
+        def project(fn):
+            chk("cspe_project_objects", fn(
+                self.records_in.data_ptr() + j * self.R * _lib.BBOX3D_RECORD_BYTES, _lib.BBOX3D_RECORD_BYTES, self.R,
+                self.obj_record.data_ptr() + j * self.N * 4, self.cam.data_ptr() + j * CAM_STRIDE * 8, B, self.N,
+                k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(), k2["loose"].data_ptr(),
+                k2["flags"].data_ptr(), main))
+
+        def keypoints(fn):
             k3 = self._k3[parity]
-            kp_fn = lib.cspe_keypoints_overlapped if ovl else lib.cspe_keypoints
-            chk("cspe_keypoints", kp_fn(
+            chk("cspe_keypoints", fn(
                 self.joints.data_ptr() + j * self.P * self.J * 12, B, self.P, self.J,
                 self.depth.data_ptr() + j * self.H * self.W * 4, self.H, self.W,
                 self.cam.data_ptr() + j * CAM_STRIDE * 8, self.keypoint_tolerance, k3["kp"].data_ptr(), k3["kz"].data_ptr(),
                 k3["vis"].data_ptr(), main))
+
+        if ovl:
+            # full-size batch: K1 first (it may stream under the previous batch's K4), K2 / K3 beside it
+            scan(lib.cspe_mask_scan_accumulate_overlapped)
+            project(lib.cspe_project_objects_overlapped)
+            if self._k3 is not None:  # K3 rides the same chain: beside the scan, done before K4
+                keypoints(lib.cspe_keypoints_overlapped)
+        else:
+            # small batch (latency case, e.g. config 1 — one 720p frame): K2 [K3] FIRST as plain launches — they wait
+            # at entry for whatever ran before (the previous batch's K4 still reading their output buffers) but
+            # release their dependents before that wait — then K1 through its overlapped entry point: it streams
+            # the mask beside K2's serial FP64 chain and waits for it (hence for everything before it) only
+            # before its first merge into the scan table.  K4 waits for K1, which completes after K2 / K3.
+            # Latency = max(K1, K2) + K4 instead of K1 + K2 + K4; nothing depends on the size of the grids.
+            project(lib.cspe_project_objects)
+            if self._k3 is not None:
+                keypoints(lib.cspe_keypoints)
+            scan(lib.cspe_mask_scan_accumulate_overlapped)
         common = (self.scan.data_ptr(), k2["uv"].data_ptr(), k2["z"].data_ptr(), k2["pose"].data_ptr(),
                   k2["loose"].data_ptr(), k2["flags"].data_ptr(), self.slot_class.data_ptr() + j * self.N * 4, B, self.N, self.H,
                   self.W, self.min_pixels, frame_base)
