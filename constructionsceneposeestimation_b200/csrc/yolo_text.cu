@@ -22,13 +22,149 @@ namespace {
 
 constexpr int kYoloThreads = 256;
 
-__device__ __forceinline__ int dec_digits(unsigned long long v) {
-  int n = 1;
-  while (v >= 10ull) {
+// The first version printed every record byte by byte into global memory through local-memory digit buffers with 64-bit
+// divisions and took 32 us per 64-frame batch (ncu) — a third of the mask scan, and its resident CTAs held registers the
+// next scan's CTAs were waiting for.  Now: lengths from compare ladders (no division), digits written right to left
+// straight at their final place in a SHARED-memory stage (32-bit arithmetic; ids beyond 2^32 take a 64-bit loop), and
+// the stage leaves as aligned 16-byte stores (it is laid out at the same offset modulo 16 as its destination).
+__device__ __forceinline__ int digits_u32(unsigned v) {
+  return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+         (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+__device__ __forceinline__ int digits_u64(unsigned long long v) {
+  if (v <= 0xffffffffull) return digits_u32(static_cast<unsigned>(v));
+  int n = 10;
+  v /= 10000000000ull;
+  while (v) {
     v /= 10ull;
     ++n;
   }
   return n;
+}
+__device__ __forceinline__ int len_i32(int v) { return v < 0 ? 1 + digits_u32(0u - static_cast<unsigned>(v)) : digits_u32(static_cast<unsigned>(v)); }
+__device__ __forceinline__ int len_i64(long long v) {
+  return v < 0 ? 1 + digits_u64(0ull - static_cast<unsigned long long>(v)) : digits_u64(static_cast<unsigned long long>(v));
+}
+
+// length of repr(round(x, 6)) for x = +-q * 1e-6 (repr6.h: repr_units6), without printing it
+__device__ __forceinline__ int len_units6(bool neg, unsigned long long q) {
+  const int s = neg ? 1 : 0;
+  if (q == 0) return s + 3;                                    // 0.0
+  if (q < 100ull) {                                            // exponent form
+    const unsigned tens = static_cast<unsigned>(q) / 10u, ones = static_cast<unsigned>(q) % 10u;
+    return s + (tens == 0 ? 5 : (ones ? 7 : 5));               // 5e-06 | 1.2e-05 | 1e-05
+  }
+  unsigned frac = static_cast<unsigned>(q % 1000000ull);
+  int fd = 6;                                                  // fractional digits kept: trailing zeros dropped, >= 1
+  while (fd > 1 && frac % 10u == 0u) {
+    frac /= 10u;
+    --fd;
+  }
+  return s + digits_u64(q / 1000000ull) + 1 + fd;
+}
+
+// cursor into the shared-memory stage
+struct Stage {
+  char* p;
+  __device__ __forceinline__ void put(char c) { *p++ = c; }
+  template <int kLen>
+  __device__ __forceinline__ void lit(const char (&s)[kLen]) {   // kLen counts the terminating NUL
+#pragma unroll
+    for (int i = 0; i < kLen - 1; ++i) p[i] = s[i];
+    p += kLen - 1;
+  }
+  __device__ __forceinline__ void u32(unsigned v) {
+    const int n = digits_u32(v);
+    for (int i = n - 1; i >= 0; --i) {
+      const unsigned q = v / 10u;
+      p[i] = static_cast<char>('0' + (v - q * 10u));
+      v = q;
+    }
+    p += n;
+  }
+  __device__ __forceinline__ void u64(unsigned long long v) {
+    if (v <= 0xffffffffull) {
+      u32(static_cast<unsigned>(v));
+      return;
+    }
+    const int n = digits_u64(v);
+    for (int i = n - 1; i >= 0; --i) {
+      const unsigned long long q = v / 10ull;
+      p[i] = static_cast<char>('0' + static_cast<int>(v - q * 10ull));
+      v = q;
+    }
+    p += n;
+  }
+  __device__ __forceinline__ void i32(int v) {
+    if (v < 0) {
+      put('-');
+      u32(0u - static_cast<unsigned>(v));
+    } else {
+      u32(static_cast<unsigned>(v));
+    }
+  }
+  __device__ __forceinline__ void i64(long long v) {
+    if (v < 0) {
+      put('-');
+      u64(0ull - static_cast<unsigned long long>(v));
+    } else {
+      u64(static_cast<unsigned long long>(v));
+    }
+  }
+  // repr(round(x, 6)), the bytes of repr_units6 (repr6.h)
+  __device__ __forceinline__ void units6(bool neg, unsigned long long q) {
+    if (neg) put('-');
+    if (q == 0) {
+      lit("0.0");
+      return;
+    }
+    if (q < 100ull) {
+      const unsigned tens = static_cast<unsigned>(q) / 10u, ones = static_cast<unsigned>(q) % 10u;
+      if (tens == 0) {
+        put(static_cast<char>('0' + ones));
+        lit("e-06");
+      } else {
+        put(static_cast<char>('0' + tens));
+        if (ones) {
+          put('.');
+          put(static_cast<char>('0' + ones));
+        }
+        lit("e-05");
+      }
+      return;
+    }
+    u64(q / 1000000ull);
+    put('.');
+    unsigned frac = static_cast<unsigned>(q % 1000000ull);
+    int fd = 6;
+    while (fd > 1 && frac % 10u == 0u) {
+      frac /= 10u;
+      --fd;
+    }
+    for (int i = fd - 1; i >= 0; --i) {   // fd digits, leading zeros included
+      const unsigned d = frac / 10u;
+      p[i] = static_cast<char>('0' + (frac - d * 10u));
+      frac = d;
+    }
+    p += fd;
+  }
+};
+
+// bytes [0, n) of a shared-memory stage -> dst, where stage[0] corresponds to dst rounded DOWN to 16 bytes (the text
+// starts at stage + (dst & 15)): whole 16-byte chunks leave as one aligned store, the ragged ends byte by byte
+template <int kThreads>
+__device__ __forceinline__ void stage_to_global(const char* stage, char* dst, long long n, int tid) {
+  const int a = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);
+  char* g0 = dst - a;
+  const long long end = a + n;   // stage / g0 relative
+  for (long long c = static_cast<long long>(tid) * 16; c < end; c += kThreads * 16) {
+    if (c >= a && c + 16 <= end) {
+      *reinterpret_cast<uint4*>(g0 + c) = *reinterpret_cast<const uint4*>(stage + c);
+    } else {
+      const long long lo = c > a ? c : a, hi = c + 16 < end ? c + 16 : end;
+      for (long long i = lo; i < hi; ++i) g0[i] = stage[i];
+    }
+  }
 }
 
 // q = round_half_even(|v| * 1e6); false when v is outside the exact domain
@@ -38,28 +174,13 @@ __device__ __forceinline__ bool fixed6_units(float v, unsigned long long* q) {
   return true;
 }
 
+// "%.6f" of +-q * 1e-6 with |value| < 2^20: q < 2^40, integer part < 2^20, fraction < 10^6 — all 32-bit after the split
 __device__ __forceinline__ int fixed6_len(float v, unsigned long long q) {
-  return (signbit(v) ? 1 : 0) + dec_digits(q / 1000000ull) + 7;
+  return (signbit(v) ? 1 : 0) + digits_u32(static_cast<unsigned>(q / 1000000ull)) + 7;
 }
 
-// bounded byte sink: counts everything, stores what fits
-struct Sink {
-  char* p;
-  long long pos, cap;
-  __device__ __forceinline__ void put(char c) {
-    if (pos < cap) p[pos] = c;
-    ++pos;
-  }
-  __device__ __forceinline__ void put_uint(unsigned long long v) {
-    char tmp[20];
-    int n = 0;
-    do {
-      tmp[n++] = static_cast<char>('0' + static_cast<int>(v % 10ull));
-      v /= 10ull;
-    } while (v);
-    while (n) put(tmp[--n]);
-  }
-};
+constexpr int kYoloMaxLine = 96;   // 11 (class) + 4 x (1 + 1 + 7 + 1 + 6) + 1 = 76 at most
+constexpr int kYoloStage = kYoloThreads * kYoloMaxLine + 16;
 
 __global__ void __launch_bounds__(kYoloThreads)
     yolo_text_kernel(const cspe_record* __restrict__ records, const int32_t* __restrict__ n_out, int N, char* text,
@@ -67,6 +188,7 @@ __global__ void __launch_bounds__(kYoloThreads)
   __shared__ int warp_sums[kYoloThreads / 32];
   __shared__ long long base_s;
   __shared__ int bad_s;
+  __shared__ __align__(16) char stage_s[kYoloStage];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   pdl_launch_dependents();  // whatever is queued behind may get placed; it waits for us before it reads
   if (tid == 0) {
@@ -89,11 +211,11 @@ __global__ void __launch_bounds__(kYoloThreads)
     unsigned long long q[4] = {0, 0, 0, 0};
     if (r < n) {
       cls = __ldcg(&rec[r].class_id);
-      len = (cls < 0 ? 1 : 0) + dec_digits(static_cast<unsigned long long>(cls < 0 ? -static_cast<long long>(cls) : cls)) + 1;
+      len = len_i32(cls) + 1;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         v[k] = __ldcg(&rec[r].yolo[k]);
-        if (!fixed6_units(v[k], &q[k])) bad_s = 1;
+        if (!fixed6_units(v[k], &q[k])) bad_s = 1;   // q stays 0: the line is printed with 0.000000, the frame flagged
         len += 1 + fixed6_len(v[k], q[k]);
       }
     }
@@ -113,30 +235,37 @@ __global__ void __launch_bounds__(kYoloThreads)
       if (w < wid) before += s;
       total += s;
     }
+    // the pass is staged in shared memory at the same offset modulo 16 as its destination, then leaves as aligned
+    // 16-byte stores (the first version stored it byte by byte from every thread)
+    const long long base = base_s;
+    char* dst = out + base;
+    const int a = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);
     if (r < n) {
-      Sink sk{out, base_s + before + incl - len, frame_stride};
-      if (cls < 0) sk.put('-');
-      sk.put_uint(static_cast<unsigned long long>(cls < 0 ? -static_cast<long long>(cls) : cls));
+      Stage st{stage_s + a + before + incl - len};
+      st.i32(cls);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        sk.put(' ');
-        if (signbit(v[k])) sk.put('-');
-        sk.put_uint(q[k] / 1000000ull);
-        sk.put('.');
-        unsigned int frac = static_cast<unsigned int>(q[k] % 1000000ull);
-        char d[6];
+        st.put(' ');
+        if (signbit(v[k])) st.put('-');
+        st.u32(static_cast<unsigned>(q[k] / 1000000ull));
+        st.put('.');
+        unsigned frac = static_cast<unsigned>(q[k] % 1000000ull);
 #pragma unroll
         for (int i = 5; i >= 0; --i) {
-          d[i] = static_cast<char>('0' + frac % 10u);
-          frac /= 10u;
+          const unsigned d = frac / 10u;
+          st.p[i] = static_cast<char>('0' + (frac - d * 10u));
+          frac = d;
         }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) sk.put(d[i]);
+        st.p += 6;
       }
-      sk.put('\n');
+      st.put('\n');
     }
     __syncthreads();
-    if (tid == 0) base_s += total;
+    long long room = frame_stride - base;   // bytes past the frame's stride are dropped but counted
+    room = room < 0 ? 0 : (room > total ? total : room);
+    stage_to_global<kYoloThreads>(stage_s, dst, room, tid);
+    __syncthreads();
+    if (tid == 0) base_s = base + total;
     __syncthreads();
   }
   if (tid == 0) n_bytes[f] = bad_s ? -1 : static_cast<int32_t>(base_s);
@@ -151,89 +280,71 @@ __global__ void __launch_bounds__(kYoloThreads)
 // annotations printed so far (the caller zeroes it at sweep start), every CTA adds the counts of the frames before it
 // in the batch, and the LAST CTA to finish (ticket in ann_state[1]) adds the batch total.
 constexpr int kCocoMaxRecord = 224;   // longest record: 10-digit ids / coordinates, two 13-character ratios
-
-// Two writers with one interface: the first pass only counts, the second stores at the final position (bounded by the
-// frame's stride), so a record is never staged in local memory.
-struct CountWriter {
-  int n = 0;
-  __device__ __forceinline__ void put(char) { ++n; }
-};
-struct TextWriter {
-  char* p;
-  long long pos, cap;
-  __device__ __forceinline__ void put(char c) {
-    if (pos < cap) p[pos] = c;
-    ++pos;
-  }
-};
-
-template <class W>
-__device__ __forceinline__ void w_lit(W& w, const char* s) {
-  for (int i = 0; s[i]; ++i) w.put(s[i]);
-}
-
-template <class W>
-__device__ __forceinline__ void w_int(W& w, long long v) {
-  if (v < 0) {
-    w.put('-');
-    v = -v;
-  }
-  char tmp[20];
-  const int n = put_decimal(static_cast<unsigned long long>(v), tmp);
-  for (int i = 0; i < n; ++i) w.put(tmp[i]);
-}
-
-template <class W>
-__device__ __forceinline__ void w_ratio(W& w, float v) {
-  char tmp[28];
-  const int n = repr_units6(signbit(v), static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(v)) * 1e6)), tmp);
-  for (int i = 0; i < n; ++i) w.put(tmp[i]);
-}
+constexpr int kCocoThreads = 128;     // records printed per pass; a frame of the configs here holds 50-100
+// shared-memory stage of one pass: 240 bytes is the true bound of a record (19-digit id, seven signed 10-digit
+// integers, two 15-character ratios) — kCocoMaxRecord is what realistic values need and what callers size strides by
+constexpr int kCocoStage = kCocoThreads * 240 + 16;
 
 struct CocoFields {
   long long ann_id;
   int frame, cls, cnt, x0, y0, x1, y1;
-  float occ, trunc;
+  unsigned long long q_occ, q_trunc;   // round-half-even(|ratio| * 1e6)
+  bool neg_occ, neg_trunc;
   bool sep;   // ", " in front (every annotation but the sweep's first)
 };
 
-template <class W>
-__device__ __forceinline__ void coco_record(W& w, const CocoFields& r) {
-  if (r.sep) w_lit(w, ", ");
-  w_lit(w, "{\"id\": ");
-  w_int(w, r.ann_id);
-  w_lit(w, ", \"image_id\": ");
-  w_int(w, r.frame);
-  w_lit(w, ", \"category_id\": ");
-  w_int(w, r.cls);
-  w_lit(w, ", \"bbox\": [");
+// the literal text of a record: ({"id": )(, "image_id": )(, "category_id": )(, "bbox": [)(], "area": )
+// (, "iscrowd": 0, "occlusion": )(, "truncation": )(}) = 7 + 14 + 17 + 11 + 11 + 29 + 16 + 1 = 106 bytes
+constexpr int kCocoLiteral = 106;
+
+__device__ __forceinline__ int coco_len(const CocoFields& r) {
+  int n = kCocoLiteral + (r.sep ? 2 : 0) + len_i64(r.ann_id) + len_i32(r.frame) + len_i32(r.cls) + len_i32(r.cnt);
   if (r.cnt > 0) {
-    w_int(w, r.x0);
-    w_lit(w, ", ");
-    w_int(w, r.y0);
-    w_lit(w, ", ");
-    w_int(w, static_cast<long long>(r.x1) - r.x0 + 1);
-    w_lit(w, ", ");
-    w_int(w, static_cast<long long>(r.y1) - r.y0 + 1);
+    const long long w = static_cast<long long>(r.x1) - r.x0 + 1, h = static_cast<long long>(r.y1) - r.y0 + 1;
+    n += len_i32(r.x0) + len_i32(r.y0) + len_i64(w) + len_i64(h) + 6;   // three ", "
   } else {
-    w_lit(w, "0, 0, 0, 0");
+    n += 10;   // 0, 0, 0, 0
   }
-  w_lit(w, "], \"area\": ");
-  w_int(w, r.cnt);
-  w_lit(w, ", \"iscrowd\": 0, \"occlusion\": ");
-  w_ratio(w, r.occ);
-  w_lit(w, ", \"truncation\": ");
-  w_ratio(w, r.trunc);
+  return n + len_units6(r.neg_occ, r.q_occ) + len_units6(r.neg_trunc, r.q_trunc);
+}
+
+__device__ __forceinline__ void coco_print(Stage& w, const CocoFields& r) {
+  if (r.sep) w.lit(", ");
+  w.lit("{\"id\": ");
+  w.i64(r.ann_id);
+  w.lit(", \"image_id\": ");
+  w.i32(r.frame);
+  w.lit(", \"category_id\": ");
+  w.i32(r.cls);
+  w.lit(", \"bbox\": [");
+  if (r.cnt > 0) {
+    w.i32(r.x0);
+    w.lit(", ");
+    w.i32(r.y0);
+    w.lit(", ");
+    w.i64(static_cast<long long>(r.x1) - r.x0 + 1);
+    w.lit(", ");
+    w.i64(static_cast<long long>(r.y1) - r.y0 + 1);
+  } else {
+    w.lit("0, 0, 0, 0");
+  }
+  w.lit("], \"area\": ");
+  w.i32(r.cnt);
+  w.lit(", \"iscrowd\": 0, \"occlusion\": ");
+  w.units6(r.neg_occ, r.q_occ);
+  w.lit(", \"truncation\": ");
+  w.units6(r.neg_trunc, r.q_trunc);
   w.put('}');
 }
 
-__global__ void __launch_bounds__(kYoloThreads)
+__global__ void __launch_bounds__(kCocoThreads)
     coco_text_kernel(const cspe_record* records, const int32_t* n_out, int B, int N, unsigned long long* ann_state,
                      char* text, long long frame_stride, int32_t* n_bytes) {
-  __shared__ int warp_sums[kYoloThreads / 32];
+  __shared__ int warp_sums[kCocoThreads / 32];
   __shared__ long long base_s, first_id_s;
-  __shared__ long long part_s[kYoloThreads / 32];
+  __shared__ long long part_s[kCocoThreads / 32];
   __shared__ int bad_s;
+  __shared__ __align__(16) char stage_s[kCocoStage];
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   pdl_launch_dependents();
   if (tid == 0) {
@@ -246,7 +357,7 @@ __global__ void __launch_bounds__(kYoloThreads)
   n = n < 0 ? 0 : (n > N ? N : n);
   // annotation id of this frame's first record: everything printed before this batch + the frames before this one
   long long before_frames = 0;
-  for (int g = tid; g < f; g += kYoloThreads) {
+  for (int g = tid; g < f; g += kCocoThreads) {
     const int m = __ldcg(n_out + g);
     before_frames += m < 0 ? 0 : (m > N ? N : m);
   }
@@ -257,13 +368,13 @@ __global__ void __launch_bounds__(kYoloThreads)
   if (tid == 0) {
     long long s = 0;
 #pragma unroll
-    for (int w = 0; w < kYoloThreads / 32; ++w) s += part_s[w];
+    for (int w = 0; w < kCocoThreads / 32; ++w) s += part_s[w];
     first_id_s = static_cast<long long>(__ldcg(ann_state)) + s + 1;
   }
   __syncthreads();
   const cspe_record* rec = records + static_cast<long long>(f) * N;
   char* out = text + static_cast<long long>(f) * frame_stride;
-  for (int r0 = 0; r0 < n; r0 += kYoloThreads) {
+  for (int r0 = 0; r0 < n; r0 += kCocoThreads) {
     const int r = r0 + tid;
     CocoFields fld{};
     int len = 0;
@@ -277,15 +388,16 @@ __global__ void __launch_bounds__(kYoloThreads)
       fld.y0 = __ldcg(&q->y_min);
       fld.x1 = __ldcg(&q->x_max);
       fld.y1 = __ldcg(&q->y_max);
-      fld.occ = __ldcg(&q->occlusion);
-      fld.trunc = __ldcg(&q->truncation);
+      const float occ = __ldcg(&q->occlusion), trunc = __ldcg(&q->truncation);
       fld.sep = fld.ann_id > 1;
-      if (!(fabsf(fld.occ) < 1048576.0f) || !(fabsf(fld.trunc) < 1048576.0f)) {
+      if (!(fabsf(occ) < 1048576.0f) || !(fabsf(trunc) < 1048576.0f)) {
         bad_s = 1;   // an unprintable ratio: the frame is flagged, nothing is written for the record
       } else {
-        CountWriter cw;
-        coco_record(cw, fld);
-        len = cw.n;
+        fld.neg_occ = signbit(occ);
+        fld.neg_trunc = signbit(trunc);
+        fld.q_occ = static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(occ)) * 1e6));
+        fld.q_trunc = static_cast<unsigned long long>(__double2ll_rn(fabs(static_cast<double>(trunc)) * 1e6));
+        len = coco_len(fld);
       }
     }
     int incl = len;
@@ -298,17 +410,25 @@ __global__ void __launch_bounds__(kYoloThreads)
     __syncthreads();
     int before = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < kYoloThreads / 32; ++w) {
+    for (int w = 0; w < kCocoThreads / 32; ++w) {
       const int sw = warp_sums[w];
       if (w < wid) before += sw;
       total += sw;
     }
+    // this pass's text goes to out + base_s; the stage mirrors the destination modulo 16
+    const long long base = base_s;
+    char* dst = out + base;
+    const int a = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);
     if (len > 0) {
-      TextWriter tw{out, base_s + before + incl - len, frame_stride};
-      coco_record(tw, fld);
+      Stage st{stage_s + a + before + incl - len};
+      coco_print(st, fld);
     }
     __syncthreads();
-    if (tid == 0) base_s += total;
+    long long room = frame_stride - base;   // bytes past the frame's stride are dropped but counted
+    room = room < 0 ? 0 : (room > total ? total : room);
+    stage_to_global<kCocoThreads>(stage_s, dst, room, tid);
+    __syncthreads();
+    if (tid == 0) base_s = base + total;
     __syncthreads();
   }
   if (tid == 0) {
@@ -359,19 +479,41 @@ __global__ void __launch_bounds__(kYoloThreads)
   n = n < 0 ? 0 : (n > stride ? stride : n);
   const long long off = off_s;
   const char* src = text + static_cast<long long>(f) * stride;
-  if (((reinterpret_cast<uintptr_t>(src)) & 15) == 0) {   // rows at a 16-byte stride: one 16-byte load per 16 bytes
-    for (long long i = static_cast<long long>(tid) * 16; i < n; i += kYoloThreads * 16) {
-      const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + i));
-      const unsigned w[4] = {v.x, v.y, v.z, v.w};
+  const long long n_full = n;   // what the row holds; only what fits below `capacity` is stored
+  if (off + n > capacity) n = capacity > off ? capacity - off : 0;
+  char* dst = packed + off;
+  if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    // rows start on a word boundary, their place in `packed` does not: every aligned 16-byte chunk of the destination
+    // is assembled from five consecutive source words with a funnel shift and leaves as ONE store (the first version
+    // stored 16 single bytes per chunk)
+    const int a = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15);
+    char* g0 = dst - a;
+    const long long end = a + n;
+    const unsigned* src32 = reinterpret_cast<const unsigned*>(src);
+    for (long long c = static_cast<long long>(tid) * 16; c < end; c += kYoloThreads * 16) {
+      if (c >= a && c + 16 <= end) {
+        const long long sidx = c - a;             // source byte of the chunk's first byte
+        const long long w0 = sidx >> 2;
+        const unsigned sh = static_cast<unsigned>(sidx & 3) * 8u;
+        unsigned w[5];
 #pragma unroll
-      for (int k = 0; k < 16; ++k)
-        if (i + k < n && off + i + k < capacity) packed[off + i + k] = static_cast<char>((w[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        for (int k = 0; k < 4; ++k) w[k] = __ldcg(src32 + w0 + k);
+        w[4] = (sh != 0u && (w0 + 4) * 4 < n) ? __ldcg(src32 + w0 + 4) : 0u;   // never read past the row's text
+        uint4 v;
+        v.x = __funnelshift_r(w[0], w[1], sh);
+        v.y = __funnelshift_r(w[1], w[2], sh);
+        v.z = __funnelshift_r(w[2], w[3], sh);
+        v.w = __funnelshift_r(w[3], w[4], sh);
+        *reinterpret_cast<uint4*>(g0 + c) = v;
+      } else {
+        const long long lo = c > a ? c : a, hi = c + 16 < end ? c + 16 : end;
+        for (long long i = lo; i < hi; ++i) g0[i] = __ldcg(src + (i - a));
+      }
     }
   } else {
-    for (long long i = tid; i < n; i += kYoloThreads)
-      if (off + i < capacity) packed[off + i] = __ldcg(src + i);
+    for (long long i = tid; i < n; i += kYoloThreads) dst[i] = __ldcg(src + i);
   }
-  if (f == B - 1 && tid == 0) *total = off + n;
+  if (f == B - 1 && tid == 0) *total = off + n_full;
 }
 
 }  // namespace
@@ -405,7 +547,7 @@ extern "C" int cspe_format_coco(const cspe_record* records, const int32_t* n_out
                "cspe_format_coco: ann_state must be 8-byte aligned");
   CSPE_REQUIRE(static_cast<long long>(N) * (kCocoMaxRecord + 2) < (1ll << 31), CSPE_ERR_UNSUPPORTED,
                "cspe_format_coco: %d slots per frame overflow the int32 byte count", N);
-  CSPE_CUDA_OK(launch_pdl(coco_text_kernel, dim3(static_cast<unsigned>(B)), dim3(kYoloThreads), 0,
+  CSPE_CUDA_OK(launch_pdl(coco_text_kernel, dim3(static_cast<unsigned>(B)), dim3(kCocoThreads), 0,
                           static_cast<cudaStream_t>(stream), records, n_out, B, N,
                           reinterpret_cast<unsigned long long*>(ann_state), text, static_cast<long long>(frame_stride),
                           n_bytes));

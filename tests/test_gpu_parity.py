@@ -1405,6 +1405,62 @@ def test_pipeline_inputs_rewritten_in_place(T, ops, mode):
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
+def test_pipeline_small_batch_order_stress(T, ops, use_graph):
+    """Batches that do not fill the device are queued K2 [K3] -> K1 -> K4 (K1 streams beside K2 and waits for it before
+    its first merge).  300 back-to-back runs with NO host synchronisation in between, the inputs flipping between two
+    scenes by device-to-device copies and every run's outputs snapshotted on the stream: many slots (a long K4) on a tiny
+    frame (a short K1) is the shape in which a K2 that started too early would overwrite what the previous K4 still
+    copies, and in which a K1 that merged too early would lose pixels to the previous K4's table reset."""
+    from constructionsceneposeestimation_b200 import synthetic, _lib
+    from constructionsceneposeestimation_b200.pipeline import LabelPipeline
+    spec = synthetic.SceneSpec(320, 180, 220, 3, 17, config_id=21)
+    sets = [helpers.oracle_pipeline(synthetic.make_batch(spec, 2, first)) for first in (0, 2)]
+    N = max(o["obj_record"].shape[1] for o in sets)
+    R = max(o["records"].shape[1] for o in sets)
+    L = (max(o["lut"].shape[1] for o in sets) + 3) & ~3
+    P, J = sets[0]["joints"].shape[1:3]
+    dev = T.device("cuda")
+    pipe = LabelPipeline(2, 180, 320, N, R, L, dev, use_graph=use_graph, num_people=P, num_joints=J)
+    assert not pipe.overlapped and N > 200
+
+    def device_inputs(o):
+        n, r, l = o["obj_record"].shape[1], o["records"].shape[1], o["lut"].shape[1]
+        lut = np.full((2, L), -1, dtype=np.int32)
+        lut[:, :l] = o["lut"]
+        obj = np.full((2, N), -1, dtype=np.int32)
+        obj[:, :n] = o["obj_record"]
+        cls = np.full((2, N), -1, dtype=np.int32)
+        cls[:, :n] = o["slot_class"]
+        rec = np.zeros((2, R, _lib.BBOX3D_RECORD_BYTES), dtype=np.uint8)
+        rec[:, :r] = o["records"].view(np.uint8).reshape(2, r, -1)
+        arrays = dict(mask=o["mask"].view(np.int32), lut=lut, obj_record=obj, slot_class=cls, records_in=rec, cam=o["cam"],
+                      joints=o["joints"], depth=o["depth"])
+        return {k: T.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in arrays.items()}
+
+    inputs = [device_inputs(o) for o in sets]
+    T.cuda.synchronize()
+    snaps = []
+    runs = 300
+    for it in range(runs):
+        for k, v in inputs[it & 1].items():
+            getattr(pipe, k).copy_(v, non_blocking=True)
+        pipe.run()
+        kp, kz, vis = pipe.keypoints
+        snaps.append((pipe.records.clone(), pipe.n_out.clone(), vis.clone(), kp.clone()))
+    T.cuda.synchronize()
+    for it, (rec, n_out, vis, kp) in enumerate(snaps):
+        o = sets[it & 1]
+        n_out = n_out.cpu().numpy()
+        assert np.array_equal(n_out, o["n_out"]), it
+        rec = rec.cpu().numpy().view(_lib.RECORD_DTYPE).reshape(2, N)
+        for f in range(2):
+            helpers.assert_records_equal(rec[f, : n_out[f]], o["recs"][f, : n_out[f]])
+        assert np.array_equal(vis.cpu().numpy(), o["vis"]) and np.array_equal(kp.cpu().numpy(), o["kp"]), it
+    assert np.array_equal(pipe.class_hist.cpu().numpy(), (runs // 2) * (sets[0]["hist"] + sets[1]["hist"]))
+    assert np.array_equal(pipe.scan.cpu().numpy(), np.tile(np.array([0, 320, 180, -1, -1], dtype=np.int32), (2, N, 1)))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
 def test_pipeline_with_keypoint_stage(T, ops, use_graph):
     """Config-3 pipeline: K3 (overlapped) rides the same PDL chain; keypoints and records equal the oracle."""
     from constructionsceneposeestimation_b200 import synthetic, _lib
