@@ -289,9 +289,17 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                         packed = packed[:, :total].copy()
                     # off the launch thread, on ONE consumer thread: the images entries and the memcpy of the chunk are
                     # native calls (no GIL); several Python workers only fought the launch thread for the interpreter
-                    # (8 workers: 199 k frames/s, the launch thread itself: 386 k)
-                    submit(lambda: (formats.coco_images_text(range(s, e), W, H),
-                                    formats.concat_rows(packed, np.array([total], dtype=np.int32), as_array=True)))
+                    # (8 workers: 199 k frames/s, the launch thread itself: 386 k).  The batches of a graph group go
+                    # to the worker as ONE job (flush_coco): a submit costs a lock, a queue and a thread wake-up, and
+                    # with eight ranks on one host those were a third of the launch thread's time
+                    coco_batch.append((s, e, packed, total))
+                    if not in_place:
+                        flush_coco(None)
+                    elif len(coco_batch) >= 3:
+                        # ... but not the whole group: a chunk lands in freshly allocated memory (0.46 MB of first-touch
+                        # page faults each), and one worker alone then needs longer for a group than the GPU does
+                        # (measured: 340-450 k frames/s with one job per group against 542 k with one per batch)
+                        flush_coco(jobs)
                 elif label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
                     submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
@@ -319,14 +327,34 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             elif emit == "records":   # raw records kept in memory (tests)
                 kept_records.extend(recs[j, : n_use[j]].copy() for j in range(nf))
 
+        coco_batch: List[Tuple[int, int, np.ndarray, int]] = []
+
+        def flush_coco(jobs: Optional[List]) -> None:
+            """One worker job for the COCO chunks collected by consume(): [(images text, annotation chunk)]."""
+            if not coco_batch:
+                return
+            items = list(coco_batch)
+            coco_batch.clear()
+
+            def job():
+                return [(formats.coco_images_text(range(s, e), W, H),
+                         formats.concat_rows(packed, np.array([total], dtype=np.int32), as_array=True))
+                        for s, e, packed, total in items]
+
+            fut = io_pool.submit(job)
+            pending.append(fut)
+            if jobs is not None:
+                jobs.append(fut)
+
         def drain(limit: int) -> None:
             """Collect finished worker jobs (keeps at most `limit` in flight); COCO chunks stay in order."""
             nonlocal text_bytes
             while len(pending) > limit:
                 r = pending.pop(0).result()
                 if emit == "coco":
-                    coco_imgs.append(r[0])
-                    coco_anns.append(r[1])
+                    for img, ann in r:
+                        coco_imgs.append(img)
+                        coco_anns.append(ann)
                 elif emit == "coco_host":
                     coco_anns.append(r)
                     text_bytes += len(r)
@@ -369,7 +397,8 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 t2 = time.perf_counter()
                 for slot, (s, e) in zip(prev.slots, pgrp):
                     consume(slot, s, e, 0, prev.jobs)
-                drain(8 * group * (64 if emit == "json" else 1))
+                flush_coco(prev.jobs)
+                drain(8 * (1 if emit == "coco" else group) * (64 if emit == "json" else 1))
                 timers["wait_s"] += t2 - t1
                 timers["consume_s"] += time.perf_counter() - t2
         if groups:
@@ -379,6 +408,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             t2 = time.perf_counter()
             for slot, (s, e) in zip(prev.slots, pgrp):
                 consume(slot, s, e, 0, prev.jobs)
+            flush_coco(prev.jobs)
             timers["wait_s"] += t2 - t1
             timers["consume_s"] += time.perf_counter() - t2
 
