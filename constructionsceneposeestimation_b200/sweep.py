@@ -100,13 +100,15 @@ class _BatchOut:
         if self.text_kind is not None:
             self.stride = (YOLO_BYTES_PER_SLOT if self.text_kind == "yolo" else COCO_BYTES_PER_SLOT) * N
             self.text = torch.empty((B, self.stride), dtype=torch.uint8, device=dev)
-            self.text_h = torch.empty((B, self.stride), dtype=torch.uint8, pin_memory=True)
+            # (COCO text reaches the host through the packed chunk, never through a strided mirror)
+            self.text_h = torch.empty((B, self.stride), dtype=torch.uint8, pin_memory=True) if self.text_kind == "yolo" else None
             self.n_bytes = torch.empty((B,), dtype=torch.int32, device=dev)
             self.n_bytes_h = torch.empty((B,), dtype=torch.int32, pin_memory=True)
             self.packed = self.packed_h = self.total = self.total_h = None
             if self.text_kind == "coco":   # the batch's annotation text as ONE chunk (cspe_pack_rows)
+                # The chunk stays on the device: once the host knows its size (total_h) it is copied straight to its
+                # final place in the sweep's pinned result buffer (run_sweep) — no pinned mirror, no host memcpy
                 self.packed = torch.empty((B * self.stride,), dtype=torch.uint8, device=dev)
-                self.packed_h = torch.empty((B * self.stride,), dtype=torch.uint8, pin_memory=True)
                 self.total = torch.zeros((1,), dtype=torch.int64, device=dev)
                 self.total_h = torch.zeros((1,), dtype=torch.int64, pin_memory=True)
 
@@ -130,13 +132,54 @@ class _BatchOut:
         cp(self.n_out_h, self.n_out, nf * 4)
         if self.text is not None:
             cp(self.n_bytes_h, self.n_bytes, nf * 4)
-            if self.packed is not None:   # the chunk sits at the front; its size is only known on the device
+            if self.packed is not None:   # only the chunk's size comes back here; the text follows when it is known
                 cp(self.total_h, self.total, 8)
-                cp(self.packed_h, self.packed, nf * self.stride)
             else:
                 cp(self.text_h, self.text, nf * self.stride)
         if self.records_h is not None:
             cp(self.records_h, self.records, nf * self.records.shape[1] * self.records.shape[2])
+
+
+class _CocoResult:
+    """The rank's COCO annotation text, contiguous in pinned host memory.  ``append`` enqueues the copy of one batch's
+    packed device chunk to the current end of the buffer on a copy stream (the host knows the chunk's size by then);
+    nothing is staged or copied on the host.  Capacity comes from a probe batch (text of one batch + 16 more digits per
+    record for ids that grow) times the number of batches; if that ever falls short another pinned chunk is opened."""
+
+    def __init__(self, lib, device: torch.device, probe: "_BatchOut", batches: int, B: int, N: int):
+        self.lib, self.device = lib, device
+        seen = int(probe.total_h[0])
+        per_batch = seen + 16 * max(1, int(probe.n_out_h.numpy().clip(0, N).sum())) + 256 if seen > 0 else B * probe.stride // 3
+        per_batch = min(max(per_batch, 4096), B * probe.stride)
+        self.per_batch = per_batch
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs: List[torch.Tensor] = [torch.empty((max(1, batches) * per_batch,), dtype=torch.uint8, pin_memory=True)]
+        self.used: List[int] = [0]
+
+    def append(self, packed: torch.Tensor, total: int) -> None:
+        if total <= 0:
+            return
+        if self.used[-1] + total > self.bufs[-1].numel():     # the estimate fell short: open another chunk
+            self.bufs.append(torch.empty((max(total, 64 * self.per_batch),), dtype=torch.uint8, pin_memory=True))
+            self.used.append(0)
+        _lib.check("cspe_memcpy_async", self.lib.cspe_memcpy_async(
+            self.bufs[-1].data_ptr() + self.used[-1], packed.data_ptr(), total, self.stream.cuda_stream))
+        self.used[-1] += total
+
+    def mark(self) -> torch.cuda.Event:
+        ev = torch.cuda.Event()
+        ev.record(self.stream)
+        return ev
+
+    def wait(self) -> None:
+        self.stream.synchronize()
+
+    def chunks(self) -> List[np.ndarray]:
+        return [b.numpy()[:u] for b, u in zip(self.bufs, self.used) if u]
+
+    @property
+    def nbytes(self) -> int:
+        return sum(self.used)
 
 
 class _GroupGraph:
@@ -157,6 +200,7 @@ class _GroupGraph:
         self.frame_base_d = torch.zeros((1,), dtype=torch.int32, device=dev)
         self.done = torch.cuda.Event()
         self.jobs: List = []     # worker jobs still reading this instance's pinned buffers
+        self.copied: Optional[torch.cuda.Event] = None   # D2H copies (another stream) still reading its device text
         side = torch.cuda.Stream(device=dev)
         p0 = pipe._parity
 
@@ -186,6 +230,9 @@ class _GroupGraph:
             job.result()
         self.jobs = []
         self.frame_base_h[0] = first_frame
+        if self.copied is not None:   # a GPU-side wait: the host does not block
+            torch.cuda.current_stream(self.pipe.device).wait_event(self.copied)
+            self.copied = None
         self.graph.replay()
         self.done.record()
 
@@ -231,14 +278,25 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         ann_state = torch.zeros((2,), dtype=torch.int64, device=device) if text_kind == "coco" else None
         # three instances with their own output buffers take turns: one is running, one is being consumed, and the worker
         # jobs that still read the third one's pinned buffers have a whole group time to finish before it is relaunched
-        n_inst = 3 if (want_records or text_kind == "coco" or label_dir is not None) else 2
+        n_inst = 3 if (want_records or label_dir is not None) else 2
+        n_inst = int(os.environ.get("CSPE_SWEEP_INSTANCES", n_inst))   # A/B switch
         graphs = [_GroupGraph(pipe, group, want_records, text_kind, ann_state) for _ in range(min(n_inst, len(groups)))]
         eager_slot = _BatchOut(pipe, want_records, want_yolo, None, text_kind, ann_state) if eager else None
         workers = max(1, min(8, (os.cpu_count() or 2) // max(1, world))) if io_threads is None else max(1, io_threads)
-        if text_kind == "coco" and io_threads is None:
-            workers = min(workers, 3)
         io_pool = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="cspe-io") \
-            if (want_records or label_dir is not None or text_kind == "coco") else None
+            if (want_records or label_dir is not None) else None
+        # COCO text formatted on the device never passes through host code: every batch's packed chunk is copied
+        # (cudaMemcpyAsync on a copy stream, enqueued as soon as the host has read the chunk's size) to its final
+        # offset in ONE pinned result buffer, so the rank's annotation text ends up contiguous with no host memcpy,
+        # no allocation and no worker thread inside the sweep.  (The previous form — packed text D2H into a pinned
+        # mirror, then a worker copying it into fresh memory — was host-bound once eight ranks shared one box: 0.76
+        # scaling efficiency at N = 8, the workers' first-touch page faults and memcpys against eight launch threads.)
+        coco_out: Optional["_CocoResult"] = None
+        if text_kind == "coco":
+            torch.cuda.synchronize(device)
+            probe = (graphs[0].slots[0] if graphs else eager_slot)    # the capture warm-up ran one batch through it
+            batches = len(head) + len(full) + len(tail)
+            coco_out = _CocoResult(lib, device, probe, batches, B, N)
         slot_strings = [formats.slot_string_table(o) for o in objects] if emit == "json" else None
 
         emitted = 0
@@ -284,23 +342,11 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                     total = int(slot.total_h[0])
                     if total != int(nb.sum()):
                         raise RuntimeError(f"COCO text of frames {s}..{e}: packed {total} bytes, sizes sum to {int(nb.sum())}")
-                    packed = slot.packed_h.numpy().reshape(1, -1)
+                    coco_out.append(slot.packed, total)      # device -> its final place, asynchronously
                     if not in_place:
-                        packed = packed[:, :total].copy()
-                    # off the launch thread, on ONE consumer thread: the images entries and the memcpy of the chunk are
-                    # native calls (no GIL); several Python workers only fought the launch thread for the interpreter
-                    # (8 workers: 199 k frames/s, the launch thread itself: 386 k).  The batches of a graph group go
-                    # to the worker as ONE job (flush_coco): a submit costs a lock, a queue and a thread wake-up, and
-                    # with eight ranks on one host those were a third of the launch thread's time
-                    coco_batch.append((s, e, packed, total))
-                    if not in_place:
-                        flush_coco(None)
-                    elif len(coco_batch) >= 3:
-                        # ... but not the whole group: a chunk lands in freshly allocated memory (0.46 MB of first-touch
-                        # page faults each), and one worker alone then needs longer for a group than the GPU does
-                        # (measured: 340-450 k frames/s with one job per group against 542 k with one per batch)
-                        flush_coco(jobs)
-                elif label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
+                        coco_out.wait()                       # the caller reuses the slot right away
+                    return
+                if label_dir is not None:   # native writer, off the launch thread, straight from the D2H buffer
                     submit(lambda: formats.write_files(label_dir, "label_", ".txt", s, text, sizes, nf))
                 return
             if not want_records:
@@ -327,35 +373,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             elif emit == "records":   # raw records kept in memory (tests)
                 kept_records.extend(recs[j, : n_use[j]].copy() for j in range(nf))
 
-        coco_batch: List[Tuple[int, int, np.ndarray, int]] = []
-
-        def flush_coco(jobs: Optional[List]) -> None:
-            """One worker job for the COCO chunks collected by consume(): [(images text, annotation chunk)]."""
-            if not coco_batch:
-                return
-            items = list(coco_batch)
-            coco_batch.clear()
-
-            def job():
-                return [(formats.coco_images_text(range(s, e), W, H),
-                         formats.concat_rows(packed, np.array([total], dtype=np.int32), as_array=True))
-                        for s, e, packed, total in items]
-
-            fut = io_pool.submit(job)
-            pending.append(fut)
-            if jobs is not None:
-                jobs.append(fut)
-
         def drain(limit: int) -> None:
             """Collect finished worker jobs (keeps at most `limit` in flight); COCO chunks stay in order."""
             nonlocal text_bytes
             while len(pending) > limit:
                 r = pending.pop(0).result()
-                if emit == "coco":
-                    for img, ann in r:
-                        coco_imgs.append(img)
-                        coco_anns.append(ann)
-                elif emit == "coco_host":
+                if emit == "coco_host":
                     coco_anns.append(r)
                     text_bytes += len(r)
                 elif isinstance(r, int) and emit == "json":
@@ -367,6 +390,12 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             ann_state.zero_()   # the capture warm-ups advanced the annotation counter
         torch.cuda.synchronize(device)
         t0 = time.perf_counter()
+        images_job = images_pool = None
+        if coco_out is not None and hi > lo:
+            # the "images" entries depend on nothing but the frame range: one native call (no GIL) on a thread of its
+            # own, beside the whole sweep (at its end it cost 15-20 ms of a 190 ms sweep)
+            images_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="cspe-coco-images")
+            images_job = images_pool.submit(formats.coco_images_text, range(lo, hi), W, H)
 
         # ---- head of the range and whatever does not fill a graph group: eager, one batch at a time ----
         def run_eager(s: int, e: int) -> None:
@@ -397,8 +426,9 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
                 t2 = time.perf_counter()
                 for slot, (s, e) in zip(prev.slots, pgrp):
                     consume(slot, s, e, 0, prev.jobs)
-                flush_coco(prev.jobs)
-                drain(8 * (1 if emit == "coco" else group) * (64 if emit == "json" else 1))
+                if coco_out is not None:
+                    prev.copied = coco_out.mark()     # the relaunch of this instance waits for these copies on the GPU
+                drain(8 * group * (64 if emit == "json" else 1))
                 timers["wait_s"] += t2 - t1
                 timers["consume_s"] += time.perf_counter() - t2
         if groups:
@@ -408,13 +438,18 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
             t2 = time.perf_counter()
             for slot, (s, e) in zip(prev.slots, pgrp):
                 consume(slot, s, e, 0, prev.jobs)
-            flush_coco(prev.jobs)
             timers["wait_s"] += t2 - t1
             timers["consume_s"] += time.perf_counter() - t2
 
         for s, e in full[len(groups) * group:] + tail:
             run_eager(s, e)
         drain(0)
+        if coco_out is not None:
+            coco_out.wait()
+            coco_anns.extend(coco_out.chunks())
+            if images_job is not None:
+                coco_imgs.append(images_job.result())
+                images_pool.shutdown()
         torch.cuda.synchronize(device)
         dt = time.perf_counter() - t0
         if io_pool is not None:
