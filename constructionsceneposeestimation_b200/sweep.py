@@ -389,6 +389,13 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         if ann_state is not None:
             ann_state.zero_()   # the capture warm-ups advanced the annotation counter
         torch.cuda.synchronize(device)
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            # all ranks enter the timed region together: what comes before it (graph capture, pinning the result
+            # buffer) takes a different time on every rank, and a rank still pinning hundreds of MB while another is
+            # already sweeping showed up as 2x run-to-run spread at N = 8
+            dist.barrier()
         t0 = time.perf_counter()
         images_job = images_pool = None
         if coco_out is not None and hi > lo:
@@ -459,8 +466,6 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         hist_host = pipe.class_hist.cpu().numpy()
         if int(hist_host.sum()) != emitted:
             raise RuntimeError(f"class histogram holds {int(hist_host.sum())} labels, n_out sums to {emitted}")
-
-        import torch.distributed as dist
 
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             gathered = sharding.all_gather_histogram(pipe.class_hist)
