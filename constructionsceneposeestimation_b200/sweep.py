@@ -391,7 +391,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         torch.cuda.synchronize(device)
         import torch.distributed as dist
 
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if world > 1 and dist.is_available() and dist.is_initialized() and dist.get_world_size() == world:
             # all ranks enter the timed region together: what comes before it (graph capture, pinning the result
             # buffer) takes a different time on every rank, and a rank still pinning hundreds of MB while another is
             # already sweeping showed up as 2x run-to-run spread at N = 8
