@@ -724,7 +724,6 @@ class ConstructionLabelWriter:
         lut.fill(-1)
         obj_record.fill(-1)
         slot_class.fill(-1)
-        rec_bytes.fill(0)
         blk.cam[:] = cams
         if same_tables:   # one scene for the whole batch: broadcast its rows
             t = tables[0]
@@ -732,12 +731,23 @@ class ConstructionLabelWriter:
             obj_record[:, :n] = t.obj_record
             slot_class[:, :n] = t.slot_class
             lut[0, t.lut_ids] = t.lut_slots
-        else:
+        else:   # frames that share a scene (a pool of frames repeated, a static scene with a few variants) fill together
+            rows_of: Dict[int, List[int]] = {}
             for i, t in enumerate(tables):
+                rows_of.setdefault(id(t), []).append(i)
+            for rows in rows_of.values():
+                t = tables[rows[0]]
                 n = len(t.objects)
-                obj_record[i, :n] = t.obj_record
-                slot_class[i, :n] = t.slot_class
-                lut[i, t.lut_ids] = t.lut_slots
+                if len(rows) == 1:
+                    i = rows[0]
+                    obj_record[i, :n] = t.obj_record
+                    slot_class[i, :n] = t.slot_class
+                    lut[i, t.lut_ids] = t.lut_slots
+                else:
+                    r = np.asarray(rows)
+                    obj_record[r, :n] = t.obj_record
+                    slot_class[r, :n] = t.slot_class
+                    lut[r[:, None], t.lut_ids[None, :]] = t.lut_slots
         if U:   # union objects point behind the frame's own records (their table entry is relative to len(primPaths))
             blk.union_offsets[:] = u_off
             blk.union_members[:] = u_mem
@@ -747,10 +757,13 @@ class ConstructionLabelWriter:
         item = BBOX3D_DTYPE.itemsize
         dt0 = rec_arrays[0].dtype if type(rec_arrays[0]) is np.ndarray else None
         if dt0 is not None and dt0.itemsize == item and \
-                all(type(r) is np.ndarray and r.ndim == 1 and len(r) == R and r.dtype == dt0 for r in rec_arrays):
-            # every frame brings R records: one C-level gather straight into the pinned block
-            np.concatenate(rec_arrays, out=rec_bytes.reshape(-1).view(rec_arrays[0].dtype))
+                all(type(r) is np.ndarray and r.ndim == 1 and len(r) == R and r.dtype == dt0 and r.flags.c_contiguous
+                    for r in rec_arrays):
+            # every frame brings R records: one C-level gather of BYTES straight into the pinned block (concatenating the
+            # structured arrays themselves goes through numpy's per-field copy: 1.2 ms instead of 0.17 ms for 64 x 222)
+            np.concatenate([r.view(np.uint8) for r in rec_arrays], out=rec_bytes.reshape(-1))
         else:
+            rec_bytes.fill(0)
             for i, r in enumerate(rec_arrays):
                 if r is not None:
                     r = np.ascontiguousarray(r)

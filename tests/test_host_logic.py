@@ -584,3 +584,24 @@ def test_union_records_oracle_is_the_aligned_range():
     assert np.allclose([got["x_max"], got["y_max"], got["z_max"]], pts.max(0), rtol=1e-6, atol=1e-6)
     assert np.array_equal(got["transform"], np.eye(4)) and np.isnan(out[0, 4]["x_min"])   # object 1 has no member
     assert out[0, :3].tobytes() == recs[0, :3].tobytes()
+
+
+def test_write_coco_file_accepts_bytes_and_array_chunks(tmp_path):
+    """write_coco_file assembles the file from pre-formatted chunks: bytes or uint8 arrays (views of the pinned result
+    buffer of a sweep), empty chunks skipped, separators only where the chunks do not carry their own."""
+    import json
+    anns = [{"id": 1, "image_id": 0, "category_id": 2, "bbox": [1, 2, 3, 4], "area": 5, "iscrowd": 0},
+            {"id": 2, "image_id": 0, "category_id": 0, "bbox": [0, 0, 1, 1], "area": 1, "iscrowd": 0},
+            {"id": 3, "image_id": 1, "category_id": 1, "bbox": [9, 9, 2, 2], "area": 3, "iscrowd": 0}]
+    chunk = lambda a: json.dumps(a)[1:-1].encode()
+    images = [formats.coco_image(0, 64, 48, "rgb_000000.png"), formats.coco_image(1, 64, 48, "rgb_000001.png")]
+    want = json.dumps({"images": images, "annotations": anns, "categories": formats.coco_categories()})
+    # host-formatter style: one chunk per batch, joined with ", "
+    formats.write_coco_file(tmp_path / "a.json", images, [chunk(anns[:2]), b"", chunk(anns[2:])])
+    assert (tmp_path / "a.json").read_text() == want
+    # device style: chunks carry their own ", " and arrive as uint8 arrays; images as pre-formatted text
+    dev = [np.frombuffer(chunk(anns[:1]), dtype=np.uint8), np.zeros(0, dtype=np.uint8),
+           np.frombuffer(b", " + chunk(anns[1:]), dtype=np.uint8)]
+    formats.write_coco_file(tmp_path / "b.json", [formats.coco_images_text(range(0, 2), 64, 48)], dev, joined=True)
+    assert (tmp_path / "b.json").read_text() == want
+    assert formats.coco_images_text(range(0, 2), 64, 48) == formats.coco_images_text([0, 1], 64, 48)
