@@ -292,7 +292,7 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
         # mirror, then a worker copying it into fresh memory — was host-bound once eight ranks shared one box: 0.76
         # scaling efficiency at N = 8, the workers' first-touch page faults and memcpys against eight launch threads.)
         coco_out: Optional["_CocoResult"] = None
-        if text_kind == "coco":
+        if text_kind == "coco" and (graphs or eager_slot is not None):   # (a rank without frames has neither)
             torch.cuda.synchronize(device)
             probe = (graphs[0].slots[0] if graphs else eager_slot)    # the capture warm-up ran one batch through it
             batches = len(head) + len(full) + len(tail)
