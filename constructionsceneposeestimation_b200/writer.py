@@ -54,6 +54,22 @@ class FrameTables:
 
 
 @dataclass
+class _HostBatch:
+    """Host side of one batch (``ConstructionLabelWriter._host_tables``)."""
+    tables: List[FrameTables]
+    frame_ids: List[int]
+    poses: List[Sequence[float]]
+    params_list: List[Mapping]
+    block: "_TableBlock"          # [lut | obj_record | slot_class | cam | records | union tables], pinned
+    same_tables: bool              # one scene for the whole batch: the LUT / union tables have ONE row
+    N: int                         # slots per frame
+    R0: int                        # bbox3d records per frame (union records follow at R0 .. R0 + U)
+    U: int                         # object-level records built on the device per frame (record_fallback="union")
+    frame_base: int
+    contiguous_ids: bool
+
+
+@dataclass
 class BatchLabels:
     """Result of one batch: device outputs, pinned host copies and the event that fences them."""
     frame_ids: List[int]
@@ -598,56 +614,13 @@ class ConstructionLabelWriter:
             per_rank = self.class_hist.detach().cpu().numpy().reshape(1, NUM_CLASSES)
         return {"per_rank": per_rank, "total": per_rank.sum(axis=0)}
 
-    # ------------------------------------------------------------------ the hot path
-    def annotate_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
-        """Enqueue the whole path for B frames (list of frame dicts or one stacked dict, like ``write_batch``)
-        and return at once; the result is fenced by ``BatchLabels.synchronize()``.
-
-        Buffer contract (INTEGRATION.md "Input lifetime"): the annotator arrays are read by the GPU after this
-        call returns — pinned host arrays by asynchronous H2D copies, CUDA tensors in place.  The CUDA stream that
-        is current on entry is made to wait for ``BatchLabels.inputs_consumed``, so producers that write those
-        buffers from that stream are ordered automatically; anything else (a host thread refilling a pinned staging
-        buffer, another stream) must call ``BatchLabels.wait_inputs_consumed()`` first."""
-        stacked: Dict[str, ArrayLike] = {}
-        if isinstance(frames, Mapping):
-            frames = _unstack(frames)
-            stacked = frames.stacked
-        if len(frames) == 0:
-            raise ValueError("annotate_batch needs at least one frame")
-        if getattr(frames, "canonical", False):   # cut from a stacked dict: only the camera payload may need work
-            frames = [self._normalise_camera(fr) for fr in frames]
-        else:
-            frames = [self._normalise(fr) for fr in frames]
+    # ------------------------------------------------------------------ host tables of a batch
+    def _host_tables(self, frames: Sequence[Mapping], H: int, W: int, missing: Sequence[int]) -> "_HostBatch":
+        """Everything the kernels need besides the pixels, for B normalised frame dicts: per-frame scene tables
+        (cached), bbox3d records, camera blocks, frame ids — laid out in ONE pinned block (``_TableBlock``).  Pure host
+        work (numpy); ``tests/test_host_logic.py`` runs it on the CPU against the test helpers' statement of the same
+        tables."""
         B = len(frames)
-        dev = self.device
-
-        # ---- the big copy first: enqueue the H2D of the masks (PCIe-bound, ~10 ms for 64 x 1080p)
-        # before building the host tables, so the table work hides under it -----------------
-        masks: List[Optional[ArrayLike]] = [_payload(fr.get("instance_segmentation")) for fr in frames]
-        missing = [i for i, m in enumerate(masks) if m is None or getattr(m, "ndim", 0) != 2]
-        shape = next(((int(m.shape[0]), int(m.shape[1])) for i, m in enumerate(masks) if i not in missing), None)
-        if shape is None:   # no mask at all: take the image size from depth, the camera, or the script default
-            shape = self._fallback_shape(frames[0])
-        H, W = shape
-        for i, m in enumerate(masks):
-            if i not in missing and tuple(m.shape) != (H, W):
-                raise ValueError(f"frame {i}: mask shape {tuple(m.shape)} differs from {(H, W)} (one [H,W] resolution per batch)")
-        caller_stream = torch.cuda.current_stream(dev)
-        with torch.cuda.device(dev):
-            # device-resident annotators (device="cuda" in Replicator) were produced on the caller's stream
-            self.stream.wait_stream(caller_stream)
-            with torch.cuda.stream(self.stream):
-                if missing:   # an absent annotator gives an empty-label frame, never an error (gcd.py:1682,1788,1919)
-                    d_mask = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
-                    present = [i for i in range(B) if i not in missing]
-                    if present:
-                        d_mask[present] = self._stack_to_device([masks[i] for i in present], torch.int32)
-                    mask_owned = True
-                else:
-                    d_mask, mask_owned = self._stack_to_device(masks, torch.int32, stacked.get("instance_segmentation"),
-                                                               return_owned=True)
-
-        # ---- host: per-frame tables ----------------------------------------------------
         tables: List[FrameTables] = []
         rec_arrays: List[Optional[np.ndarray]] = []
         cams = np.zeros((B, CAM_STRIDE), dtype=np.float64)
@@ -772,6 +745,62 @@ class ConstructionLabelWriter:
                     rec_bytes[i, : len(r)] = r.view(np.uint8).reshape(len(r), -1)
                 else:
                     obj_record[i, :] = -1
+
+        return _HostBatch(tables, frame_ids, poses, params_list, blk, same_tables, N, R0, U, frame_base, contiguous_ids)
+
+    # ------------------------------------------------------------------ the hot path
+    def annotate_batch(self, frames: Union[Sequence[Mapping], Mapping]) -> BatchLabels:
+        """Enqueue the whole path for B frames (list of frame dicts or one stacked dict, like ``write_batch``)
+        and return at once; the result is fenced by ``BatchLabels.synchronize()``.
+
+        Buffer contract (INTEGRATION.md "Input lifetime"): the annotator arrays are read by the GPU after this
+        call returns — pinned host arrays by asynchronous H2D copies, CUDA tensors in place.  The CUDA stream that
+        is current on entry is made to wait for ``BatchLabels.inputs_consumed``, so producers that write those
+        buffers from that stream are ordered automatically; anything else (a host thread refilling a pinned staging
+        buffer, another stream) must call ``BatchLabels.wait_inputs_consumed()`` first."""
+        stacked: Dict[str, ArrayLike] = {}
+        if isinstance(frames, Mapping):
+            frames = _unstack(frames)
+            stacked = frames.stacked
+        if len(frames) == 0:
+            raise ValueError("annotate_batch needs at least one frame")
+        if getattr(frames, "canonical", False):   # cut from a stacked dict: only the camera payload may need work
+            frames = [self._normalise_camera(fr) for fr in frames]
+        else:
+            frames = [self._normalise(fr) for fr in frames]
+        B = len(frames)
+        dev = self.device
+
+        # ---- the big copy first: enqueue the H2D of the masks (PCIe-bound, ~10 ms for 64 x 1080p)
+        # before building the host tables, so the table work hides under it -----------------
+        masks: List[Optional[ArrayLike]] = [_payload(fr.get("instance_segmentation")) for fr in frames]
+        missing = [i for i, m in enumerate(masks) if m is None or getattr(m, "ndim", 0) != 2]
+        shape = next(((int(m.shape[0]), int(m.shape[1])) for i, m in enumerate(masks) if i not in missing), None)
+        if shape is None:   # no mask at all: take the image size from depth, the camera, or the script default
+            shape = self._fallback_shape(frames[0])
+        H, W = shape
+        for i, m in enumerate(masks):
+            if i not in missing and tuple(m.shape) != (H, W):
+                raise ValueError(f"frame {i}: mask shape {tuple(m.shape)} differs from {(H, W)} (one [H,W] resolution per batch)")
+        caller_stream = torch.cuda.current_stream(dev)
+        with torch.cuda.device(dev):
+            # device-resident annotators (device="cuda" in Replicator) were produced on the caller's stream
+            self.stream.wait_stream(caller_stream)
+            with torch.cuda.stream(self.stream):
+                if missing:   # an absent annotator gives an empty-label frame, never an error (gcd.py:1682,1788,1919)
+                    d_mask = torch.zeros((B, H, W), dtype=torch.int32, device=dev)
+                    present = [i for i in range(B) if i not in missing]
+                    if present:
+                        d_mask[present] = self._stack_to_device([masks[i] for i in present], torch.int32)
+                    mask_owned = True
+                else:
+                    d_mask, mask_owned = self._stack_to_device(masks, torch.int32, stacked.get("instance_segmentation"),
+                                                               return_owned=True)
+
+        # ---- host: per-frame tables (numpy only; overlaps the mask copy enqueued above) ------------------
+        hb = self._host_tables(frames, H, W, missing)
+        tables, frame_ids, poses, params_list, blk = hb.tables, hb.frame_ids, hb.poses, hb.params_list, hb.block
+        same_tables, N, R0, U, frame_base, contiguous_ids = hb.same_tables, hb.N, hb.R0, hb.U, hb.frame_base, hb.contiguous_ids
 
         # ---- device: uploads + kernels on the writer's stream ----------------------------
         owned: List[Tuple[Tuple, torch.Tensor]] = list(blk.buffers)

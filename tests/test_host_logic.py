@@ -605,3 +605,85 @@ def test_write_coco_file_accepts_bytes_and_array_chunks(tmp_path):
     formats.write_coco_file(tmp_path / "b.json", [formats.coco_images_text(range(0, 2), 64, 48)], dev, joined=True)
     assert (tmp_path / "b.json").read_text() == want
     assert formats.coco_images_text(range(0, 2), 64, 48) == formats.coco_images_text([0, 1], 64, 48)
+
+
+def _host_only_writer(record_fallback="first_mesh"):
+    """A ConstructionLabelWriter without a device: just what _host_tables touches (the constructor needs CUDA and the
+    built library — this box has no GPU).  Ordinary memory stands in for the pinned blocks; test scaffolding only."""
+    import torch
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    w = ConstructionLabelWriter.__new__(ConstructionLabelWriter)
+    w.device = torch.device("cpu")
+    w.record_fallback = record_fallback
+    w.resolver = classes.ObjectRootResolver(None, split_people=True)
+    w.near, w.far = 0.5, 250.0
+    w.max_lut_entries = 1 << 28
+    w._tables_cache = {}
+    w._warned_empty_lut = False
+    w._next_frame_id = 0
+
+    def take(kind, shape, dtype, owned):
+        t = torch.zeros(shape, dtype=dtype)
+        owned.append(((kind, shape, dtype), t))
+        return t
+
+    w._take_pinned = take
+    return w
+
+
+@pytest.mark.parametrize("fallback", ["first_mesh", "union"])
+def test_writer_host_tables_match_the_helpers(fallback):
+    """ConstructionLabelWriter._host_tables (the numpy-only half of annotate_batch) lays out the same LUT / slot /
+    record / camera tables as the test helpers build from classes.py + the oracle's camera packing — for a list of
+    frame dicts, for the same frames cut from ONE stacked dict, and for a batch that shows one scene (shared tables)."""
+    from constructionsceneposeestimation_b200 import writer as W
+    spec = synthetic.SceneSpec(640, 360, 24, 3, 17, config_id=31)
+    frames = synthetic.make_batch(spec, 4)
+    want = helpers.host_tables(frames, fallback=fallback)
+    lut_w, obj_w, cls_w, rec_w, cam_w, objs_w = want
+    R0 = helpers.host_tables.union[0]
+    records_in = helpers.host_tables.union[3]      # before the union pass (the device builds those records)
+    stacked = {
+        "instance_segmentation": {"data": np.stack([f["instance_segmentation"]["data"] for f in frames]),
+                                  "info": [f["instance_segmentation"]["info"] for f in frames]},
+        "bounding_box_3d": {"data": [f["bounding_box_3d"]["data"] for f in frames],
+                            "info": [f["bounding_box_3d"]["info"] for f in frames]},
+        "camera_pose": np.asarray([f["camera_pose"] for f in frames]),
+        "camera_params": [f["camera_params"] for f in frames],
+        "frame_id": 40,
+    }
+    for form in ("list", "stacked"):
+        w = _host_only_writer(fallback)
+        if form == "list":
+            fr = [w._normalise(f) for f in frames]
+        else:
+            cut = W._unstack(stacked)
+            assert cut.canonical
+            fr = [w._normalise_camera(f) for f in cut]
+        hb = w._host_tables(fr, 360, 640, [])
+        blk = hb.block
+        assert not hb.same_tables and hb.N == obj_w.shape[1] and hb.R0 == R0
+        assert hb.frame_ids == ([0, 1, 2, 3] if form == "list" else [40, 41, 42, 43]) and hb.contiguous_ids
+        L = lut_w.shape[1]
+        assert np.array_equal(blk.lut[:, :L], lut_w) and (blk.lut[:, L:] == -1).all()
+        assert np.array_equal(blk.obj_record, obj_w) and np.array_equal(blk.slot_class, cls_w)
+        assert np.array_equal(blk.cam, cam_w)
+        got_recs = blk.records.reshape(4, -1).view(O.BBOX3D_DTYPE).reshape(4, -1)
+        assert got_recs[:, :R0].tobytes() == records_in[:, :R0].tobytes()
+        assert [[o.prim_path for o in t.objects] for t in hb.tables] == [[o.prim_path for o in objs] for objs in objs_w]
+        if fallback == "union":
+            off, mem = helpers.host_tables.union[1], helpers.host_tables.union[2]
+            assert hb.U == off.shape[1] - 1 > 0
+            assert np.array_equal(blk.union_offsets, off) and np.array_equal(blk.union_members, mem)
+        else:
+            assert hb.U == 0
+    # one scene for the whole batch: ONE LUT row, broadcast slot tables; frames without records or ids
+    w = _host_only_writer(fallback)
+    same = [dict(frames[0], frame_id=7 + 2 * i) for i in range(3)]
+    same[1] = dict(same[1], bounding_box_3d={"data": None, "info": frames[0]["bounding_box_3d"]["info"]})
+    hb = w._host_tables([w._normalise(f) for f in same], 360, 640, [])
+    assert hb.same_tables and hb.block.lut.shape[0] == 1 and not hb.contiguous_ids and hb.frame_ids == [7, 9, 11]
+    assert np.array_equal(hb.block.lut[0, :lut_w.shape[1]], lut_w[0])
+    assert np.array_equal(hb.block.slot_class, np.repeat(cls_w[:1], 3, axis=0))
+    assert (hb.block.obj_record[1] == -1).all() and np.array_equal(hb.block.obj_record[0], obj_w[0])   # no records -> no boxes
+    assert (hb.block.records[1] == 0).all()
