@@ -244,7 +244,10 @@ def run_sweep(num_frames: int, rank: int = 0, world: int = 1, device: Optional[t
     device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     lo, hi = sharding.frame_range(rank, world, num_frames)
     spec = synthetic.CONFIGS[config]
-    key = (config, pool_frames, id(spec))
+    # keyed on the spec's VALUE: id(spec) of a spec that has been garbage collected can come back for a different one
+    # (the suspected cause of a one-off failure of a sweep test that followed another test's temporary "_t" config)
+    import dataclasses
+    key = (config, pool_frames, dataclasses.astuple(spec))
     if key not in _POOL_CACHE:   # the same pool on every rank: frame g = pool[g % B]
         _POOL_CACHE.clear()
         pool = synthetic.make_batch(spec, pool_frames, first_frame=0)
