@@ -60,6 +60,17 @@ def test_argument_validation_without_gpu(libcspe_path):
     with pytest.raises(_lib.CspeError):
         _lib.check("cspe_project_objects", rc)
     assert lib.cspe_mask_scan(None, 0, 4, 4, None, 0, 0, 1, None, None) == 0  # empty batch is a no-op
+    # round-2 entry points: object-level records, device text, row packing
+    assert lib.cspe_union_records(None, 96, 4, 2, None, 0, None, 0, 1, 3, None) == -1      # base + U > recs_per_frame
+    assert b"exceeds recs_per_frame" in lib.cspe_last_error()
+    assert lib.cspe_union_records(None, 96, 8, 2, None, 0, None, 0, 1, 3, None) == -1 and b"null" in lib.cspe_last_error()
+    assert lib.cspe_union_records(None, 96, 8, 2, None, 0, None, 0, 0, 3, None) == 0       # nothing to do
+    assert lib.cspe_union_records(None, 90, 8, 2, None, 0, None, 0, 1, 3, None) == -1 and b"rec_stride" in lib.cspe_last_error()
+    assert lib.cspe_format_coco(None, None, 1, 4, None, None, 64, None, None) == -1 and b"null" in lib.cspe_last_error()
+    assert lib.cspe_format_coco(None, None, 0, 4, None, None, 64, None, None) == 0
+    assert lib.cspe_format_yolo(None, None, -1, 4, None, 64, None, None) == -1 and b"negative" in lib.cspe_last_error()
+    assert lib.cspe_pack_rows(None, 64, None, 2, None, 0, None, None) == -1 and b"null" in lib.cspe_last_error()
+    assert lib.cspe_format_coco_images_host(0, 3, 64, 48, None, 10) == -1                   # capacity without a buffer
 
 
 def test_no_cpu_fallback_in_product():
