@@ -8,5 +8,5 @@ python - <<PY
 import json
 d=json.loads([l for l in open('gpurun_out/f_bench.json') if l.startswith('{')][-1])
 print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['e2e'].get('frac_of_pcie'), d['e2e']['device_resident']['value'], d['cpu_baseline']['value'], d['clocks'])
-print({k: round(v['frac'],3) for k,v in d.get('roofline_stress',{}).items()})
+print({k: round(v['frac'], 3) for k, v in d.get('roofline_stress', {}).get('cases', {}).items()})
 PY
