@@ -687,3 +687,52 @@ def test_writer_host_tables_match_the_helpers(fallback):
     assert np.array_equal(hb.block.slot_class, np.repeat(cls_w[:1], 3, axis=0))
     assert (hb.block.obj_record[1] == -1).all() and np.array_equal(hb.block.obj_record[0], obj_w[0])   # no records -> no boxes
     assert (hb.block.records[1] == 0).all()
+
+
+def test_union_plan_property():
+    """Random scenes (roots with / without a record of their own, 1-4 meshes, meshes without records, a crane part):
+    record_index_for("union") and union_members agree object by object, members are exactly the records of the
+    object's mesh paths, pack_union round-trips, and the other fallbacks are untouched by the union rule."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(st.booleans(), st.integers(1, 4), st.integers(0, 15)), min_size=1, max_size=12), st.booleans())
+    def run(objs_spec, with_crane):
+        paths = []
+        for i, (own, n_mesh, drop_mask) in enumerate(objs_spec):
+            root = f"{synthetic.FENCE_PREFIX}{i + 3:02d}"
+            if own:
+                paths.append(root)
+            for m in range(n_mesh):
+                if not (drop_mask >> m) & 1:            # a mesh without a bbox3d record simply is not listed
+                    paths.append(f"{root}/Mesh_{m}")
+        if with_crane:
+            paths += [f"{synthetic.CRANE_ROOT}/{synthetic.CRANE_CHILDREN[0]}/part_0", f"{synthetic.CRANE_ROOT}/{synthetic.CRANE_CHILDREN[0]}/part_1"]
+        if not paths:
+            return
+        res = classes.ObjectRootResolver()
+        objs = classes.aggregate_objects(paths, res)
+        idx = classes.record_index_for(objs, paths, "union")
+        first = classes.record_index_for(objs, paths, "first_mesh")
+        ref = classes.record_index_for(objs, paths, "reference")
+        plan = dict(classes.union_members(objs, paths))
+        u = 0
+        for slot, o in enumerate(objs):
+            own = o.actual_prim_path in paths
+            multi = "#" not in o.prim_path and len(o.mesh_paths) > 1
+            if own:
+                assert idx[slot] == first[slot] == ref[slot] == paths.index(o.actual_prim_path) and slot not in plan
+            elif multi:
+                assert slot in plan and idx[slot] == (len(paths) + u) | classes.RECORD_APPROX_BIT
+                assert plan[slot] == [paths.index(mp) for mp in o.mesh_paths] and ref[slot] == -1
+                assert first[slot] == plan[slot][0] | classes.RECORD_APPROX_BIT
+                u += 1
+            else:   # single mesh or a crane part: the reference's own first-mesh rule, exact
+                assert slot not in plan and idx[slot] == first[slot] == paths.index(o.mesh_paths[0])
+        assert u == len(plan)
+        off, mem, U = classes.pack_union([list(plan.items()), []])
+        assert U == len(plan) and off[1].tolist() == [0] * (U + 1)
+        for k, (slot, members) in enumerate(plan.items()):
+            assert mem[0, off[0, k]: off[0, k + 1]].tolist() == members
+
+    run()
