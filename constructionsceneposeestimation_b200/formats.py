@@ -335,3 +335,43 @@ def coco_keypoint_block(kp: np.ndarray, vis: np.ndarray) -> Dict[str, object]:
 
 def coco_image(image_id: int, width: int, height: int, file_name: str) -> Dict[str, object]:
     return {"id": int(image_id), "width": int(width), "height": int(height), "file_name": file_name}
+
+
+def pointcloud_annotator_rows(pcd) -> Optional[np.ndarray]:
+    """The (N, 6) ``x y z r g b`` matrix the reference writes for a Replicator ``pointcloud`` annotator payload
+    (``save_pointcloud_with_rgb``, gcd.py:715-769 — the capture loop's FIRST choice for ``pointcloud_%06d.txt``, before
+    the depth-map fallback of gcd.py:1729-1759), or None where the reference writes nothing.
+
+    ``pcd["data"]`` is xyz (N, 3) — a single point may arrive flat (3,); ``pcd["pointRgb"]`` is (N, 3 | 4) colours (the
+    alpha column is dropped), a single flat colour, or absent / empty / malformed -> white (255); when the two lengths
+    disagree both are cut to the shorter one.  The matrix is ``np.hstack([xyz, rgb])`` exactly as the reference builds
+    it (dtype promotion included), so ``np.savetxt(fmt='%.6f')`` — or ``cspe_format_fixed6`` on its float64 copy — prints
+    the reference's bytes."""
+    try:
+        if pcd is None or "data" not in pcd:
+            return None
+        xyz = pcd["data"]
+        if xyz is None or len(xyz) == 0:
+            return None
+        xyz = np.asarray(xyz)
+        if xyz.ndim == 1:
+            if len(xyz) != 3:
+                return None
+            xyz = xyz.reshape(1, 3)
+        n = xyz.shape[0]
+        white = lambda: np.ones((n, 3)) * 255      # float64, like the reference's default
+        colours = pcd.get("pointRgb") if hasattr(pcd, "get") else None
+        if colours is None:
+            rgb = white()
+        else:
+            colours = np.asarray(colours)
+            if colours.ndim == 1:
+                rgb = colours[:3].reshape(1, 3) if len(colours) in (3, 4) else white()
+            else:
+                rgb = colours[:, :3] if colours.shape[1] >= 3 else colours
+        if xyz.shape[0] != rgb.shape[0]:
+            m = min(xyz.shape[0], rgb.shape[0])
+            xyz, rgb = xyz[:m], rgb[:m]
+        return np.hstack([xyz, rgb])
+    except Exception:   # the reference wraps the whole function in try / except and skips the file (gcd.py:771-776)
+        return None

@@ -93,6 +93,8 @@ class BatchLabels:
     # recorded on the writer's stream after the last kernel / copy that reads the caller's annotator buffers
     inputs_consumed: Optional[torch.cuda.Event] = None
     missing_masks: Optional[List[int]] = None   # batch indices whose instance_segmentation annotator was absent
+    # (N, 6) x y z r g b rows of the frames that brought a ``pointcloud`` annotator payload (gcd.py:1720-1727), else None
+    pointcloud_rows: Optional[List[Optional[np.ndarray]]] = None
 
     def wait_inputs_consumed(self) -> "BatchLabels":
         """Block the host until the GPU no longer reads the annotator buffers this batch was built from (pinned
@@ -536,10 +538,36 @@ class ConstructionLabelWriter:
         # the caller may reuse its annotator buffers as soon as inputs_consumed has fired.
         if {"pointcloud", "rgb_png"} & set(self.formats) and self.output_dir is not None:
             labels.rgb_images = self._snapshot_rgb(frames, labels)
+        if "pointcloud" in self.formats and self.output_dir is not None:
+            # the capture loop's first choice for pointcloud_%06d.txt is the pointcloud annotator itself
+            # (gcd.py:1720-1727); its small host arrays are turned into the (N, 6) matrix right here
+            rows = [self._pointcloud_payload_rows(fr) for fr in frames]
+            if any(r is not None for r in rows):
+                labels.pointcloud_rows = rows
         self._pending.append((labels, None))
         while len(self._pending) > self.max_pending:
             self._serialise(*self._pending.pop(0))
         return labels
+
+    @staticmethod
+    def _pointcloud_payload_rows(fr: Mapping) -> Optional[np.ndarray]:
+        """formats.pointcloud_annotator_rows of the frame's ``pointcloud`` annotator payload, if it brought one.  The
+        reference reads ``pointRgb`` next to ``data`` (gcd.py:735); Replicator versions that deliver it under ``info``
+        are accepted too.  CUDA tensors are brought to the host (the cloud is a few thousand points)."""
+        payload = None
+        for key, value in fr.items():   # keys may still carry a render-product suffix here
+            if isinstance(key, str) and _annotator_name(key)[0] == "pointcloud":
+                payload = value
+        if not isinstance(payload, Mapping) or payload.get("data") is None:
+            return None
+        host = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
+        colours = payload.get("pointRgb")
+        if colours is None and isinstance(payload.get("info"), Mapping):
+            colours = payload["info"].get("pointRgb")
+        pcd = {"data": host(payload["data"])}
+        if colours is not None:
+            pcd["pointRgb"] = host(colours)
+        return formats.pointcloud_annotator_rows(pcd)
 
     def _snapshot_rgb(self, frames, labels: BatchLabels) -> List[Optional[torch.Tensor]]:
         dev = self.device
@@ -1065,17 +1093,22 @@ class ConstructionLabelWriter:
                 with open(os.path.join(ddir, f"depth_{labels.frame_ids[f0 + k]:06d}.csv"), "wb") as fh:
                     fh.write(self._host_bytes(text, offs[k], offs[k + 1]))
 
-    def _write_pointclouds(self, labels: BatchLabels, chunk: int = 8) -> Optional[List[int]]:
-        """gcd.py:1729-1759: pointcloud/pointcloud_%06d.txt from the depth maps and the RGB images of the batch;
-        returns the number of points per frame (None when the batch has no depth).  The clouds of ``chunk`` frames
+    def _write_pointclouds(self, labels: BatchLabels, chunk: int = 8) -> Optional[List[Optional[int]]]:
+        """gcd.py:1716-1759: pointcloud/pointcloud_%06d.txt — from the frame's pointcloud annotator payload when it brought
+        one (gcd.py:1720-1727), else from the depth map and the RGB image of the frame (gcd.py:1729-1759);
+        returns the number of points per depth-derived cloud (None for the batch when there is nothing to write, None
+        for a frame written from its annotator payload).  The clouds of ``chunk`` frames
         come out of one pair of launches (``cspe_depth_to_pointcloud_batch``), the text of each is formatted on the
         device and only its bytes cross PCIe."""
         depth = labels.device_outputs.get("depth")
-        if depth is None:
+        B = len(labels.frame_ids)
+        # a frame that brought a pointcloud annotator payload is written from it (the reference's first choice,
+        # gcd.py:1720-1727 -> save_pointcloud_with_rgb); only the others fall back to the depth map
+        given = labels.pointcloud_rows if labels.pointcloud_rows is not None else [None] * B
+        if depth is None and not any(g is not None for g in given):
             return None
         pdir = os.path.join(self.output_dir, "pointcloud")
         os.makedirs(pdir, exist_ok=True)
-        B = depth.shape[0]
         rgbs = labels.rgb_images if labels.rgb_images is not None else [None] * B
         counts: List[int] = []
         for f0 in range(0, B, chunk):
@@ -1083,9 +1116,15 @@ class ConstructionLabelWriter:
             part = rgbs[f0:f0 + nb]
             with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
                 d_rgb = None
-                if all(r is not None for r in part) and len({tuple(r.shape) for r in part}) == 1:
+                if depth is None or all(g is not None for g in given[f0:f0 + nb]):
+                    clouds = [torch.empty((0, 6), dtype=torch.float64, device=self.device)] * nb   # nothing to derive
+                else:
+                    clouds = None
+                if clouds is None and all(r is not None for r in part) and len({tuple(r.shape) for r in part}) == 1:
                     d_rgb = torch.stack([r.to(self.device) for r in part]).contiguous()
-                if d_rgb is not None or all(r is None for r in part):
+                if clouds is not None:
+                    pass
+                elif d_rgb is not None or all(r is None for r in part):
                     pts, offsets = ops.depth_to_pointcloud_batch(depth[f0:f0 + nb], d_rgb, labels.device_outputs["cam"][f0:f0 + nb])
                     offs = offsets.cpu().tolist()
                     clouds = [pts[offs[k]:offs[k + 1]] for k in range(nb)]
@@ -1096,8 +1135,11 @@ class ConstructionLabelWriter:
                         p1, n1 = ops.depth_to_pointcloud(depth[f0 + k], r, labels.device_outputs["cam"][f0 + k])
                         clouds.append(p1[: int(n1.item())])
                 for k, cloud in enumerate(clouds):
+                    if given[f0 + k] is not None:   # float64 copy: float32 coordinates print the same decimals
+                        cloud = torch.from_numpy(np.ascontiguousarray(given[f0 + k], dtype=np.float64)).to(self.device)
                     points = int(cloud.shape[0])
-                    counts.append(points)
+                    # the reference's logger counts only clouds of the depth-map fallback (gcd.py:1754): None = not logged
+                    counts.append(points if given[f0 + k] is None else None)
                     if points == 0:   # the reference saves nothing for an empty cloud (gcd.py:1749)
                         continue
                     text, n_bytes, _ = ops.format_fixed6(cloud, header="x y z r g b")

@@ -143,6 +143,44 @@ def make_pointcloud(ref):
     return out.shape
 
 
+def pointcloud_annotator_cases():
+    """Payloads of Replicator's pointcloud annotator as save_pointcloud_with_rgb meets them (gcd.py:715-769)."""
+    rng = np.random.default_rng(17)
+    xyz = (rng.normal(size=(37, 3)) * np.array([12.0, 12.0, 3.0])).astype(np.float32)
+    xyz[0] = (0.0, -0.0, 1e-7)
+    xyz[1] = (123456.789, -0.0000005, 2.5)
+    rgba = rng.integers(0, 256, (37, 4), dtype=np.uint8)
+    return [
+        ("rgba", {"data": xyz, "pointRgb": rgba}),
+        ("rgb3", {"data": xyz, "pointRgb": rgba[:, :3].copy()}),
+        ("no_rgb", {"data": xyz}),
+        ("rgb_none", {"data": xyz, "pointRgb": None}),
+        ("rgb_empty", {"data": xyz, "pointRgb": np.zeros((0,), dtype=np.uint8)}),
+        ("rgb_short", {"data": xyz, "pointRgb": rgba[:20]}),
+        ("rgb_long", {"data": xyz[:11], "pointRgb": rgba}),
+        ("rgb_flat_garbage", {"data": xyz, "pointRgb": rgba.reshape(-1)}),
+        ("rgb_two_columns", {"data": xyz, "pointRgb": rgba[:, :2].copy()}),
+        ("single_point_flat", {"data": xyz[5], "pointRgb": rgba[5]}),
+        ("single_point_flat_rgb3", {"data": xyz[6], "pointRgb": rgba[6, :3].copy()}),
+        ("float_colours", {"data": xyz.astype(np.float64), "pointRgb": rng.random((37, 4))}),
+        ("xyz_flat_garbage", {"data": xyz.reshape(-1)[:7], "pointRgb": rgba}),
+        ("xyz_empty", {"data": np.zeros((0, 3), dtype=np.float32), "pointRgb": rgba}),
+        ("xyz_none", {"data": None, "pointRgb": rgba}),
+    ]
+
+
+def make_pointcloud_annotator(ref):
+    """The text save_pointcloud_with_rgb writes for each payload (None = it writes no file)."""
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for name, payload in pointcloud_annotator_cases():
+            path = Path(tmp) / f"{name}.txt"
+            ref.save_pointcloud_with_rgb(payload, str(path))
+            out[name] = path.read_text() if path.exists() else None
+    (HERE / "pointcloud_annotator.json").write_text(json.dumps(out, indent=1))
+    return sum(v is not None for v in out.values())
+
+
 def make_depth_stats(ref):
     rng = np.random.default_rng(11)
     cases = {}
@@ -303,12 +341,13 @@ def main():
         n_paths = make_paths(ref)
         n_recs, raised = make_transforms(ref)
         pc_shape = make_pointcloud(ref)
+        n_pc_files = make_pointcloud_annotator(ref)
         stats = make_depth_stats(ref)
         n_text = make_label_json(ref)
         n_quality = make_quality_log(ref)
         n_objects, n_posed = make_frame_golden(ref)
     meta = {"numpy": np.__version__, "scipy": scipy.__version__, "paths": n_paths, "records": n_recs,
-            "mirrored_transform_raises": raised, "pointcloud_shape": list(pc_shape), "depth_cases": stats,
+            "mirrored_transform_raises": raised, "pointcloud_shape": list(pc_shape), "pointcloud_annotator_files": n_pc_files, "depth_cases": stats,
             "label_text_bytes": n_text, "quality_frames": n_quality, "frame_objects": n_objects,
             "frame_objects_with_record": n_posed, "source": str(reference_extract.REFERENCE_SCRIPT)}
     (HERE / "META.json").write_text(json.dumps(meta, indent=1))

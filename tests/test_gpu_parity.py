@@ -1683,6 +1683,49 @@ def test_writer_depth_csv_and_pointcloud_files(T, ops, tmp_path):
                                                                         frames[0]["camera_params"], frames[0]["camera_pose"]))
 
 
+def test_writer_pointcloud_annotator_payload(T, ops, tmp_path):
+    """A frame that brings Replicator's pointcloud annotator payload gets its pointcloud_%06d.txt from it — the capture
+    loop's first choice (gcd.py:1720-1727 -> save_pointcloud_with_rgb, gcd.py:715-769) — byte for byte the text the
+    reference's own function wrote (tests/golden/pointcloud_annotator.json); frames without a payload (or with one the
+    reference rejects) keep the depth-map fallback (gcd.py:1729-1759)."""
+    import importlib.util
+    import json
+    from constructionsceneposeestimation_b200 import synthetic
+    from constructionsceneposeestimation_b200.writer import ConstructionLabelWriter
+    gold = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+    spec = importlib.util.spec_from_file_location("make_golden", gold / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = json.loads((gold / "pointcloud_annotator.json").read_text())
+    cases = dict(mg.pointcloud_annotator_cases())
+    names = ["rgba", "no_rgb", "rgb_short", "single_point_flat", "float_colours", "rgb_two_columns", "xyz_empty"]
+    base = synthetic.make_batch(synthetic.SceneSpec(160, 96, 8, 1, 17, config_id=8, with_rgb=True), len(names) + 1, first_frame=10)
+    frames = []
+    for k, fr in enumerate(base):
+        fr = dict(fr)
+        if k < len(names):
+            key = "pointcloud" if k % 2 == 0 else "pointcloud-RenderProduct_Replicator"     # suffixed keys as Replicator sends them
+            fr[key] = cases[names[k]]
+        frames.append(fr)
+    w = ConstructionLabelWriter(str(tmp_path / "a"), formats=("pointcloud",), split_people=True)
+    w.write_batch(frames)
+    summary = w.on_final_frame()
+    plain = ConstructionLabelWriter(str(tmp_path / "b"), formats=("pointcloud",), split_people=True)   # no payloads at all
+    plain.write_batch(base)
+    plain.on_final_frame()
+    for k, fr in enumerate(frames):
+        name = f"pointcloud_{fr['frame_id']:06d}.txt"
+        got = (tmp_path / "a" / "pointcloud" / name).read_text()
+        fallback = (tmp_path / "b" / "pointcloud" / name).read_text()
+        if k < len(names) and want[names[k]] is not None:
+            assert got == want[names[k]], names[k]                 # the reference's bytes
+            assert got != fallback
+        else:
+            assert got == fallback, k                              # "xyz_empty" and the frame without a payload
+    # the reference's logger counts only the depth-map fallback clouds (gcd.py:1754)
+    assert summary["quality"]["pointcloud_stats"] == {"valid": 2, "empty": 0, "insufficient": 0}
+
+
 # ------------------------------------------------------------------ kernels against the reference's own outputs
 GOLD = __import__("pathlib").Path(__file__).resolve().parent / "golden"
 

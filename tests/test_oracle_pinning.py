@@ -291,3 +291,64 @@ def test_mask_scan_formulations_agree(seed):
 
     if c_oracle.available():
         assert np.array_equal(a, c_oracle.mask_scan(mask, lut, N))
+
+
+def test_pointcloud_annotator_rows_golden(tmp_path):
+    """formats.pointcloud_annotator_rows == what the reference's save_pointcloud_with_rgb writes (gcd.py:715-769) for
+    every payload shape it special-cases: RGBA / RGB / missing / empty / short / long / flat / two-column colours, a
+    single flat point, float colours, malformed and empty xyz.  The golden texts were written by the reference's own
+    function (make_golden.py); here np.savetxt prints our matrix — the device formatter is held to np.savetxt's
+    bytes by the GPU tests."""
+    import importlib.util
+    from constructionsceneposeestimation_b200 import formats
+    spec = importlib.util.spec_from_file_location("make_golden", GOLD / "make_golden.py")
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    want = json.loads((GOLD / "pointcloud_annotator.json").read_text())
+    cases = mg.pointcloud_annotator_cases()
+    assert sorted(want) == sorted(name for name, _ in cases) and sum(v is None for v in want.values()) == 3
+    for name, payload in cases:
+        rows = formats.pointcloud_annotator_rows(payload)
+        if want[name] is None:
+            assert rows is None, name
+            continue
+        assert rows is not None and rows.ndim == 2 and rows.shape[1] in (5, 6), name
+        path = tmp_path / f"{name}.txt"
+        np.savetxt(path, rows, fmt="%.6f", delimiter=" ", header="x y z r g b", comments="")     # gcd.py:768-769
+        assert path.read_text() == want[name], name
+        # the float64 copy the writer formats on the device prints the same text
+        np.savetxt(path, rows.astype(np.float64), fmt="%.6f", delimiter=" ", header="x y z r g b", comments="")
+        assert path.read_text() == want[name], name
+    assert formats.pointcloud_annotator_rows(None) is None and formats.pointcloud_annotator_rows({}) is None
+
+
+@needs_reference
+def test_pointcloud_annotator_rows_live(tmp_path):
+    """The same comparison against the reference function executed here, on random payloads."""
+    from constructionsceneposeestimation_b200 import formats
+    ref = reference_extract.load()
+    rng = np.random.default_rng(23)
+    import contextlib
+    import io
+    for trial in range(40):
+        n = int(rng.integers(1, 50))
+        payload = {"data": (rng.normal(size=(n, 3)) * 30).astype(np.float32)}
+        kind = trial % 4
+        if kind == 0:
+            payload["pointRgb"] = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+        elif kind == 1:
+            payload["pointRgb"] = rng.integers(0, 256, (int(rng.integers(1, 60)), 3), dtype=np.uint8)
+        elif kind == 2:
+            payload["pointRgb"] = rng.random((n, 4)).astype(np.float32)
+        path = tmp_path / "ref.txt"
+        if path.exists():
+            path.unlink()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ref.save_pointcloud_with_rgb(payload, str(path))
+        rows = formats.pointcloud_annotator_rows(payload)
+        if not path.exists():
+            assert rows is None
+            continue
+        mine = tmp_path / "mine.txt"
+        np.savetxt(mine, rows, fmt="%.6f", delimiter=" ", header="x y z r g b", comments="")
+        assert mine.read_text() == path.read_text(), trial
