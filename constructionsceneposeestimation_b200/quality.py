@@ -6,6 +6,9 @@ the reference's summary keeps working.  The depth entry comes from the statistic
 already reduced (``cspe_depth_stats``, f2) instead of five numpy passes over the depth map
 (gcd.py:318-330); label / point-cloud / RGB entries take the counts the kernels return.
 
+``report()`` is the readable text of the reference's ``_generate_report`` (gcd.py:420-457), pinned by the report the
+reference's own logger returned for a scripted run (``tests/golden/quality_log.json``).
+
 The issue strings are data in that file — the reference's own report groups frames by the text
 before the first ``:`` (gcd.py:449-453) — so they are kept verbatim.
 """
@@ -141,7 +144,35 @@ class FrameQualityLog:
                 counts[key] = counts.get(key, 0) + 1
         return dict(sorted(counts.items(), key=lambda kv: kv[1], reverse=True))
 
+    def report(self) -> str:
+        """The readable run report of the reference's logger (``_generate_report``, gcd.py:420-457): the counters of
+        ``summary()`` as text, then the issues grouped by type, most frequent first."""
+        st = self.summary()["statistics"]
+        pc, rgb, dp, lb, oc = st["pointcloud_stats"], st["rgb_stats"], st["depth_stats"], st["label_stats"], st["object_count"]
+        lines = ["=== 数据生成汇总报告 ===", "",
+                 "总体统计:",
+                 f"  尝试帧数: {st['total_frames_attempted']}",
+                 f"  成功帧数: {st['successful_frames']}",
+                 f"  失败帧数: {st['failed_frames']}",
+                 f"  成功率: {st['success_rate'] * 100:.1f}%",
+                 f"  总重试次数: {st['retry_count']}", "",
+                 "点云质量:",
+                 f"  有效: {pc['valid']}", f"  为空: {pc['empty']}", f"  不足: {pc['insufficient']}", "",
+                 "RGB图像:",
+                 f"  成功: {rgb['valid']}", f"  失败: {rgb['failed']}", "",
+                 "深度图:",
+                 f"  有效: {dp['valid']}", f"  失败: {dp['failed']}", f"  全零: {dp['all_zero']}", f"  全无穷: {dp['all_inf']}", "",
+                 "标签识别:",
+                 f"  有效: {lb['valid']}", f"  为空: {lb['empty']}", f"  总物体数: {oc['total']}",
+                 f"  平均每帧: {oc['per_frame_avg']:.2f}", "",
+                 "常见问题:"]
+        lines += [f"  {kind}: {count} 次" for kind, count in self.issue_counts().items()]
+        return "\n".join(lines) + "\n"
+
     def save_summary(self, path: Optional[str] = None) -> Dict[str, object]:
+        """``generation_summary.json`` (gcd.py:406-407) and, next to it, the readable report (the reference appends
+        it to its detail log, gcd.py:410-413; here it is a file of its own, ``generation_report.txt`` — the per-frame
+        lines of that detail log are not reproduced)."""
         data = self.summary()
         if path is None and self.log_dir is not None:
             os.makedirs(self.log_dir, exist_ok=True)
@@ -149,4 +180,8 @@ class FrameQualityLog:
         if path is not None:
             with open(path, "w", encoding="utf-8") as f:
                 json.dump(data, f, indent=2, ensure_ascii=False)
+            base = os.path.basename(path)
+            name = base.replace("summary", "report").rsplit(".", 1)[0] + ".txt" if "summary" in base else base + ".report.txt"
+            with open(os.path.join(os.path.dirname(path), name), "w", encoding="utf-8") as f:
+                f.write(self.report())
         return data

@@ -242,7 +242,8 @@ def make_quality_log(ref):
         summary = json.loads((Path(tmp) / "generation_summary.json").read_text(encoding="utf-8"))
     issue_lines = [ln.strip() for ln in report.split("常见问题:\n")[1].splitlines() if ln.strip()]
     (HERE / "quality_log.json").write_text(json.dumps({"events": QUALITY_EVENTS, "summary": summary,
-                                                       "issue_lines": issue_lines}, ensure_ascii=False, indent=1))
+                                                       "issue_lines": issue_lines, "report": report},
+                                                      ensure_ascii=False, indent=1))
     return len(summary["frame_logs"])
 
 

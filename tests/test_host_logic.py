@@ -244,6 +244,13 @@ def test_quality_log_matches_reference_logger(tmp_path):
     assert on_disk == gold["summary"]
     assert list(on_disk["statistics"]) == list(gold["summary"]["statistics"])       # key order too
     assert [f"{k}: {v} 次" for k, v in log.issue_counts().items()] == gold["issue_lines"]   # gcd.py:447-455
+    # the readable report: the text the reference's own _generate_report returned (gcd.py:420-457), and its file
+    assert log.report() == gold["report"]
+    assert (tmp_path / "logs" / "generation_report.txt").read_text(encoding="utf-8") == gold["report"]
+    log.save_summary(str(tmp_path / "logs" / "generation_summary_rank03.json"))
+    assert (tmp_path / "logs" / "generation_report_rank03.txt").read_text(encoding="utf-8") == gold["report"]
+    empty = __import__("constructionsceneposeestimation_b200.quality", fromlist=["FrameQualityLog"]).FrameQualityLog()
+    assert "成功率: 0.0%" in empty.report() and empty.report().endswith("常见问题:\n")
 
 
 def test_depth_quality_from_device_record_layout():
