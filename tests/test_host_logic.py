@@ -743,3 +743,61 @@ def test_union_plan_property():
             assert mem[0, off[0, k]: off[0, k + 1]].tolist() == members
 
     run()
+
+
+def test_writer_host_tables_edge_cases():
+    """_host_tables on the inputs the reference tolerates (gcd.py:1682, 1788, 1919, 2024-2027): scenes of different
+    sizes in one batch (padding), a frame without bbox3d, records / primPaths of different lengths (cut to the
+    shorter), no idToLabels entry that resolves (one warning), an id space too sparse for the dense LUT (clear error),
+    default camera (script constants) and identity pose when the frame brings none."""
+    import warnings as W
+    spec_a = synthetic.SceneSpec(320, 180, 10, 2, 17, config_id=41)
+    spec_b = synthetic.SceneSpec(320, 180, 18, 2, 17, config_id=42)
+    fa, fb = synthetic.make_frame(spec_a, 0), synthetic.make_frame(spec_b, 1)
+    w = _host_only_writer()
+    hb = w._host_tables([w._normalise(fa), w._normalise(fb)], 180, 320, [])
+    na, nb = len(hb.tables[0].objects), len(hb.tables[1].objects)
+    assert na < nb == hb.N and not hb.same_tables
+    assert (hb.block.obj_record[0, na:] == -1).all() and (hb.block.slot_class[0, na:] == -1).all()
+    ra, rb = len(fa["bounding_box_3d"]["data"]), len(fb["bounding_box_3d"]["data"])
+    assert hb.R0 == max(ra, rb) and (hb.block.records[0, ra:] == 0).all()
+    # records longer than primPaths (and the other way round): both cut to the shorter, tables built from the cut paths
+    long_recs = dict(fa, bounding_box_3d={"data": np.concatenate([fa["bounding_box_3d"]["data"]] * 2),
+                                          "info": fa["bounding_box_3d"]["info"]})
+    short_recs = dict(fa, bounding_box_3d={"data": fa["bounding_box_3d"]["data"][:5], "info": fa["bounding_box_3d"]["info"]})
+    hb2 = w._host_tables([w._normalise(long_recs), w._normalise(short_recs)], 180, 320, [])
+    assert hb2.R0 == ra and len(hb2.tables[0].objects) == na
+    paths5 = fa["bounding_box_3d"]["info"]["primPaths"][:5]
+    objs5 = classes.aggregate_objects(paths5, w.resolver)
+    assert [o.prim_path for o in hb2.tables[1].objects] == [o.prim_path for o in objs5]
+    assert (hb2.block.records[1, 5:] == 0).all()
+    # no bbox3d at all, no camera: defaults of the script, identity pose, frame ids continue from the last call
+    bare = {"instance_segmentation": fa["instance_segmentation"]}
+    w._next_frame_id = 12
+    hb3 = w._host_tables([w._normalise(bare), w._normalise(bare)], 180, 320, [])
+    assert hb3.frame_ids == [12, 13] and hb3.N == 1 and (hb3.block.obj_record == -1).all() and hb3.same_tables
+    cam = hb3.block.cam[0]
+    assert cam[:3].tolist() == [0, 0, 0] and np.array_equal(cam[3:12].reshape(3, 3), np.eye(3))
+    assert cam[18] == 320 and cam[19] == 180 and cam[16] == 0.5 and cam[17] == 250.0
+    # idToLabels that resolves to nothing: one warning for the whole run
+    unresolved = dict(fa, instance_segmentation={"data": fa["instance_segmentation"]["data"],
+                                                 "info": {"idToLabels": {"7": "/World/Nothing/here"}}})
+    with W.catch_warnings(record=True) as seen:
+        W.simplefilter("always")
+        w._host_tables([w._normalise(unresolved)], 180, 320, [])
+        w._host_tables([w._normalise(unresolved)], 180, 320, [])
+    assert len([x for x in seen if "idToLabels" in str(x.message)]) == 1
+    # ... but not for a frame whose mask is missing anyway
+    w2 = _host_only_writer()
+    with W.catch_warnings(record=True) as seen:
+        W.simplefilter("always")
+        w2._host_tables([w2._normalise(unresolved)], 180, 320, [0])
+    assert not seen
+    # an id space too sparse for the dense id -> slot table
+    w3 = _host_only_writer()
+    w3.max_lut_entries = 1 << 10
+    labels = dict(fa["instance_segmentation"]["info"]["idToLabels"])
+    labels[str(1 << 20)] = fa["bounding_box_3d"]["info"]["primPaths"][0]     # a path that resolves to an object
+    sparse = dict(fa, instance_segmentation={"data": fa["instance_segmentation"]["data"], "info": {"idToLabels": labels}})
+    with pytest.raises(ValueError, match="id->slot table"):
+        w3._host_tables([w3._normalise(sparse)], 180, 320, [])
